@@ -1,0 +1,299 @@
+/*
+ * rt_b200.h -- C ABI of the B200-native per-pixel path for GP1_Raytracer_2223.
+ *
+ * The reference has no plugin / FFI seam: the boundary it offers is the C++
+ * call `pRenderer->Render(pScene)` (reference source/main.cpp:91 ->
+ * source/Renderer.cpp:34-98).  This header is the C-ABI a drop-in
+ * `dae::Renderer` binds instead of running `RenderPixel`
+ * (source/Renderer.cpp:100-182) on the host.  Every entry point names the
+ * reference interface it replaces.  Plain pointers and sizes only; all
+ * pointers are caller-owned and are only read (or, for destinations, written)
+ * during the call.  One context per Renderer; calls on one context are
+ * serialised by the caller, exactly like the reference's main thread
+ * (source/main.cpp:56-111).
+ *
+ * There is no CPU fallback behind this interface: without a CUDA device
+ * `rt_create` fails with RT_ERR_NO_DEVICE.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+typedef struct rt_context rt_context;
+
+/* Every call returns one of these; rt_last_error() gives the text. */
+enum rt_status
+{
+	RT_OK = 0,
+	RT_ERR_INVALID_ARGUMENT = 1,
+	RT_ERR_CUDA = 2,
+	RT_ERR_NO_DEVICE = 3,
+	RT_ERR_BAD_STATE = 4,
+	RT_ERR_CAPACITY = 5
+};
+
+/* Renderer::LightingMode, source/Renderer.h:40-48 (same numeric order, F3 cycles +1 mod 4). */
+enum rt_lighting_mode
+{
+	RT_LIGHTING_OBSERVED_AREA = 0,
+	RT_LIGHTING_RADIANCE = 1,
+	RT_LIGHTING_BRDF = 2,
+	RT_LIGHTING_COMBINED = 3
+};
+
+/* TriangleCullMode, source/DataTypes.h:29-34. */
+enum rt_cull_mode
+{
+	RT_CULL_FRONT_FACE = 0,
+	RT_CULL_BACK_FACE = 1,
+	RT_CULL_NONE = 2
+};
+
+/* LightType, source/DataTypes.h:522-526. */
+enum rt_light_type
+{
+	RT_LIGHT_POINT = 0,
+	RT_LIGHT_DIRECTIONAL = 1
+};
+
+/*
+ * Tag of the union that replaces the virtual Material::Shade
+ * (source/Material.h:27): one value per concrete class.
+ */
+enum rt_material_tag
+{
+	RT_MATERIAL_SOLID_COLOR = 0,   /* Material_SolidColor   source/Material.h:34-48  : color            */
+	RT_MATERIAL_LAMBERT = 1,       /* Material_Lambert      source/Material.h:54-68  : color, p0 = kd   */
+	RT_MATERIAL_LAMBERT_PHONG = 2, /* Material_LambertPhong source/Material.h:74-94  : color, p0 = kd, p1 = ks, p2 = exponent */
+	RT_MATERIAL_COOK_TORRENCE = 3  /* Material_CookTorrence source/Material.h:99-129 : color = albedo, p0 = metalness, p1 = roughness */
+};
+
+typedef struct rt_material_desc
+{
+	int32_t tag;      /* rt_material_tag */
+	float color[3];
+	float p0;
+	float p1;
+	float p2;
+	float reserved;
+} rt_material_desc;
+
+/* Scene::GetSphereGeometries(), source/Scene.h:41; Sphere source/DataTypes.h:13-19, as SoA. */
+typedef struct rt_spheres_soa
+{
+	const float* origin_x;
+	const float* origin_y;
+	const float* origin_z;
+	const float* radius;
+	const uint8_t* material_index;
+	int32_t count;
+} rt_spheres_soa;
+
+/* Scene::GetPlaneGeometries(), source/Scene.h:40; Plane source/DataTypes.h:21-27, as SoA. */
+typedef struct rt_planes_soa
+{
+	const float* origin_x;
+	const float* origin_y;
+	const float* origin_z;
+	const float* normal_x;
+	const float* normal_y;
+	const float* normal_z;
+	const uint8_t* material_index;
+	int32_t count;
+} rt_planes_soa;
+
+/* Scene::GetLights(), source/Scene.h:42; Light source/DataTypes.h:528-536, as SoA. */
+typedef struct rt_lights_soa
+{
+	const float* origin_x;
+	const float* origin_y;
+	const float* origin_z;
+	const float* direction_x;   /* carried for completeness; the reference never reads it on this path (source/Utils.h:347-348) */
+	const float* direction_y;
+	const float* direction_z;
+	const float* color_r;
+	const float* color_g;
+	const float* color_b;
+	const float* intensity;
+	const int32_t* type;        /* rt_light_type */
+	int32_t count;
+} rt_lights_soa;
+
+/*
+ * One TriangleMesh (source/DataTypes.h:109-156) after UpdateTransforms()
+ * (source/DataTypes.h:210-236): world-space `transformedPositions`, `indices`,
+ * and per-triangle `transformedNormals`.  Re-upload whenever UpdateTransforms
+ * ran.  aabb_min/aabb_max may be NULL: the library then derives a box over the
+ * indexed vertices (the shipped BVH build never fills
+ * transformedMin/MaxAABB, source/DataTypes.h:231-235).
+ */
+typedef struct rt_mesh_desc
+{
+	const float* positions;     /* 3 * vertex_count, xyz interleaved as in std::vector<Vector3> */
+	int32_t vertex_count;
+	const int32_t* indices;     /* 3 * triangle_count */
+	const float* normals;       /* 3 * triangle_count floats: one face normal per triangle */
+	int32_t triangle_count;
+	int32_t cull_mode;          /* rt_cull_mode */
+	uint8_t material_index;
+	const float* aabb_min;      /* 3 floats or NULL */
+	const float* aabb_max;      /* 3 floats or NULL */
+} rt_mesh_desc;
+
+/*
+ * What RenderPixel reads from dae::Camera (source/Camera.h:24-40) after
+ * CalculateCameraToWorld() (source/Camera.h:43-53): origin, fov (already
+ * tan(fovAngle/2), source/Camera.h:55-59) and rows 0..2 of cameraToWorld.
+ * These stay host-computed so tanf/cosf/sinf come from the caller's libm.
+ */
+typedef struct rt_camera
+{
+	float origin[3];
+	float fov;
+	float right[3];
+	float up[3];
+	float forward[3];
+} rt_camera;
+
+/*
+ * Renderer state read per frame (source/Renderer.h:49-61) plus the surface
+ * format shifts SDL_MapRGB uses (source/Renderer.cpp:178-181).
+ */
+typedef struct rt_frame_desc
+{
+	int32_t width;              /* m_Width  */
+	int32_t height;             /* m_Height */
+	float aspect_ratio;         /* m_AspectRatio = width / float(height), source/Renderer.cpp:31 */
+	int32_t lighting_mode;      /* rt_lighting_mode, m_CurrentLightingMode */
+	int32_t shadows_enabled;    /* m_ShadowsEnabled */
+	uint8_t r_shift;            /* SDL_PixelFormat::Rshift (16 for XRGB8888) */
+	uint8_t g_shift;            /* 8 */
+	uint8_t b_shift;            /* 0 */
+	uint8_t reserved;
+	uint32_t alpha_mask;        /* SDL_PixelFormat::Amask, OR-ed into every pixel (0 for XRGB8888) */
+} rt_frame_desc;
+
+/* Device-side timing of the most recent rt_render* call, from CUDA events. */
+typedef struct rt_timing
+{
+	float kernel_ms;            /* pixel kernel, max over the context's devices */
+	float gather_ms;            /* band gather to device 0 (0 with one device) */
+	float d2h_ms;               /* device 0 -> host copy (0 for device-only renders) */
+	float total_ms;             /* first launch to last completion */
+	int32_t kernel_launches;    /* launches of our kernels during the call */
+	int32_t reserved;
+} rt_timing;
+
+/*
+ * Per-frame test histogram reproduced by the counters build of the kernel
+ * (SURVEY.md section 8(d)): used only to turn kernel time into algorithmic
+ * FLOP/s.  Indices documented in DESIGN.md.
+ */
+#define RT_COUNTER_SLOTS 40
+typedef struct rt_counters
+{
+	uint64_t slot[RT_COUNTER_SLOTS];
+} rt_counters;
+
+/* Slot meanings; the FLOP weight of each event is the table in SURVEY.md section 8(d). */
+enum rt_counter_slot
+{
+	RT_CNT_PIXELS = 0,              /* ray-gen 38, output stage 11 */
+	RT_CNT_HIT_PIXELS = 1,          /* +6: offset origin */
+	RT_CNT_SPHERE_P_DISC = 2,       /* primary sphere test rejected on the discriminant: 16 */
+	RT_CNT_SPHERE_P_TREJ = 3,       /* rejected on t range: 19 */
+	RT_CNT_SPHERE_P_HIT = 4,        /* hit, record written: 28 */
+	RT_CNT_SPHERE_P_CLOSEST = 5,    /* became closest: +9 (normalise) */
+	RT_CNT_SPHERE_S_DISC = 6,       /* shadow-ray sphere test: 16 */
+	RT_CNT_SPHERE_S_TREJ = 7,       /* 19 */
+	RT_CNT_SPHERE_S_HIT = 8,        /* 19 */
+	RT_CNT_PLANE_P_TEST = 9,        /* 14 */
+	RT_CNT_PLANE_P_HIT = 10,        /* +6 */
+	RT_CNT_PLANE_S_TEST = 11,       /* 14 */
+	RT_CNT_SLAB_P_TEST = 12,        /* 22 */
+	RT_CNT_SLAB_P_PASS = 13,
+	RT_CNT_SLAB_S_TEST = 14,        /* 22 */
+	RT_CNT_SLAB_S_PASS = 15,
+	RT_CNT_TRI_P_CULLED = 16,       /* parallel or culled: 5 */
+	RT_CNT_TRI_P_DEGENERATE = 17,   /* |a| < eps: 25 */
+	RT_CNT_TRI_P_UREJ = 18,         /* 35 */
+	RT_CNT_TRI_P_VREJ = 19,         /* 51 */
+	RT_CNT_TRI_P_TREJ = 20,         /* 57 */
+	RT_CNT_TRI_P_HIT = 21,          /* 63 */
+	RT_CNT_TRI_S_CULLED = 22,
+	RT_CNT_TRI_S_DEGENERATE = 23,
+	RT_CNT_TRI_S_UREJ = 24,
+	RT_CNT_TRI_S_VREJ = 25,
+	RT_CNT_TRI_S_TREJ = 26,
+	RT_CNT_TRI_S_HIT = 27,
+	RT_CNT_LIGHT_ITERATIONS = 28,   /* 15 each */
+	RT_CNT_SHADOW_RAYS = 29,
+	RT_CNT_OCCLUDED = 30,
+	RT_CNT_LIT = 31,                /* un-shadowed light evaluations: 27 each in Combined mode */
+	RT_CNT_SHADE_SOLID = 32,        /* 0 */
+	RT_CNT_SHADE_LAMBERT = 33,      /* 6 */
+	RT_CNT_SHADE_PHONG = 34,        /* 33 */
+	RT_CNT_SHADE_COOK_TORRENCE = 35 /* 112 */
+};
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+
+/* Replaces `new Renderer(pWindow)` (source/Renderer.cpp:24-32) as far as device state goes.
+ * device_ids == NULL or n_devices == 0 selects the current CUDA device only. */
+int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx);
+int rt_destroy(rt_context* ctx);
+const char* rt_last_error(const rt_context* ctx);   /* ctx may be NULL: creation errors */
+int rt_abi_version(void);
+int rt_device_count(const rt_context* ctx);
+
+/* ---- scene upload (replaces the by-reference reads at source/Renderer.cpp:36-38 and
+ *      source/Scene.cpp:29-96; call after Scene::Initialize and whenever the data changed) ------ */
+int rt_upload_spheres(rt_context* ctx, const rt_spheres_soa* spheres);
+int rt_upload_planes(rt_context* ctx, const rt_planes_soa* planes);
+int rt_upload_lights(rt_context* ctx, const rt_lights_soa* lights);
+int rt_upload_materials(rt_context* ctx, const rt_material_desc* materials, int32_t count);
+int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count);
+int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh);
+
+/* ---- render ----------------------------------------------------------------------------------- */
+
+/* Replaces Renderer::Render (source/Renderer.cpp:34-98): blocking; on return host_dst holds
+ * height rows of width uint32 pixels, row stride pitch_bytes (>= 4*width), exactly what the
+ * reference leaves in m_pBufferPixels.  Row bands are split over the context's devices and
+ * gathered on device 0 before the copy out. */
+int rt_render(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+              uint32_t* host_dst, int32_t pitch_bytes);
+
+/* Same frame, left in device 0's frame buffer (no host copy): kernel-only measurement. */
+int rt_render_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame);
+
+/* Copy the frame of the last rt_render_device out of device 0. */
+int rt_download_frame(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes);
+
+/* One rank's share of a frame, for one-process-per-GPU launches: renders rows
+ * [row_begin, row_begin + row_count) of the frame on the context's first device into
+ * device_dst (tightly packed, row_count * width uint32) on `cuda_stream` (a cudaStream_t,
+ * NULL = the context's own stream).  Asynchronous with respect to the host when a stream
+ * is given. */
+int rt_render_rows_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                          int32_t row_begin, int32_t row_count, void* device_dst, void* cuda_stream);
+
+int rt_get_timing(const rt_context* ctx, rt_timing* out_timing);
+
+/* Counters build of the same kernel: fills the test histogram for one frame (slow path,
+ * measurement only; the frame it renders is identical). */
+int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                   rt_counters* out_counters);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RT_B200_H */

@@ -1,0 +1,76 @@
+/*
+ * TEST INFRASTRUCTURE -- CPU restatement of the reference's per-pixel path.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker.  The product
+ * (gp1_raytracer_2223_b200/csrc, include/rt_b200.h) never links or calls it.
+ *
+ * Parity status: PINNED.  tests/test_oracle_port.py checks this restatement bit-for-bit
+ * against frames rendered by the unmodified reference sources compiled in this repo's
+ * build container (oracle/Makefile `ref`, fixtures under tests/golden/).  The reference
+ * ships no golden vectors of its own.
+ */
+#ifndef RT_ORACLE_H
+#define RT_ORACLE_H
+
+#include "../../include/rt_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* BVHNode, reference source/DataTypes.h:43-54. */
+typedef struct rto_bvh_node
+{
+	float min_aabb[3];
+	float max_aabb[3];
+	uint32_t first_idx;
+	uint32_t idx_count;
+	uint32_t left_node;
+} rto_bvh_node;
+
+typedef struct rto_mesh
+{
+	rt_mesh_desc desc;
+	const rto_bvh_node* nodes;   /* may be NULL when only the slab + linear path is wanted */
+	int32_t node_count;
+} rto_mesh;
+
+typedef struct rto_scene
+{
+	rt_spheres_soa spheres;
+	rt_planes_soa planes;
+	rt_lights_soa lights;
+	const rt_material_desc* materials;
+	int32_t material_count;
+	const rto_mesh* meshes;
+	int32_t mesh_count;
+} rto_scene;
+
+enum rto_mesh_path
+{
+	RTO_MESH_SLAB_LINEAR = 0,    /* reference source/Utils.h:298-325 (#else branch): the north-star algorithm */
+	RTO_MESH_BVH = 1             /* reference source/Utils.h:296-297 + 246-288: what the reference ships      */
+};
+
+/*
+ * Renders rows [row_begin, row_begin + row_count) into dst (tightly packed).  threads <= 0
+ * uses the OpenMP default.  counters may be NULL; when given (slab-linear path only) it
+ * receives the test histogram of SURVEY.md section 8(d), indices as in DESIGN.md.
+ * Returns 0 on success.
+ */
+int rto_render_rows(const rto_scene* scene, const rt_camera* camera, const rt_frame_desc* frame,
+                    int32_t mesh_path, int32_t row_begin, int32_t row_count, uint32_t* dst,
+                    int32_t threads, rt_counters* counters);
+
+/* The box the slab-linear path tests: min/max over the indexed vertices, started from
+ * +FLT_MAX / +FLT_MIN exactly like BVH root bounds (reference source/DataTypes.h:310-321,
+ * source/Vector3.cpp:13-14), so that it equals the shipped build's root-node box. */
+void rto_mesh_bounds(const rt_mesh_desc* mesh, float out_min[3], float out_max[3]);
+
+uint64_t rto_fnv1a64(const void* data, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,289 @@
+// TEST INFRASTRUCTURE (oracle build only) -- not part of the shipped product.
+//
+// Headless driver around the UNMODIFIED reference sources.  It is compiled
+// together with /root/reference/source/{Vector3,Vector4,Matrix,Scene,Renderer,
+// Timer}.cpp (see oracle/Makefile) and does what the reference's main loop does
+// (source/main.cpp:41-49, 88-91): build a window-sized surface, a Renderer and a
+// Scene, call Scene::Initialize(), optionally Scene::Update(), then
+// Renderer::Render(pScene).  Nothing here computes a pixel: frames come out of
+// the reference's own Renderer::RenderPixel (source/Renderer.cpp:100-182).
+//
+// Outputs:
+//   --out FILE         raw little-endian uint32 XRGB8888 frame (W*H*4 bytes)
+//   --dump-scene FILE  the scene exactly as RenderPixel sees it, flattened to the
+//                      "RTSC0001" layout read by gp1_raytracer_2223_b200/scene_file.py
+//                      and oracle/port (fixtures under tests/golden/ come from this)
+//   stdout             one JSON line: per-frame Render() times, thread count, FNV-1a-64
+//
+// Built with -fno-access-control so the dump can read Scene::m_TriangleMeshGeometries
+// (protected, source/Scene.h:50) and the private material parameters
+// (source/Material.h:46-47,65-67,89-93,125-128) without touching reference headers.
+#include "sdl_stub.h"
+
+#include "Renderer.h"
+#include "Scene.h"
+#include "Material.h"
+#include "Timer.h"
+#include "Utils.h"
+
+#include <omp.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace dae;
+
+namespace
+{
+	struct Options
+	{
+		std::string scene = "W4_Bunny";
+		int width = 640;
+		int height = 480;
+		int mode = 3;          // LightingMode::Combined (source/Renderer.h:49)
+		int shadows = 1;       // m_ShadowsEnabled default (source/Renderer.h:50)
+		int frames = 1;
+		int warmup = 0;
+		int threads = 0;       // 0 = leave OpenMP default (all cores)
+		bool haveTime = false;
+		float time = 0.f;      // Timer::GetTotal() fed to Scene::Update
+		bool haveMeshYaw = false;
+		float meshYaw = 0.f;   // direct TriangleMesh::RotateY on every mesh
+		bool haveCamOrigin = false;
+		float camOrigin[3] = { 0, 0, 0 };
+		bool haveCamRot = false;
+		float camPitch = 0.f, camYaw = 0.f;
+		bool haveFov = false;
+		float fovAngle = 45.f;
+		std::string out;
+		std::string dump;
+		std::string resources; // directory that CONTAINS "Resources/"
+	};
+
+	[[noreturn]] void Usage(const char* why)
+	{
+		std::fprintf(stderr,
+			"ref_render: %s\n"
+			"usage: ref_render --scene {W1|W2|W3|W3_Test|W4_Reference|W4_Bunny|W4_Optional}\n"
+			"  [--width W --height H] [--mode 0..3] [--shadows 0|1] [--frames N] [--warmup N]\n"
+			"  [--threads T] [--time SECONDS] [--mesh-yaw RAD] [--cam-origin X Y Z]\n"
+			"  [--cam-rot PITCH YAW] [--fov DEGREES] [--out FILE] [--dump-scene FILE]\n"
+			"  [--resources DIR]\n", why);
+		std::exit(2);
+	}
+
+	Options Parse(int argc, char** argv)
+	{
+		Options o;
+		auto need = [&](int i, int n) { if (i + n >= argc) Usage("missing value"); };
+		for (int i = 1; i < argc; ++i)
+		{
+			const std::string a = argv[i];
+			if (a == "--scene") { need(i, 1); o.scene = argv[++i]; }
+			else if (a == "--width") { need(i, 1); o.width = std::atoi(argv[++i]); }
+			else if (a == "--height") { need(i, 1); o.height = std::atoi(argv[++i]); }
+			else if (a == "--mode") { need(i, 1); o.mode = std::atoi(argv[++i]); }
+			else if (a == "--shadows") { need(i, 1); o.shadows = std::atoi(argv[++i]); }
+			else if (a == "--frames") { need(i, 1); o.frames = std::atoi(argv[++i]); }
+			else if (a == "--warmup") { need(i, 1); o.warmup = std::atoi(argv[++i]); }
+			else if (a == "--threads") { need(i, 1); o.threads = std::atoi(argv[++i]); }
+			else if (a == "--time") { need(i, 1); o.haveTime = true; o.time = std::strtof(argv[++i], nullptr); }
+			else if (a == "--mesh-yaw") { need(i, 1); o.haveMeshYaw = true; o.meshYaw = std::strtof(argv[++i], nullptr); }
+			else if (a == "--cam-origin") { need(i, 3); o.haveCamOrigin = true; for (int k = 0; k < 3; ++k) o.camOrigin[k] = std::strtof(argv[++i], nullptr); }
+			else if (a == "--cam-rot") { need(i, 2); o.haveCamRot = true; o.camPitch = std::strtof(argv[++i], nullptr); o.camYaw = std::strtof(argv[++i], nullptr); }
+			else if (a == "--fov") { need(i, 1); o.haveFov = true; o.fovAngle = std::strtof(argv[++i], nullptr); }
+			else if (a == "--out") { need(i, 1); o.out = argv[++i]; }
+			else if (a == "--dump-scene") { need(i, 1); o.dump = argv[++i]; }
+			else if (a == "--resources") { need(i, 1); o.resources = argv[++i]; }
+			else Usage(("unknown argument " + a).c_str());
+		}
+		if (o.width <= 0 || o.height <= 0 || o.frames < 0 || o.mode < 0 || o.mode > 3) Usage("bad value");
+		return o;
+	}
+
+	Scene* MakeScene(const std::string& name)
+	{
+		if (name == "W1") return new Scene_W1();
+		if (name == "W2") return new Scene_W2();
+		if (name == "W3") return new Scene_W3();
+		if (name == "W3_Test") return new Scene_W3_TestScene();
+		if (name == "W4_Reference") return new Scene_W4_ReferenceScene();
+		if (name == "W4_Bunny") return new Scene_W4_BunnyScene();
+		if (name == "W4_Optional") return new Scene_W4_OptionalScene();
+		// Scene_W4_TestScene is not offered: in the shipped configuration it dereferences a null
+		// pBVHNodes (source/Scene.cpp:306-310 vs source/DataTypes.h:231-232,296).
+		Usage("unknown scene");
+	}
+
+	uint64_t Fnv1a64(const void* data, size_t bytes)
+	{
+		const unsigned char* p = static_cast<const unsigned char*>(data);
+		uint64_t h = 0xcbf29ce484222325ull;
+		for (size_t i = 0; i < bytes; ++i) { h ^= p[i]; h *= 0x100000001b3ull; }
+		return h;
+	}
+
+	struct Writer
+	{
+		FILE* f;
+		void I32(int32_t v) { std::fwrite(&v, 4, 1, f); }
+		void U32(uint32_t v) { std::fwrite(&v, 4, 1, f); }
+		void F32(float v) { std::fwrite(&v, 4, 1, f); }
+		void V3(const Vector3& v) { F32(v.x); F32(v.y); F32(v.z); }
+		void C3(const ColorRGB& c) { F32(c.r); F32(c.g); F32(c.b); }
+	};
+
+	// Flatten what RenderPixel / GetClosestHit / DoesHit read.  Layout: see scene_file.py.
+	void DumpScene(const Options& o, Scene* pScene, float aspect, const char* path)
+	{
+		FILE* f = std::fopen(path, "wb");
+		if (!f) { std::perror(path); std::exit(1); }
+		Writer w{ f };
+		std::fwrite("RTSC0001", 1, 8, f);
+		w.I32(o.width); w.I32(o.height); w.I32(o.mode); w.I32(o.shadows);
+		w.F32(aspect);
+
+		Camera& cam = pScene->GetCamera();
+		cam.CalculateCameraToWorld();
+		w.V3(cam.origin);
+		w.F32(cam.fov);
+		w.V3(Vector3{ cam.cameraToWorld.data[0] });
+		w.V3(Vector3{ cam.cameraToWorld.data[1] });
+		w.V3(Vector3{ cam.cameraToWorld.data[2] });
+
+		const auto& spheres = pScene->GetSphereGeometries();
+		const auto& planes = pScene->GetPlaneGeometries();
+		const auto& lights = pScene->GetLights();
+		const auto& materials = pScene->m_Materials;
+		const auto& meshes = pScene->m_TriangleMeshGeometries;
+		w.I32((int32_t)spheres.size()); w.I32((int32_t)planes.size()); w.I32((int32_t)lights.size());
+		w.I32((int32_t)materials.size()); w.I32((int32_t)meshes.size());
+
+		for (const Sphere& s : spheres) { w.V3(s.origin); w.F32(s.radius); w.I32(s.materialIndex); }
+		for (const Plane& p : planes) { w.V3(p.origin); w.V3(p.normal); w.I32(p.materialIndex); }
+		for (const Light& l : lights) { w.V3(l.origin); w.V3(l.direction); w.C3(l.color); w.F32(l.intensity); w.I32((int32_t)l.type); }
+		for (Material* m : materials)
+		{
+			int32_t tag = -1; ColorRGB c{}; float p0 = 0, p1 = 0, p2 = 0;
+			if (auto* s = dynamic_cast<Material_SolidColor*>(m)) { tag = 0; c = s->m_Color; }
+			else if (auto* l = dynamic_cast<Material_Lambert*>(m)) { tag = 1; c = l->m_DiffuseColor; p0 = l->m_DiffuseReflectance; }
+			else if (auto* lp = dynamic_cast<Material_LambertPhong*>(m)) { tag = 2; c = lp->m_DiffuseColor; p0 = lp->m_DiffuseReflectance; p1 = lp->m_SpecularReflectance; p2 = lp->m_PhongExponent; }
+			else if (auto* ct = dynamic_cast<Material_CookTorrence*>(m)) { tag = 3; c = ct->m_Albedo; p0 = ct->m_Metalness; p1 = ct->m_Roughness; }
+			else { std::fprintf(stderr, "unknown material class\n"); std::exit(1); }
+			w.I32(tag); w.C3(c); w.F32(p0); w.F32(p1); w.F32(p2); w.F32(0.f);
+		}
+		for (const TriangleMesh& m : meshes)
+		{
+			const int32_t nV = (int32_t)m.transformedPositions.size();
+			const int32_t nT = (int32_t)(m.indices.size() / 3);
+			const int32_t nNodes = m.pBVHNodes ? (int32_t)m.nodesUsed : 0;
+			w.I32(nV); w.I32(nT); w.I32((int32_t)m.cullMode); w.I32(m.materialIndex); w.I32(nNodes);
+			for (const Vector3& p : m.transformedPositions) w.V3(p);
+			for (int idx : m.indices) w.I32(idx);
+			for (const Vector3& n : m.transformedNormals) w.V3(n);
+			for (int32_t i = 0; i < nNodes; ++i)
+			{
+				const BVHNode& n = m.pBVHNodes[i];
+				w.V3(n.minAABB); w.V3(n.maxAABB); w.U32(n.firstIdx); w.U32(n.idxCount); w.U32(n.leftNode);
+			}
+		}
+		std::fclose(f);
+	}
+}
+
+int main(int argc, char** argv)
+{
+	const Options o = Parse(argc, argv);
+
+	// The scenes open "Resources/<name>.obj" relative to the cwd (source/Scene.cpp:307,413,450).
+	std::string res = o.resources;
+	if (res.empty())
+	{
+		char exe[4096];
+		const ssize_t n = readlink("/proc/self/exe", exe, sizeof(exe) - 1);
+		if (n > 0) { exe[n] = 0; res = exe; res = res.substr(0, res.find_last_of('/')); }
+	}
+	std::string out = o.out, dump = o.dump;
+	auto absolutise = [](std::string& p)
+	{
+		if (!p.empty() && p[0] != '/') { char cwd[4096]; if (getcwd(cwd, sizeof cwd)) p = std::string(cwd) + "/" + p; }
+	};
+	absolutise(out); absolutise(dump);
+	if (!res.empty() && chdir(res.c_str()) != 0) { std::perror(res.c_str()); return 1; }
+
+	if (o.threads > 0) omp_set_num_threads(o.threads);
+
+	SDL_Window* pWindow = GP1_CreateHeadlessWindow(o.width, o.height);
+	Timer* pTimer = new Timer();
+	Renderer* pRenderer = new Renderer(pWindow);
+	Scene* pScene = MakeScene(o.scene);
+	pScene->Initialize();
+
+	// Renderer starts at Combined + shadows on (source/Renderer.h:49-50); reach the requested
+	// state through the same public toggles F3/F2 drive (source/main.cpp:67-78).
+	for (int m = 3; m != o.mode; m = (m + 1) % 4) pRenderer->CycleLightingMode();
+	if (!o.shadows) pRenderer->ToggleShadows();
+
+	Camera& cam = pScene->GetCamera();
+	if (o.haveFov) cam.SetCameraFOV(o.fovAngle);
+	if (o.haveTime)
+	{
+		pTimer->m_TotalTime = o.time;   // what Timer::GetTotal() returns (source/Timer.h:30)
+		pTimer->m_ElapsedTime = 0.f;
+		pScene->Update(pTimer);          // mesh yaw from the timer (source/Scene.cpp:391-400, 431-437)
+	}
+	if (o.haveMeshYaw)
+	{
+		for (TriangleMesh& m : pScene->m_TriangleMeshGeometries) { m.RotateY(o.meshYaw); m.UpdateTransforms(); }
+	}
+	if (o.haveCamOrigin) cam.origin = { o.camOrigin[0], o.camOrigin[1], o.camOrigin[2] };
+	if (o.haveCamRot)
+	{
+		cam.totalPitch = o.camPitch; cam.totalYaw = o.camYaw;
+		cam.CalculateForwardVector();    // source/Camera.h:61-66
+	}
+
+	std::vector<double> ms;
+	for (int i = 0; i < o.warmup; ++i) pRenderer->Render(pScene);
+	for (int i = 0; i < o.frames; ++i)
+	{
+		const auto t0 = std::chrono::steady_clock::now();
+		pRenderer->Render(pScene);
+		const auto t1 = std::chrono::steady_clock::now();
+		ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+	}
+
+	const size_t bytes = (size_t)o.width * (size_t)o.height * 4u;
+	const uint64_t hash = Fnv1a64(pWindow->surface.pixels, bytes);
+	if (!out.empty())
+	{
+		FILE* f = std::fopen(out.c_str(), "wb");
+		if (!f) { std::perror(out.c_str()); return 1; }
+		std::fwrite(pWindow->surface.pixels, 1, bytes, f);
+		std::fclose(f);
+	}
+	if (!dump.empty()) DumpScene(o, pScene, pRenderer->m_AspectRatio, dump.c_str());
+
+	std::vector<double> sorted = ms;
+	std::sort(sorted.begin(), sorted.end());
+	const double median = sorted.empty() ? 0.0 : sorted[sorted.size() / 2];
+	std::printf("{\"scene\": \"%s\", \"width\": %d, \"height\": %d, \"mode\": %d, \"shadows\": %d, "
+		"\"threads\": %d, \"frames\": %d, \"warmup\": %d, \"ms_median\": %.6f, \"ms_min\": %.6f, \"ms\": [",
+		o.scene.c_str(), o.width, o.height, o.mode, o.shadows, omp_get_max_threads(), o.frames, o.warmup,
+		median, sorted.empty() ? 0.0 : sorted.front());
+	for (size_t i = 0; i < ms.size(); ++i) std::printf("%s%.6f", i ? ", " : "", ms[i]);
+	std::printf("], \"fnv1a64\": \"%016llx\", \"path\": \"reference BVH traversal (source/Utils.h:296-297)\"}\n",
+		(unsigned long long)hash);
+
+	delete pScene;
+	delete pRenderer;
+	delete pTimer;
+	GP1_DestroyHeadlessWindow(pWindow);
+	return 0;
+}

@@ -1,0 +1,110 @@
+"""TEST INFRASTRUCTURE: ctypes front end of oracle/port/librt_oracle.so (the CPU restatement).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from gp1_raytracer_2223_b200._abi import (SceneViews, camera_struct, frame_struct, rt_camera, rt_counters,
+                                          rt_frame_desc, rt_lights_soa, rt_material_desc, rt_mesh_desc,
+                                          rt_planes_soa, rt_spheres_soa)
+from gp1_raytracer_2223_b200.scene_file import BVH_NODE_DTYPE, FlatScene
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "port", "librt_oracle.so")
+
+MESH_SLAB_LINEAR = 0
+MESH_BVH = 1
+
+
+class rto_bvh_node(C.Structure):
+    _fields_ = [("min_aabb", C.c_float * 3), ("max_aabb", C.c_float * 3), ("first_idx", C.c_uint32),
+                ("idx_count", C.c_uint32), ("left_node", C.c_uint32)]
+
+
+class rto_mesh(C.Structure):
+    _fields_ = [("desc", rt_mesh_desc), ("nodes", C.POINTER(rto_bvh_node)), ("node_count", C.c_int32)]
+
+
+class rto_scene(C.Structure):
+    _fields_ = [("spheres", rt_spheres_soa), ("planes", rt_planes_soa), ("lights", rt_lights_soa),
+                ("materials", C.POINTER(rt_material_desc)), ("material_count", C.c_int32),
+                ("meshes", C.POINTER(rto_mesh)), ("mesh_count", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc only; does not need /root/reference)."""
+    src = os.path.join(HERE, "port", "rt_oracle.c")
+    if force or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "port"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.rto_render_rows.restype = C.c_int
+        _lib.rto_render_rows.argtypes = [C.POINTER(rto_scene), C.POINTER(rt_camera), C.POINTER(rt_frame_desc),
+                                         C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                         C.POINTER(rt_counters)]
+        _lib.rto_fnv1a64.restype = C.c_uint64
+        _lib.rto_fnv1a64.argtypes = [C.c_void_p, C.c_uint64]
+    return _lib
+
+
+def fnv1a64(buf: np.ndarray) -> int:
+    a = np.ascontiguousarray(buf)
+    return int(lib().rto_fnv1a64(a.ctypes.data, a.nbytes))
+
+
+class OracleScene:
+    def __init__(self, scene: FlatScene):
+        self.views = SceneViews(scene)
+        n = len(scene.meshes)
+        self._meshes = (rto_mesh * max(n, 1))()
+        self._nodes = []
+        self.has_bvh = n > 0
+        for i, m in enumerate(scene.meshes):
+            self._meshes[i].desc = self.views.meshes[i]
+            if m.bvh_nodes is not None and len(m.bvh_nodes):
+                nodes = np.ascontiguousarray(m.bvh_nodes, dtype=BVH_NODE_DTYPE)
+                self._nodes.append(nodes)
+                self._meshes[i].nodes = C.cast(nodes.ctypes.data, C.POINTER(rto_bvh_node))
+                self._meshes[i].node_count = len(nodes)
+            else:
+                self.has_bvh = False
+        self.c = rto_scene(self.views.spheres, self.views.planes, self.views.lights,
+                           C.cast(self.views.materials, C.POINTER(rt_material_desc)), self.views.material_count,
+                           C.cast(self._meshes, C.POINTER(rto_mesh)), n)
+
+
+def render(scene: FlatScene, width: int, height: int, lighting_mode: int = 3, shadows: bool = True,
+           mesh_path: int = MESH_SLAB_LINEAR, row_begin: int = 0, row_count: int | None = None, threads: int = 0,
+           counters: bool = False, camera=None, aspect_ratio: float | None = None, shifts=(16, 8, 0),
+           alpha_mask: int = 0):
+    """Render rows with the CPU restatement.  Returns uint32 (rows, width) [and counters]."""
+    if row_count is None:
+        row_count = height - row_begin
+    osc = OracleScene(scene)
+    cam = camera_struct(camera if camera is not None else scene.camera)
+    frame = frame_struct(width, height, lighting_mode, shadows, aspect_ratio, shifts, alpha_mask)
+    out = np.empty((row_count, width), dtype=np.uint32)
+    cnt = rt_counters() if counters else None
+    rc = lib().rto_render_rows(C.byref(osc.c), C.byref(cam), C.byref(frame), mesh_path, row_begin, row_count,
+                               out.ctypes.data, threads, C.byref(cnt) if counters else None)
+    if rc != 0:
+        raise RuntimeError(f"rto_render_rows failed ({rc})")
+    if counters:
+        return out, np.array(list(cnt.slot), dtype=np.uint64)
+    return out
