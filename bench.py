@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: Renderer::Render of Scene_W4_BunnyScene at 3840x2160,
+Combined lighting, shadows on (BASELINE.json configs[4], the north-star target).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step is one frame.  Metric: Mrays/s (primary + shadow rays of the frame / time).
+  value      device-timed (CUDA events on the launching stream), scene resident in HBM, frame left in
+             HBM on rank 0 (N > 1: strip render on every rank + NCCL gather + unstripe on rank 0)
+  e2e        the same frame through the reference-facing C ABI with HOST buffers: per step the
+             re-transformed mesh goes host -> device (rt_upload_mesh, what Scene::Update produces each
+             frame) and the finished frame comes device -> host (rt_render into pinned memory)
+  roofline   FP32: algorithmic FLOP of the frame (SURVEY.md 8(d) table x the counters build's event
+             counts) / kernel time, against the FP32 issue peak measured live on the same GPU
+  cpu_baseline  the reference's own parallel CPU loop (oracle/_ref/ref_render, the unmodified
+             reference sources compiled in the build container) on this box's host cores
+
+`--impl reference` prints the reference arm: the same metric from the reference binary alone.
+The oracle is only ever the checker / the reported baseline here, never the measured product.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "Scene_W4_BunnyScene 3840x2160 Combined lighting, shadows on, pose after Initialize()"
+FIXTURE = os.path.join(ROOT, "tests", "golden", "bunny_4k.rtsc")
+WIDTH, HEIGHT = 3840, 2160
+RAYS_PER_FRAME = WIDTH * HEIGHT * 4          # 1 primary + 3 shadow rays per pixel (every pixel hits; re-checked below)
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_render")
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.index, self.period = index, period_s
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.handle, self.nv.NVML_CLOCK_SM)))
+                mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def merge(self, other):
+        self.samples += other.samples
+        self.reasons |= other.reasons
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the unmodified reference compiled under oracle/_ref
+# ------------------------------------------------------------------------------------------------
+def run_reference(frames: int, warmup: int, threads: int = 0):
+    """Times Renderer::Render of the reference binary on the host cores.  Returns the driver's JSON."""
+    args = [REF_BIN, "--scene", "W4_Bunny", "--width", str(WIDTH), "--height", str(HEIGHT), "--mode", "3",
+            "--shadows", "1", "--frames", str(frames), "--warmup", str(warmup)]
+    if threads:
+        args += ["--threads", str(threads)]
+    out = subprocess.run(args, check=True, capture_output=True, text=True).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+def run_port(frames: int, warmup: int):
+    """Fallback when oracle/_ref is absent: the C restatement (kind 'port')."""
+    from gp1_raytracer_2223_b200 import load_rtsc
+    from oracle import rt_oracle
+    scene = load_rtsc(FIXTURE)
+    ms = []
+    for i in range(warmup + frames):
+        t0 = time.perf_counter()
+        rt_oracle.render(scene, WIDTH, HEIGHT)
+        if i >= warmup:
+            ms.append((time.perf_counter() - t0) * 1e3)
+    return {"ms": ms, "ms_median": statistics.median(ms), "threads": os.cpu_count(),
+            "path": "C restatement, slab + linear triangle loop"}
+
+
+def reference_available():
+    return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
+
+
+def bounded_reference_run(steps: int, warmup: int, budget_s: float):
+    """Runs at most `steps` frames, fewer if they would not fit in `budget_s` seconds."""
+    runner = run_reference if reference_available() else run_port
+    probe = runner(1, 1)                       # 1 warm-up + 1 timed frame: estimate the frame time
+    est_ms = probe["ms_median"]
+    frames = max(1, min(steps, int(budget_s * 1e3 / max(est_ms, 1e-3))))
+    res = runner(frames, min(warmup, 2))
+    kind = "reference" if reference_available() else "port"
+    return res, frames, kind
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    res, frames, kind = bounded_reference_run(args.steps, args.warmup, budget_s=150.0)
+    ms = statistics.mean(res["ms"])
+    value = RAYS_PER_FRAME / (ms * 1e-3) / 1e6
+    sample = f"{frames} full {WIDTH}x{HEIGHT} frames of Renderer::Render" + ("" if frames == args.steps else f" (of {args.steps} requested steps; bounded to ~150 s)")
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": frames, "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "reference scene (Scene_W4_BunnyScene, deterministic)",
+        "config": {"workload": WORKLOAD, "rays_per_frame": RAYS_PER_FRAME, "path": res.get("path")},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": res["threads"], "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        sys.exit("bench.py measures the CUDA path; no GPU is visible (there is no CPU fallback)")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit(f"--gpus {args.gpus} needs a torchrun launch with {args.gpus} ranks (one process per GPU)")
+        sys.exit(f"--gpus {args.gpus} does not match WORLD_SIZE {world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from gp1_raytracer_2223_b200 import Renderer, bands, build, load_rtsc
+    from gp1_raytracer_2223_b200.flops import algorithmic_flops, rays
+    build.build()
+
+    scene = load_rtsc(FIXTURE)
+    mesh = scene.meshes[0]
+    r = Renderer(WIDTH, HEIGHT, device_ids=[local_rank])
+    r.SetScene(scene)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload accounting from the counters build (rank 0 only; not timed) -----------------
+    counters = r.count_frame() if rank == 0 else None
+    if rank == 0:
+        flop_per_frame = algorithmic_flops(counters, 3)
+        assert rays(counters) == RAYS_PER_FRAME, (rays(counters), RAYS_PER_FRAME)
+    spr = bands.strips_per_rank(HEIGHT, world)
+    band = torch.empty((spr * bands.STRIP_ROWS, WIDTH), dtype=torch.int32, device="cuda")
+    frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda") if rank == 0 else None
+    gathered = torch.empty((world,) + tuple(band.shape), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+    host_frame = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory() if rank == 0 else None
+
+    def device_step():
+        """Inputs resident; result = the whole frame in rank 0's HBM."""
+        if world == 1:
+            r.render_strips_device(0, 1, frame_dev.data_ptr(), stream)
+        else:
+            r.render_strips_device(rank, world, band.data_ptr(), stream)
+            if rank == 0:
+                dist.gather(band, list(gathered.unbind(0)), dst=0)
+                r.unstripe_device(gathered.data_ptr(), frame_dev.data_ptr(), world, spr, stream)
+            else:
+                dist.gather(band, None, dst=0)
+
+    def e2e_step():
+        """Host buffers in, host buffer out, through the C ABI."""
+        r.ctx.upload_mesh(0, mesh)                                  # H2D: what UpdateTransforms produced this frame
+        if world == 1:
+            r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + D2H, blocking
+        else:
+            device_step()
+            if rank == 0:
+                host_frame.copy_(frame_dev, non_blocking=True)
+            torch.cuda.synchronize()
+
+    # ---- device-timed region ---------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kstarts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    kends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    with sampler:
+        for i in range(args.steps):
+            flush.zero_()                      # evict the frame buffer from L2 between timed steps
+            starts[i].record()
+            if world == 1:
+                device_step()
+            else:
+                kstarts[i].record()
+                r.render_strips_device(rank, world, band.data_ptr(), stream)
+                kends[i].record()
+                if rank == 0:
+                    dist.gather(band, list(gathered.unbind(0)), dst=0)
+                    r.unstripe_device(gathered.data_ptr(), frame_dev.data_ptr(), world, spr, stream)
+                else:
+                    dist.gather(band, None, dst=0)
+            ends[i].record()
+        barrier()
+    step_ms = torch.tensor([s.elapsed_time(e) for s, e in zip(starts, ends)], dtype=torch.float64, device="cuda")
+    kern_ms = step_ms.clone() if world == 1 else torch.tensor([s.elapsed_time(e) for s, e in zip(kstarts, kends)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)     # per step, the slowest rank
+        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(step_ms.sum())
+    kernel_ms = float(kern_ms.mean())
+
+    # ---- end-to-end region -----------------------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        sampler2 = ClockSampler(local_rank)
+        with sampler2:
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()
+            barrier()
+            t1 = time.perf_counter()
+        sampler.merge(sampler2)
+        e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        e2e_ms = float(e2e_s) * 1e3 / args.steps
+        h2d = int(mesh.positions.nbytes + mesh.indices.nbytes + mesh.normals.nbytes) * world
+        e2e = {"value": RAYS_PER_FRAME / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": WIDTH * HEIGHT * 4}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline (rank 0's GPU) -----------------------------------------------------------------
+    peak_nofma = r.ctx.measure_fp32_peak(False)
+    peak_fma = r.ctx.measure_fp32_peak(True)
+    flop_per_launch = flop_per_frame / world                   # strips are dealt round-robin: ~1/N of the frame each
+    achieved = flop_per_launch / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp32", "achieved": achieved, "peak": peak_nofma["tflops"], "unit": "TFLOP/s",
+        "frac": achieved / peak_nofma["tflops"], "traffic": traffic,
+        "peak_source": "measured live: FMUL+FADD issue peak of this GPU (rt_measure_fp32_peak); the reference's arithmetic is unfused, so FFMA is not available to this path",
+        "peak_fma": peak_fma["tflops"], "frac_of_fma_peak": achieved / peak_fma["tflops"],
+        "algorithmic_gflop_per_frame": flop_per_frame / 1e9, "kernel": "rt::render_kernel<Combined, shadows>",
+        "kernel_ms": kernel_ms,
+        "hbm": {"bytes_per_launch": WIDTH * HEIGHT * 4 // world, "achieved_gbs": WIDTH * HEIGHT * 4 / world / (kernel_ms * 1e-3) / 1e9,
+                "peak_gbs": _measured_peaks().get("hbm_gbs")},
+    }
+
+    # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        res, frames, kind = bounded_reference_run(30, 1, budget_s=15.0)
+        ms = statistics.mean(res["ms"])
+        cpu_baseline = {"value": RAYS_PER_FRAME / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": res["threads"],
+                        "kind": kind, "ms_per_frame": ms,
+                        "sample": f"{frames} full {WIDTH}x{HEIGHT} frames of the reference's Renderer::Render ({res.get('path')})"}
+
+    ms_per_step = total_ms / args.steps
+    line = {
+        "metric": "Mrays/s", "value": RAYS_PER_FRAME / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "reference scene fixture tests/golden/bunny_4k.rtsc (dumped from the reference's Scene_W4_BunnyScene::Initialize; deterministic, no RNG)",
+        "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "rays_per_frame": RAYS_PER_FRAME,
+                   "triangles": int(mesh.triangle_count), "lights": 3, "partition": f"{bands.STRIP_ROWS}-row strips round-robin over {world} rank(s), NCCL gather to rank 0",
+                   "l2": f"{L2_FLUSH_BYTES >> 20} MiB memset between timed steps (outside the event pairs)"},
+        "clocks": sampler.summary(),
+        "e2e": e2e,
+        "gpu_launches": args.steps * (world + (1 if world > 1 else 0)),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def _measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

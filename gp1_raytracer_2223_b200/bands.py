@@ -1,0 +1,70 @@
+"""Row-strip partition of a frame across ranks and the gather to rank 0.
+
+SURVEY.md 8(e): every pixel is independent, the scene is replicated, the only exchange is
+the gather of the finished rows on rank 0.  The frame is cut into strips of ``STRIP_ROWS``
+rows (one CTA row of the kernel) dealt round-robin: rank r renders strips r, r + world, ...
+into a packed band, which balances the expensive lower-middle rows of the bunny scene over
+all ranks.  Bands are padded to ``strips_per_rank`` strips so the gather is uniform.
+
+Everything here is index arithmetic plus torch.distributed calls (NCCL on GPUs, gloo in the
+CPU tests); the only device work besides the collective is the library's unstripe kernel.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+
+STRIP_ROWS = 8
+
+
+def total_strips(height: int) -> int:
+    return (height + STRIP_ROWS - 1) // STRIP_ROWS
+
+
+def strips_per_rank(height: int, world: int) -> int:
+    return (total_strips(height) + world - 1) // world
+
+
+def strips_of_rank(height: int, world: int, rank: int):
+    return list(range(rank, total_strips(height), world))
+
+
+def band_rows(height: int, world: int) -> int:
+    """Rows in one (padded) packed band."""
+    return strips_per_rank(height, world) * STRIP_ROWS
+
+
+def rows_of_rank(height: int, world: int, rank: int):
+    """(frame_row, band_row) pairs this rank owns, in band order."""
+    out = []
+    for local, strip in enumerate(strips_of_rank(height, world, rank)):
+        for r in range(STRIP_ROWS):
+            y = strip * STRIP_ROWS + r
+            if y < height:
+                out.append((y, local * STRIP_ROWS + r))
+    return out
+
+
+def unstripe_numpy(bands: np.ndarray, width: int, height: int, world: int) -> np.ndarray:
+    """Reference (host) statement of the unstripe step: bands is (world, band_rows, width)."""
+    frame = np.empty((height, width), dtype=bands.dtype)
+    for rank in range(world):
+        for y, b in rows_of_rank(height, world, rank):
+            frame[y] = bands[rank, b]
+    return frame
+
+
+def gather_bands(band, rank: int, world: int, dst: int = 0, group=None):
+    """torch.distributed gather of equally sized bands on ``dst``; returns (world, ...) on dst, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return band.unsqueeze(0)
+    if rank == dst:
+        out = torch.empty((world,) + tuple(band.shape), dtype=band.dtype, device=band.device)
+        dist.gather(band, list(out.unbind(0)), dst=dst, group=group)
+        return out
+    dist.gather(band, None, dst=dst, group=group)
+    return None

@@ -1,0 +1,794 @@
+// C-ABI implementation (include/rt_b200.h): context, scene replication to every device,
+// kernel launch, row-strip split over the context's GPUs with the gather fused into the
+// kernel's stores (peer-mapped frame buffer on device 0), and the copy out to the host
+// surface.  There is deliberately no host fallback: every entry point fails loudly when
+// CUDA is not there.
+#include "rt_kernel.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace
+{
+	thread_local std::string g_create_error;
+
+	struct HostMesh
+	{
+		std::vector<float4> triangles;   // 3 per triangle
+		float aabb_min[3] = { 0, 0, 0 };
+		float aabb_max[3] = { 0, 0, 0 };
+		int32_t cull_mode = RT_CULL_BACK_FACE;
+		int32_t material = 0;
+		bool uploaded = false;
+	};
+
+	// Offsets (in floats) of the SoA arrays inside the per-device float arena.
+	struct ArenaLayout
+	{
+		static constexpr int sphere = 0;                                   // ox, oy, oz, r
+		static constexpr int plane = sphere + 4 * rt::kMaxSpheres;         // ox, oy, oz, nx, ny, nz
+		static constexpr int light = plane + 6 * rt::kMaxPlanes;           // ox, oy, oz, r, g, b, intensity
+		static constexpr int total = light + 7 * rt::kMaxLights;
+	};
+
+	struct DeviceState
+	{
+		int device = -1;
+		cudaStream_t stream = nullptr;
+		float* d_arena = nullptr;          // ArenaLayout::total floats
+		uint8_t* d_bytes = nullptr;        // sphere materials, plane materials
+		int32_t* d_light_type = nullptr;
+		float4* d_materials = nullptr;     // 2 * kMaxMaterials
+		float4* d_mesh_table = nullptr;    // 3 * kMaxMeshes
+		float4* d_triangles = nullptr;
+		size_t triangle_capacity = 0;      // in float4
+		uint32_t* d_frame = nullptr;
+		size_t frame_capacity = 0;         // in pixels
+		unsigned long long* d_counters = nullptr;
+		cudaEvent_t ev_begin = nullptr, ev_kernel = nullptr, ev_done = nullptr;
+		rt::SceneDevice view{};
+	};
+}
+
+struct rt_context
+{
+	std::vector<DeviceState> devs;
+	std::string error;
+	bool peer_stores = false;           // every device can store into device 0's frame buffer
+
+	// host copies of the static scene (SoA, as uploaded)
+	std::vector<float> arena = std::vector<float>(ArenaLayout::total, 0.f);
+	std::vector<uint8_t> bytes = std::vector<uint8_t>(rt::kMaxSpheres + rt::kMaxPlanes, 0);
+	std::vector<int32_t> light_type = std::vector<int32_t>(rt::kMaxLights, 0);
+	std::vector<float4> materials = std::vector<float4>(2 * rt::kMaxMaterials, make_float4(0, 0, 0, 0));
+	int32_t n_spheres = 0, n_planes = 0, n_lights = 0, n_materials = 0;
+	std::vector<HostMesh> meshes;
+
+	cudaEvent_t ev_gather = nullptr, ev_d2h = nullptr;   // on device 0
+	rt_timing timing{};
+	int32_t last_width = 0, last_height = 0;
+
+	void* registered_host = nullptr;    // host surface we pinned ourselves
+	size_t registered_bytes = 0;
+	void* staging = nullptr;            // pinned bounce buffer when the surface cannot be pinned
+	size_t staging_bytes = 0;
+};
+
+namespace
+{
+	int fail(rt_context* ctx, int code, const char* fmt, ...)
+	{
+		char buf[512];
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(buf, sizeof buf, fmt, ap);
+		va_end(ap);
+		if (ctx) ctx->error = buf; else g_create_error = buf;
+		return code;
+	}
+
+#define RT_CUDA(ctx, call)                                                                      \
+	do {                                                                                        \
+		const cudaError_t e_ = (call);                                                          \
+		if (e_ != cudaSuccess)                                                                  \
+			return fail((ctx), RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+	inline float bits_as_float(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
+
+	using KernelFn = void (*)(const rt::SceneDevice, const rt::FrameParams);
+
+	KernelFn pick_kernel(int mode, int shadows)
+	{
+		static const KernelFn table[4][2] = {
+			{ rt::render_kernel<RT_LIGHTING_OBSERVED_AREA, 0, false>, rt::render_kernel<RT_LIGHTING_OBSERVED_AREA, 1, false> },
+			{ rt::render_kernel<RT_LIGHTING_RADIANCE, 0, false>, rt::render_kernel<RT_LIGHTING_RADIANCE, 1, false> },
+			{ rt::render_kernel<RT_LIGHTING_BRDF, 0, false>, rt::render_kernel<RT_LIGHTING_BRDF, 1, false> },
+			{ rt::render_kernel<RT_LIGHTING_COMBINED, 0, false>, rt::render_kernel<RT_LIGHTING_COMBINED, 1, false> },
+		};
+		return table[mode][shadows ? 1 : 0];
+	}
+
+	int validate_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame)
+	{
+		if (!camera || !frame) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "camera and frame must not be NULL");
+		if (frame->width <= 0 || frame->height <= 0 || frame->width > 65536 || frame->height > 65536)
+			return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame size %d x %d out of range", frame->width, frame->height);
+		if (frame->lighting_mode < 0 || frame->lighting_mode > 3)
+			return fail(ctx, RT_ERR_INVALID_ARGUMENT, "lighting_mode %d out of range", frame->lighting_mode);
+		if (frame->r_shift > 24 || frame->g_shift > 24 || frame->b_shift > 24)
+			return fail(ctx, RT_ERR_INVALID_ARGUMENT, "pixel format shifts out of range");
+		for (const HostMesh& m : ctx->meshes)
+			if (!m.uploaded) return fail(ctx, RT_ERR_BAD_STATE, "rt_set_mesh_count announced a mesh that was never uploaded");
+		return RT_OK;
+	}
+
+	rt::FrameParams make_params(const rt_camera* c, const rt_frame_desc* f)
+	{
+		rt::FrameParams p{};
+		p.cam_ox = c->origin[0]; p.cam_oy = c->origin[1]; p.cam_oz = c->origin[2]; p.fov = c->fov;
+		p.right_x = c->right[0]; p.right_y = c->right[1]; p.right_z = c->right[2];
+		p.up_x = c->up[0]; p.up_y = c->up[1]; p.up_z = c->up[2];
+		p.fwd_x = c->forward[0]; p.fwd_y = c->forward[1]; p.fwd_z = c->forward[2];
+		p.aspect = f->aspect_ratio;
+		p.width = f->width; p.height = f->height;
+		p.lighting_mode = f->lighting_mode; p.shadows = f->shadows_enabled ? 1 : 0;
+		p.r_shift = f->r_shift; p.g_shift = f->g_shift; p.b_shift = f->b_shift; p.alpha_mask = f->alpha_mask;
+		return p;
+	}
+
+	int ensure_frame(rt_context* ctx, DeviceState& d, size_t pixels)
+	{
+		if (d.frame_capacity >= pixels) return RT_OK;
+		RT_CUDA(ctx, cudaSetDevice(d.device));
+		if (d.d_frame) { RT_CUDA(ctx, cudaStreamSynchronize(d.stream)); RT_CUDA(ctx, cudaFree(d.d_frame)); d.d_frame = nullptr; }
+		RT_CUDA(ctx, cudaMalloc(&d.d_frame, pixels * sizeof(uint32_t)));
+		d.frame_capacity = pixels;
+		return RT_OK;
+	}
+
+	void refresh_view(rt_context* ctx, DeviceState& d)
+	{
+		rt::SceneDevice& v = d.view;
+		const float* a = d.d_arena;
+		v.sphere_ox = a + ArenaLayout::sphere; v.sphere_oy = v.sphere_ox + rt::kMaxSpheres;
+		v.sphere_oz = v.sphere_oy + rt::kMaxSpheres; v.sphere_r = v.sphere_oz + rt::kMaxSpheres;
+		v.plane_ox = a + ArenaLayout::plane; v.plane_oy = v.plane_ox + rt::kMaxPlanes; v.plane_oz = v.plane_oy + rt::kMaxPlanes;
+		v.plane_nx = v.plane_oz + rt::kMaxPlanes; v.plane_ny = v.plane_nx + rt::kMaxPlanes; v.plane_nz = v.plane_ny + rt::kMaxPlanes;
+		v.light_ox = a + ArenaLayout::light; v.light_oy = v.light_ox + rt::kMaxLights; v.light_oz = v.light_oy + rt::kMaxLights;
+		v.light_r = v.light_oz + rt::kMaxLights; v.light_g = v.light_r + rt::kMaxLights; v.light_b = v.light_g + rt::kMaxLights;
+		v.light_intensity = v.light_b + rt::kMaxLights;
+		v.sphere_mat = d.d_bytes; v.plane_mat = d.d_bytes + rt::kMaxSpheres;
+		v.light_type = d.d_light_type;
+		v.materials = d.d_materials;
+		v.mesh_table = d.d_mesh_table;
+		v.triangles = d.d_triangles;
+		v.n_spheres = ctx->n_spheres; v.n_planes = ctx->n_planes; v.n_lights = ctx->n_lights;
+		v.n_materials = ctx->n_materials; v.n_meshes = (int32_t)ctx->meshes.size();
+	}
+
+	// Push the host copies of the small static arrays to every device (a few KB).
+	int push_static(rt_context* ctx)
+	{
+		for (DeviceState& d : ctx->devs)
+		{
+			RT_CUDA(ctx, cudaSetDevice(d.device));
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_arena, ctx->arena.data(), sizeof(float) * ArenaLayout::total, cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_bytes, ctx->bytes.data(), ctx->bytes.size(), cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_light_type, ctx->light_type.data(), sizeof(int32_t) * rt::kMaxLights, cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_materials, ctx->materials.data(), sizeof(float4) * 2 * rt::kMaxMaterials, cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+			refresh_view(ctx, d);
+		}
+		return RT_OK;
+	}
+
+	// Rebuild the mesh table + concatenated triangle stream and push them to every device.
+	int push_meshes(rt_context* ctx)
+	{
+		std::vector<float4> table(3 * rt::kMaxMeshes, make_float4(0, 0, 0, 0));
+		std::vector<float4> tris;
+		int32_t first = 0;
+		for (size_t m = 0; m < ctx->meshes.size(); ++m)
+		{
+			const HostMesh& hm = ctx->meshes[m];
+			const int32_t count = (int32_t)(hm.triangles.size() / 3);
+			table[3 * m + 0] = make_float4(hm.aabb_min[0], hm.aabb_min[1], hm.aabb_min[2], bits_as_float(first));
+			table[3 * m + 1] = make_float4(hm.aabb_max[0], hm.aabb_max[1], hm.aabb_max[2], bits_as_float(count));
+			table[3 * m + 2] = make_float4(bits_as_float(hm.cull_mode), bits_as_float(hm.material), 0.f, 0.f);
+			tris.insert(tris.end(), hm.triangles.begin(), hm.triangles.end());
+			first += count;
+		}
+		for (DeviceState& d : ctx->devs)
+		{
+			RT_CUDA(ctx, cudaSetDevice(d.device));
+			if (tris.size() > d.triangle_capacity)
+			{
+				RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+				if (d.d_triangles) RT_CUDA(ctx, cudaFree(d.d_triangles));
+				d.d_triangles = nullptr;
+				const size_t cap = std::max<size_t>(tris.size(), 3 * 1024);
+				RT_CUDA(ctx, cudaMalloc(&d.d_triangles, cap * sizeof(float4)));
+				d.triangle_capacity = cap;
+			}
+			if (!tris.empty())
+				RT_CUDA(ctx, cudaMemcpyAsync(d.d_triangles, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_mesh_table, table.data(), sizeof(float4) * 3 * rt::kMaxMeshes, cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+			refresh_view(ctx, d);
+		}
+		return RT_OK;
+	}
+
+	inline float std_min_f(float a, float b) { return (b < a) ? b : a; }
+	inline float std_max_f(float a, float b) { return (a < b) ? b : a; }
+
+	// Launch one device's share.  `dst` must be addressable from device d.
+	int launch(rt_context* ctx, DeviceState& d, rt::FrameParams p, cudaStream_t stream, int n_strips)
+	{
+		if (n_strips <= 0) return RT_OK;
+		p.vector_store = (p.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dst) & 15u) == 0);
+		const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)n_strips, 1);
+		if (grid.y > 65535u) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame too tall for one launch");
+		KernelFn k = pick_kernel(p.lighting_mode, p.shadows);
+		k<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
+		RT_CUDA(ctx, cudaGetLastError());
+		ctx->timing.kernel_launches++;
+		return RT_OK;
+	}
+
+	// Render the whole frame into device 0's frame buffer, split over all devices.
+	int render_to_device0(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame)
+	{
+		int rc = validate_frame(ctx, camera, frame);
+		if (rc != RT_OK) return rc;
+		const size_t pixels = (size_t)frame->width * (size_t)frame->height;
+		const int n = (int)ctx->devs.size();
+		DeviceState& d0 = ctx->devs[0];
+		if ((rc = ensure_frame(ctx, d0, pixels)) != RT_OK) return rc;
+		ctx->timing = rt_timing{};
+		ctx->last_width = frame->width; ctx->last_height = frame->height;
+
+		const int total_strips = (frame->height + rt::kBlockH - 1) / rt::kBlockH;
+		rt::FrameParams base = make_params(camera, frame);
+
+		if (n == 1 || ctx->peer_stores)
+		{
+			// 8-row strips dealt round-robin; every device stores straight into device 0's frame
+			// (for k > 0 those are peer stores over NVLink: render and gather are one kernel).
+			for (int k = 0; k < n; ++k)
+			{
+				DeviceState& d = ctx->devs[k];
+				RT_CUDA(ctx, cudaSetDevice(d.device));
+				rt::FrameParams p = base;
+				p.row_begin = 0; p.row_end = frame->height;
+				p.strip_first = k; p.strip_step = n;
+				p.dst_full_frame = 1; p.dst = d0.d_frame;
+				const int strips = (total_strips - k + n - 1) / n;
+				RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
+				if ((rc = launch(ctx, d, p, d.stream, strips)) != RT_OK) return rc;
+				RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+			}
+			RT_CUDA(ctx, cudaSetDevice(d0.device));
+			for (int k = 1; k < n; ++k) RT_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->devs[k].ev_kernel, 0));
+			RT_CUDA(ctx, cudaEventRecord(ctx->ev_gather, d0.stream));
+		}
+		else
+		{
+			// No peer mapping: contiguous bands rendered locally, then one peer copy per band.
+			const int band_strips = (total_strips + n - 1) / n;
+			for (int k = 0; k < n; ++k)
+			{
+				DeviceState& d = ctx->devs[k];
+				const int row_begin = std::min(frame->height, k * band_strips * rt::kBlockH);
+				const int row_end = std::min(frame->height, (k + 1) * band_strips * rt::kBlockH);
+				const int rows = row_end - row_begin;
+				RT_CUDA(ctx, cudaSetDevice(d.device));
+				RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
+				if (rows > 0)
+				{
+					rt::FrameParams p = base;
+					p.row_begin = row_begin; p.row_end = row_end; p.strip_first = 0; p.strip_step = 1;
+					if (k == 0) { p.dst_full_frame = 1; p.dst = d0.d_frame; }
+					else
+					{
+						if ((rc = ensure_frame(ctx, d, (size_t)rows * frame->width)) != RT_OK) return rc;
+						p.dst_full_frame = 0; p.dst = d.d_frame;
+					}
+					if ((rc = launch(ctx, d, p, d.stream, (rows + rt::kBlockH - 1) / rt::kBlockH)) != RT_OK) return rc;
+				}
+				RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+				if (k > 0 && rows > 0)
+					RT_CUDA(ctx, cudaMemcpyPeerAsync(d0.d_frame + (size_t)row_begin * frame->width, d0.device, d.d_frame, d.device,
+					                                 (size_t)rows * frame->width * sizeof(uint32_t), d.stream));
+				RT_CUDA(ctx, cudaEventRecord(d.ev_done, d.stream));
+			}
+			RT_CUDA(ctx, cudaSetDevice(d0.device));
+			for (int k = 1; k < n; ++k) RT_CUDA(ctx, cudaStreamWaitEvent(d0.stream, ctx->devs[k].ev_done, 0));
+			RT_CUDA(ctx, cudaEventRecord(ctx->ev_gather, d0.stream));
+		}
+		return RT_OK;
+	}
+
+	int collect_timing(rt_context* ctx, bool with_d2h)
+	{
+		DeviceState& d0 = ctx->devs[0];
+		float kernel_ms = 0.f;
+		for (DeviceState& d : ctx->devs)
+		{
+			RT_CUDA(ctx, cudaSetDevice(d.device));
+			RT_CUDA(ctx, cudaEventSynchronize(d.ev_kernel));
+			float ms = 0.f;
+			RT_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_kernel));
+			kernel_ms = std::max(kernel_ms, ms);
+		}
+		RT_CUDA(ctx, cudaSetDevice(d0.device));
+		RT_CUDA(ctx, cudaEventSynchronize(ctx->ev_gather));
+		float to_gather = 0.f, to_end = 0.f;
+		RT_CUDA(ctx, cudaEventElapsedTime(&to_gather, d0.ev_begin, ctx->ev_gather));
+		ctx->timing.kernel_ms = kernel_ms;
+		ctx->timing.gather_ms = std::max(0.f, to_gather - kernel_ms);
+		if (with_d2h)
+		{
+			RT_CUDA(ctx, cudaEventSynchronize(ctx->ev_d2h));
+			RT_CUDA(ctx, cudaEventElapsedTime(&to_end, d0.ev_begin, ctx->ev_d2h));
+			ctx->timing.d2h_ms = to_end - to_gather;
+			ctx->timing.total_ms = to_end;
+		}
+		else
+		{
+			ctx->timing.d2h_ms = 0.f;
+			ctx->timing.total_ms = to_gather;
+		}
+		return RT_OK;
+	}
+
+	// Make `host` a legal target for an asynchronous device-to-host copy.  Returns the pointer
+	// to copy into (host itself, or the pinned bounce buffer) through `target`.
+	int prepare_host(rt_context* ctx, void* host, size_t bytes, void** target)
+	{
+		cudaPointerAttributes attr{};
+		const cudaError_t e = cudaPointerGetAttributes(&attr, host);
+		if (e == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged)) { *target = host; return RT_OK; }
+		cudaGetLastError();
+		if (ctx->registered_host == host && ctx->registered_bytes >= bytes) { *target = host; return RT_OK; }
+		if (ctx->registered_host) { cudaHostUnregister(ctx->registered_host); ctx->registered_host = nullptr; ctx->registered_bytes = 0; }
+		if (cudaHostRegister(host, bytes, cudaHostRegisterPortable) == cudaSuccess)
+		{
+			ctx->registered_host = host; ctx->registered_bytes = bytes; *target = host; return RT_OK;
+		}
+		cudaGetLastError();
+		if (ctx->staging_bytes < bytes)
+		{
+			if (ctx->staging) cudaFreeHost(ctx->staging);
+			ctx->staging = nullptr; ctx->staging_bytes = 0;
+			RT_CUDA(ctx, cudaHostAlloc(&ctx->staging, bytes, cudaHostAllocPortable));
+			ctx->staging_bytes = bytes;
+		}
+		*target = ctx->staging;
+		return RT_OK;
+	}
+
+	int download(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes, bool record_event)
+	{
+		DeviceState& d0 = ctx->devs[0];
+		const int W = ctx->last_width, H = ctx->last_height;
+		if (W <= 0 || H <= 0) return fail(ctx, RT_ERR_BAD_STATE, "no frame has been rendered yet");
+		if (!host_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "host_dst must not be NULL");
+		if (pitch_bytes < 4 * W || (pitch_bytes & 3)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "pitch_bytes %d too small or unaligned for width %d", pitch_bytes, W);
+		const size_t span = (size_t)pitch_bytes * (size_t)(H - 1) + (size_t)W * 4u;
+		void* target = nullptr;
+		int rc = prepare_host(ctx, host_dst, span, &target);
+		if (rc != RT_OK) return rc;
+		RT_CUDA(ctx, cudaSetDevice(d0.device));
+		if (pitch_bytes == 4 * W)
+			RT_CUDA(ctx, cudaMemcpyAsync(target, d0.d_frame, (size_t)W * H * 4u, cudaMemcpyDeviceToHost, d0.stream));
+		else
+			RT_CUDA(ctx, cudaMemcpy2DAsync(target, (size_t)pitch_bytes, d0.d_frame, (size_t)W * 4u, (size_t)W * 4u, (size_t)H, cudaMemcpyDeviceToHost, d0.stream));
+		if (record_event) RT_CUDA(ctx, cudaEventRecord(ctx->ev_d2h, d0.stream));
+		RT_CUDA(ctx, cudaStreamSynchronize(d0.stream));
+		if (target != host_dst)
+		{
+			if (pitch_bytes == 4 * W) memcpy(host_dst, target, (size_t)W * H * 4u);
+			else for (int y = 0; y < H; ++y) memcpy((char*)host_dst + (size_t)y * pitch_bytes, (char*)target + (size_t)y * pitch_bytes, (size_t)W * 4u);
+		}
+		return RT_OK;
+	}
+}
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+const char* rt_last_error(const rt_context* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int rt_device_count(const rt_context* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx)
+{
+	if (!out_ctx) return fail(nullptr, RT_ERR_INVALID_ARGUMENT, "out_ctx must not be NULL");
+	*out_ctx = nullptr;
+	int available = 0;
+	if (cudaGetDeviceCount(&available) != cudaSuccess || available <= 0)
+	{
+		cudaGetLastError();
+		return fail(nullptr, RT_ERR_NO_DEVICE, "no CUDA device is visible: this library has no CPU path");
+	}
+	std::vector<int> ids;
+	if (!device_ids || n_devices <= 0)
+	{
+		int cur = 0;
+		if (cudaGetDevice(&cur) != cudaSuccess) return fail(nullptr, RT_ERR_CUDA, "cudaGetDevice failed");
+		ids.push_back(cur);
+	}
+	else
+	{
+		for (int i = 0; i < n_devices; ++i)
+		{
+			if (device_ids[i] < 0 || device_ids[i] >= available) return fail(nullptr, RT_ERR_INVALID_ARGUMENT, "device id %d not in [0, %d)", device_ids[i], available);
+			if (std::find(ids.begin(), ids.end(), device_ids[i]) != ids.end()) return fail(nullptr, RT_ERR_INVALID_ARGUMENT, "device id %d listed twice", device_ids[i]);
+			ids.push_back(device_ids[i]);
+		}
+	}
+
+	rt_context* ctx = new rt_context();
+	int previous = 0;
+	cudaGetDevice(&previous);
+	auto bail = [&](int code) { g_create_error = ctx->error; rt_destroy(ctx); cudaSetDevice(previous); return code; };
+#define RT_CREATE(call) do { const cudaError_t e_ = (call); if (e_ != cudaSuccess) { fail(ctx, RT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); return bail(RT_ERR_CUDA); } } while (0)
+
+	for (int id : ids)
+	{
+		cudaDeviceProp prop{};
+		RT_CREATE(cudaGetDeviceProperties(&prop, id));
+		if (prop.major < 10)
+		{
+			fail(ctx, RT_ERR_NO_DEVICE, "device %d (%s) is sm_%d%d; this library carries sm_100a code only", id, prop.name, prop.major, prop.minor);
+			return bail(RT_ERR_NO_DEVICE);
+		}
+		DeviceState d;
+		d.device = id;
+		RT_CREATE(cudaSetDevice(id));
+		RT_CREATE(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+		RT_CREATE(cudaMalloc(&d.d_arena, sizeof(float) * ArenaLayout::total));
+		RT_CREATE(cudaMalloc(&d.d_bytes, rt::kMaxSpheres + rt::kMaxPlanes));
+		RT_CREATE(cudaMalloc(&d.d_light_type, sizeof(int32_t) * rt::kMaxLights));
+		RT_CREATE(cudaMalloc(&d.d_materials, sizeof(float4) * 2 * rt::kMaxMaterials));
+		RT_CREATE(cudaMalloc(&d.d_mesh_table, sizeof(float4) * 3 * rt::kMaxMeshes));
+		RT_CREATE(cudaMalloc(&d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS));
+		RT_CREATE(cudaEventCreate(&d.ev_begin));
+		RT_CREATE(cudaEventCreate(&d.ev_kernel));
+		RT_CREATE(cudaEventCreate(&d.ev_done));
+		ctx->devs.push_back(d);
+	}
+	RT_CREATE(cudaSetDevice(ids[0]));
+	RT_CREATE(cudaEventCreate(&ctx->ev_gather));
+	RT_CREATE(cudaEventCreate(&ctx->ev_d2h));
+
+	// Peer-map device 0's memory into every other device so their kernels can store the
+	// finished pixels straight into the gathered frame.
+	ctx->peer_stores = ids.size() > 1;
+	for (size_t k = 1; k < ids.size(); ++k)
+	{
+		int can = 0;
+		RT_CREATE(cudaDeviceCanAccessPeer(&can, ids[k], ids[0]));
+		if (!can) { ctx->peer_stores = false; continue; }
+		RT_CREATE(cudaSetDevice(ids[k]));
+		const cudaError_t e = cudaDeviceEnablePeerAccess(ids[0], 0);
+		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ctx->peer_stores = false;
+		cudaGetLastError();
+	}
+	int rc = push_static(ctx);
+	if (rc == RT_OK) rc = push_meshes(ctx);
+	if (rc != RT_OK) return bail(rc);
+	cudaSetDevice(previous);
+	*out_ctx = ctx;
+	return RT_OK;
+#undef RT_CREATE
+}
+
+int rt_destroy(rt_context* ctx)
+{
+	if (!ctx) return RT_OK;
+	for (DeviceState& d : ctx->devs)
+	{
+		cudaSetDevice(d.device);
+		if (d.stream) cudaStreamSynchronize(d.stream);
+		cudaFree(d.d_arena); cudaFree(d.d_bytes); cudaFree(d.d_light_type); cudaFree(d.d_materials);
+		cudaFree(d.d_mesh_table); cudaFree(d.d_triangles); cudaFree(d.d_frame); cudaFree(d.d_counters);
+		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
+		if (d.ev_kernel) cudaEventDestroy(d.ev_kernel);
+		if (d.ev_done) cudaEventDestroy(d.ev_done);
+		if (d.stream) cudaStreamDestroy(d.stream);
+	}
+	if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);
+	if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
+	if (ctx->registered_host) cudaHostUnregister(ctx->registered_host);
+	if (ctx->staging) cudaFreeHost(ctx->staging);
+	cudaGetLastError();
+	delete ctx;
+	return RT_OK;
+}
+
+int rt_upload_spheres(rt_context* ctx, const rt_spheres_soa* s)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!s || s->count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad sphere array");
+	if (s->count > rt::kMaxSpheres) return fail(ctx, RT_ERR_CAPACITY, "%d spheres exceed the capacity of %d", s->count, rt::kMaxSpheres);
+	if (s->count > 0 && (!s->origin_x || !s->origin_y || !s->origin_z || !s->radius || !s->material_index))
+		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "sphere SoA has a NULL array");
+	float* a = ctx->arena.data() + ArenaLayout::sphere;
+	for (int i = 0; i < s->count; ++i)
+	{
+		a[i] = s->origin_x[i]; a[rt::kMaxSpheres + i] = s->origin_y[i]; a[2 * rt::kMaxSpheres + i] = s->origin_z[i];
+		a[3 * rt::kMaxSpheres + i] = s->radius[i];
+		ctx->bytes[i] = s->material_index[i];
+	}
+	ctx->n_spheres = s->count;
+	return push_static(ctx);
+}
+
+int rt_upload_planes(rt_context* ctx, const rt_planes_soa* p)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!p || p->count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad plane array");
+	if (p->count > rt::kMaxPlanes) return fail(ctx, RT_ERR_CAPACITY, "%d planes exceed the capacity of %d", p->count, rt::kMaxPlanes);
+	if (p->count > 0 && (!p->origin_x || !p->origin_y || !p->origin_z || !p->normal_x || !p->normal_y || !p->normal_z || !p->material_index))
+		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "plane SoA has a NULL array");
+	float* a = ctx->arena.data() + ArenaLayout::plane;
+	const int M = rt::kMaxPlanes;
+	for (int i = 0; i < p->count; ++i)
+	{
+		a[i] = p->origin_x[i]; a[M + i] = p->origin_y[i]; a[2 * M + i] = p->origin_z[i];
+		a[3 * M + i] = p->normal_x[i]; a[4 * M + i] = p->normal_y[i]; a[5 * M + i] = p->normal_z[i];
+		ctx->bytes[rt::kMaxSpheres + i] = p->material_index[i];
+	}
+	ctx->n_planes = p->count;
+	return push_static(ctx);
+}
+
+int rt_upload_lights(rt_context* ctx, const rt_lights_soa* l)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!l || l->count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad light array");
+	if (l->count > rt::kMaxLights) return fail(ctx, RT_ERR_CAPACITY, "%d lights exceed the capacity of %d", l->count, rt::kMaxLights);
+	if (l->count > 0 && (!l->origin_x || !l->origin_y || !l->origin_z || !l->color_r || !l->color_g || !l->color_b || !l->intensity || !l->type))
+		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "light SoA has a NULL array");
+	float* a = ctx->arena.data() + ArenaLayout::light;
+	const int M = rt::kMaxLights;
+	for (int i = 0; i < l->count; ++i)
+	{
+		a[i] = l->origin_x[i]; a[M + i] = l->origin_y[i]; a[2 * M + i] = l->origin_z[i];
+		a[3 * M + i] = l->color_r[i]; a[4 * M + i] = l->color_g[i]; a[5 * M + i] = l->color_b[i];
+		a[6 * M + i] = l->intensity[i];
+		ctx->light_type[i] = l->type[i];
+	}
+	ctx->n_lights = l->count;
+	return push_static(ctx);
+}
+
+int rt_upload_materials(rt_context* ctx, const rt_material_desc* materials, int32_t count)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (count < 0 || (count > 0 && !materials)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad material array");
+	if (count > rt::kMaxMaterials) return fail(ctx, RT_ERR_CAPACITY, "%d materials exceed the capacity of %d", count, rt::kMaxMaterials);
+	for (int i = 0; i < count; ++i)
+	{
+		const rt_material_desc& m = materials[i];
+		if (m.tag < RT_MATERIAL_SOLID_COLOR || m.tag > RT_MATERIAL_COOK_TORRENCE) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "material %d has unknown tag %d", i, m.tag);
+		ctx->materials[2 * i] = make_float4(bits_as_float(m.tag), m.color[0], m.color[1], m.color[2]);
+		ctx->materials[2 * i + 1] = make_float4(m.p0, m.p1, m.p2, 0.f);
+	}
+	ctx->n_materials = count;
+	return push_static(ctx);
+}
+
+int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (mesh_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "negative mesh count");
+	if (mesh_count > rt::kMaxMeshes) return fail(ctx, RT_ERR_CAPACITY, "%d meshes exceed the capacity of %d", mesh_count, rt::kMaxMeshes);
+	ctx->meshes.resize((size_t)mesh_count);
+	if (mesh_count == 0) return push_meshes(ctx);
+	return RT_OK;
+}
+
+int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (mesh_id < 0 || mesh_id >= (int32_t)ctx->meshes.size()) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "mesh id %d outside the announced count %d", mesh_id, (int)ctx->meshes.size());
+	if (!mesh || mesh->triangle_count < 0 || mesh->vertex_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad mesh descriptor");
+	if (mesh->triangle_count > 0 && (!mesh->positions || !mesh->indices || !mesh->normals)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "mesh has a NULL array");
+	if (mesh->cull_mode < RT_CULL_FRONT_FACE || mesh->cull_mode > RT_CULL_NONE) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown cull mode %d", mesh->cull_mode);
+	for (int i = 0; i < 3 * mesh->triangle_count; ++i)
+		if (mesh->indices[i] < 0 || mesh->indices[i] >= mesh->vertex_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "index %d of mesh %d is out of range", i, mesh_id);
+
+	HostMesh& hm = ctx->meshes[(size_t)mesh_id];
+	hm.triangles.resize(3 * (size_t)mesh->triangle_count);
+	// Bounds of the indexed vertices, started like a BVH root box (reference
+	// source/DataTypes.h:310-321 with MaxVector / MinVector of source/Vector3.cpp:13-14).
+	float bmin[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, bmax[3] = { FLT_MIN, FLT_MIN, FLT_MIN };
+	for (int t = 0; t < mesh->triangle_count; ++t)
+	{
+		const float* v0 = mesh->positions + 3 * (size_t)mesh->indices[3 * t];
+		const float* v1 = mesh->positions + 3 * (size_t)mesh->indices[3 * t + 1];
+		const float* v2 = mesh->positions + 3 * (size_t)mesh->indices[3 * t + 2];
+		const float* n = mesh->normals + 3 * (size_t)t;
+		// e1 = v1 - v0, e2 = v2 - v0 (reference source/Utils.h:143-144): single IEEE subtractions
+		hm.triangles[3 * t + 0] = make_float4(v0[0], v0[1], v0[2], n[0]);
+		hm.triangles[3 * t + 1] = make_float4(v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2], n[1]);
+		hm.triangles[3 * t + 2] = make_float4(v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2], n[2]);
+		const float* vs[3] = { v0, v1, v2 };
+		for (const float* v : vs)
+			for (int k = 0; k < 3; ++k) { bmin[k] = std_min_f(bmin[k], v[k]); bmax[k] = std_max_f(bmax[k], v[k]); }
+	}
+	for (int k = 0; k < 3; ++k)
+	{
+		hm.aabb_min[k] = mesh->aabb_min ? mesh->aabb_min[k] : bmin[k];
+		hm.aabb_max[k] = mesh->aabb_max ? mesh->aabb_max[k] : bmax[k];
+	}
+	hm.cull_mode = mesh->cull_mode;
+	hm.material = mesh->material_index;
+	hm.uploaded = true;
+	for (const HostMesh& m : ctx->meshes) if (!m.uploaded) return RT_OK;   // push once every announced mesh is there
+	return push_meshes(ctx);
+}
+
+int rt_render_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	int rc = render_to_device0(ctx, camera, frame);
+	if (rc != RT_OK) return rc;
+	RT_CUDA(ctx, cudaSetDevice(ctx->devs[0].device));
+	RT_CUDA(ctx, cudaStreamSynchronize(ctx->devs[0].stream));
+	return collect_timing(ctx, false);
+}
+
+int rt_render(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame, uint32_t* host_dst, int32_t pitch_bytes)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!host_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "host_dst must not be NULL");
+	int rc = render_to_device0(ctx, camera, frame);
+	if (rc != RT_OK) return rc;
+	if ((rc = download(ctx, host_dst, pitch_bytes, true)) != RT_OK) return rc;
+	return collect_timing(ctx, true);
+}
+
+int rt_download_frame(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	return download(ctx, host_dst, pitch_bytes, false);
+}
+
+int rt_render_rows_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                          int32_t row_begin, int32_t row_count, void* device_dst, void* cuda_stream)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	int rc = validate_frame(ctx, camera, frame);
+	if (rc != RT_OK) return rc;
+	if (row_begin < 0 || row_count < 0 || row_begin + row_count > frame->height) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "rows [%d, %d) outside the frame", row_begin, row_begin + row_count);
+	if (!device_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "device_dst must not be NULL");
+	DeviceState& d = ctx->devs[0];
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+	rt::FrameParams p = make_params(camera, frame);
+	p.row_begin = row_begin; p.row_end = row_begin + row_count;
+	p.strip_first = 0; p.strip_step = 1; p.dst_full_frame = 0; p.dst = (uint32_t*)device_dst;
+	ctx->timing = rt_timing{};
+	rc = launch(ctx, d, p, stream, (row_count + rt::kBlockH - 1) / rt::kBlockH);
+	if (rc != RT_OK) return rc;
+	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
+	return RT_OK;
+}
+
+int rt_render_strips_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                            int32_t strip_first, int32_t strip_step, void* device_dst, void* cuda_stream)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	int rc = validate_frame(ctx, camera, frame);
+	if (rc != RT_OK) return rc;
+	if (strip_step <= 0 || strip_first < 0 || strip_first >= strip_step) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "strip_first %d / strip_step %d is not a rank / world pair", strip_first, strip_step);
+	if (!device_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "device_dst must not be NULL");
+	DeviceState& d = ctx->devs[0];
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+	const int total_strips = (frame->height + rt::kBlockH - 1) / rt::kBlockH;
+	rt::FrameParams p = make_params(camera, frame);
+	p.row_begin = 0; p.row_end = frame->height;
+	p.strip_first = strip_first; p.strip_step = strip_step; p.dst_full_frame = 0; p.dst = (uint32_t*)device_dst;
+	ctx->timing = rt_timing{};
+	rc = launch(ctx, d, p, stream, (total_strips - strip_first + strip_step - 1) / strip_step);
+	if (rc != RT_OK) return rc;
+	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
+	return RT_OK;
+}
+
+int rt_unstripe_device(rt_context* ctx, const void* device_src, void* device_dst, int32_t width, int32_t height,
+                       int32_t world, int32_t strips_per_rank, void* cuda_stream)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!device_src || !device_dst || width <= 0 || height <= 0 || world <= 0 || strips_per_rank <= 0)
+		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad unstripe arguments");
+	const int total_strips = (height + rt::kBlockH - 1) / rt::kBlockH;
+	if ((long long)world * strips_per_rank < total_strips) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "%d x %d strips do not cover %d rows", world, strips_per_rank, height);
+	DeviceState& d = ctx->devs[0];
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+	const int vec = (width % 4 == 0) && ((reinterpret_cast<uintptr_t>(device_src) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(device_dst) & 15u) == 0);
+	const long long units = vec ? (long long)width / 4 * height : (long long)width * height;
+	const int threads = 256;
+	const unsigned blocks = (unsigned)std::min<long long>((units + threads - 1) / threads, 148LL * 16);
+	rt::unstripe_kernel<<<blocks, threads, 0, stream>>>((const uint32_t*)device_src, (uint32_t*)device_dst, width, height, world, strips_per_rank, vec);
+	RT_CUDA(ctx, cudaGetLastError());
+	ctx->timing.kernel_launches++;
+	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
+	return RT_OK;
+}
+
+int rt_get_timing(const rt_context* ctx, rt_timing* out_timing)
+{
+	if (!ctx || !out_timing) return RT_ERR_INVALID_ARGUMENT;
+	*out_timing = ctx->timing;
+	return RT_OK;
+}
+
+int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame, rt_counters* out_counters)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!out_counters) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "out_counters must not be NULL");
+	int rc = validate_frame(ctx, camera, frame);
+	if (rc != RT_OK) return rc;
+	DeviceState& d = ctx->devs[0];
+	const size_t pixels = (size_t)frame->width * (size_t)frame->height;
+	if ((rc = ensure_frame(ctx, d, pixels)) != RT_OK) return rc;
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	RT_CUDA(ctx, cudaMemsetAsync(d.d_counters, 0, sizeof(unsigned long long) * RT_COUNTER_SLOTS, d.stream));
+	rt::FrameParams p = make_params(camera, frame);
+	p.row_begin = 0; p.row_end = frame->height; p.strip_first = 0; p.strip_step = 1;
+	p.dst_full_frame = 1; p.dst = d.d_frame; p.counters = d.d_counters;
+	p.vector_store = (p.width % 4 == 0);
+	const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)((p.height + rt::kBlockH - 1) / rt::kBlockH), 1);
+	rt::render_kernel<-1, -1, true><<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
+	RT_CUDA(ctx, cudaGetLastError());
+	RT_CUDA(ctx, cudaMemcpyAsync(out_counters->slot, d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS, cudaMemcpyDeviceToHost, d.stream));
+	RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+	ctx->last_width = frame->width; ctx->last_height = frame->height;
+	return RT_OK;
+}
+
+int rt_measure_fp32_peak(rt_context* ctx, int32_t use_fma, double* out_tflops, float* out_ms)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!out_tflops) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "out_tflops must not be NULL");
+	DeviceState& d = ctx->devs[0];
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaDeviceProp prop{};
+	RT_CUDA(ctx, cudaGetDeviceProperties(&prop, d.device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iterations = 1 << 15;
+	float* sink = reinterpret_cast<float*>(d.d_counters);
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; ++rep)   // first repetition warms the clocks up
+	{
+		RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
+		if (use_fma) rt::fp32_peak_kernel<true><<<blocks, threads, 0, d.stream>>>(sink, 0.999f, 1e-3f, iterations);
+		else rt::fp32_peak_kernel<false><<<blocks, threads, 0, d.stream>>>(sink, 0.999f, 1e-3f, iterations);
+		RT_CUDA(ctx, cudaGetLastError());
+		RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+		RT_CUDA(ctx, cudaEventSynchronize(d.ev_kernel));
+		float ms = 0.f;
+		RT_CUDA(ctx, cudaEventElapsedTime(&ms, d.ev_begin, d.ev_kernel));
+		if (rep > 0) best = std::min(best, ms);
+	}
+	const double flops = 2.0 * 8.0 * (double)iterations * (double)blocks * (double)threads;
+	*out_tflops = flops / ((double)best * 1e-3) / 1e12;
+	if (out_ms) *out_ms = best;
+	return RT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,582 @@
+// The pixel kernel: one thread per pixel, warps own 8x4 pixel tiles, a 256-thread CTA owns a
+// 32x8 pixel strip segment.  Replaces Renderer::RenderPixel (reference
+// source/Renderer.cpp:100-182) and everything it calls:
+//   Scene::GetClosestHit / DoesHit        source/Scene.cpp:29-96
+//   GeometryUtils::HitTest_* / SlabTest   source/Utils.h:15-216, 290-327 (#else branch)
+//   LightUtils                            source/Utils.h:341-369
+//   Material::Shade x4, BRDF::*           source/Material.h:34-129, source/BRDFs.h:14-99
+//   ColorRGB::MaxToOne + pack             source/ColorRGB.h:12-17, source/Renderer.cpp:176-181
+//
+// Data movement: spheres, planes, lights, materials and the mesh table are staged from the
+// SoA upload buffers into shared memory once per CTA; triangles are streamed as three float4
+// per triangle (v0|nx, e1|ny, e2|nz) with warp-uniform 128-bit loads that live in L1/L2; the
+// only HBM traffic is the 4 B/pixel result, written with 128-bit stores.
+#pragma once
+
+#include "rt_device.cuh"
+#include "../../include/rt_b200.h"
+
+namespace rt
+{
+	constexpr int kMaxSpheres = 64;
+	constexpr int kMaxPlanes = 64;
+	constexpr int kMaxLights = 16;
+	constexpr int kMaxMaterials = 256;   // materialIndex is an unsigned char in the reference
+	constexpr int kMaxMeshes = 32;
+
+	constexpr int kTileW = 8;            // pixels per warp tile
+	constexpr int kTileH = 4;
+	constexpr int kBlockW = 32;          // pixels per CTA strip segment
+	constexpr int kBlockH = 8;
+	constexpr int kThreads = 256;
+
+	// Device views of the uploaded SoA buffers (one copy per GPU).
+	struct SceneDevice
+	{
+		const float* sphere_ox; const float* sphere_oy; const float* sphere_oz; const float* sphere_r;
+		const uint8_t* sphere_mat;
+		const float* plane_ox; const float* plane_oy; const float* plane_oz;
+		const float* plane_nx; const float* plane_ny; const float* plane_nz;
+		const uint8_t* plane_mat;
+		const float* light_ox; const float* light_oy; const float* light_oz;
+		const float* light_r; const float* light_g; const float* light_b;
+		const float* light_intensity;
+		const int32_t* light_type;
+		const float4* materials;       // 2 float4 per material: {tag bits, r, g, b} {p0, p1, p2, -}
+		const float4* mesh_table;      // 3 float4 per mesh: {min xyz, first triangle}, {max xyz, triangle count}, {cull, material, -, -}
+		const float4* triangles;       // 3 float4 per triangle: {v0 xyz, n.x} {e1 xyz, n.y} {e2 xyz, n.z}
+		int32_t n_spheres, n_planes, n_lights, n_materials, n_meshes;
+	};
+
+	struct FrameParams
+	{
+		float cam_ox, cam_oy, cam_oz, fov;
+		float right_x, right_y, right_z;
+		float up_x, up_y, up_z;
+		float fwd_x, fwd_y, fwd_z;
+		float aspect;
+		int32_t width, height;
+		int32_t row_begin, row_end;      // rows of the frame this launch may touch
+		int32_t strip_first, strip_step; // CTA row k renders 8-row strip (k * strip_step + strip_first) counted from row_begin
+		int32_t dst_full_frame;          // 1: dst addresses the whole frame (row = py); 0: dst is this launch's packed band
+		int32_t lighting_mode, shadows;
+		uint32_t r_shift, g_shift, b_shift, alpha_mask;
+		int32_t vector_store;            // 1 when width % 4 == 0 and dst is 16-byte aligned
+		uint32_t* dst;
+		unsigned long long* counters;    // counters build only
+	};
+
+	struct Ray
+	{
+		V3 o, d, inv;
+		float tmin, tmax;
+	};
+
+	struct Hit
+	{
+		V3 origin, normal;
+		float t;
+		int material;
+		bool did;
+	};
+
+	struct SharedScene
+	{
+		float4 sphere[kMaxSpheres];          // {ox, oy, oz, radius}
+		float4 plane_o[kMaxPlanes];          // {ox, oy, oz, material bits}
+		float4 plane_n[kMaxPlanes];          // {nx, ny, nz, -}
+		float4 light_a[kMaxLights];          // {ox, oy, oz, intensity}
+		float4 light_b[kMaxLights];          // {r, g, b, type bits}
+		float4 mesh[3 * kMaxMeshes];
+		float4 material[2 * kMaxMaterials];
+		uint8_t sphere_mat[kMaxSpheres];
+	};
+
+	template <bool COUNT>
+	struct Counters
+	{
+		__device__ __forceinline__ void hit(int) {}
+		__device__ __forceinline__ void flush(unsigned long long*) {}
+	};
+	template <>
+	struct Counters<true>
+	{
+		unsigned int c[RT_COUNTER_SLOTS];
+		__device__ Counters() { for (int i = 0; i < RT_COUNTER_SLOTS; ++i) c[i] = 0; }
+		__device__ __forceinline__ void hit(int slot) { c[slot]++; }
+		__device__ void flush(unsigned long long* out)
+		{
+			for (int i = 0; i < RT_COUNTER_SLOTS; ++i)
+			{
+				const unsigned int s = __reduce_add_sync(0xffffffffu, c[i]);
+				if ((threadIdx.x & 31) == 0 && s) atomicAdd(&out[i], (unsigned long long)s);
+			}
+		}
+	};
+
+	__device__ __forceinline__ Ray make_ray(V3 o, V3 d, float tmin, float tmax)
+	{
+		Ray r;
+		r.o = o; r.d = d;
+		r.inv = v3(quo(1.f, d.x), quo(1.f, d.y), quo(1.f, d.z));   // DataTypes.h:550-563
+		r.tmin = tmin; r.tmax = tmax;
+		return r;
+	}
+
+	// HitTest_Sphere, Utils.h:52-71.  Returns t through `t_out`.
+	template <bool SHADOW, bool COUNT>
+	__device__ __forceinline__ bool hit_sphere(const float4 s, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	{
+		const V3 ov = v3(s) - ray.o;
+		const float ov2 = dot(ov, ov);
+		const float p = dot(ray.d, ov);
+		const float perp = sub(ov2, mul(p, p));
+		const float r2 = mul(s.w, s.w);
+		if (r2 < perp) { cnt.hit(SHADOW ? RT_CNT_SPHERE_S_DISC : RT_CNT_SPHERE_P_DISC); return false; }
+		const float t = sub(p, root(sub(r2, perp)));
+		if (t < ray.tmin || t > ray.tmax) { cnt.hit(SHADOW ? RT_CNT_SPHERE_S_TREJ : RT_CNT_SPHERE_P_TREJ); return false; }
+		cnt.hit(SHADOW ? RT_CNT_SPHERE_S_HIT : RT_CNT_SPHERE_P_HIT);
+		t_out = t;
+		return true;
+	}
+
+	// HitTest_Plane, Utils.h:82-98.
+	template <bool SHADOW, bool COUNT>
+	__device__ __forceinline__ bool hit_plane(const float4 po, const float4 pn, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	{
+		const V3 n = v3(pn);
+		const float t = quo(dot(v3(po) - ray.o, n), dot(ray.d, n));
+		cnt.hit(SHADOW ? RT_CNT_PLANE_S_TEST : RT_CNT_PLANE_P_TEST);
+		if (t >= ray.tmin && t < ray.tmax) { t_out = t; return true; }
+		return false;
+	}
+
+	// SlabTest_TriangleMesh, Utils.h:194-216.
+	__device__ __forceinline__ bool slab_test(const float4 bmin, const float4 bmax, const Ray& ray)
+	{
+		const float tx1 = mul(sub(bmin.x, ray.o.x), ray.inv.x);
+		const float tx2 = mul(sub(bmax.x, ray.o.x), ray.inv.x);
+		float t_min = std_min(tx1, tx2);
+		float t_max = std_max(tx1, tx2);
+		const float ty1 = mul(sub(bmin.y, ray.o.y), ray.inv.y);
+		const float ty2 = mul(sub(bmax.y, ray.o.y), ray.inv.y);
+		t_min = std_max(t_min, std_min(ty1, ty2));
+		t_max = std_min(t_max, std_max(ty1, ty2));
+		const float tz1 = mul(sub(bmin.z, ray.o.z), ray.inv.z);
+		const float tz2 = mul(sub(bmax.z, ray.o.z), ray.inv.z);
+		t_min = std_max(t_min, std_min(tz1, tz2));
+		t_max = std_min(t_max, std_max(tz1, tz2));
+		return t_max > 0 && t_max >= t_min;
+	}
+
+	// HitTest_Triangle, Utils.h:109-184, on the precomputed {v0, e1 = v1 - v0, e2 = v2 - v0, n}
+	// record (the two subtractions are the same IEEE operations wherever they run).
+	// `cull` is the mode already inverted for shadow rays (Utils.h:114-127).
+	template <bool SHADOW, bool COUNT>
+	__device__ __forceinline__ bool hit_triangle(const float4 a0, const float4 a1, const float4 a2, int cull,
+	                                              const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	{
+		constexpr int base = SHADOW ? RT_CNT_TRI_S_CULLED : RT_CNT_TRI_P_CULLED;
+		const V3 n = v3(a0.w, a1.w, a2.w);
+		const float cull_dot = dot(n, ray.d);
+		if (fabsf(cull_dot) < FLT_EPSILON) { cnt.hit(base); return false; }
+		if (cull == RT_CULL_FRONT_FACE) { if (cull_dot < 0.f) { cnt.hit(base); return false; } }
+		else if (cull == RT_CULL_BACK_FACE) { if (cull_dot > 0.f) { cnt.hit(base); return false; } }
+
+		const V3 e1 = v3(a1), e2 = v3(a2);
+		const V3 h = cross(ray.d, e2);
+		const float a = dot(e1, h);
+		if (fabsf(a) < FLT_EPSILON) { cnt.hit(base + 1); return false; }
+
+		const float f = quo(1.f, a);
+		const V3 s = ray.o - v3(a0);
+		const float u = mul(f, dot(s, h));
+		if (u < 0.f || u > 1.f) { cnt.hit(base + 2); return false; }
+
+		const V3 q = cross(s, e1);
+		const float v = mul(f, dot(ray.d, q));
+		if (v < 0.f || add(u, v) > 1.f) { cnt.hit(base + 3); return false; }
+
+		const float t = mul(f, dot(e2, q));
+		if (t < ray.tmin || t >= ray.tmax) { cnt.hit(base + 4); return false; }
+		cnt.hit(base + 5);
+		t_out = t;
+		return true;
+	}
+
+	// Scene::GetClosestHit, Scene.cpp:29-66: spheres, planes, meshes in order; strict '<' keeps
+	// the first primitive on ties.  The reference's shared scratch HitRecord never changes the
+	// outcome (its stale t is always >= the running closest t), so a plain running minimum is
+	// the same function.
+	template <bool COUNT>
+	__device__ __forceinline__ Hit closest_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		Hit best;
+		best.t = FLT_MAX; best.did = false; best.material = 0;
+		best.origin = v3(0.f, 0.f, 0.f); best.normal = v3(0.f, 0.f, 0.f);
+
+		int best_sphere = -1;
+		for (int i = 0; i < dev.n_spheres; ++i)
+		{
+			float t;
+			if (hit_sphere<false>(sc.sphere[i], ray, t, cnt))
+			{
+				if (t < best.t) { best.t = t; best_sphere = i; cnt.hit(RT_CNT_SPHERE_P_CLOSEST); }
+			}
+		}
+		if (best_sphere >= 0)
+		{
+			const float4 s = sc.sphere[best_sphere];
+			best.did = true;
+			best.material = sc.sphere_mat[best_sphere];
+			best.origin = ray.o + ray.d * best.t;          // Utils.h:67
+			best.normal = best.origin - v3(s);             // Utils.h:68
+			normalize(best.normal);                        // Scene.cpp:40
+		}
+
+		for (int i = 0; i < dev.n_planes; ++i)
+		{
+			float t;
+			const float4 po = sc.plane_o[i], pn = sc.plane_n[i];
+			if (hit_plane<false>(po, pn, ray, t, cnt))
+			{
+				cnt.hit(RT_CNT_PLANE_P_HIT);
+				if (t < best.t)
+				{
+					best.t = t; best.did = true;
+					best.material = __float_as_int(po.w);
+					best.normal = v3(pn);                      // Utils.h:91
+					best.origin = ray.o + ray.d * t;           // Utils.h:92
+				}
+			}
+		}
+
+		for (int m = 0; m < dev.n_meshes; ++m)
+		{
+			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			cnt.hit(RT_CNT_SLAB_P_TEST);
+			if (!slab_test(bmin, bmax, ray)) continue;
+			cnt.hit(RT_CNT_SLAB_P_PASS);
+			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
+			const int cull = __float_as_int(info.x);
+			const float4* tri = dev.triangles + 3 * (size_t)first;
+			int best_tri = -1;
+			for (int i = 0; i < count; ++i)
+			{
+				const float4 a0 = __ldg(tri + 3 * i), a1 = __ldg(tri + 3 * i + 1), a2 = __ldg(tri + 3 * i + 2);
+				float t;
+				if (hit_triangle<false>(a0, a1, a2, cull, ray, t, cnt))
+				{
+					if (t < best.t) { best.t = t; best_tri = i; }
+				}
+			}
+			if (best_tri >= 0)
+			{
+				const float4 a0 = __ldg(tri + 3 * best_tri), a1 = __ldg(tri + 3 * best_tri + 1), a2 = __ldg(tri + 3 * best_tri + 2);
+				best.did = true;
+				best.material = __float_as_int(info.y);
+				best.normal = v3(a0.w, a1.w, a2.w);            // Utils.h:178: the stored face normal
+				best.origin = ray.o + ray.d * best.t;          // Utils.h:162
+			}
+		}
+		return best;
+	}
+
+	// Scene::DoesHit, Scene.cpp:68-96: any-hit in the same order.
+	template <bool COUNT>
+	__device__ __forceinline__ bool does_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		float t;
+		for (int i = 0; i < dev.n_spheres; ++i)
+			if (hit_sphere<true>(sc.sphere[i], ray, t, cnt)) return true;
+		for (int i = 0; i < dev.n_planes; ++i)
+			if (hit_plane<true>(sc.plane_o[i], sc.plane_n[i], ray, t, cnt)) return true;
+		for (int m = 0; m < dev.n_meshes; ++m)
+		{
+			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			cnt.hit(RT_CNT_SLAB_S_TEST);
+			if (!slab_test(bmin, bmax, ray)) continue;
+			cnt.hit(RT_CNT_SLAB_S_PASS);
+			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
+			int cull = __float_as_int(info.x);
+			// Utils.h:114-127: shadow rays see the opposite cull mode.
+			cull = (cull == RT_CULL_FRONT_FACE) ? RT_CULL_BACK_FACE : (cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : cull);
+			const float4* tri = dev.triangles + 3 * (size_t)first;
+			for (int i = 0; i < count; ++i)
+			{
+				const float4 a0 = __ldg(tri + 3 * i), a1 = __ldg(tri + 3 * i + 1), a2 = __ldg(tri + 3 * i + 2);
+				if (hit_triangle<true>(a0, a1, a2, cull, ray, t, cnt)) return true;
+			}
+		}
+		return false;
+	}
+
+	constexpr float kPi = 3.14159265358979323846f;   // MathHelpers.h:7
+
+	// BRDF::GeometryFunction_SchlickGGX, BRDFs.h:78-86.
+	__device__ __forceinline__ float schlick_ggx(V3 n, V3 v, float roughness)
+	{
+		const float a = mul(roughness, roughness);
+		const float a1 = add(a, 1.f);
+		const float k = quo(mul(a1, a1), 8.f);
+		const float c = std_max(dot(n, v), 0.f);
+		return quo(c, add(mul(c, sub(1.f, k)), k));
+	}
+
+	// Material::Shade as a tagged-union switch (Material.h:41-44, 60-63, 83-87, 107-123).
+	template <bool COUNT>
+	__device__ __forceinline__ V3 shade(const SharedScene& sc, int material, V3 n, V3 l, V3 v, Counters<COUNT>& cnt)
+	{
+		const float4 m0 = sc.material[2 * material], m1 = sc.material[2 * material + 1];
+		const int tag = __float_as_int(m0.x);
+		const V3 color = v3(m0.y, m0.z, m0.w);
+		if (tag == RT_MATERIAL_SOLID_COLOR)
+		{
+			cnt.hit(RT_CNT_SHADE_SOLID);
+			return color;
+		}
+		if (tag == RT_MATERIAL_LAMBERT || tag == RT_MATERIAL_LAMBERT_PHONG)
+		{
+			// BRDF::Lambert(kd, cd) = (cd * kd) / PI, BRDFs.h:14-17
+			V3 out = v3(quo(mul(color.x, m1.x), kPi), quo(mul(color.y, m1.x), kPi), quo(mul(color.z, m1.x), kPi));
+			if (tag == RT_MATERIAL_LAMBERT) { cnt.hit(RT_CNT_SHADE_LAMBERT); return out; }
+			cnt.hit(RT_CNT_SHADE_PHONG);
+			// BRDF::Phong, BRDFs.h:33-40
+			const float nl = std_max(dot(n, l), 0.f);
+			const V3 reflect = l - n * mul(2.f, nl);
+			const float cosa = std_max(dot(reflect, v), 0.f);
+			const float spec = mul(m1.y, power(cosa, m1.z));
+			return v3(add(out.x, spec), add(out.y, spec), add(out.z, spec));
+		}
+		if (tag == RT_MATERIAL_COOK_TORRENCE)
+		{
+			cnt.hit(RT_CNT_SHADE_COOK_TORRENCE);
+			const float metal = m1.x, rough = m1.y;
+			V3 h = v + l;
+			normalize(h);
+			const bool dielectric = (metal == 0.f);
+			const V3 f0 = dielectric ? v3(0.04f, 0.04f, 0.04f) : color;
+			// FresnelFunction_Schlick, BRDFs.h:49-53
+			const float pw = power(sub(1.f, std_max(dot(h, v), 0.f)), 5.f);
+			const V3 F = v3(add(f0.x, mul(sub(1.f, f0.x), pw)), add(f0.y, mul(sub(1.f, f0.y), pw)), add(f0.z, mul(sub(1.f, f0.z), pw)));
+			// NormalDistribution_GGX, BRDFs.h:62-68
+			const float a = mul(rough, rough);
+			const float a2 = mul(a, a);
+			const float nh = std_max(dot(n, h), 0.f);
+			const float inner = add(mul(mul(nh, nh), sub(mul(a, a), 1.f)), 1.f);
+			const float D = quo(a2, mul(kPi, mul(inner, inner)));
+			// GeometryFunction_Smith, BRDFs.h:96-99
+			const float G = mul(schlick_ggx(n, v, rough), schlick_ggx(n, l, rough));
+			const float denom = mul(mul(4.f, std_max(dot(v, n), 0.0001f)), std_max(dot(l, n), 0.0001f));
+			const V3 spec = v3(quo(mul(mul(F.x, D), G), denom), quo(mul(mul(F.y, D), G), denom), quo(mul(mul(F.z, D), G), denom));
+			const V3 kd = dielectric ? v3(sub(1.f, F.x), sub(1.f, F.y), sub(1.f, F.z)) : v3(0.f, 0.f, 0.f);
+			const V3 diff = v3(quo(mul(color.x, kd.x), kPi), quo(mul(color.y, kd.y), kPi), quo(mul(color.z, kd.z), kPi));
+			return diff + spec;
+		}
+		return v3(0.f, 0.f, 0.f);
+	}
+
+	// LightUtils::GetRadiance, Utils.h:355-369 (note: measured from the un-offset hit origin).
+	__device__ __forceinline__ V3 radiance(const float4 la, const float4 lb, V3 target)
+	{
+		const int type = __float_as_int(lb.w);
+		const V3 color = v3(lb);
+		if (type == RT_LIGHT_POINT)
+		{
+			const V3 d = v3(la) - target;
+			return color * quo(la.w, dot(d, d));
+		}
+		if (type == RT_LIGHT_DIRECTIONAL) return color * la.w;
+		return v3(0.f, 0.f, 0.f);
+	}
+
+	template <int MODE, int SHADOWS, bool COUNT>
+	__device__ __forceinline__ uint32_t render_pixel(const SharedScene& sc, const SceneDevice& dev, const FrameParams& p,
+	                                                  int px, int py, Counters<COUNT>& cnt)
+	{
+		const int mode = (MODE >= 0) ? MODE : p.lighting_mode;
+		const bool shadows = (SHADOWS >= 0) ? (SHADOWS != 0) : (p.shadows != 0);
+		cnt.hit(RT_CNT_PIXELS);
+
+		// Renderer.cpp:107-108 (the two expressions really do associate differently)
+		const float cx = mul(mul(sub(mul(2.f, quo(add((float)px, 0.5f), (float)p.width)), 1.f), p.aspect), p.fov);
+		const float cy = mul(sub(1.f, quo(mul(2.f, add((float)py, 0.5f)), (float)p.height)), p.fov);
+
+		// Matrix::TransformVector(cx, cy, 1), Matrix.cpp:35-42; x * 1.f is exact
+		V3 d = v3(add(add(mul(p.right_x, cx), mul(p.up_x, cy)), p.fwd_x),
+		          add(add(mul(p.right_y, cx), mul(p.up_y, cy)), p.fwd_y),
+		          add(add(mul(p.right_z, cx), mul(p.up_z, cy)), p.fwd_z));
+		normalize(d);
+		const Ray view = make_ray(v3(p.cam_ox, p.cam_oy, p.cam_oz), d, 0.0001f, FLT_MAX);
+
+		const Hit hit = closest_hit(sc, dev, view, cnt);
+
+		float shadow_factor = 1.f;
+		V3 color = v3(0.f, 0.f, 0.f);
+		if (hit.did)
+		{
+			cnt.hit(RT_CNT_HIT_PIXELS);
+			const V3 origin_offset = hit.origin + hit.normal * 0.0001f;   // Renderer.cpp:126
+			const V3 view_neg = neg(d);
+			for (int li = 0; li < dev.n_lights; ++li)
+			{
+				cnt.hit(RT_CNT_LIGHT_ITERATIONS);
+				const float4 la = sc.light_a[li], lb = sc.light_b[li];
+				const int ltype = __float_as_int(lb.w);
+				// GetDirectionToLight, Utils.h:341-353: light.origin - p for both light types
+				V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
+				const float mag = normalize(l);
+
+				if (shadows)
+				{
+					cnt.hit(RT_CNT_SHADOW_RAYS);
+					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);
+					if (does_hit(sc, dev, shadow_ray, cnt))
+					{
+						cnt.hit(RT_CNT_OCCLUDED);
+						shadow_factor = mul(shadow_factor, 0.95f);     // Renderer.cpp:139-140
+						continue;
+					}
+				}
+				cnt.hit(RT_CNT_LIT);
+
+				if (mode == RT_LIGHTING_COMBINED)
+				{
+					const float oa = std_max(dot(hit.normal, l), 0.f);
+					const V3 e = radiance(la, lb, hit.origin);
+					const V3 brdf = shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+					// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
+					color = color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
+				}
+				else if (mode == RT_LIGHTING_OBSERVED_AREA)
+				{
+					const float oa = std_max(dot(hit.normal, l), 0.f);
+					color = color + v3(oa, oa, oa);
+				}
+				else if (mode == RT_LIGHTING_RADIANCE)
+				{
+					color = color + radiance(la, lb, hit.origin);
+				}
+				else if (mode == RT_LIGHTING_BRDF)
+				{
+					color = color + shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+				}
+			}
+			color = color * shadow_factor;                                  // Renderer.cpp:173
+		}
+
+		// ColorRGB::MaxToOne, ColorRGB.h:12-17
+		const float max_value = std_max(color.x, std_max(color.y, color.z));
+		if (max_value > 1.f) { color.x = quo(color.x, max_value); color.y = quo(color.y, max_value); color.z = quo(color.z, max_value); }
+
+		// static_cast<uint8_t>(c * 255) (truncation; the x86 reference goes through cvttss2si
+		// and keeps the low byte) + SDL_MapRGB, Renderer.cpp:178-181
+		const uint32_t R = (uint32_t)__float2int_rz(mul(color.x, 255.f)) & 0xffu;
+		const uint32_t G = (uint32_t)__float2int_rz(mul(color.y, 255.f)) & 0xffu;
+		const uint32_t B = (uint32_t)__float2int_rz(mul(color.z, 255.f)) & 0xffu;
+		return (R << p.r_shift) | (G << p.g_shift) | (B << p.b_shift) | p.alpha_mask;
+	}
+
+	__device__ __forceinline__ void stage_scene(SharedScene& sc, const SceneDevice& dev)
+	{
+		const int tid = threadIdx.x;
+		for (int i = tid; i < dev.n_spheres; i += kThreads)
+		{
+			sc.sphere[i] = make_float4(dev.sphere_ox[i], dev.sphere_oy[i], dev.sphere_oz[i], dev.sphere_r[i]);
+			sc.sphere_mat[i] = dev.sphere_mat[i];
+		}
+		for (int i = tid; i < dev.n_planes; i += kThreads)
+		{
+			sc.plane_o[i] = make_float4(dev.plane_ox[i], dev.plane_oy[i], dev.plane_oz[i], __int_as_float((int)dev.plane_mat[i]));
+			sc.plane_n[i] = make_float4(dev.plane_nx[i], dev.plane_ny[i], dev.plane_nz[i], 0.f);
+		}
+		for (int i = tid; i < dev.n_lights; i += kThreads)
+		{
+			sc.light_a[i] = make_float4(dev.light_ox[i], dev.light_oy[i], dev.light_oz[i], dev.light_intensity[i]);
+			sc.light_b[i] = make_float4(dev.light_r[i], dev.light_g[i], dev.light_b[i], __int_as_float(dev.light_type[i]));
+		}
+		for (int i = tid; i < 3 * dev.n_meshes; i += kThreads) sc.mesh[i] = dev.mesh_table[i];
+		for (int i = tid; i < 2 * dev.n_materials; i += kThreads) sc.material[i] = dev.materials[i];
+	}
+
+	template <int MODE, int SHADOWS, bool COUNT>
+	__global__ void __launch_bounds__(kThreads)
+	render_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
+	{
+		__shared__ SharedScene sc;
+		stage_scene(sc, dev);
+		__syncthreads();
+
+		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		const int tx = lane & (kTileW - 1), ty = lane >> 3;
+		const int wx = warp & 3, wy = warp >> 2;
+		const int px = blockIdx.x * kBlockW + wx * kTileW + tx;
+		const int local_y = wy * kTileH + ty;
+		const int py = p.row_begin + ((int)blockIdx.y * p.strip_step + p.strip_first) * kBlockH + local_y;
+		const bool valid = (px < p.width) && (py < p.row_end);
+
+		Counters<COUNT> cnt;
+		uint32_t pixel = 0;
+		if (valid) pixel = render_pixel<MODE, SHADOWS, COUNT>(sc, dev, p, px, py, cnt);
+		if (COUNT) cnt.flush(p.counters);
+
+		const int dst_row = p.dst_full_frame ? py : ((int)blockIdx.y * kBlockH + local_y);
+		uint32_t* row = p.dst + (size_t)dst_row * (size_t)p.width;
+		if (p.vector_store)
+		{
+			// four neighbouring pixels of a tile row -> one 128-bit store
+			const uint32_t p1 = __shfl_down_sync(0xffffffffu, pixel, 1);
+			const uint32_t p2 = __shfl_down_sync(0xffffffffu, pixel, 2);
+			const uint32_t p3 = __shfl_down_sync(0xffffffffu, pixel, 3);
+			if (valid && (tx & 3) == 0) *reinterpret_cast<uint4*>(row + px) = make_uint4(pixel, p1, p2, p3);
+		}
+		else if (valid)
+		{
+			row[px] = pixel;
+		}
+	}
+
+	// Root-rank tail of the band gather: band r holds strips r, r + world, ... packed; write the
+	// frame in row order.  Pure copy (4 B read + 4 B write per pixel), 128-bit when aligned.
+	__global__ void __launch_bounds__(256)
+	unstripe_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int width, int height, int world,
+	                int strips_per_rank, int vec)
+	{
+		const long long row_units = vec ? width / 4 : width;
+		const long long units = row_units * height;
+		const long long band_pixels = (long long)strips_per_rank * kBlockH * width;
+		for (long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x; u < units; u += (long long)gridDim.x * blockDim.x)
+		{
+			const int y = (int)(u / row_units);
+			const int xu = (int)(u - (long long)y * row_units);
+			const int strip = y / kBlockH, in_strip = y - strip * kBlockH;
+			const int rank = strip % world, local = strip / world;
+			const long long src_row = (long long)rank * band_pixels + ((long long)local * kBlockH + in_strip) * width;
+			if (vec)
+				reinterpret_cast<uint4*>(dst + (long long)y * width)[xu] = __ldg(reinterpret_cast<const uint4*>(src + src_row) + xu);
+			else
+				dst[(long long)y * width + xu] = __ldg(src + src_row + xu);
+		}
+	}
+
+	// Roofline probe: 8 independent dependent-chains per thread, all in registers.
+	template <bool FMA>
+	__global__ void __launch_bounds__(256)
+	fp32_peak_kernel(float* out, float a, float b, int iterations)
+	{
+		float acc[8];
+		for (int i = 0; i < 8; ++i) acc[i] = (float)(threadIdx.x + i) * 1e-3f;
+		for (int it = 0; it < iterations; ++it)
+		{
+#pragma unroll
+			for (int i = 0; i < 8; ++i)
+			{
+				if (FMA) acc[i] = __fmaf_rn(acc[i], a, b);
+				else acc[i] = __fadd_rn(__fmul_rn(acc[i], a), b);
+			}
+		}
+		float s = 0.f;
+		for (int i = 0; i < 8; ++i) s += acc[i];
+		if (s == 123.456f) out[0] = s;   // never true in practice; keeps the chain alive
+	}
+}

@@ -285,12 +285,32 @@ int rt_download_frame(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes);
 int rt_render_rows_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
                           int32_t row_begin, int32_t row_count, void* device_dst, void* cuda_stream);
 
+/* Same, for load-balanced interleaving: the frame is cut into strips of RT_STRIP_ROWS rows and
+ * this call renders strips strip_first, strip_first + strip_step, ... (rank, world size) into
+ * device_dst, packed in that order (every strip occupies RT_STRIP_ROWS * width pixels; the rows
+ * of the last strip that fall outside the frame are left untouched). */
+#define RT_STRIP_ROWS 8
+int rt_render_strips_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                            int32_t strip_first, int32_t strip_step, void* device_dst, void* cuda_stream);
+
+/* The gather's last step on the root rank: `device_src` holds `world` packed strip bands back to
+ * back (each strips_per_rank * RT_STRIP_ROWS * width pixels, band r = strips r, r + world, ...);
+ * writes the height x width frame to device_dst. */
+int rt_unstripe_device(rt_context* ctx, const void* device_src, void* device_dst, int32_t width, int32_t height,
+                       int32_t world, int32_t strips_per_rank, void* cuda_stream);
+
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing);
 
 /* Counters build of the same kernel: fills the test histogram for one frame (slow path,
  * measurement only; the frame it renders is identical). */
 int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
                    rt_counters* out_counters);
+
+/* FP32 roofline denominator, measured on the device the context owns: a register-resident
+ * chain of independent FP32 operations on every SM.  use_fma = 0 issues FMUL + FADD pairs
+ * (what this path can use: the reference's arithmetic is unfused), 1 issues FFMA.  Returns
+ * TFLOP/s (one FLOP per add or multiply, two per FMA) and the kernel time. */
+int rt_measure_fp32_peak(rt_context* ctx, int32_t use_fma, double* out_tflops, float* out_ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,65 @@
+"""Pins the CPU restatement (oracle/port) against the frames of the compiled reference.
+
+Every golden frame under tests/golden/ was rendered by the unmodified reference sources
+(oracle/_ref/ref_render, see tests/golden/make_golden.py).  The restatement must reproduce
+each of them bit for bit, with both mesh paths: the slab + linear loop the north star names
+(reference source/Utils.h:298-325) and the BVH traversal the reference ships (Utils.h:246-297).
+"""
+import numpy as np
+import pytest
+
+from conftest import MANIFEST, golden_names, load_golden_frame, load_golden_scene
+from oracle import rt_oracle
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_port_matches_reference_frame(name):
+    info = MANIFEST[name]
+    scene = load_golden_scene(name)
+    want = load_golden_frame(name)
+    paths = [rt_oracle.MESH_SLAB_LINEAR]
+    if scene.meshes and all(m.bvh_nodes is not None for m in scene.meshes):
+        paths.append(rt_oracle.MESH_BVH)
+    for path in paths:
+        got = rt_oracle.render(scene, info["width"], info["height"], info["mode"], bool(info["shadows"]), mesh_path=path)
+        assert np.array_equal(got, want), f"{name}: path {path} differs in {(got != want).sum()} pixels"
+        assert f"{rt_oracle.fnv1a64(got):016x}" == info["fnv1a64"]
+
+
+def test_dump_carries_frame_state():
+    for name, info in MANIFEST.items():
+        s = load_golden_scene(name)
+        assert (s.width, s.height, s.lighting_mode, s.shadows_enabled) == (info["width"], info["height"], info["mode"], info["shadows"])
+        assert s.aspect_ratio == pytest.approx(info["width"] / info["height"], rel=1e-6)
+
+
+def test_w1_is_black():
+    # Scene_W1 never sets a fov and has no lights (reference source/Scene.cpp:164-184): all-black frame
+    assert not load_golden_frame("w1_640").any()
+
+
+def test_rows_are_independent():
+    """Any row band equals the same rows of the full frame (basis of the multi-GPU split)."""
+    scene = load_golden_scene("bunny_333x77")
+    full = rt_oracle.render(scene, 333, 77)
+    band = rt_oracle.render(scene, 333, 77, row_begin=19, row_count=33)
+    assert np.array_equal(band, full[19:52])
+
+
+def test_thread_count_does_not_matter():
+    scene = load_golden_scene("w4ref_101x203")
+    a = rt_oracle.render(scene, 101, 203, threads=1)
+    b = rt_oracle.render(scene, 101, 203, threads=4)
+    assert np.array_equal(a, b)
+
+
+def test_counters_match_survey_table():
+    """SURVEY.md 8(d) [probe] counts for the bunny at 640x480, pose P0."""
+    scene = load_golden_scene("bunny_640")
+    _, c = rt_oracle.render(scene, 640, 480, counters=True)
+    assert c[0] == 307200 and c[1] == 307200                    # every pixel hits
+    assert c[12] == 307200 and c[13] == 54288                   # primary slab tests / passes
+    assert sum(c[16:22]) == 54288 * 292                          # 15.85 M primary triangle tests
+    assert c[29] == 3 * 307200                                   # one shadow ray per light per hit pixel
+    rays = int(c[0] + c[29])
+    assert rays == 1228800
