@@ -205,6 +205,8 @@ namespace
 			tris.insert(tris.end(), hm.triangles.begin(), hm.triangles.end());
 			first += count;
 		}
+		// the kernel's triangle loops read up to two records ahead of the one they test
+		for (int k = 0; k < 6; ++k) tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
 		for (DeviceState& d : ctx->devs)
 		{
 			RT_CUDA(ctx, cudaSetDevice(d.device));

@@ -169,39 +169,90 @@ namespace rt
 		return t_max > 0 && t_max >= t_min;
 	}
 
-	// HitTest_Triangle, Utils.h:109-184, on the precomputed {v0, e1 = v1 - v0, e2 = v2 - v0, n}
-	// record (the two subtractions are the same IEEE operations wherever they run).
-	// `cull` is the mode already inverted for shadow rays (Utils.h:114-127).
+	// One triangle of the stream: {v0 xyz, n.x} {e1 xyz, n.y} {e2 xyz, n.z}, e1 = v1 - v0 and
+	// e2 = v2 - v0 precomputed at upload (reference source/Utils.h:143-144: the same two IEEE
+	// subtractions wherever they run).
+	struct Tri
+	{
+		float4 a0, a1, a2;
+	};
+	__device__ __forceinline__ Tri load_tri(const float4* p)
+	{
+		Tri t;
+		t.a0 = __ldg(p); t.a1 = __ldg(p + 1); t.a2 = __ldg(p + 2);
+		return t;
+	}
+
+	// The two early outs at the top of HitTest_Triangle (Utils.h:111-139) folded into one
+	// comparison per cull mode.  CULL is the mode that applies to this ray kind (already
+	// inverted for shadow rays, Utils.h:114-127).  Same truth table as the reference, NaN included:
+	//   front-face culling: reject if |c| < eps or c < 0   <=>  pass iff !(c < eps)
+	//   back-face culling:  reject if |c| < eps or c > 0   <=>  pass iff !(c > -eps)
+	//   no culling:         reject if |c| < eps
+	template <int CULL>
+	__device__ __forceinline__ bool cull_pass(float c)
+	{
+		if (CULL == RT_CULL_FRONT_FACE) return !(c < FLT_EPSILON);
+		if (CULL == RT_CULL_BACK_FACE) return !(c > -FLT_EPSILON);
+		return !(fabsf(c) < FLT_EPSILON);
+	}
+
+	// Moeller-Trumbore body of HitTest_Triangle, Utils.h:143-160, after the cull test passed.
+	// `s` = ray origin - v0 is passed in so that rays sharing an origin share it.
 	template <bool SHADOW, bool COUNT>
-	__device__ __forceinline__ bool hit_triangle(const float4 a0, const float4 a1, const float4 a2, int cull,
-	                                              const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	__device__ __forceinline__ bool triangle_body(const Tri& T, V3 o, V3 d, V3 s, float tmin, float tmax, float& t_out, Counters<COUNT>& cnt)
 	{
 		constexpr int base = SHADOW ? RT_CNT_TRI_S_CULLED : RT_CNT_TRI_P_CULLED;
-		const V3 n = v3(a0.w, a1.w, a2.w);
-		const float cull_dot = dot(n, ray.d);
-		if (fabsf(cull_dot) < FLT_EPSILON) { cnt.hit(base); return false; }
-		if (cull == RT_CULL_FRONT_FACE) { if (cull_dot < 0.f) { cnt.hit(base); return false; } }
-		else if (cull == RT_CULL_BACK_FACE) { if (cull_dot > 0.f) { cnt.hit(base); return false; } }
-
-		const V3 e1 = v3(a1), e2 = v3(a2);
-		const V3 h = cross(ray.d, e2);
+		const V3 e1 = v3(T.a1), e2 = v3(T.a2);
+		const V3 h = cross(d, e2);
 		const float a = dot(e1, h);
 		if (fabsf(a) < FLT_EPSILON) { cnt.hit(base + 1); return false; }
 
 		const float f = quo(1.f, a);
-		const V3 s = ray.o - v3(a0);
 		const float u = mul(f, dot(s, h));
 		if (u < 0.f || u > 1.f) { cnt.hit(base + 2); return false; }
 
 		const V3 q = cross(s, e1);
-		const float v = mul(f, dot(ray.d, q));
+		const float v = mul(f, dot(d, q));
 		if (v < 0.f || add(u, v) > 1.f) { cnt.hit(base + 3); return false; }
 
 		const float t = mul(f, dot(e2, q));
-		if (t < ray.tmin || t >= ray.tmax) { cnt.hit(base + 4); return false; }
+		if (t < tmin || t >= tmax) { cnt.hit(base + 4); return false; }
 		cnt.hit(base + 5);
 		t_out = t;
 		return true;
+	}
+
+	// Closest hit over one mesh's triangles (HitTest_TriangleMesh, Utils.h:300-324, #else branch):
+	// every triangle in upload order, strict '<' so the first triangle wins ties.  The stream is
+	// software-pipelined one triangle ahead (the buffer carries one padding record at its end).
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ void closest_one(const Tri& T, int i, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	{
+		const float c = dot(v3(T.a0.w, T.a1.w, T.a2.w), ray.d);
+		if (cull_pass<CULL>(c))
+		{
+			float t;
+			if (triangle_body<false>(T, ray.o, ray.d, ray.o - v3(T.a0), ray.tmin, ray.tmax, t, cnt))
+			{
+				if (t < best_t) { best_t = t; best_tri = i; }
+			}
+		}
+		else cnt.hit(RT_CNT_TRI_P_CULLED);
+	}
+
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ void mesh_closest(const float4* tri, int count, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	{
+		// two records in flight, ping-pong (the buffer carries two padding records at its end)
+		Tri A = load_tri(tri);
+		for (int i = 0; i < count; i += 2)
+		{
+			const Tri B = load_tri(tri + 3 * (i + 1));
+			closest_one<CULL>(A, i, ray, best_t, best_tri, cnt);
+			A = load_tri(tri + 3 * (i + 2));
+			if (i + 1 < count) closest_one<CULL>(B, i + 1, ray, best_t, best_tri, cnt);
+		}
 	}
 
 	// Scene::GetClosestHit, Scene.cpp:29-66: spheres, planes, meshes in order; strict '<' keeps
@@ -261,25 +312,44 @@ namespace rt
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
 			int best_tri = -1;
-			for (int i = 0; i < count; ++i)
-			{
-				const float4 a0 = __ldg(tri + 3 * i), a1 = __ldg(tri + 3 * i + 1), a2 = __ldg(tri + 3 * i + 2);
-				float t;
-				if (hit_triangle<false>(a0, a1, a2, cull, ray, t, cnt))
-				{
-					if (t < best.t) { best.t = t; best_tri = i; }
-				}
-			}
+			if (cull == RT_CULL_BACK_FACE) mesh_closest<RT_CULL_BACK_FACE>(tri, count, ray, best.t, best_tri, cnt);
+			else if (cull == RT_CULL_FRONT_FACE) mesh_closest<RT_CULL_FRONT_FACE>(tri, count, ray, best.t, best_tri, cnt);
+			else mesh_closest<RT_CULL_NONE>(tri, count, ray, best.t, best_tri, cnt);
 			if (best_tri >= 0)
 			{
-				const float4 a0 = __ldg(tri + 3 * best_tri), a1 = __ldg(tri + 3 * best_tri + 1), a2 = __ldg(tri + 3 * best_tri + 2);
+				const Tri T = load_tri(tri + 3 * best_tri);
 				best.did = true;
 				best.material = __float_as_int(info.y);
-				best.normal = v3(a0.w, a1.w, a2.w);            // Utils.h:178: the stored face normal
+				best.normal = v3(T.a0.w, T.a1.w, T.a2.w);      // Utils.h:178: the stored face normal
 				best.origin = ray.o + ray.d * best.t;          // Utils.h:162
 			}
 		}
 		return best;
+	}
+
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ bool shadow_one(const Tri& T, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		const float c = dot(v3(T.a0.w, T.a1.w, T.a2.w), ray.d);
+		if (!cull_pass<CULL>(c)) { cnt.hit(RT_CNT_TRI_S_CULLED); return false; }
+		float t;
+		return triangle_body<true>(T, ray.o, ray.d, ray.o - v3(T.a0), ray.tmin, ray.tmax, t, cnt);
+	}
+
+	// Any hit over one mesh's triangles (HitTest_TriangleMesh with ignoreHitRecord, Utils.h:300-324):
+	// upload order, stop at the first hit.
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ bool mesh_any(const float4* tri, int count, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		Tri A = load_tri(tri);
+		for (int i = 0; i < count; i += 2)
+		{
+			const Tri B = load_tri(tri + 3 * (i + 1));
+			if (shadow_one<CULL>(A, ray, cnt)) return true;
+			A = load_tri(tri + 3 * (i + 2));
+			if (i + 1 < count && shadow_one<CULL>(B, ray, cnt)) return true;
+		}
+		return false;
 	}
 
 	// Scene::DoesHit, Scene.cpp:68-96: any-hit in the same order.
@@ -298,15 +368,14 @@ namespace rt
 			if (!slab_test(bmin, bmax, ray)) continue;
 			cnt.hit(RT_CNT_SLAB_S_PASS);
 			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
-			int cull = __float_as_int(info.x);
-			// Utils.h:114-127: shadow rays see the opposite cull mode.
-			cull = (cull == RT_CULL_FRONT_FACE) ? RT_CULL_BACK_FACE : (cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : cull);
+			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
-			for (int i = 0; i < count; ++i)
-			{
-				const float4 a0 = __ldg(tri + 3 * i), a1 = __ldg(tri + 3 * i + 1), a2 = __ldg(tri + 3 * i + 2);
-				if (hit_triangle<true>(a0, a1, a2, cull, ray, t, cnt)) return true;
-			}
+			// Utils.h:114-127: shadow rays see the opposite cull mode
+			bool hit;
+			if (cull == RT_CULL_BACK_FACE) hit = mesh_any<RT_CULL_FRONT_FACE>(tri, count, ray, cnt);
+			else if (cull == RT_CULL_FRONT_FACE) hit = mesh_any<RT_CULL_BACK_FACE>(tri, count, ray, cnt);
+			else hit = mesh_any<RT_CULL_NONE>(tri, count, ray, cnt);
+			if (hit) return true;
 		}
 		return false;
 	}
@@ -430,7 +499,7 @@ namespace rt
 				if (shadows)
 				{
 					cnt.hit(RT_CNT_SHADOW_RAYS);
-					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);
+					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);   // Renderer.cpp:136
 					if (does_hit(sc, dev, shadow_ray, cnt))
 					{
 						cnt.hit(RT_CNT_OCCLUDED);

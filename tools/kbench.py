@@ -1,0 +1,31 @@
+#!/usr/bin/env python
+"""Quick kernel A/B: renders fixtures N times through rt_render_device, prints mean/min kernel ms
+and checks the frame against the reference-rendered golden.  Usage: python tools/kbench.py [names...]"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import MANIFEST, load_golden_frame, load_golden_scene  # noqa: E402
+from gp1_raytracer_2223_b200 import Renderer  # noqa: E402
+
+names = [a for a in sys.argv[1:] if not a.startswith("-")] or ["bunny_4k", "bunny_640", "w3_640", "w4ref_640"]
+reps = 20
+for name in names:
+    info = MANIFEST[name]
+    r = Renderer(info["width"], info["height"])
+    for _ in range((info["mode"] - 3) % 4):
+        r.CycleLightingMode()
+    if not info["shadows"]:
+        r.ToggleShadows()
+    r.SetScene(load_golden_scene(name))
+    for _ in range(3):
+        r.render_device()
+    ms = [r.render_device()["kernel_ms"] for _ in range(reps)]
+    got = r.download()
+    diff = int((got != load_golden_frame(name)).sum())
+    print(f"{name:24s} kernel ms mean {np.mean(ms):.4f} min {np.min(ms):.4f}  diff_px {diff}")
+    r.close()
