@@ -5,10 +5,11 @@ import ctypes as C
 
 import numpy as np
 
-from .scene_file import Camera, FlatScene, Mesh
+from .scene_file import BVH_NODE_DTYPE, Camera, FlatScene, Mesh
 
 RT_COUNTER_SLOTS = 40
-RT_B200_ABI_VERSION = 1
+RT_B200_ABI_VERSION = 2
+MESH_PATH_AUTO, MESH_PATH_SLAB_LINEAR, MESH_PATH_BVH = 0, 1, 2
 
 c_float_p = C.POINTER(C.c_float)
 c_u8_p = C.POINTER(C.c_uint8)
@@ -38,10 +39,16 @@ class rt_lights_soa(C.Structure):
                 ("intensity", c_float_p), ("type", c_i32_p), ("count", C.c_int32)]
 
 
+class rt_bvh_node(C.Structure):
+    _fields_ = [("min_aabb", C.c_float * 3), ("max_aabb", C.c_float * 3), ("first_idx", C.c_uint32),
+                ("idx_count", C.c_uint32), ("left_node", C.c_uint32)]
+
+
 class rt_mesh_desc(C.Structure):
     _fields_ = [("positions", c_float_p), ("vertex_count", C.c_int32), ("indices", c_i32_p),
                 ("normals", c_float_p), ("triangle_count", C.c_int32), ("cull_mode", C.c_int32),
-                ("material_index", C.c_uint8), ("aabb_min", c_float_p), ("aabb_max", c_float_p)]
+                ("material_index", C.c_uint8), ("aabb_min", c_float_p), ("aabb_max", c_float_p),
+                ("bvh_nodes", C.POINTER(rt_bvh_node)), ("bvh_node_count", C.c_int32)]
 
 
 class rt_camera(C.Structure):
@@ -112,14 +119,19 @@ class SceneViews:
         self.material_count = k
         self.meshes = [self.mesh_desc(m) for m in s.meshes]
 
-    def mesh_desc(self, m: Mesh) -> rt_mesh_desc:
+    def mesh_desc(self, m: Mesh, with_bvh: bool = True) -> rt_mesh_desc:
         pos = np.ascontiguousarray(m.positions, dtype=np.float32)
         idx = np.ascontiguousarray(m.indices, dtype=np.int32)
         nrm = np.ascontiguousarray(m.normals, dtype=np.float32)
         self._keep += [pos, idx, nrm]
+        nodes, n_nodes = None, 0
+        if with_bvh and m.bvh_nodes is not None and len(m.bvh_nodes):
+            arr = np.ascontiguousarray(m.bvh_nodes, dtype=BVH_NODE_DTYPE)
+            self._keep.append(arr)
+            nodes, n_nodes = C.cast(arr.ctypes.data, C.POINTER(rt_bvh_node)), len(arr)
         return rt_mesh_desc(_fp(pos.reshape(-1)), int(pos.shape[0]), idx.reshape(-1).ctypes.data_as(c_i32_p),
                             _fp(nrm.reshape(-1)), int(idx.shape[0]), int(m.cull_mode), int(m.material_index),
-                            None, None)
+                            None, None, nodes, n_nodes)
 
 
 def camera_struct(cam: Camera) -> rt_camera:

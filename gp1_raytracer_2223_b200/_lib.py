@@ -26,6 +26,7 @@ SYMBOLS = {
     "rt_upload_lights": (C.c_int, [_ctx, C.POINTER(rt_lights_soa)]),
     "rt_upload_materials": (C.c_int, [_ctx, C.POINTER(rt_material_desc), C.c_int32]),
     "rt_set_mesh_count": (C.c_int, [_ctx, C.c_int32]),
+    "rt_set_mesh_path": (C.c_int, [_ctx, C.c_int32]),
     "rt_upload_mesh": (C.c_int, [_ctx, C.c_int32, C.POINTER(rt_mesh_desc)]),
     "rt_render": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_void_p, C.c_int32]),
     "rt_render_device": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc)]),
@@ -38,7 +39,8 @@ SYMBOLS = {
                                      C.c_void_p]),
     "rt_get_timing": (C.c_int, [_ctx, C.POINTER(rt_timing)]),
     "rt_measure_fp32_peak": (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
-    "rt_count_frame": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.POINTER(rt_counters)]),
+    "rt_count_frame": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32,
+                                 C.POINTER(rt_counters)]),
 }
 
 _lib = None

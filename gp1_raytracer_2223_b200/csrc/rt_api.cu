@@ -21,6 +21,7 @@ namespace
 	struct HostMesh
 	{
 		std::vector<float4> triangles;   // 3 per triangle
+		std::vector<float4> nodes;       // 2 per BVH node, threaded (rt::BvhLink); empty when the mesh came without nodes
 		float aabb_min[3] = { 0, 0, 0 };
 		float aabb_max[3] = { 0, 0, 0 };
 		int32_t cull_mode = RT_CULL_BACK_FACE;
@@ -48,6 +49,8 @@ namespace
 		float4* d_mesh_table = nullptr;    // 3 * kMaxMeshes
 		float4* d_triangles = nullptr;
 		size_t triangle_capacity = 0;      // in float4
+		float4* d_nodes = nullptr;
+		size_t node_capacity = 0;          // in float4
 		uint32_t* d_frame = nullptr;
 		size_t frame_capacity = 0;         // in pixels
 		unsigned long long* d_counters = nullptr;
@@ -61,6 +64,7 @@ struct rt_context
 	std::vector<DeviceState> devs;
 	std::string error;
 	bool peer_stores = false;           // every device can store into device 0's frame buffer
+	int32_t mesh_path = RT_MESH_PATH_AUTO;
 
 	// host copies of the static scene (SoA, as uploaded)
 	std::vector<float> arena = std::vector<float>(ArenaLayout::total, 0.f);
@@ -104,15 +108,28 @@ namespace
 
 	using KernelFn = void (*)(const rt::SceneDevice, const rt::FrameParams);
 
-	KernelFn pick_kernel(int mode, int shadows)
+	KernelFn pick_kernel(int mode, int shadows, bool bvh)
 	{
-		static const KernelFn table[4][2] = {
-			{ rt::render_kernel<RT_LIGHTING_OBSERVED_AREA, 0, false>, rt::render_kernel<RT_LIGHTING_OBSERVED_AREA, 1, false> },
-			{ rt::render_kernel<RT_LIGHTING_RADIANCE, 0, false>, rt::render_kernel<RT_LIGHTING_RADIANCE, 1, false> },
-			{ rt::render_kernel<RT_LIGHTING_BRDF, 0, false>, rt::render_kernel<RT_LIGHTING_BRDF, 1, false> },
-			{ rt::render_kernel<RT_LIGHTING_COMBINED, 0, false>, rt::render_kernel<RT_LIGHTING_COMBINED, 1, false> },
+#define RT_ROW(M) { { rt::render_kernel<M, 0, false, false>, rt::render_kernel<M, 1, false, false> }, { rt::render_kernel<M, 0, true, false>, rt::render_kernel<M, 1, true, false> } }
+		static const KernelFn table[4][2][2] = {
+			RT_ROW(RT_LIGHTING_OBSERVED_AREA), RT_ROW(RT_LIGHTING_RADIANCE), RT_ROW(RT_LIGHTING_BRDF), RT_ROW(RT_LIGHTING_COMBINED),
 		};
-		return table[mode][shadows ? 1 : 0];
+#undef RT_ROW
+		return table[mode][bvh ? 1 : 0][shadows ? 1 : 0];
+	}
+
+	// The mesh body a frame runs (the reference's `#ifdef BVH`), or -1 with the error set.
+	int resolve_mesh_path(rt_context* ctx, int requested)
+	{
+		bool all_have_nodes = true;
+		for (const HostMesh& m : ctx->meshes) if (!m.triangles.empty() && m.nodes.empty()) all_have_nodes = false;
+		if (requested == RT_MESH_PATH_SLAB_LINEAR) return RT_MESH_PATH_SLAB_LINEAR;
+		if (requested == RT_MESH_PATH_BVH)
+		{
+			if (!all_have_nodes) { fail(ctx, RT_ERR_BAD_STATE, "RT_MESH_PATH_BVH was requested but a mesh was uploaded without BVH nodes"); return -1; }
+			return RT_MESH_PATH_BVH;
+		}
+		return (all_have_nodes && !ctx->meshes.empty()) ? RT_MESH_PATH_BVH : RT_MESH_PATH_SLAB_LINEAR;
 	}
 
 	int validate_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame)
@@ -169,6 +186,7 @@ namespace
 		v.materials = d.d_materials;
 		v.mesh_table = d.d_mesh_table;
 		v.triangles = d.d_triangles;
+		v.bvh_nodes = d.d_nodes;
 		v.n_spheres = ctx->n_spheres; v.n_planes = ctx->n_planes; v.n_lights = ctx->n_lights;
 		v.n_materials = ctx->n_materials; v.n_meshes = (int32_t)ctx->meshes.size();
 	}
@@ -193,16 +211,18 @@ namespace
 	int push_meshes(rt_context* ctx)
 	{
 		std::vector<float4> table(3 * rt::kMaxMeshes, make_float4(0, 0, 0, 0));
-		std::vector<float4> tris;
+		std::vector<float4> tris, nodes;
 		int32_t first = 0;
 		for (size_t m = 0; m < ctx->meshes.size(); ++m)
 		{
 			const HostMesh& hm = ctx->meshes[m];
 			const int32_t count = (int32_t)(hm.triangles.size() / 3);
+			const int32_t first_node = (int32_t)(nodes.size() / 2), node_count = (int32_t)(hm.nodes.size() / 2);
 			table[3 * m + 0] = make_float4(hm.aabb_min[0], hm.aabb_min[1], hm.aabb_min[2], bits_as_float(first));
 			table[3 * m + 1] = make_float4(hm.aabb_max[0], hm.aabb_max[1], hm.aabb_max[2], bits_as_float(count));
-			table[3 * m + 2] = make_float4(bits_as_float(hm.cull_mode), bits_as_float(hm.material), 0.f, 0.f);
+			table[3 * m + 2] = make_float4(bits_as_float(hm.cull_mode), bits_as_float(hm.material), bits_as_float(first_node), bits_as_float(node_count));
 			tris.insert(tris.end(), hm.triangles.begin(), hm.triangles.end());
+			nodes.insert(nodes.end(), hm.nodes.begin(), hm.nodes.end());
 			first += count;
 		}
 		// the kernel's triangle loops read up to two records ahead of the one they test
@@ -221,6 +241,17 @@ namespace
 			}
 			if (!tris.empty())
 				RT_CUDA(ctx, cudaMemcpyAsync(d.d_triangles, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
+			if (nodes.size() > d.node_capacity)
+			{
+				RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+				if (d.d_nodes) RT_CUDA(ctx, cudaFree(d.d_nodes));
+				d.d_nodes = nullptr;
+				const size_t cap = std::max<size_t>(nodes.size(), 2 * 1024);
+				RT_CUDA(ctx, cudaMalloc(&d.d_nodes, cap * sizeof(float4)));
+				d.node_capacity = cap;
+			}
+			if (!nodes.empty())
+				RT_CUDA(ctx, cudaMemcpyAsync(d.d_nodes, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
 			RT_CUDA(ctx, cudaMemcpyAsync(d.d_mesh_table, table.data(), sizeof(float4) * 3 * rt::kMaxMeshes, cudaMemcpyHostToDevice, d.stream));
 			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
 			refresh_view(ctx, d);
@@ -235,10 +266,12 @@ namespace
 	int launch(rt_context* ctx, DeviceState& d, rt::FrameParams p, cudaStream_t stream, int n_strips)
 	{
 		if (n_strips <= 0) return RT_OK;
+		const int path = resolve_mesh_path(ctx, ctx->mesh_path);
+		if (path < 0) return RT_ERR_BAD_STATE;
 		p.vector_store = (p.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dst) & 15u) == 0);
 		const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)n_strips, 1);
 		if (grid.y > 65535u) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame too tall for one launch");
-		KernelFn k = pick_kernel(p.lighting_mode, p.shadows);
+		KernelFn k = pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH);
 		k<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
 		RT_CUDA(ctx, cudaGetLastError());
 		ctx->timing.kernel_launches++;
@@ -404,6 +437,56 @@ namespace
 	}
 }
 
+namespace
+{
+	// Turns the reference's BVHNode array into the threaded layout of rt::BvhLink.  Every index is
+	// validated: a malformed tree is an error, never a hang or an out-of-bounds read on the GPU.
+	int thread_bvh(rt_context* ctx, const rt_mesh_desc* mesh, std::vector<float4>& out)
+	{
+		out.clear();
+		const int32_t n = mesh->bvh_node_count;
+		if (!mesh->bvh_nodes || n <= 0 || mesh->triangle_count == 0) return RT_OK;
+		if (n > rt::BvhLink::kEscapeMask - 1) return fail(ctx, RT_ERR_CAPACITY, "%d BVH nodes exceed the capacity of %d", n, rt::BvhLink::kEscapeMask - 1);
+		out.assign(2 * (size_t)n, make_float4(0.f, 0.f, 0.f, 0.f));
+		std::vector<char> seen((size_t)n, 0);
+		struct Item { int32_t node, escape; };
+		std::vector<Item> stack;
+		stack.push_back({ 0, -1 });
+		int64_t covered = 0;
+		while (!stack.empty())
+		{
+			const Item it = stack.back();
+			stack.pop_back();
+			if (it.node < 0 || it.node >= n) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH child index %d outside [0, %d)", it.node, n);
+			if (seen[it.node]) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH node %d is reachable twice", it.node);
+			seen[it.node] = 1;
+			const rt_bvh_node& nd = mesh->bvh_nodes[it.node];
+			int32_t first, leaf_tris = 0;
+			if (nd.idx_count > 0)
+			{
+				if (nd.idx_count % 3 || nd.first_idx % 3 || (uint64_t)nd.first_idx + nd.idx_count > 3ull * (uint64_t)mesh->triangle_count)
+					return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH leaf %d owns indices [%u, %u) outside the mesh", it.node, nd.first_idx, nd.first_idx + nd.idx_count);
+				leaf_tris = (int32_t)(nd.idx_count / 3);
+				if (leaf_tris > rt::BvhLink::kMaxLeafTriangles) return fail(ctx, RT_ERR_CAPACITY, "BVH leaf with %d triangles exceeds the capacity of %d", leaf_tris, rt::BvhLink::kMaxLeafTriangles);
+				first = (int32_t)(nd.first_idx / 3);
+				covered += leaf_tris;
+			}
+			else
+			{
+				first = (int32_t)nd.left_node;
+				// recursion order of Utils.h:285-286: left, then left + 1; left's subtree is followed by left + 1
+				stack.push_back({ first + 1, it.escape });
+				stack.push_back({ first, first + 1 });
+			}
+			out[2 * (size_t)it.node + 0] = make_float4(nd.min_aabb[0], nd.min_aabb[1], nd.min_aabb[2], bits_as_float(first));
+			out[2 * (size_t)it.node + 1] = make_float4(nd.max_aabb[0], nd.max_aabb[1], nd.max_aabb[2],
+			                                            bits_as_float((it.escape + 1) | (leaf_tris << rt::BvhLink::kEscapeBits)));
+		}
+		if (covered != mesh->triangle_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH leaves cover %lld of %d triangles", (long long)covered, mesh->triangle_count);
+		return RT_OK;
+	}
+}
+
 extern "C" {
 
 int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
@@ -503,7 +586,7 @@ int rt_destroy(rt_context* ctx)
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_arena); cudaFree(d.d_bytes); cudaFree(d.d_light_type); cudaFree(d.d_materials);
-		cudaFree(d.d_mesh_table); cudaFree(d.d_triangles); cudaFree(d.d_frame); cudaFree(d.d_counters);
+		cudaFree(d.d_mesh_table); cudaFree(d.d_triangles); cudaFree(d.d_nodes); cudaFree(d.d_frame); cudaFree(d.d_counters);
 		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
 		if (d.ev_kernel) cudaEventDestroy(d.ev_kernel);
 		if (d.ev_done) cudaEventDestroy(d.ev_done);
@@ -601,6 +684,14 @@ int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count)
 	return RT_OK;
 }
 
+int rt_set_mesh_path(rt_context* ctx, int32_t mesh_path)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (mesh_path < RT_MESH_PATH_AUTO || mesh_path > RT_MESH_PATH_BVH) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown mesh path %d", mesh_path);
+	ctx->mesh_path = mesh_path;
+	return RT_OK;
+}
+
 int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
@@ -637,6 +728,9 @@ int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
 	}
 	hm.cull_mode = mesh->cull_mode;
 	hm.material = mesh->material_index;
+	if (mesh->bvh_node_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "negative BVH node count");
+	const int brc = thread_bvh(ctx, mesh, hm.nodes);
+	if (brc != RT_OK) { hm.uploaded = false; return brc; }
 	hm.uploaded = true;
 	for (const HostMesh& m : ctx->meshes) if (!m.uploaded) return RT_OK;   // push once every announced mesh is there
 	return push_meshes(ctx);
@@ -740,12 +834,15 @@ int rt_get_timing(const rt_context* ctx, rt_timing* out_timing)
 	return RT_OK;
 }
 
-int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame, rt_counters* out_counters)
+int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame, int32_t mesh_path, rt_counters* out_counters)
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
 	if (!out_counters) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "out_counters must not be NULL");
 	int rc = validate_frame(ctx, camera, frame);
 	if (rc != RT_OK) return rc;
+	if (mesh_path < RT_MESH_PATH_AUTO || mesh_path > RT_MESH_PATH_BVH) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown mesh path %d", mesh_path);
+	const int path = resolve_mesh_path(ctx, mesh_path);
+	if (path < 0) return RT_ERR_BAD_STATE;
 	DeviceState& d = ctx->devs[0];
 	const size_t pixels = (size_t)frame->width * (size_t)frame->height;
 	if ((rc = ensure_frame(ctx, d, pixels)) != RT_OK) return rc;
@@ -756,7 +853,8 @@ int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc
 	p.dst_full_frame = 1; p.dst = d.d_frame; p.counters = d.d_counters;
 	p.vector_store = (p.width % 4 == 0);
 	const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)((p.height + rt::kBlockH - 1) / rt::kBlockH), 1);
-	rt::render_kernel<-1, -1, true><<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
+	if (path == RT_MESH_PATH_BVH) rt::render_kernel<-1, -1, true, true><<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
+	else rt::render_kernel<-1, -1, false, true><<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
 	RT_CUDA(ctx, cudaGetLastError());
 	RT_CUDA(ctx, cudaMemcpyAsync(out_counters->slot, d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS, cudaMemcpyDeviceToHost, d.stream));
 	RT_CUDA(ctx, cudaStreamSynchronize(d.stream));

@@ -43,8 +43,9 @@ namespace rt
 		const float* light_intensity;
 		const int32_t* light_type;
 		const float4* materials;       // 2 float4 per material: {tag bits, r, g, b} {p0, p1, p2, -}
-		const float4* mesh_table;      // 3 float4 per mesh: {min xyz, first triangle}, {max xyz, triangle count}, {cull, material, -, -}
+		const float4* mesh_table;      // 3 float4 per mesh: {min xyz, first triangle}, {max xyz, triangle count}, {cull, material, first BVH node, BVH node count}
 		const float4* triangles;       // 3 float4 per triangle: {v0 xyz, n.x} {e1 xyz, n.y} {e2 xyz, n.z}
+		const float4* bvh_nodes;       // 2 float4 per node: {min xyz, first}, {max xyz, link}; see BvhLink
 		int32_t n_spheres, n_planes, n_lights, n_materials, n_meshes;
 	};
 
@@ -255,11 +256,97 @@ namespace rt
 		}
 	}
 
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ bool shadow_one(const Tri& T, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		const float c = dot(v3(T.a0.w, T.a1.w, T.a2.w), ray.d);
+		if (!cull_pass<CULL>(c)) { cnt.hit(RT_CNT_TRI_S_CULLED); return false; }
+		float t;
+		return triangle_body<true>(T, ray.o, ray.d, ray.o - v3(T.a0), ray.tmin, ray.tmax, t, cnt);
+	}
+
+	// Any hit over one mesh's triangles (HitTest_TriangleMesh with ignoreHitRecord, Utils.h:300-324):
+	// upload order, stop at the first hit.
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ bool mesh_any(const float4* tri, int count, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		Tri A = load_tri(tri);
+		for (int i = 0; i < count; i += 2)
+		{
+			const Tri B = load_tri(tri + 3 * (i + 1));
+			if (shadow_one<CULL>(A, ray, cnt)) return true;
+			A = load_tri(tri + 3 * (i + 2));
+			if (i + 1 < count && shadow_one<CULL>(B, ray, cnt)) return true;
+		}
+		return false;
+	}
+
+	// ---- the reference's shipped mesh path: IntersectionTest_BVH, Utils.h:246-288 ------------------
+	//
+	// The nodes are the reference's own (TriangleMesh::BuildBVH output, uploaded as they are), so the
+	// box tests, the set of triangles a ray meets and their order are the reference's by
+	// construction.  The recursion (left child, then left + 1) is unrolled at upload time into a
+	// threaded tree: every node carries the index of the node that follows its subtree in that
+	// depth-first order ("escape"), so the walk needs no stack:
+	//     hit box:  inner -> first child;  leaf -> test its triangles, then escape
+	//     miss box: escape
+	// Leaves own contiguous triangle ranges in ascending order, so triangles are met in upload
+	// order, exactly as the recursion meets them (strict '<' tie-breaking is preserved).
+	struct BvhLink
+	{
+		// node.w words: first = left child (inner) or first triangle (leaf), relative to the mesh;
+		// link  = (escape + 1) | (leaf triangle count << kEscapeBits); escape + 1 == 0 ends the walk
+		static constexpr int kEscapeBits = 20;
+		static constexpr int kEscapeMask = (1 << kEscapeBits) - 1;
+		static constexpr int kMaxLeafTriangles = (1 << (31 - kEscapeBits)) - 1;
+	};
+
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ void bvh_closest(const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	{
+		int node = 0;
+		while (node >= 0)
+		{
+			const float4 n0 = __ldg(nodes + 2 * node), n1 = __ldg(nodes + 2 * node + 1);
+			const int link = __float_as_int(n1.w);
+			const int escape = (link & BvhLink::kEscapeMask) - 1;
+			cnt.hit(RT_CNT_BVH_P_NODE);
+			if (!slab_test(n0, n1, ray)) { node = escape; continue; }
+			const int count = link >> BvhLink::kEscapeBits;
+			const int first = __float_as_int(n0.w);
+			if (count == 0) { node = first; continue; }
+			for (int k = 0; k < count; ++k)
+				closest_one<CULL>(load_tri(tri + 3 * (first + k)), first + k, ray, best_t, best_tri, cnt);
+			node = escape;
+		}
+	}
+
+	template <int CULL, bool COUNT>
+	__device__ __forceinline__ bool bvh_any(const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		int node = 0;
+		while (node >= 0)
+		{
+			const float4 n0 = __ldg(nodes + 2 * node), n1 = __ldg(nodes + 2 * node + 1);
+			const int link = __float_as_int(n1.w);
+			const int escape = (link & BvhLink::kEscapeMask) - 1;
+			cnt.hit(RT_CNT_BVH_S_NODE);
+			if (!slab_test(n0, n1, ray)) { node = escape; continue; }
+			const int count = link >> BvhLink::kEscapeBits;
+			const int first = __float_as_int(n0.w);
+			if (count == 0) { node = first; continue; }
+			for (int k = 0; k < count; ++k)
+				if (shadow_one<CULL>(load_tri(tri + 3 * (first + k)), ray, cnt)) return true;
+			node = escape;
+		}
+		return false;
+	}
+
 	// Scene::GetClosestHit, Scene.cpp:29-66: spheres, planes, meshes in order; strict '<' keeps
 	// the first primitive on ties.  The reference's shared scratch HitRecord never changes the
 	// outcome (its stale t is always >= the running closest t), so a plain running minimum is
 	// the same function.
-	template <bool COUNT>
+	template <bool BVH, bool COUNT>
 	__device__ __forceinline__ Hit closest_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
 	{
 		Hit best;
@@ -305,16 +392,27 @@ namespace rt
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
 			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
-			cnt.hit(RT_CNT_SLAB_P_TEST);
-			if (!slab_test(bmin, bmax, ray)) continue;
-			cnt.hit(RT_CNT_SLAB_P_PASS);
 			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
 			int best_tri = -1;
-			if (cull == RT_CULL_BACK_FACE) mesh_closest<RT_CULL_BACK_FACE>(tri, count, ray, best.t, best_tri, cnt);
-			else if (cull == RT_CULL_FRONT_FACE) mesh_closest<RT_CULL_FRONT_FACE>(tri, count, ray, best.t, best_tri, cnt);
-			else mesh_closest<RT_CULL_NONE>(tri, count, ray, best.t, best_tri, cnt);
+			if (BVH)
+			{
+				if (count == 0) continue;
+				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+				if (cull == RT_CULL_BACK_FACE) bvh_closest<RT_CULL_BACK_FACE>(nodes, tri, ray, best.t, best_tri, cnt);
+				else if (cull == RT_CULL_FRONT_FACE) bvh_closest<RT_CULL_FRONT_FACE>(nodes, tri, ray, best.t, best_tri, cnt);
+				else bvh_closest<RT_CULL_NONE>(nodes, tri, ray, best.t, best_tri, cnt);
+			}
+			else
+			{
+				cnt.hit(RT_CNT_SLAB_P_TEST);
+				if (!slab_test(bmin, bmax, ray)) continue;
+				cnt.hit(RT_CNT_SLAB_P_PASS);
+				if (cull == RT_CULL_BACK_FACE) mesh_closest<RT_CULL_BACK_FACE>(tri, count, ray, best.t, best_tri, cnt);
+				else if (cull == RT_CULL_FRONT_FACE) mesh_closest<RT_CULL_FRONT_FACE>(tri, count, ray, best.t, best_tri, cnt);
+				else mesh_closest<RT_CULL_NONE>(tri, count, ray, best.t, best_tri, cnt);
+			}
 			if (best_tri >= 0)
 			{
 				const Tri T = load_tri(tri + 3 * best_tri);
@@ -327,33 +425,8 @@ namespace rt
 		return best;
 	}
 
-	template <int CULL, bool COUNT>
-	__device__ __forceinline__ bool shadow_one(const Tri& T, const Ray& ray, Counters<COUNT>& cnt)
-	{
-		const float c = dot(v3(T.a0.w, T.a1.w, T.a2.w), ray.d);
-		if (!cull_pass<CULL>(c)) { cnt.hit(RT_CNT_TRI_S_CULLED); return false; }
-		float t;
-		return triangle_body<true>(T, ray.o, ray.d, ray.o - v3(T.a0), ray.tmin, ray.tmax, t, cnt);
-	}
-
-	// Any hit over one mesh's triangles (HitTest_TriangleMesh with ignoreHitRecord, Utils.h:300-324):
-	// upload order, stop at the first hit.
-	template <int CULL, bool COUNT>
-	__device__ __forceinline__ bool mesh_any(const float4* tri, int count, const Ray& ray, Counters<COUNT>& cnt)
-	{
-		Tri A = load_tri(tri);
-		for (int i = 0; i < count; i += 2)
-		{
-			const Tri B = load_tri(tri + 3 * (i + 1));
-			if (shadow_one<CULL>(A, ray, cnt)) return true;
-			A = load_tri(tri + 3 * (i + 2));
-			if (i + 1 < count && shadow_one<CULL>(B, ray, cnt)) return true;
-		}
-		return false;
-	}
-
 	// Scene::DoesHit, Scene.cpp:68-96: any-hit in the same order.
-	template <bool COUNT>
+	template <bool BVH, bool COUNT>
 	__device__ __forceinline__ bool does_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
 	{
 		float t;
@@ -364,17 +437,28 @@ namespace rt
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
 			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
-			cnt.hit(RT_CNT_SLAB_S_TEST);
-			if (!slab_test(bmin, bmax, ray)) continue;
-			cnt.hit(RT_CNT_SLAB_S_PASS);
 			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
 			// Utils.h:114-127: shadow rays see the opposite cull mode
 			bool hit;
-			if (cull == RT_CULL_BACK_FACE) hit = mesh_any<RT_CULL_FRONT_FACE>(tri, count, ray, cnt);
-			else if (cull == RT_CULL_FRONT_FACE) hit = mesh_any<RT_CULL_BACK_FACE>(tri, count, ray, cnt);
-			else hit = mesh_any<RT_CULL_NONE>(tri, count, ray, cnt);
+			if (BVH)
+			{
+				if (count == 0) continue;
+				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+				if (cull == RT_CULL_BACK_FACE) hit = bvh_any<RT_CULL_FRONT_FACE>(nodes, tri, ray, cnt);
+				else if (cull == RT_CULL_FRONT_FACE) hit = bvh_any<RT_CULL_BACK_FACE>(nodes, tri, ray, cnt);
+				else hit = bvh_any<RT_CULL_NONE>(nodes, tri, ray, cnt);
+			}
+			else
+			{
+				cnt.hit(RT_CNT_SLAB_S_TEST);
+				if (!slab_test(bmin, bmax, ray)) continue;
+				cnt.hit(RT_CNT_SLAB_S_PASS);
+				if (cull == RT_CULL_BACK_FACE) hit = mesh_any<RT_CULL_FRONT_FACE>(tri, count, ray, cnt);
+				else if (cull == RT_CULL_FRONT_FACE) hit = mesh_any<RT_CULL_BACK_FACE>(tri, count, ray, cnt);
+				else hit = mesh_any<RT_CULL_NONE>(tri, count, ray, cnt);
+			}
 			if (hit) return true;
 		}
 		return false;
@@ -459,7 +543,7 @@ namespace rt
 		return v3(0.f, 0.f, 0.f);
 	}
 
-	template <int MODE, int SHADOWS, bool COUNT>
+	template <int MODE, int SHADOWS, bool BVH, bool COUNT>
 	__device__ __forceinline__ uint32_t render_pixel(const SharedScene& sc, const SceneDevice& dev, const FrameParams& p,
 	                                                  int px, int py, Counters<COUNT>& cnt)
 	{
@@ -478,7 +562,7 @@ namespace rt
 		normalize(d);
 		const Ray view = make_ray(v3(p.cam_ox, p.cam_oy, p.cam_oz), d, 0.0001f, FLT_MAX);
 
-		const Hit hit = closest_hit(sc, dev, view, cnt);
+		const Hit hit = closest_hit<BVH>(sc, dev, view, cnt);
 
 		float shadow_factor = 1.f;
 		V3 color = v3(0.f, 0.f, 0.f);
@@ -500,7 +584,7 @@ namespace rt
 				{
 					cnt.hit(RT_CNT_SHADOW_RAYS);
 					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);   // Renderer.cpp:136
-					if (does_hit(sc, dev, shadow_ray, cnt))
+					if (does_hit<BVH>(sc, dev, shadow_ray, cnt))
 					{
 						cnt.hit(RT_CNT_OCCLUDED);
 						shadow_factor = mul(shadow_factor, 0.95f);     // Renderer.cpp:139-140
@@ -568,7 +652,7 @@ namespace rt
 		for (int i = tid; i < 2 * dev.n_materials; i += kThreads) sc.material[i] = dev.materials[i];
 	}
 
-	template <int MODE, int SHADOWS, bool COUNT>
+	template <int MODE, int SHADOWS, bool BVH, bool COUNT>
 	__global__ void __launch_bounds__(kThreads)
 	render_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
@@ -586,7 +670,7 @@ namespace rt
 
 		Counters<COUNT> cnt;
 		uint32_t pixel = 0;
-		if (valid) pixel = render_pixel<MODE, SHADOWS, COUNT>(sc, dev, p, px, py, cnt);
+		if (valid) pixel = render_pixel<MODE, SHADOWS, BVH, COUNT>(sc, dev, p, px, py, cnt);
 		if (COUNT) cnt.flush(p.counters);
 
 		const int dst_row = p.dst_full_frame ? py : ((int)blockIdx.y * kBlockH + local_y);

@@ -69,6 +69,10 @@ class Context:
             self.check(self.lib.rt_upload_mesh(self.handle, i, C.byref(m)), "rt_upload_mesh")
         return v
 
+    def set_mesh_path(self, mesh_path: int) -> None:
+        """The reference's compile-time `#define BVH` as a run-time choice (0 auto, 1 slab + linear, 2 BVH)."""
+        self.check(self.lib.rt_set_mesh_path(self.handle, int(mesh_path)), "rt_set_mesh_path")
+
     def upload_mesh(self, mesh_id: int, mesh) -> None:
         """Re-upload one mesh after TriangleMesh::UpdateTransforms (reference source/DataTypes.h:210-236)."""
         v = SceneViews.__new__(SceneViews)
@@ -168,12 +172,13 @@ class Renderer:
         self.ctx.check(self.ctx.lib.rt_unstripe_device(self.ctx.handle, src_ptr, dst_ptr, self.width, self.height, world,
                                                        strips_per_rank, stream), "rt_unstripe_device")
 
-    def count_frame(self, camera=None) -> np.ndarray:
+    def count_frame(self, camera=None, mesh_path: int = 1) -> np.ndarray:
+        """Test histogram of one frame; mesh_path 1 = slab + linear (the algorithmic counts), 2 = BVH."""
         cam = camera_struct(camera if camera is not None else self.scene.camera)
         frame = self._frame()
         cnt = rt_counters()
-        self.ctx.check(self.ctx.lib.rt_count_frame(self.ctx.handle, C.byref(cam), C.byref(frame), C.byref(cnt)),
-                       "rt_count_frame")
+        self.ctx.check(self.ctx.lib.rt_count_frame(self.ctx.handle, C.byref(cam), C.byref(frame), int(mesh_path),
+                                                   C.byref(cnt)), "rt_count_frame")
         return np.array(list(cnt.slot), dtype=np.uint64)
 
     def _frame(self):

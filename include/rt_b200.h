@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef struct rt_context rt_context;
 
@@ -126,6 +126,26 @@ typedef struct rt_lights_soa
 	int32_t count;
 } rt_lights_soa;
 
+/* BVHNode, source/DataTypes.h:43-54, exactly as TriangleMesh::BuildBVH (source/DataTypes.h:294-389)
+ * leaves it in pBVHNodes: a leaf has idx_count > 0 and owns indices [first_idx, first_idx + idx_count);
+ * an inner node's children are left_node and left_node + 1. */
+typedef struct rt_bvh_node
+{
+	float min_aabb[3];
+	float max_aabb[3];
+	uint32_t first_idx;
+	uint32_t idx_count;
+	uint32_t left_node;
+} rt_bvh_node;
+
+/* Which of the reference's two HitTest_TriangleMesh bodies runs (source/Utils.h:296-325). */
+enum rt_mesh_path
+{
+	RT_MESH_PATH_AUTO = 0,         /* BVH when every mesh came with nodes, else slab + linear */
+	RT_MESH_PATH_SLAB_LINEAR = 1,  /* `#else` branch, source/Utils.h:298-325: mesh AABB, then every triangle */
+	RT_MESH_PATH_BVH = 2           /* `#ifdef BVH` branch, source/Utils.h:296-297 + 246-288: what the reference ships */
+};
+
 /*
  * One TriangleMesh (source/DataTypes.h:109-156) after UpdateTransforms()
  * (source/DataTypes.h:210-236): world-space `transformedPositions`, `indices`,
@@ -145,6 +165,8 @@ typedef struct rt_mesh_desc
 	uint8_t material_index;
 	const float* aabb_min;      /* 3 floats or NULL */
 	const float* aabb_max;      /* 3 floats or NULL */
+	const rt_bvh_node* bvh_nodes;  /* TriangleMesh::pBVHNodes (source/DataTypes.h:149) or NULL */
+	int32_t bvh_node_count;        /* TriangleMesh::nodesUsed (source/DataTypes.h:151); 0 without nodes */
 } rt_mesh_desc;
 
 /*
@@ -240,7 +262,9 @@ enum rt_counter_slot
 	RT_CNT_SHADE_SOLID = 32,        /* 0 */
 	RT_CNT_SHADE_LAMBERT = 33,      /* 6 */
 	RT_CNT_SHADE_PHONG = 34,        /* 33 */
-	RT_CNT_SHADE_COOK_TORRENCE = 35 /* 112 */
+	RT_CNT_SHADE_COOK_TORRENCE = 35,/* 112 */
+	RT_CNT_BVH_P_NODE = 36,         /* BVH path only: node box tests by primary rays, 22 each */
+	RT_CNT_BVH_S_NODE = 37          /* BVH path only: node box tests by shadow rays */
 };
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
@@ -260,6 +284,9 @@ int rt_upload_planes(rt_context* ctx, const rt_planes_soa* planes);
 int rt_upload_lights(rt_context* ctx, const rt_lights_soa* lights);
 int rt_upload_materials(rt_context* ctx, const rt_material_desc* materials, int32_t count);
 int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count);
+/* Compile-time `#define BVH` of the reference (source/DataTypes.h:8, source/Utils.h:6) as a run-time
+ * choice; default RT_MESH_PATH_AUTO.  RT_MESH_PATH_BVH fails at render time if a mesh has no nodes. */
+int rt_set_mesh_path(rt_context* ctx, int32_t mesh_path);
 int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh);
 
 /* ---- render ----------------------------------------------------------------------------------- */
@@ -302,9 +329,10 @@ int rt_unstripe_device(rt_context* ctx, const void* device_src, void* device_dst
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing);
 
 /* Counters build of the same kernel: fills the test histogram for one frame (slow path,
- * measurement only; the frame it renders is identical). */
+ * measurement only; the frame it renders is identical).  mesh_path selects which mesh body is
+ * counted (RT_MESH_PATH_SLAB_LINEAR gives the algorithmic counts of SURVEY.md 8(d)). */
 int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
-                   rt_counters* out_counters);
+                   int32_t mesh_path, rt_counters* out_counters);
 
 /* FP32 roofline denominator, measured on the device the context owns: a register-resident
  * chain of independent FP32 operations on every SM.  use_fma = 0 issues FMUL + FADD pairs

@@ -215,9 +215,13 @@ void rto_mesh_bounds(const rt_mesh_desc* m, float out_min[3], float out_max[3])
 
 /* IntersectionTest_BVH, Utils.h:246-288. */
 static void bvh_traverse(const rto_mesh* mesh, unsigned node_idx, const ray_t* ray, int* did_hit,
-                         hit_t* hit_record, hit_t* current, int ignore)
+                         hit_t* hit_record, hit_t* current, int ignore, uint64_t* cnt)
 {
-	const rto_bvh_node* node = &mesh->nodes[node_idx];
+	const rto_bvh_node* node = &mesh->desc.bvh_nodes[node_idx];
+	/* The reference keeps walking sibling subtrees after an any-hit leaf returned (Utils.h:274 only
+	 * leaves the leaf); nothing it finds there can change the boolean, so stop here. */
+	if (ignore && *did_hit) return;
+	CNT(ignore ? RT_CNT_BVH_S_NODE : RT_CNT_BVH_P_NODE);
 	if (!slab_test(node->min_aabb, node->max_aabb, ray)) return;
 	if (node->idx_count > 0)
 	{
@@ -227,7 +231,7 @@ static void bvh_traverse(const rto_mesh* mesh, unsigned node_idx, const ray_t* r
 			const int leaf = (int)node->first_idx + idx;
 			if (hit_triangle(mesh_pos(m, m->indices[leaf]), mesh_pos(m, m->indices[leaf + 1]),
 			                 mesh_pos(m, m->indices[leaf + 2]), mesh_nrm(m, leaf / 3),
-			                 m->cull_mode, m->material_index, ray, current, ignore, NULL))
+			                 m->cull_mode, m->material_index, ray, current, ignore, cnt))
 			{
 				*did_hit = 1;
 				if (ignore) return;
@@ -237,8 +241,8 @@ static void bvh_traverse(const rto_mesh* mesh, unsigned node_idx, const ray_t* r
 	}
 	else
 	{
-		bvh_traverse(mesh, node->left_node, ray, did_hit, hit_record, current, ignore);
-		bvh_traverse(mesh, node->left_node + 1, ray, did_hit, hit_record, current, ignore);
+		bvh_traverse(mesh, node->left_node, ray, did_hit, hit_record, current, ignore, cnt);
+		bvh_traverse(mesh, node->left_node + 1, ray, did_hit, hit_record, current, ignore, cnt);
 	}
 }
 
@@ -258,7 +262,7 @@ static int hit_mesh(const world_t* w, int mi, const ray_t* ray, hit_t* hit_recor
 	int did_hit = 0;
 	if (w->mesh_path == RTO_MESH_BVH)
 	{
-		bvh_traverse(mesh, 0, ray, &did_hit, hit_record, &closest, ignore);
+		bvh_traverse(mesh, 0, ray, &did_hit, hit_record, &closest, ignore, cnt);
 		return did_hit;
 	}
 	CNT(ignore ? RT_CNT_SLAB_S_TEST : RT_CNT_SLAB_P_TEST);
@@ -521,8 +525,7 @@ int rto_render_rows(const rto_scene* scene, const rt_camera* camera, const rt_fr
 	if (frame->width <= 0 || frame->height <= 0 || row_begin < 0 || row_count < 0 || row_begin + row_count > frame->height) return 1;
 	if (mesh_path == RTO_MESH_BVH)
 	{
-		if (counters) return 1;
-		for (int i = 0; i < scene->mesh_count; ++i) if (!scene->meshes[i].nodes) return 1;
+		for (int i = 0; i < scene->mesh_count; ++i) if (!scene->meshes[i].desc.bvh_nodes) return 1;
 	}
 
 	float (*bounds)[6] = NULL;

@@ -19,21 +19,12 @@
 extern "C" {
 #endif
 
-/* BVHNode, reference source/DataTypes.h:43-54. */
-typedef struct rto_bvh_node
-{
-	float min_aabb[3];
-	float max_aabb[3];
-	uint32_t first_idx;
-	uint32_t idx_count;
-	uint32_t left_node;
-} rto_bvh_node;
+/* BVH nodes travel inside rt_mesh_desc (bvh_nodes / bvh_node_count). */
+typedef rt_bvh_node rto_bvh_node;
 
 typedef struct rto_mesh
 {
 	rt_mesh_desc desc;
-	const rto_bvh_node* nodes;   /* may be NULL when only the slab + linear path is wanted */
-	int32_t node_count;
 } rto_mesh;
 
 typedef struct rto_scene
@@ -55,8 +46,9 @@ enum rto_mesh_path
 
 /*
  * Renders rows [row_begin, row_begin + row_count) into dst (tightly packed).  threads <= 0
- * uses the OpenMP default.  counters may be NULL; when given (slab-linear path only) it
- * receives the test histogram of SURVEY.md section 8(d), indices as in DESIGN.md.
+ * uses the OpenMP default.  counters may be NULL; when given it receives the test histogram
+ * of SURVEY.md section 8(d) (enum rt_counter_slot); on the BVH path the slab slots stay 0 and
+ * the node box tests are counted in RT_CNT_BVH_P_NODE / RT_CNT_BVH_S_NODE.
  * Returns 0 on success.
  */
 int rto_render_rows(const rto_scene* scene, const rt_camera* camera, const rt_frame_desc* frame,

@@ -14,7 +14,7 @@ import numpy as np
 from gp1_raytracer_2223_b200._abi import (SceneViews, camera_struct, frame_struct, rt_camera, rt_counters,
                                           rt_frame_desc, rt_lights_soa, rt_material_desc, rt_mesh_desc,
                                           rt_planes_soa, rt_spheres_soa)
-from gp1_raytracer_2223_b200.scene_file import BVH_NODE_DTYPE, FlatScene
+from gp1_raytracer_2223_b200.scene_file import FlatScene
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "port", "librt_oracle.so")
@@ -23,13 +23,8 @@ MESH_SLAB_LINEAR = 0
 MESH_BVH = 1
 
 
-class rto_bvh_node(C.Structure):
-    _fields_ = [("min_aabb", C.c_float * 3), ("max_aabb", C.c_float * 3), ("first_idx", C.c_uint32),
-                ("idx_count", C.c_uint32), ("left_node", C.c_uint32)]
-
-
 class rto_mesh(C.Structure):
-    _fields_ = [("desc", rt_mesh_desc), ("nodes", C.POINTER(rto_bvh_node)), ("node_count", C.c_int32)]
+    _fields_ = [("desc", rt_mesh_desc)]
 
 
 class rto_scene(C.Structure):
@@ -73,17 +68,9 @@ class OracleScene:
         self.views = SceneViews(scene)
         n = len(scene.meshes)
         self._meshes = (rto_mesh * max(n, 1))()
-        self._nodes = []
-        self.has_bvh = n > 0
-        for i, m in enumerate(scene.meshes):
+        self.has_bvh = n > 0 and all(m.bvh_nodes is not None and len(m.bvh_nodes) for m in scene.meshes)
+        for i in range(n):
             self._meshes[i].desc = self.views.meshes[i]
-            if m.bvh_nodes is not None and len(m.bvh_nodes):
-                nodes = np.ascontiguousarray(m.bvh_nodes, dtype=BVH_NODE_DTYPE)
-                self._nodes.append(nodes)
-                self._meshes[i].nodes = C.cast(nodes.ctypes.data, C.POINTER(rto_bvh_node))
-                self._meshes[i].node_count = len(nodes)
-            else:
-                self.has_bvh = False
         self.c = rto_scene(self.views.spheres, self.views.planes, self.views.lights,
                            C.cast(self.views.materials, C.POINTER(rt_material_desc)), self.views.material_count,
                            C.cast(self._meshes, C.POINTER(rto_mesh)), n)

@@ -23,7 +23,7 @@ def declared_functions():
 
 def test_header_and_binding_agree(lib):
     names = declared_functions()
-    assert len(names) >= 18
+    assert len(names) >= 20
     assert set(names) == set(_lib.SYMBOLS), set(names) ^ set(_lib.SYMBOLS)
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in rt_b200.h but not exported"
@@ -41,7 +41,8 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_abi.rt_timing) == 24
     assert C.sizeof(_abi.rt_counters) == 8 * _abi.RT_COUNTER_SLOTS
     assert C.sizeof(_abi.rt_spheres_soa) == 48
-    assert C.sizeof(_abi.rt_mesh_desc) == 64
+    assert C.sizeof(_abi.rt_mesh_desc) == 80
+    assert C.sizeof(_abi.rt_bvh_node) == 36
 
 
 def test_no_cpu_fallback(lib):

@@ -40,9 +40,15 @@ def make_renderer(name, **kw):
     return r
 
 
+@pytest.mark.parametrize("mesh_path", [1, 2], ids=["slab_linear", "bvh"])
 @pytest.mark.parametrize("name", golden_names())
-def test_frame_matches_reference(gpu, name):
+def test_frame_matches_reference(gpu, name, mesh_path):
+    """Both bodies of HitTest_TriangleMesh (reference source/Utils.h:296-325): the slab + linear loop and
+    the BVH walk over the reference's own nodes."""
+    if mesh_path == 2 and not load_golden_scene(name).meshes:
+        pytest.skip("scene has no triangle mesh")
     r = make_renderer(name)
+    r.ctx.set_mesh_path(mesh_path)
     got = r.Render()
     want = load_golden_frame(name)
     identical, max_err, n_diff = compare_frames(got, want)
@@ -70,9 +76,13 @@ def test_counters_match_oracle(gpu):
         info = MANIFEST[name]
         scene = load_golden_scene(name)
         r = make_renderer(name)
-        _, want = rt_oracle.render(scene, info["width"], info["height"], info["mode"], bool(info["shadows"]), counters=True)
-        got = r.count_frame()
-        assert np.array_equal(got[:36], want[:36]), (name, np.nonzero(got[:36] != want[:36]))
+        for gpu_path, oracle_path in ((1, rt_oracle.MESH_SLAB_LINEAR), (2, rt_oracle.MESH_BVH)):
+            if gpu_path == 2 and not scene.meshes:
+                continue
+            _, want = rt_oracle.render(scene, info["width"], info["height"], info["mode"], bool(info["shadows"]),
+                                       mesh_path=oracle_path, counters=True)
+            got = r.count_frame(mesh_path=gpu_path)
+            assert np.array_equal(got[:38], want[:38]), (name, gpu_path, np.nonzero(got[:38] != want[:38]))
         r.close()
 
 
@@ -180,6 +190,37 @@ def test_empty_scene_and_errors(gpu):
     assert lib.rt_set_mesh_count(h, 0) == 0
     assert lib.rt_render(h, None, None, None, 0) != 0
     assert lib.rt_download_frame(h, None, 0) != 0
+    r.close()
+
+
+def test_default_path_is_the_shipped_bvh_and_bad_trees_are_rejected(gpu):
+    import ctypes as C
+    from gp1_raytracer_2223_b200._abi import SceneViews
+    scene = load_golden_scene("bunny_320_yaw10")
+    r = make_renderer("bunny_320_yaw10")
+    assert np.array_equal(r.Render(), load_golden_frame("bunny_320_yaw10"))     # auto -> BVH (nodes were uploaded)
+    # a mesh without nodes under a forced BVH path is an error, not a silent fallback
+    v = SceneViews.__new__(SceneViews)
+    v._keep = []
+    desc = SceneViews.mesh_desc(v, scene.meshes[0], with_bvh=False)
+    assert r.ctx.lib.rt_upload_mesh(r.ctx.handle, 0, C.byref(desc)) == 0
+    r.ctx.set_mesh_path(2)
+    cam_ok = False
+    try:
+        r.Render()
+    except Exception as e:
+        cam_ok = "without BVH nodes" in str(e)
+    assert cam_ok
+    r.ctx.set_mesh_path(0)
+    assert np.array_equal(r.Render(), load_golden_frame("bunny_320_yaw10"))     # auto -> slab + linear now
+    # corrupt trees: child index out of range, and a cycle
+    import copy
+    for corrupt in ("range", "cycle"):
+        bad = copy.deepcopy(scene.meshes[0])
+        inner = int(np.nonzero(bad.bvh_nodes["idx_count"] == 0)[0][-1])
+        bad.bvh_nodes["left_node"][inner] = 10_000_000 if corrupt == "range" else 0
+        d = SceneViews.mesh_desc(v, bad)
+        assert r.ctx.lib.rt_upload_mesh(r.ctx.handle, 0, C.byref(d)) != 0
     r.close()
 
 
