@@ -6,7 +6,11 @@ Combined lighting, shadows on (BASELINE.json configs[4], the north-star target).
 
 A step is one frame.  Metric: Mrays/s (primary + shadow rays of the frame / time).
   value      device-timed (CUDA events on the launching stream), scene resident in HBM, frame left in
-             HBM on rank 0 (N > 1: strip render on every rank + NCCL gather + unstripe on rank 0)
+             HBM on rank 0 (N > 1: strip render on every rank + NCCL gather + unstripe on rank 0).
+             Headline = the library's default mesh path: the reference's shipped BVH walk over the
+             reference's own nodes (source/Utils.h:246-297).  The slab + every-triangle body the north
+             star names (source/Utils.h:298-325) is measured the same way and reported under
+             "north_star_slab_linear" with its own roofline.
   e2e        the same frame through the reference-facing C ABI with HOST buffers: per step the
              re-transformed mesh goes host -> device (rt_upload_mesh, what Scene::Update produces each
              frame) and the finished frame comes device -> host (rt_render into pinned memory)
@@ -214,10 +218,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- workload accounting from the counters build (rank 0 only; not timed) -----------------
-    counters = r.count_frame() if rank == 0 else None
+    PATHS = {"bvh": 2, "slab_linear": 1}
+    flop_per_frame = {}
     if rank == 0:
-        flop_per_frame = algorithmic_flops(counters, 3)
-        assert rays(counters) == RAYS_PER_FRAME, (rays(counters), RAYS_PER_FRAME)
+        for pname, pid in PATHS.items():
+            counters = r.count_frame(mesh_path=pid)
+            flop_per_frame[pname] = algorithmic_flops(counters, 3)
+            assert rays(counters) == RAYS_PER_FRAME, (rays(counters), RAYS_PER_FRAME)
     spr = bands.strips_per_rank(HEIGHT, world)
     band = torch.empty((spr * bands.STRIP_ROWS, WIDTH), dtype=torch.int32, device="cuda")
     frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda") if rank == 0 else None
@@ -249,39 +256,44 @@ def main():
             torch.cuda.synchronize()
 
     # ---- device-timed region ---------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        device_step()
-    barrier()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kstarts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    kends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    barrier()
-    with sampler:
-        for i in range(args.steps):
-            flush.zero_()                      # evict the frame buffer from L2 between timed steps
-            starts[i].record()
-            if world == 1:
-                device_step()
-            else:
-                kstarts[i].record()
-                r.render_strips_device(rank, world, band.data_ptr(), stream)
-                kends[i].record()
-                if rank == 0:
-                    dist.gather(band, list(gathered.unbind(0)), dst=0)
-                    r.unstripe_device(gathered.data_ptr(), frame_dev.data_ptr(), world, spr, stream)
-                else:
-                    dist.gather(band, None, dst=0)
-            ends[i].record()
+    def timed_device_region(sampler):
+        for _ in range(max(args.warmup, 3)):
+            device_step()
         barrier()
-    step_ms = torch.tensor([s.elapsed_time(e) for s, e in zip(starts, ends)], dtype=torch.float64, device="cuda")
-    kern_ms = step_ms.clone() if world == 1 else torch.tensor([s.elapsed_time(e) for s, e in zip(kstarts, kends)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)     # per step, the slowest rank
-        dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(step_ms.sum())
-    kernel_ms = float(kern_ms.mean())
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        kstarts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        kends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        barrier()
+        with sampler:
+            for i in range(args.steps):
+                flush.zero_()                      # evict the frame buffer from L2 between timed steps
+                starts[i].record()
+                if world == 1:
+                    device_step()
+                else:
+                    kstarts[i].record()
+                    r.render_strips_device(rank, world, band.data_ptr(), stream)
+                    kends[i].record()
+                    if rank == 0:
+                        dist.gather(band, list(gathered.unbind(0)), dst=0)
+                        r.unstripe_device(gathered.data_ptr(), frame_dev.data_ptr(), world, spr, stream)
+                    else:
+                        dist.gather(band, None, dst=0)
+                ends[i].record()
+            barrier()
+        step_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(starts, ends)], dtype=torch.float64, device="cuda")
+        kern_ms = step_ms.clone() if world == 1 else torch.tensor([a.elapsed_time(b) for a, b in zip(kstarts, kends)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)     # per step, the slowest rank
+            dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
+        return float(step_ms.sum()), float(kern_ms.mean())
+
+    sampler = ClockSampler(local_rank)
+    r.ctx.set_mesh_path(PATHS["slab_linear"])
+    slab_total_ms, slab_kernel_ms = timed_device_region(ClockSampler(local_rank))
+    r.ctx.set_mesh_path(0)                                     # default: BVH, the fixture carries the reference's nodes
+    total_ms, kernel_ms = timed_device_region(sampler)
 
     # ---- end-to-end region -----------------------------------------------------------------------
     e2e = None
@@ -314,8 +326,6 @@ def main():
     # ---- roofline (rank 0's GPU) -----------------------------------------------------------------
     peak_nofma = r.ctx.measure_fp32_peak(False)
     peak_fma = r.ctx.measure_fp32_peak(True)
-    flop_per_launch = flop_per_frame / world                   # strips are dealt round-robin: ~1/N of the frame each
-    achieved = flop_per_launch / (kernel_ms * 1e-3) / 1e12
     traffic = None
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
@@ -323,16 +333,30 @@ def main():
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {
-        "bound": "fp32", "achieved": achieved, "peak": peak_nofma["tflops"], "unit": "TFLOP/s",
-        "frac": achieved / peak_nofma["tflops"], "traffic": traffic,
-        "peak_source": "measured live: FMUL+FADD issue peak of this GPU (rt_measure_fp32_peak); the reference's arithmetic is unfused, so FFMA is not available to this path",
-        "peak_fma": peak_fma["tflops"], "frac_of_fma_peak": achieved / peak_fma["tflops"],
-        "algorithmic_gflop_per_frame": flop_per_frame / 1e9, "kernel": "rt::render_kernel<Combined, shadows>",
-        "kernel_ms": kernel_ms,
-        "hbm": {"bytes_per_launch": WIDTH * HEIGHT * 4 // world, "achieved_gbs": WIDTH * HEIGHT * 4 / world / (kernel_ms * 1e-3) / 1e9,
-                "peak_gbs": _measured_peaks().get("hbm_gbs")},
-    }
+
+    def roofline_of(pname, k_ms, kernel_name):
+        # strips are dealt round-robin: every launch does ~1/N of the frame's work
+        flop_per_launch = flop_per_frame[pname] / world
+        achieved = flop_per_launch / (k_ms * 1e-3) / 1e12
+        return {
+            "bound": "fp32", "achieved": achieved, "peak": peak_nofma["tflops"], "unit": "TFLOP/s",
+            "frac": achieved / peak_nofma["tflops"], "traffic": traffic if pname == "bvh" else None,
+            "peak_source": "measured live on this GPU (rt_measure_fp32_peak): FMUL+FADD issue peak; the reference's arithmetic is unfused, so FFMA is not available to this path",
+            "peak_fma": peak_fma["tflops"], "frac_of_fma_peak": achieved / peak_fma["tflops"],
+            "algorithmic_gflop_per_frame": flop_per_frame[pname] / 1e9,
+            "flop_definition": "SURVEY.md 8(d) weights x the event counts of this mesh path (counters build of the same kernel)",
+            "kernel": kernel_name, "kernel_ms": k_ms,
+            "hbm": {"bytes_per_launch": WIDTH * HEIGHT * 4 // world, "achieved_gbs": WIDTH * HEIGHT * 4 / world / (k_ms * 1e-3) / 1e9,
+                    "peak_gbs": _measured_peaks().get("hbm_gbs")},
+        }
+
+    roofline = roofline_of("bvh", kernel_ms, "rt::render_kernel<Combined, shadows, BVH>")
+    # the same kernel time against the north-star algorithm's FLOP count (what a brute-force kernel would have to do)
+    roofline["survey_algorithmic_gflop_per_frame"] = flop_per_frame["slab_linear"] / 1e9
+    roofline["survey_algorithmic_tflops_equivalent"] = flop_per_frame["slab_linear"] / world / (kernel_ms * 1e-3) / 1e12
+    slab_ms_per_step = slab_total_ms / args.steps
+    north_star = {"value": RAYS_PER_FRAME / (slab_ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": slab_ms_per_step,
+                  "roofline": roofline_of("slab_linear", slab_kernel_ms, "rt::render_kernel<Combined, shadows, slab + linear>")}
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
     cpu_baseline = None
@@ -355,7 +379,9 @@ def main():
         "clocks": sampler.summary(),
         "e2e": e2e,
         "gpu_launches": args.steps * (world + (1 if world > 1 else 0)),
+        "mesh_path": "bvh (reference's shipped IntersectionTest_BVH over the reference's own nodes)",
         "roofline": roofline,
+        "north_star_slab_linear": north_star,
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))

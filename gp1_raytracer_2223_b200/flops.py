@@ -21,6 +21,7 @@ WEIGHTS = {
     22: 5, 23: 25, 24: 35, 25: 51, 26: 57, 27: 63,   # shadow triangle exits
     28: 15,          # light iteration setup
     32: 0, 33: 6, 34: 33, 35: 112,   # Shade per material class
+    36: 22, 37: 22,                  # BVH path: node box tests (same arithmetic as the mesh slab test)
 }
 # per un-shadowed light evaluation (slot 31), by lighting mode
 LIT_WEIGHT = {3: 27, 0: 9, 1: 15, 2: 3}
