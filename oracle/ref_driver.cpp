@@ -278,8 +278,12 @@ int main(int argc, char** argv)
 		o.scene.c_str(), o.width, o.height, o.mode, o.shadows, omp_get_max_threads(), o.frames, o.warmup,
 		median, sorted.empty() ? 0.0 : sorted.front());
 	for (size_t i = 0; i < ms.size(); ++i) std::printf("%s%.6f", i ? ", " : "", ms[i]);
-	std::printf("], \"fnv1a64\": \"%016llx\", \"path\": \"reference BVH traversal (source/Utils.h:296-297)\"}\n",
-		(unsigned long long)hash);
+#ifdef GP1_DROPIN
+	const char* path = "drop-in Renderer -> librt_b200.so (B200)";
+#else
+	const char* path = "reference BVH traversal (source/Utils.h:296-297)";
+#endif
+	std::printf("], \"fnv1a64\": \"%016llx\", \"path\": \"%s\"}\n", (unsigned long long)hash, path);
 
 	delete pScene;
 	delete pRenderer;
