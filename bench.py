@@ -172,7 +172,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -181,6 +181,12 @@ def reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
+    # The contract is ONE JSON line on stdout: keep the real stdout aside and send everything else
+    # (NCCL banners, library chatter) to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -384,11 +390,20 @@ def main():
         "north_star_slab_linear": north_star,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def _measured_peaks():

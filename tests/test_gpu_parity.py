@@ -238,3 +238,24 @@ def test_full_size_properties(gpu):
     torch.cuda.synchronize()
     assert np.array_equal(band.cpu().numpy().view(np.uint32), a[1403:1467])
     r.close()
+
+
+def test_in_process_multi_device_matches_single(gpu):
+    """rt_create with several devices: strips are rendered on every GPU and stored straight into device 0's
+    frame (peer stores).  Must be bit-identical to the one-GPU frame."""
+    torch = gpu
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    want = load_golden_frame("bunny_640")
+    for ids in ([0, 1], list(range(n)), [1, 0]):
+        r = make_renderer("bunny_640", device_ids=ids)
+        assert r.ctx.device_count == len(ids)
+        for path in (1, 2):
+            r.ctx.set_mesh_path(path)
+            assert np.array_equal(r.Render(), want), (ids, path)
+        r.close()
+    r = make_renderer("bunny_4k", device_ids=list(range(n)))
+    assert np.array_equal(r.Render(), load_golden_frame("bunny_4k"))
+    print("multi-device timing", r.ctx.timing())
+    r.close()
