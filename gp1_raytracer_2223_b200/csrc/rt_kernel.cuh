@@ -71,6 +71,7 @@ namespace rt
 	{
 		V3 o, d, inv;
 		float tmin, tmax;
+		bool nan_safe;   // no component of inv is infinite: the slab products cannot be 0 * inf = NaN
 	};
 
 	struct Hit
@@ -121,6 +122,7 @@ namespace rt
 		r.o = o; r.d = d;
 		r.inv = v3(quo(1.f, d.x), quo(1.f, d.y), quo(1.f, d.z));   // DataTypes.h:550-563
 		r.tmin = tmin; r.tmax = tmax;
+		r.nan_safe = (fabsf(r.inv.x) < INFINITY) && (fabsf(r.inv.y) < INFINITY) && (fabsf(r.inv.z) < INFINITY);
 		return r;
 	}
 
@@ -152,8 +154,32 @@ namespace rt
 		return false;
 	}
 
-	// SlabTest_TriangleMesh, Utils.h:194-216.
-	__device__ __forceinline__ bool slab_test(const float4 bmin, const float4 bmax, const Ray& ray)
+	// SlabTest_TriangleMesh / SlabTest_BVH, Utils.h:194-216, 221-243.
+	//
+	// FAST = true replaces the std::min / std::max ternaries by FMNMX (fminf / fmaxf).  The two only
+	// differ when an operand is NaN (and in the sign of a zero result, which the final comparisons
+	// cannot see).  A NaN can only come from 0 * inf, i.e. from an infinite 1/dir component, so rays
+	// whose inverse direction is finite (Ray::nan_safe, all but axis-parallel rays) take the fast
+	// form with the same boolean result; the others take the literal one.
+	template <bool FAST>
+	__device__ __forceinline__ bool slab_test(const float4 bmin, const float4 bmax, const Ray& ray);
+
+	template <>
+	__device__ __forceinline__ bool slab_test<true>(const float4 bmin, const float4 bmax, const Ray& ray)
+	{
+		const float tx1 = mul(sub(bmin.x, ray.o.x), ray.inv.x);
+		const float tx2 = mul(sub(bmax.x, ray.o.x), ray.inv.x);
+		const float ty1 = mul(sub(bmin.y, ray.o.y), ray.inv.y);
+		const float ty2 = mul(sub(bmax.y, ray.o.y), ray.inv.y);
+		const float tz1 = mul(sub(bmin.z, ray.o.z), ray.inv.z);
+		const float tz2 = mul(sub(bmax.z, ray.o.z), ray.inv.z);
+		const float t_min = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
+		const float t_max = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
+		return t_max > 0 && t_max >= t_min;
+	}
+
+	template <>
+	__device__ __forceinline__ bool slab_test<false>(const float4 bmin, const float4 bmax, const Ray& ray)
 	{
 		const float tx1 = mul(sub(bmin.x, ray.o.x), ray.inv.x);
 		const float tx2 = mul(sub(bmax.x, ray.o.x), ray.inv.x);
@@ -301,7 +327,7 @@ namespace rt
 		static constexpr int kMaxLeafTriangles = (1 << (31 - kEscapeBits)) - 1;
 	};
 
-	template <int CULL, bool COUNT>
+	template <int CULL, bool FAST, bool COUNT>
 	__device__ __forceinline__ void bvh_closest(const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
 	{
 		int node = 0;
@@ -311,7 +337,7 @@ namespace rt
 			const int link = __float_as_int(n1.w);
 			const int escape = (link & BvhLink::kEscapeMask) - 1;
 			cnt.hit(RT_CNT_BVH_P_NODE);
-			if (!slab_test(n0, n1, ray)) { node = escape; continue; }
+			if (!slab_test<FAST>(n0, n1, ray)) { node = escape; continue; }
 			const int count = link >> BvhLink::kEscapeBits;
 			const int first = __float_as_int(n0.w);
 			if (count == 0) { node = first; continue; }
@@ -321,7 +347,7 @@ namespace rt
 		}
 	}
 
-	template <int CULL, bool COUNT>
+	template <int CULL, bool FAST, bool COUNT>
 	__device__ __forceinline__ bool bvh_any(const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
 	{
 		int node = 0;
@@ -331,7 +357,7 @@ namespace rt
 			const int link = __float_as_int(n1.w);
 			const int escape = (link & BvhLink::kEscapeMask) - 1;
 			cnt.hit(RT_CNT_BVH_S_NODE);
-			if (!slab_test(n0, n1, ray)) { node = escape; continue; }
+			if (!slab_test<FAST>(n0, n1, ray)) { node = escape; continue; }
 			const int count = link >> BvhLink::kEscapeBits;
 			const int first = __float_as_int(n0.w);
 			if (count == 0) { node = first; continue; }
@@ -340,6 +366,23 @@ namespace rt
 			node = escape;
 		}
 		return false;
+	}
+
+	template <bool FAST, bool COUNT>
+	__device__ __forceinline__ void bvh_closest_any_cull(int cull, const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	{
+		if (cull == RT_CULL_BACK_FACE) bvh_closest<RT_CULL_BACK_FACE, FAST>(nodes, tri, ray, best_t, best_tri, cnt);
+		else if (cull == RT_CULL_FRONT_FACE) bvh_closest<RT_CULL_FRONT_FACE, FAST>(nodes, tri, ray, best_t, best_tri, cnt);
+		else bvh_closest<RT_CULL_NONE, FAST>(nodes, tri, ray, best_t, best_tri, cnt);
+	}
+
+	// Utils.h:114-127: shadow rays see the opposite cull mode
+	template <bool FAST, bool COUNT>
+	__device__ __forceinline__ bool bvh_any_any_cull(int cull, const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		if (cull == RT_CULL_BACK_FACE) return bvh_any<RT_CULL_FRONT_FACE, FAST>(nodes, tri, ray, cnt);
+		if (cull == RT_CULL_FRONT_FACE) return bvh_any<RT_CULL_BACK_FACE, FAST>(nodes, tri, ray, cnt);
+		return bvh_any<RT_CULL_NONE, FAST>(nodes, tri, ray, cnt);
 	}
 
 	// Scene::GetClosestHit, Scene.cpp:29-66: spheres, planes, meshes in order; strict '<' keeps
@@ -400,14 +443,13 @@ namespace rt
 			{
 				if (count == 0) continue;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				if (cull == RT_CULL_BACK_FACE) bvh_closest<RT_CULL_BACK_FACE>(nodes, tri, ray, best.t, best_tri, cnt);
-				else if (cull == RT_CULL_FRONT_FACE) bvh_closest<RT_CULL_FRONT_FACE>(nodes, tri, ray, best.t, best_tri, cnt);
-				else bvh_closest<RT_CULL_NONE>(nodes, tri, ray, best.t, best_tri, cnt);
+				if (!ray.nan_safe) bvh_closest_any_cull<false>(cull, nodes, tri, ray, best.t, best_tri, cnt);
+				else bvh_closest_any_cull<true>(cull, nodes, tri, ray, best.t, best_tri, cnt);
 			}
 			else
 			{
 				cnt.hit(RT_CNT_SLAB_P_TEST);
-				if (!slab_test(bmin, bmax, ray)) continue;
+				if (!(ray.nan_safe ? slab_test<true>(bmin, bmax, ray) : slab_test<false>(bmin, bmax, ray))) continue;
 				cnt.hit(RT_CNT_SLAB_P_PASS);
 				if (cull == RT_CULL_BACK_FACE) mesh_closest<RT_CULL_BACK_FACE>(tri, count, ray, best.t, best_tri, cnt);
 				else if (cull == RT_CULL_FRONT_FACE) mesh_closest<RT_CULL_FRONT_FACE>(tri, count, ray, best.t, best_tri, cnt);
@@ -446,14 +488,13 @@ namespace rt
 			{
 				if (count == 0) continue;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				if (cull == RT_CULL_BACK_FACE) hit = bvh_any<RT_CULL_FRONT_FACE>(nodes, tri, ray, cnt);
-				else if (cull == RT_CULL_FRONT_FACE) hit = bvh_any<RT_CULL_BACK_FACE>(nodes, tri, ray, cnt);
-				else hit = bvh_any<RT_CULL_NONE>(nodes, tri, ray, cnt);
+				if (!ray.nan_safe) hit = bvh_any_any_cull<false>(cull, nodes, tri, ray, cnt);
+				else hit = bvh_any_any_cull<true>(cull, nodes, tri, ray, cnt);
 			}
 			else
 			{
 				cnt.hit(RT_CNT_SLAB_S_TEST);
-				if (!slab_test(bmin, bmax, ray)) continue;
+				if (!(ray.nan_safe ? slab_test<true>(bmin, bmax, ray) : slab_test<false>(bmin, bmax, ray))) continue;
 				cnt.hit(RT_CNT_SLAB_S_PASS);
 				if (cull == RT_CULL_BACK_FACE) hit = mesh_any<RT_CULL_FRONT_FACE>(tri, count, ray, cnt);
 				else if (cull == RT_CULL_FRONT_FACE) hit = mesh_any<RT_CULL_BACK_FACE>(tri, count, ray, cnt);

@@ -259,3 +259,24 @@ def test_in_process_multi_device_matches_single(gpu):
     assert np.array_equal(r.Render(), load_golden_frame("bunny_4k"))
     print("multi-device timing", r.ctx.timing())
     r.close()
+
+
+def test_axis_parallel_rays_take_the_literal_slab_test(gpu):
+    """Rays with a zero direction component have an infinite 1/dir; on a box face through the ray origin the
+    slab products are 0 * inf = NaN and std::min/max semantics decide (reference source/Utils.h:197-215).
+    Odd width + axis-aligned camera puts d.x == 0 on the centre column; fov 0 makes every ray (0, 0, 1)."""
+    from oracle import rt_oracle
+    scene = load_golden_scene("w4ref_101x203")
+    for origin, fov in (((-0.75, 4.5, -9.0), scene.camera.fov), ((0.75, 3.0, -9.0), scene.camera.fov),
+                        ((-0.75, 5.0, -9.0), 0.0), ((0.0, 4.5, -9.0), 0.0)):
+        scene.camera.origin[:] = origin
+        scene.camera.fov = fov
+        r = make_renderer("w4ref_101x203")
+        r.SetScene(scene)
+        for gpu_path, oracle_path in ((1, rt_oracle.MESH_SLAB_LINEAR), (2, rt_oracle.MESH_BVH)):
+            r.ctx.set_mesh_path(gpu_path)
+            want = rt_oracle.render(scene, 101, 203, mesh_path=oracle_path)
+            got = r.Render()
+            identical, max_err, n_diff = compare_frames(got, want)
+            assert n_diff == 0 or (identical >= MIN_IDENTICAL and max_err <= MAX_LSB), (origin, fov, gpu_path, n_diff, max_err)
+        r.close()
