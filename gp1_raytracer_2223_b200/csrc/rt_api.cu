@@ -5,11 +5,13 @@
 // CUDA is not there.
 #include "rt_kernel.cuh"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -55,6 +57,9 @@ namespace
 		size_t frame_capacity = 0;         // in pixels
 		unsigned long long* d_counters = nullptr;
 		cudaEvent_t ev_begin = nullptr, ev_kernel = nullptr, ev_done = nullptr;
+		cudaStream_t copy_stream = nullptr;                 // device-to-host copies that overlap the next band's kernel
+		cudaEvent_t ev_band[16] = {};
+		unsigned int* d_band_done = nullptr;                // kMaxBands counters for the single-launch progressive present
 		rt::SceneDevice view{};
 	};
 }
@@ -487,6 +492,114 @@ namespace
 	}
 }
 
+namespace
+{
+	// cuStreamWaitValue32 through the runtime's driver entry point lookup: no link-time dependency on
+	// libcuda, so the library still loads on a box without a driver.
+	typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+	WaitValue32Fn wait_value32()
+	{
+		static const WaitValue32Fn fn = []() -> WaitValue32Fn {
+			if (const char* e = getenv("RT_B200_NO_STREAM_WAIT")) if (atoi(e)) return nullptr;
+			void* p = nullptr;
+			cudaDriverEntryPointQueryResult st = cudaDriverEntryPointSymbolNotFound;
+			if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+			return reinterpret_cast<WaitValue32Fn>(p);
+		}();
+		return fn;
+	}
+
+	// One device: rt_render overlaps the present copy with the rendering.  The frame is cut into bands
+	// of strips.  Preferred form ("progressive present"): ONE kernel launch; every CTA bumps its band's
+	// counter when its pixels are in memory, and the copy stream waits on each counter with
+	// cuStreamWaitValue32 before it sends that band to the host surface - no launch boundaries, no
+	// tail per band.  Fallback (no stream memory operations): one launch per band + events.
+	int render_pipelined(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame, uint32_t* host_dst, int32_t pitch_bytes)
+	{
+		int rc = validate_frame(ctx, camera, frame);
+		if (rc != RT_OK) return rc;
+		const int W = frame->width, H = frame->height;
+		if (pitch_bytes < 4 * W || (pitch_bytes & 3)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "pitch_bytes %d too small or unaligned for width %d", pitch_bytes, W);
+		DeviceState& d = ctx->devs[0];
+		if ((rc = ensure_frame(ctx, d, (size_t)W * (size_t)H)) != RT_OK) return rc;
+		const size_t span = (size_t)pitch_bytes * (size_t)(H - 1) + (size_t)W * 4u;
+		void* target = nullptr;
+		if ((rc = prepare_host(ctx, host_dst, span, &target)) != RT_OK) return rc;
+		ctx->timing = rt_timing{};
+		ctx->last_width = W; ctx->last_height = H;
+
+		const WaitValue32Fn wait = wait_value32();
+		static const int requested = [] { const char* e = getenv("RT_B200_PIPELINE_BANDS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 64) ? v : 0; }();
+		const int total_strips = (H + rt::kBlockH - 1) / rt::kBlockH;
+		const int grid_x = (W + rt::kBlockW - 1) / rt::kBlockW;
+		// a band should hold enough CTAs to be worth a copy of its own
+		const int max_bands = std::max(1, (int)(((long long)total_strips * grid_x) / 2048));
+		const int wanted = requested ? requested : (wait ? 16 : 4);
+		const int bands = std::min(std::min(std::min(wanted, wait ? 64 : 16), max_bands), total_strips);
+		const int strips_per_band = (total_strips + bands - 1) / bands;
+
+		RT_CUDA(ctx, cudaSetDevice(d.device));
+		rt::FrameParams base = make_params(camera, frame);
+		auto copy_band = [&](int r0, int r1) -> int
+		{
+			char* dst = (char*)target + (size_t)r0 * (size_t)pitch_bytes;
+			const uint32_t* src = d.d_frame + (size_t)r0 * (size_t)W;
+			if (pitch_bytes == 4 * W)
+				RT_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)(r1 - r0) * W * 4u, cudaMemcpyDeviceToHost, d.copy_stream));
+			else
+				RT_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch_bytes, src, (size_t)W * 4u, (size_t)W * 4u, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, d.copy_stream));
+			return RT_OK;
+		};
+
+		if (wait)
+		{
+			RT_CUDA(ctx, cudaMemsetAsync(d.d_band_done, 0, sizeof(unsigned int) * 64, d.stream));
+			RT_CUDA(ctx, cudaEventRecord(d.ev_band[0], d.stream));
+			RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_band[0], 0));      // counters are zero before anyone polls them
+			RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
+			rt::FrameParams p = base;
+			p.row_begin = 0; p.row_end = H; p.strip_first = 0; p.strip_step = 1; p.dst_full_frame = 1; p.dst = d.d_frame;
+			p.band_done = d.d_band_done; p.strips_per_band = strips_per_band;
+			if ((rc = launch(ctx, d, p, d.stream, total_strips)) != RT_OK) return rc;
+			RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+			for (int b = 0; b < bands; ++b)
+			{
+				const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
+				if (s1 <= s0) break;
+				const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)((s1 - s0) * grid_x), CU_STREAM_WAIT_VALUE_GEQ);
+				if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
+				if ((rc = copy_band(s0 * rt::kBlockH, std::min(H, s1 * rt::kBlockH))) != RT_OK) return rc;
+			}
+		}
+		else
+		{
+			RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
+			for (int b = 0; b < bands; ++b)
+			{
+				const int r0 = std::min(H, b * strips_per_band * rt::kBlockH), r1 = std::min(H, (b + 1) * strips_per_band * rt::kBlockH);
+				if (r1 <= r0) break;
+				rt::FrameParams p = base;
+				p.row_begin = r0; p.row_end = r1; p.strip_first = 0; p.strip_step = 1; p.dst_full_frame = 1; p.dst = d.d_frame;
+				if ((rc = launch(ctx, d, p, d.stream, (r1 - r0 + rt::kBlockH - 1) / rt::kBlockH)) != RT_OK) return rc;
+				RT_CUDA(ctx, cudaEventRecord(d.ev_band[b], d.stream));
+				RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_band[b], 0));
+				if ((rc = copy_band(r0, r1)) != RT_OK) return rc;
+			}
+			RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+		}
+		RT_CUDA(ctx, cudaEventRecord(ctx->ev_gather, d.stream));
+		RT_CUDA(ctx, cudaEventRecord(ctx->ev_d2h, d.copy_stream));
+		RT_CUDA(ctx, cudaStreamSynchronize(d.copy_stream));
+		RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+		if (target != host_dst)
+		{
+			if (pitch_bytes == 4 * W) memcpy(host_dst, target, (size_t)W * H * 4u);
+			else for (int y = 0; y < H; ++y) memcpy((char*)host_dst + (size_t)y * pitch_bytes, (char*)target + (size_t)y * pitch_bytes, (size_t)W * 4u);
+		}
+		return collect_timing(ctx, true);
+	}
+}
+
 extern "C" {
 
 int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
@@ -550,6 +663,9 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		RT_CREATE(cudaEventCreate(&d.ev_begin));
 		RT_CREATE(cudaEventCreate(&d.ev_kernel));
 		RT_CREATE(cudaEventCreate(&d.ev_done));
+		RT_CREATE(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
+		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 64));
 		ctx->devs.push_back(d);
 	}
 	RT_CREATE(cudaSetDevice(ids[0]));
@@ -586,10 +702,12 @@ int rt_destroy(rt_context* ctx)
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_arena); cudaFree(d.d_bytes); cudaFree(d.d_light_type); cudaFree(d.d_materials);
-		cudaFree(d.d_mesh_table); cudaFree(d.d_triangles); cudaFree(d.d_nodes); cudaFree(d.d_frame); cudaFree(d.d_counters);
+		cudaFree(d.d_mesh_table); cudaFree(d.d_triangles); cudaFree(d.d_nodes); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done);
 		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
 		if (d.ev_kernel) cudaEventDestroy(d.ev_kernel);
 		if (d.ev_done) cudaEventDestroy(d.ev_done);
+		for (cudaEvent_t e : d.ev_band) if (e) cudaEventDestroy(e);
+		if (d.copy_stream) { cudaStreamSynchronize(d.copy_stream); cudaStreamDestroy(d.copy_stream); }
 		if (d.stream) cudaStreamDestroy(d.stream);
 	}
 	if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);
@@ -750,6 +868,7 @@ int rt_render(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* fra
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
 	if (!host_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "host_dst must not be NULL");
+	if (ctx->devs.size() == 1) return render_pipelined(ctx, camera, frame, host_dst, pitch_bytes);
 	int rc = render_to_device0(ctx, camera, frame);
 	if (rc != RT_OK) return rc;
 	if ((rc = download(ctx, host_dst, pitch_bytes, true)) != RT_OK) return rc;

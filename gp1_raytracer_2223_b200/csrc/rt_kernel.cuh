@@ -65,6 +65,8 @@ namespace rt
 		int32_t vector_store;            // 1 when width % 4 == 0 and dst is 16-byte aligned
 		uint32_t* dst;
 		unsigned long long* counters;    // counters build only
+		unsigned int* band_done;         // progressive present: band_done[b] counts the finished CTAs of band b (NULL = off)
+		int32_t strips_per_band;
 	};
 
 	struct Ray
@@ -143,13 +145,30 @@ namespace rt
 		return true;
 	}
 
+	// Can t = RN(num / den) satisfy tmin <= t < tmax (tmin = 1e-4)?  Returns false only when that is
+	// impossible, so the IEEE division is skipped for the planes a ray cannot reach:
+	//   num or den zero          -> t is +-0, +-inf or NaN
+	//   opposite signs           -> t <= -0
+	//   |num| > |den|*tmax*(1+1e-6) (computed without underflow) -> num/den > tmax, and rounding is monotonic
+	// NaN operands fall through to the exact test.
+	__device__ __forceinline__ bool plane_may_hit(float num, float den, float tmax)
+	{
+		if (num == 0.f || den == 0.f) return false;
+		if ((__float_as_int(num) ^ __float_as_int(den)) < 0) return false;
+		const float bound = mul(mul(fabsf(den), tmax), 1.000001f);
+		if (bound > 1e-30f && fabsf(num) > bound) return false;
+		return true;
+	}
+
 	// HitTest_Plane, Utils.h:82-98.
 	template <bool SHADOW, bool COUNT>
 	__device__ __forceinline__ bool hit_plane(const float4 po, const float4 pn, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
 	{
 		const V3 n = v3(pn);
-		const float t = quo(dot(v3(po) - ray.o, n), dot(ray.d, n));
+		const float num = dot(v3(po) - ray.o, n), den = dot(ray.d, n);
 		cnt.hit(SHADOW ? RT_CNT_PLANE_S_TEST : RT_CNT_PLANE_P_TEST);
+		if (!plane_may_hit(num, den, ray.tmax)) return false;
+		const float t = quo(num, den);
 		if (t >= ray.tmin && t < ray.tmax) { t_out = t; return true; }
 		return false;
 	}
@@ -531,8 +550,8 @@ namespace rt
 		}
 		if (tag == RT_MATERIAL_LAMBERT || tag == RT_MATERIAL_LAMBERT_PHONG)
 		{
-			// BRDF::Lambert(kd, cd) = (cd * kd) / PI, BRDFs.h:14-17
-			V3 out = v3(quo(mul(color.x, m1.x), kPi), quo(mul(color.y, m1.x), kPi), quo(mul(color.z, m1.x), kPi));
+			// BRDF::Lambert(kd, cd) = (cd * kd) / PI, BRDFs.h:14-17: already evaluated by stage_scene
+			V3 out = color;
 			if (tag == RT_MATERIAL_LAMBERT) { cnt.hit(RT_CNT_SHADE_LAMBERT); return out; }
 			cnt.hit(RT_CNT_SHADE_PHONG);
 			// BRDF::Phong, BRDFs.h:33-40
@@ -690,7 +709,22 @@ namespace rt
 			sc.light_b[i] = make_float4(dev.light_r[i], dev.light_g[i], dev.light_b[i], __int_as_float(dev.light_type[i]));
 		}
 		for (int i = tid; i < 3 * dev.n_meshes; i += kThreads) sc.mesh[i] = dev.mesh_table[i];
-		for (int i = tid; i < 2 * dev.n_materials; i += kThreads) sc.material[i] = dev.materials[i];
+		for (int i = tid; i < dev.n_materials; i += kThreads)
+		{
+			float4 m0 = dev.materials[2 * i];
+			const float4 m1 = dev.materials[2 * i + 1];
+			const int tag = __float_as_int(m0.x);
+			if (tag == RT_MATERIAL_LAMBERT || tag == RT_MATERIAL_LAMBERT_PHONG)
+			{
+				// BRDF::Lambert(kd, cd) = (cd * kd) / PI (BRDFs.h:14-17) depends on the material only:
+				// evaluate it once per CTA with the same three operations per channel
+				m0.y = quo(mul(m0.y, m1.x), 3.14159265358979323846f);
+				m0.z = quo(mul(m0.z, m1.x), 3.14159265358979323846f);
+				m0.w = quo(mul(m0.w, m1.x), 3.14159265358979323846f);
+			}
+			sc.material[2 * i] = m0;
+			sc.material[2 * i + 1] = m1;
+		}
 	}
 
 	template <int MODE, int SHADOWS, bool BVH, bool COUNT>
@@ -727,6 +761,20 @@ namespace rt
 		else if (valid)
 		{
 			row[px] = pixel;
+		}
+
+		if (p.band_done)
+		{
+			// Tell the copy stream (cuStreamWaitValue32 on band_done[b]) that this CTA's pixels are in
+			// memory: CTA barrier, then one release-ordered reduction per CTA.  A release (MEMBAR.ALL.GPU)
+			// is enough here; __threadfence() would also invalidate the SM's L1 (CCTL.IVALL) and evict the
+			// BVH nodes and triangles the other resident CTAs are streaming.
+			__syncthreads();
+			if (threadIdx.x == 0)
+			{
+				unsigned int* counter = p.band_done + blockIdx.y / p.strips_per_band;
+				asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
+			}
 		}
 	}
 
