@@ -40,19 +40,25 @@ namespace
 		static constexpr int total = light + 7 * rt::kMaxLights;
 	};
 
+	// Byte offsets inside the per-device static block (and its pinned host mirror): one copy per upload.
+	struct StaticBlock
+	{
+		static constexpr size_t arena = 0;
+		static constexpr size_t materials = (arena + sizeof(float) * ArenaLayout::total + 15) & ~size_t(15);
+		static constexpr size_t light_type = materials + sizeof(float4) * 2 * rt::kMaxMaterials;
+		static constexpr size_t bytes = light_type + sizeof(int32_t) * rt::kMaxLights;
+		static constexpr size_t total = (bytes + rt::kMaxSpheres + rt::kMaxPlanes + 15) & ~size_t(15);
+	};
+
 	struct DeviceState
 	{
 		int device = -1;
 		cudaStream_t stream = nullptr;
-		float* d_arena = nullptr;          // ArenaLayout::total floats
-		uint8_t* d_bytes = nullptr;        // sphere materials, plane materials
-		int32_t* d_light_type = nullptr;
-		float4* d_materials = nullptr;     // 2 * kMaxMaterials
-		float4* d_mesh_table = nullptr;    // 3 * kMaxMeshes
-		float4* d_triangles = nullptr;
-		size_t triangle_capacity = 0;      // in float4
-		float4* d_nodes = nullptr;
-		size_t node_capacity = 0;          // in float4
+		uint8_t* d_static = nullptr;       // StaticBlock: SoA arena, materials, light types, material indices
+		float4* d_mesh = nullptr;          // mesh table (3 * kMaxMeshes) | triangle stream | BVH nodes, one block
+		size_t mesh_capacity = 0;          // in float4
+		size_t triangle_offset = 0, node_offset = 0;   // in float4, inside d_mesh
+		cudaEvent_t ev_upload = nullptr;   // last scene copy on this device (pinned source may be reused after it)
 		uint32_t* d_frame = nullptr;
 		size_t frame_capacity = 0;         // in pixels
 		unsigned long long* d_counters = nullptr;
@@ -71,11 +77,14 @@ struct rt_context
 	bool peer_stores = false;           // every device can store into device 0's frame buffer
 	int32_t mesh_path = RT_MESH_PATH_AUTO;
 
-	// host copies of the static scene (SoA, as uploaded)
-	std::vector<float> arena = std::vector<float>(ArenaLayout::total, 0.f);
-	std::vector<uint8_t> bytes = std::vector<uint8_t>(rt::kMaxSpheres + rt::kMaxPlanes, 0);
-	std::vector<int32_t> light_type = std::vector<int32_t>(rt::kMaxLights, 0);
-	std::vector<float4> materials = std::vector<float4>(2 * rt::kMaxMaterials, make_float4(0, 0, 0, 0));
+	// pinned host mirror of the static block (SoA, as uploaded) and of the mesh block
+	uint8_t* h_static = nullptr;
+	float* arena = nullptr;             // views into h_static
+	float4* materials = nullptr;
+	int32_t* light_type = nullptr;
+	uint8_t* bytes = nullptr;
+	float4* h_mesh = nullptr;
+	size_t h_mesh_capacity = 0;         // in float4
 	int32_t n_spheres = 0, n_planes = 0, n_lights = 0, n_materials = 0;
 	std::vector<HostMesh> meshes;
 
@@ -178,7 +187,7 @@ namespace
 	void refresh_view(rt_context* ctx, DeviceState& d)
 	{
 		rt::SceneDevice& v = d.view;
-		const float* a = d.d_arena;
+		const float* a = reinterpret_cast<const float*>(d.d_static + StaticBlock::arena);
 		v.sphere_ox = a + ArenaLayout::sphere; v.sphere_oy = v.sphere_ox + rt::kMaxSpheres;
 		v.sphere_oz = v.sphere_oy + rt::kMaxSpheres; v.sphere_r = v.sphere_oz + rt::kMaxSpheres;
 		v.plane_ox = a + ArenaLayout::plane; v.plane_oy = v.plane_ox + rt::kMaxPlanes; v.plane_oz = v.plane_oy + rt::kMaxPlanes;
@@ -186,79 +195,88 @@ namespace
 		v.light_ox = a + ArenaLayout::light; v.light_oy = v.light_ox + rt::kMaxLights; v.light_oz = v.light_oy + rt::kMaxLights;
 		v.light_r = v.light_oz + rt::kMaxLights; v.light_g = v.light_r + rt::kMaxLights; v.light_b = v.light_g + rt::kMaxLights;
 		v.light_intensity = v.light_b + rt::kMaxLights;
-		v.sphere_mat = d.d_bytes; v.plane_mat = d.d_bytes + rt::kMaxSpheres;
-		v.light_type = d.d_light_type;
-		v.materials = d.d_materials;
-		v.mesh_table = d.d_mesh_table;
-		v.triangles = d.d_triangles;
-		v.bvh_nodes = d.d_nodes;
+		v.sphere_mat = d.d_static + StaticBlock::bytes; v.plane_mat = v.sphere_mat + rt::kMaxSpheres;
+		v.light_type = reinterpret_cast<const int32_t*>(d.d_static + StaticBlock::light_type);
+		v.materials = reinterpret_cast<const float4*>(d.d_static + StaticBlock::materials);
+		v.mesh_table = d.d_mesh;
+		v.triangles = d.d_mesh + d.triangle_offset;
+		v.bvh_nodes = d.d_mesh + d.node_offset;
 		v.n_spheres = ctx->n_spheres; v.n_planes = ctx->n_planes; v.n_lights = ctx->n_lights;
 		v.n_materials = ctx->n_materials; v.n_meshes = (int32_t)ctx->meshes.size();
 	}
 
-	// Push the host copies of the small static arrays to every device (a few KB).
+	// The pinned mirrors are about to be rewritten: wait until every device has consumed them.
+	int wait_uploads(rt_context* ctx)
+	{
+		for (DeviceState& d : ctx->devs) RT_CUDA(ctx, cudaEventSynchronize(d.ev_upload));
+		return RT_OK;
+	}
+
+	// Push the pinned mirror of the small static arrays to every device: one asynchronous copy each,
+	// ordered before any later launch on the device's stream (ev_upload orders foreign streams).
 	int push_static(rt_context* ctx)
 	{
 		for (DeviceState& d : ctx->devs)
 		{
 			RT_CUDA(ctx, cudaSetDevice(d.device));
-			RT_CUDA(ctx, cudaMemcpyAsync(d.d_arena, ctx->arena.data(), sizeof(float) * ArenaLayout::total, cudaMemcpyHostToDevice, d.stream));
-			RT_CUDA(ctx, cudaMemcpyAsync(d.d_bytes, ctx->bytes.data(), ctx->bytes.size(), cudaMemcpyHostToDevice, d.stream));
-			RT_CUDA(ctx, cudaMemcpyAsync(d.d_light_type, ctx->light_type.data(), sizeof(int32_t) * rt::kMaxLights, cudaMemcpyHostToDevice, d.stream));
-			RT_CUDA(ctx, cudaMemcpyAsync(d.d_materials, ctx->materials.data(), sizeof(float4) * 2 * rt::kMaxMaterials, cudaMemcpyHostToDevice, d.stream));
-			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_static, ctx->h_static, StaticBlock::total, cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
 			refresh_view(ctx, d);
 		}
 		return RT_OK;
 	}
 
-	// Rebuild the mesh table + concatenated triangle stream and push them to every device.
+	// Rebuild the mesh block (table | triangle stream | BVH nodes) in the pinned mirror and push it to
+	// every device with one asynchronous copy.
 	int push_meshes(rt_context* ctx)
 	{
-		std::vector<float4> table(3 * rt::kMaxMeshes, make_float4(0, 0, 0, 0));
-		std::vector<float4> tris, nodes;
-		int32_t first = 0;
+		size_t n_tris = 0, n_nodes = 0;
+		for (const HostMesh& hm : ctx->meshes) { n_tris += hm.triangles.size(); n_nodes += hm.nodes.size(); }
+		const size_t table = 3 * (size_t)rt::kMaxMeshes;
+		const size_t tri_off = table, node_off = tri_off + n_tris + 6;     // + two padding records: the loops read ahead
+		const size_t total = node_off + n_nodes;
+		int rc = wait_uploads(ctx);
+		if (rc != RT_OK) return rc;
+		if (total > ctx->h_mesh_capacity)
+		{
+			if (ctx->h_mesh) cudaFreeHost(ctx->h_mesh);
+			ctx->h_mesh = nullptr; ctx->h_mesh_capacity = 0;
+			const size_t cap = std::max<size_t>(total + total / 2, 8 * 1024);
+			RT_CUDA(ctx, cudaHostAlloc(&ctx->h_mesh, cap * sizeof(float4), cudaHostAllocPortable));
+			ctx->h_mesh_capacity = cap;
+		}
+		float4* h = ctx->h_mesh;
+		for (size_t i = 0; i < table; ++i) h[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+		int32_t first = 0, first_node = 0;
+		float4* tris = h + tri_off;
+		float4* nodes = h + node_off;
 		for (size_t m = 0; m < ctx->meshes.size(); ++m)
 		{
 			const HostMesh& hm = ctx->meshes[m];
-			const int32_t count = (int32_t)(hm.triangles.size() / 3);
-			const int32_t first_node = (int32_t)(nodes.size() / 2), node_count = (int32_t)(hm.nodes.size() / 2);
-			table[3 * m + 0] = make_float4(hm.aabb_min[0], hm.aabb_min[1], hm.aabb_min[2], bits_as_float(first));
-			table[3 * m + 1] = make_float4(hm.aabb_max[0], hm.aabb_max[1], hm.aabb_max[2], bits_as_float(count));
-			table[3 * m + 2] = make_float4(bits_as_float(hm.cull_mode), bits_as_float(hm.material), bits_as_float(first_node), bits_as_float(node_count));
-			tris.insert(tris.end(), hm.triangles.begin(), hm.triangles.end());
-			nodes.insert(nodes.end(), hm.nodes.begin(), hm.nodes.end());
-			first += count;
+			const int32_t count = (int32_t)(hm.triangles.size() / 3), node_count = (int32_t)(hm.nodes.size() / 2);
+			h[3 * m + 0] = make_float4(hm.aabb_min[0], hm.aabb_min[1], hm.aabb_min[2], bits_as_float(first));
+			h[3 * m + 1] = make_float4(hm.aabb_max[0], hm.aabb_max[1], hm.aabb_max[2], bits_as_float(count));
+			h[3 * m + 2] = make_float4(bits_as_float(hm.cull_mode), bits_as_float(hm.material), bits_as_float(first_node), bits_as_float(node_count));
+			if (count) memcpy(tris + 3 * (size_t)first, hm.triangles.data(), hm.triangles.size() * sizeof(float4));
+			if (node_count) memcpy(nodes + 2 * (size_t)first_node, hm.nodes.data(), hm.nodes.size() * sizeof(float4));
+			first += count; first_node += node_count;
 		}
-		// the kernel's triangle loops read up to two records ahead of the one they test
-		for (int k = 0; k < 6; ++k) tris.push_back(make_float4(0.f, 0.f, 0.f, 0.f));
+		for (int k = 0; k < 6; ++k) tris[n_tris + k] = make_float4(0.f, 0.f, 0.f, 0.f);
 		for (DeviceState& d : ctx->devs)
 		{
 			RT_CUDA(ctx, cudaSetDevice(d.device));
-			if (tris.size() > d.triangle_capacity)
+			if (total > d.mesh_capacity)
 			{
-				RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
-				if (d.d_triangles) RT_CUDA(ctx, cudaFree(d.d_triangles));
-				d.d_triangles = nullptr;
-				const size_t cap = std::max<size_t>(tris.size(), 3 * 1024);
-				RT_CUDA(ctx, cudaMalloc(&d.d_triangles, cap * sizeof(float4)));
-				d.triangle_capacity = cap;
+				RT_CUDA(ctx, cudaDeviceSynchronize());
+				if (d.d_mesh) RT_CUDA(ctx, cudaFree(d.d_mesh));
+				d.d_mesh = nullptr;
+				const size_t cap = std::max<size_t>(total + total / 2, 8 * 1024);
+				RT_CUDA(ctx, cudaMalloc(&d.d_mesh, cap * sizeof(float4)));
+				d.mesh_capacity = cap;
 			}
-			if (!tris.empty())
-				RT_CUDA(ctx, cudaMemcpyAsync(d.d_triangles, tris.data(), tris.size() * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
-			if (nodes.size() > d.node_capacity)
-			{
-				RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
-				if (d.d_nodes) RT_CUDA(ctx, cudaFree(d.d_nodes));
-				d.d_nodes = nullptr;
-				const size_t cap = std::max<size_t>(nodes.size(), 2 * 1024);
-				RT_CUDA(ctx, cudaMalloc(&d.d_nodes, cap * sizeof(float4)));
-				d.node_capacity = cap;
-			}
-			if (!nodes.empty())
-				RT_CUDA(ctx, cudaMemcpyAsync(d.d_nodes, nodes.data(), nodes.size() * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
-			RT_CUDA(ctx, cudaMemcpyAsync(d.d_mesh_table, table.data(), sizeof(float4) * 3 * rt::kMaxMeshes, cudaMemcpyHostToDevice, d.stream));
-			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+			d.triangle_offset = tri_off; d.node_offset = node_off;
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_mesh, h, total * sizeof(float4), cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
 			refresh_view(ctx, d);
 		}
 		return RT_OK;
@@ -276,6 +294,7 @@ namespace
 		p.vector_store = (p.width % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dst) & 15u) == 0);
 		const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)n_strips, 1);
 		if (grid.y > 65535u) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame too tall for one launch");
+		if (stream != d.stream) RT_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_upload, 0));   // scene copies ride d.stream
 		KernelFn k = pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH);
 		k<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
 		RT_CUDA(ctx, cudaGetLastError());
@@ -407,6 +426,8 @@ namespace
 		if (ctx->staging_bytes < bytes)
 		{
 			if (ctx->staging) cudaFreeHost(ctx->staging);
+	if (ctx->h_static) cudaFreeHost(ctx->h_static);
+	if (ctx->h_mesh) cudaFreeHost(ctx->h_mesh);
 			ctx->staging = nullptr; ctx->staging_bytes = 0;
 			RT_CUDA(ctx, cudaHostAlloc(&ctx->staging, bytes, cudaHostAllocPortable));
 			ctx->staging_bytes = bytes;
@@ -654,11 +675,9 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		d.device = id;
 		RT_CREATE(cudaSetDevice(id));
 		RT_CREATE(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-		RT_CREATE(cudaMalloc(&d.d_arena, sizeof(float) * ArenaLayout::total));
-		RT_CREATE(cudaMalloc(&d.d_bytes, rt::kMaxSpheres + rt::kMaxPlanes));
-		RT_CREATE(cudaMalloc(&d.d_light_type, sizeof(int32_t) * rt::kMaxLights));
-		RT_CREATE(cudaMalloc(&d.d_materials, sizeof(float4) * 2 * rt::kMaxMaterials));
-		RT_CREATE(cudaMalloc(&d.d_mesh_table, sizeof(float4) * 3 * rt::kMaxMeshes));
+		RT_CREATE(cudaMalloc(&d.d_static, StaticBlock::total));
+		RT_CREATE(cudaEventCreateWithFlags(&d.ev_upload, cudaEventDisableTiming));
+		RT_CREATE(cudaEventRecord(d.ev_upload, d.stream));
 		RT_CREATE(cudaMalloc(&d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS));
 		RT_CREATE(cudaEventCreate(&d.ev_begin));
 		RT_CREATE(cudaEventCreate(&d.ev_kernel));
@@ -669,6 +688,12 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		ctx->devs.push_back(d);
 	}
 	RT_CREATE(cudaSetDevice(ids[0]));
+	RT_CREATE(cudaHostAlloc(&ctx->h_static, StaticBlock::total, cudaHostAllocPortable));
+	memset(ctx->h_static, 0, StaticBlock::total);
+	ctx->arena = reinterpret_cast<float*>(ctx->h_static + StaticBlock::arena);
+	ctx->materials = reinterpret_cast<float4*>(ctx->h_static + StaticBlock::materials);
+	ctx->light_type = reinterpret_cast<int32_t*>(ctx->h_static + StaticBlock::light_type);
+	ctx->bytes = ctx->h_static + StaticBlock::bytes;
 	RT_CREATE(cudaEventCreate(&ctx->ev_gather));
 	RT_CREATE(cudaEventCreate(&ctx->ev_d2h));
 
@@ -701,8 +726,8 @@ int rt_destroy(rt_context* ctx)
 	{
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
-		cudaFree(d.d_arena); cudaFree(d.d_bytes); cudaFree(d.d_light_type); cudaFree(d.d_materials);
-		cudaFree(d.d_mesh_table); cudaFree(d.d_triangles); cudaFree(d.d_nodes); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done);
+		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done);
+		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
 		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
 		if (d.ev_kernel) cudaEventDestroy(d.ev_kernel);
 		if (d.ev_done) cudaEventDestroy(d.ev_done);
@@ -714,6 +739,8 @@ int rt_destroy(rt_context* ctx)
 	if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
 	if (ctx->registered_host) cudaHostUnregister(ctx->registered_host);
 	if (ctx->staging) cudaFreeHost(ctx->staging);
+	if (ctx->h_static) cudaFreeHost(ctx->h_static);
+	if (ctx->h_mesh) cudaFreeHost(ctx->h_mesh);
 	cudaGetLastError();
 	delete ctx;
 	return RT_OK;
@@ -726,7 +753,8 @@ int rt_upload_spheres(rt_context* ctx, const rt_spheres_soa* s)
 	if (s->count > rt::kMaxSpheres) return fail(ctx, RT_ERR_CAPACITY, "%d spheres exceed the capacity of %d", s->count, rt::kMaxSpheres);
 	if (s->count > 0 && (!s->origin_x || !s->origin_y || !s->origin_z || !s->radius || !s->material_index))
 		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "sphere SoA has a NULL array");
-	float* a = ctx->arena.data() + ArenaLayout::sphere;
+	if (int w = wait_uploads(ctx)) return w;
+	float* a = ctx->arena + ArenaLayout::sphere;
 	for (int i = 0; i < s->count; ++i)
 	{
 		a[i] = s->origin_x[i]; a[rt::kMaxSpheres + i] = s->origin_y[i]; a[2 * rt::kMaxSpheres + i] = s->origin_z[i];
@@ -744,7 +772,8 @@ int rt_upload_planes(rt_context* ctx, const rt_planes_soa* p)
 	if (p->count > rt::kMaxPlanes) return fail(ctx, RT_ERR_CAPACITY, "%d planes exceed the capacity of %d", p->count, rt::kMaxPlanes);
 	if (p->count > 0 && (!p->origin_x || !p->origin_y || !p->origin_z || !p->normal_x || !p->normal_y || !p->normal_z || !p->material_index))
 		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "plane SoA has a NULL array");
-	float* a = ctx->arena.data() + ArenaLayout::plane;
+	if (int w = wait_uploads(ctx)) return w;
+	float* a = ctx->arena + ArenaLayout::plane;
 	const int M = rt::kMaxPlanes;
 	for (int i = 0; i < p->count; ++i)
 	{
@@ -763,7 +792,8 @@ int rt_upload_lights(rt_context* ctx, const rt_lights_soa* l)
 	if (l->count > rt::kMaxLights) return fail(ctx, RT_ERR_CAPACITY, "%d lights exceed the capacity of %d", l->count, rt::kMaxLights);
 	if (l->count > 0 && (!l->origin_x || !l->origin_y || !l->origin_z || !l->color_r || !l->color_g || !l->color_b || !l->intensity || !l->type))
 		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "light SoA has a NULL array");
-	float* a = ctx->arena.data() + ArenaLayout::light;
+	if (int w = wait_uploads(ctx)) return w;
+	float* a = ctx->arena + ArenaLayout::light;
 	const int M = rt::kMaxLights;
 	for (int i = 0; i < l->count; ++i)
 	{
@@ -782,9 +812,11 @@ int rt_upload_materials(rt_context* ctx, const rt_material_desc* materials, int3
 	if (count < 0 || (count > 0 && !materials)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad material array");
 	if (count > rt::kMaxMaterials) return fail(ctx, RT_ERR_CAPACITY, "%d materials exceed the capacity of %d", count, rt::kMaxMaterials);
 	for (int i = 0; i < count; ++i)
+		if (materials[i].tag < RT_MATERIAL_SOLID_COLOR || materials[i].tag > RT_MATERIAL_COOK_TORRENCE) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "material %d has unknown tag %d", i, materials[i].tag);
+	if (int w = wait_uploads(ctx)) return w;
+	for (int i = 0; i < count; ++i)
 	{
 		const rt_material_desc& m = materials[i];
-		if (m.tag < RT_MATERIAL_SOLID_COLOR || m.tag > RT_MATERIAL_COOK_TORRENCE) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "material %d has unknown tag %d", i, m.tag);
 		ctx->materials[2 * i] = make_float4(bits_as_float(m.tag), m.color[0], m.color[1], m.color[2]);
 		ctx->materials[2 * i + 1] = make_float4(m.p0, m.p1, m.p2, 0.f);
 	}
