@@ -11,7 +11,7 @@ from ._abi import (rt_camera, rt_counters, rt_frame_desc, rt_lights_soa, rt_mate
                    rt_planes_soa, rt_spheres_soa, rt_timing)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(HERE, "librt_b200.so")   # override: A/B builds
 
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)
 _ctx = C.c_void_p
@@ -27,6 +27,7 @@ SYMBOLS = {
     "rt_upload_materials": (C.c_int, [_ctx, C.POINTER(rt_material_desc), C.c_int32]),
     "rt_set_mesh_count": (C.c_int, [_ctx, C.c_int32]),
     "rt_set_mesh_path": (C.c_int, [_ctx, C.c_int32]),
+    "rt_set_kernel_variant": (C.c_int, [_ctx, C.c_int32]),
     "rt_upload_mesh": (C.c_int, [_ctx, C.c_int32, C.POINTER(rt_mesh_desc)]),
     "rt_render": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_void_p, C.c_int32]),
     "rt_render_device": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc)]),

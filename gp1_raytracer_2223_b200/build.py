@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
 SOURCES = ["rt_api.cu"]
-HEADERS = ["rt_kernel.cuh", "rt_device.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
+HEADERS = ["rt_kernel.cuh", "rt_kernel_x2.cuh", "rt_device.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -45,7 +45,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("RT_B200_NVCC_EXTRA", "").split() + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
     # nvcc's default host compiler must be the system g++ (a CXX override in the environment
     # points at a toolchain without all runtime pieces)
     if os.path.exists("/usr/bin/g++"):

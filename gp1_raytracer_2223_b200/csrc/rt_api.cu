@@ -4,6 +4,7 @@
 // surface.  There is deliberately no host fallback: every entry point fails loudly when
 // CUDA is not there.
 #include "rt_kernel.cuh"
+#include "rt_kernel_x2.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -76,6 +77,7 @@ struct rt_context
 	std::string error;
 	bool peer_stores = false;           // every device can store into device 0's frame buffer
 	int32_t mesh_path = RT_MESH_PATH_AUTO;
+	int32_t kernel_variant = RT_KERNEL_AUTO;
 
 	// pinned host mirror of the static block (SoA, as uploaded) and of the mesh block
 	uint8_t* h_static = nullptr;
@@ -125,6 +127,16 @@ namespace
 	KernelFn pick_kernel(int mode, int shadows, bool bvh)
 	{
 #define RT_ROW(M) { { rt::render_kernel<M, 0, false, false>, rt::render_kernel<M, 1, false, false> }, { rt::render_kernel<M, 0, true, false>, rt::render_kernel<M, 1, true, false> } }
+		static const KernelFn table[4][2][2] = {
+			RT_ROW(RT_LIGHTING_OBSERVED_AREA), RT_ROW(RT_LIGHTING_RADIANCE), RT_ROW(RT_LIGHTING_BRDF), RT_ROW(RT_LIGHTING_COMBINED),
+		};
+#undef RT_ROW
+		return table[mode][bvh ? 1 : 0][shadows ? 1 : 0];
+	}
+
+	KernelFn pick_kernel_x2(int mode, int shadows, bool bvh)
+	{
+#define RT_ROW(M) { { rt::x2::render_kernel_x2<M, 0, false>, rt::x2::render_kernel_x2<M, 1, false> }, { rt::x2::render_kernel_x2<M, 0, true>, rt::x2::render_kernel_x2<M, 1, true> } }
 		static const KernelFn table[4][2][2] = {
 			RT_ROW(RT_LIGHTING_OBSERVED_AREA), RT_ROW(RT_LIGHTING_RADIANCE), RT_ROW(RT_LIGHTING_BRDF), RT_ROW(RT_LIGHTING_COMBINED),
 		};
@@ -295,8 +307,11 @@ namespace
 		const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)n_strips, 1);
 		if (grid.y > 65535u) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame too tall for one launch");
 		if (stream != d.stream) RT_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_upload, 0));   // scene copies ride d.stream
-		KernelFn k = pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH);
-		k<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
+		static_assert(rt::x2::kBlockW == rt::kBlockW, "both kernels must cut the frame into the same CTA grid");
+		p.k_neg0 = make_float2(-0.f, -0.f); p.k_one = make_float2(1.f, 1.f); p.k_mone = make_float2(-1.f, -1.f);
+		const bool packed = ctx->kernel_variant == RT_KERNEL_PACKED;   // AUTO = scalar: the faster build today
+		if (packed) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::x2::kThreads, 0, stream>>>(d.view, p);
+		else pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
 		RT_CUDA(ctx, cudaGetLastError());
 		ctx->timing.kernel_launches++;
 		return RT_OK;
@@ -839,6 +854,14 @@ int rt_set_mesh_path(rt_context* ctx, int32_t mesh_path)
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
 	if (mesh_path < RT_MESH_PATH_AUTO || mesh_path > RT_MESH_PATH_BVH) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown mesh path %d", mesh_path);
 	ctx->mesh_path = mesh_path;
+	return RT_OK;
+}
+
+int rt_set_kernel_variant(rt_context* ctx, int32_t variant)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (variant < RT_KERNEL_AUTO || variant > RT_KERNEL_PACKED) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", variant);
+	ctx->kernel_variant = variant;
 	return RT_OK;
 }
 

@@ -26,9 +26,13 @@ namespace rt
 
 	constexpr int kTileW = 8;            // pixels per warp tile
 	constexpr int kTileH = 4;
-	constexpr int kBlockW = 32;          // pixels per CTA strip segment
+#ifndef RT_BLOCK_W
+#define RT_BLOCK_W 32
+#endif
+	constexpr int kBlockW = RT_BLOCK_W;  // pixels per CTA strip segment
 	constexpr int kBlockH = 8;
-	constexpr int kThreads = 256;
+	constexpr int kThreads = kBlockW * kBlockH;
+	constexpr int kWarpsX = kBlockW / kTileW;
 
 	// Device views of the uploaded SoA buffers (one copy per GPU).
 	struct SceneDevice
@@ -67,6 +71,7 @@ namespace rt
 		unsigned long long* counters;    // counters build only
 		unsigned int* band_done;         // progressive present: band_done[b] counts the finished CTAs of band b (NULL = off)
 		int32_t strips_per_band;
+		float2 k_neg0, k_one, k_mone;    // (-0,-0), (1,1), (-1,-1): run-time operands of the packed kernel's FFMA2 (rt_kernel_x2.cuh)
 	};
 
 	struct Ray
@@ -690,26 +695,27 @@ namespace rt
 		return (R << p.r_shift) | (G << p.g_shift) | (B << p.b_shift) | p.alpha_mask;
 	}
 
+	template <int THREADS>
 	__device__ __forceinline__ void stage_scene(SharedScene& sc, const SceneDevice& dev)
 	{
 		const int tid = threadIdx.x;
-		for (int i = tid; i < dev.n_spheres; i += kThreads)
+		for (int i = tid; i < dev.n_spheres; i += THREADS)
 		{
 			sc.sphere[i] = make_float4(dev.sphere_ox[i], dev.sphere_oy[i], dev.sphere_oz[i], dev.sphere_r[i]);
 			sc.sphere_mat[i] = dev.sphere_mat[i];
 		}
-		for (int i = tid; i < dev.n_planes; i += kThreads)
+		for (int i = tid; i < dev.n_planes; i += THREADS)
 		{
 			sc.plane_o[i] = make_float4(dev.plane_ox[i], dev.plane_oy[i], dev.plane_oz[i], __int_as_float((int)dev.plane_mat[i]));
 			sc.plane_n[i] = make_float4(dev.plane_nx[i], dev.plane_ny[i], dev.plane_nz[i], 0.f);
 		}
-		for (int i = tid; i < dev.n_lights; i += kThreads)
+		for (int i = tid; i < dev.n_lights; i += THREADS)
 		{
 			sc.light_a[i] = make_float4(dev.light_ox[i], dev.light_oy[i], dev.light_oz[i], dev.light_intensity[i]);
 			sc.light_b[i] = make_float4(dev.light_r[i], dev.light_g[i], dev.light_b[i], __int_as_float(dev.light_type[i]));
 		}
-		for (int i = tid; i < 3 * dev.n_meshes; i += kThreads) sc.mesh[i] = dev.mesh_table[i];
-		for (int i = tid; i < dev.n_materials; i += kThreads)
+		for (int i = tid; i < 3 * dev.n_meshes; i += THREADS) sc.mesh[i] = dev.mesh_table[i];
+		for (int i = tid; i < dev.n_materials; i += THREADS)
 		{
 			float4 m0 = dev.materials[2 * i];
 			const float4 m1 = dev.materials[2 * i + 1];
@@ -732,12 +738,12 @@ namespace rt
 	render_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
 		__shared__ SharedScene sc;
-		stage_scene(sc, dev);
+		stage_scene<kThreads>(sc, dev);
 		__syncthreads();
 
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 		const int tx = lane & (kTileW - 1), ty = lane >> 3;
-		const int wx = warp & 3, wy = warp >> 2;
+		const int wx = warp % kWarpsX, wy = warp / kWarpsX;
 		const int px = blockIdx.x * kBlockW + wx * kTileW + tx;
 		const int local_y = wy * kTileH + ty;
 		const int py = p.row_begin + ((int)blockIdx.y * p.strip_step + p.strip_first) * kBlockH + local_y;

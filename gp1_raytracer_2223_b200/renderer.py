@@ -73,6 +73,10 @@ class Context:
         """The reference's compile-time `#define BVH` as a run-time choice (0 auto, 1 slab + linear, 2 BVH)."""
         self.check(self.lib.rt_set_mesh_path(self.handle, int(mesh_path)), "rt_set_mesh_path")
 
+    def set_kernel_variant(self, variant: int) -> None:
+        """0 auto (= scalar today), 1 scalar one-pixel kernel, 2 packed two-pixel FFMA2 kernel."""
+        self.check(self.lib.rt_set_kernel_variant(self.handle, int(variant)), "rt_set_kernel_variant")
+
     def upload_mesh(self, mesh_id: int, mesh) -> None:
         """Re-upload one mesh after TriangleMesh::UpdateTransforms (reference source/DataTypes.h:210-236)."""
         v = SceneViews.__new__(SceneViews)

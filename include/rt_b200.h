@@ -289,6 +289,17 @@ int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count);
 int rt_set_mesh_path(rt_context* ctx, int32_t mesh_path);
 int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh);
 
+/* Which build of the pixel kernel renders frames.  Both compute the same function, bit for bit.
+ *   RT_KERNEL_SCALAR  one pixel per thread (default; also what rt_count_frame instruments)
+ *   RT_KERNEL_PACKED  two pixels per thread on Blackwell's packed FP32 (FFMA2) */
+enum rt_kernel_variant
+{
+	RT_KERNEL_AUTO = 0,
+	RT_KERNEL_SCALAR = 1,
+	RT_KERNEL_PACKED = 2
+};
+int rt_set_kernel_variant(rt_context* ctx, int32_t variant);
+
 /* ---- render ----------------------------------------------------------------------------------- */
 
 /* Replaces Renderer::Render (source/Renderer.cpp:34-98): blocking; on return host_dst holds

@@ -58,6 +58,25 @@ def test_frame_matches_reference(gpu, name, mesh_path):
     r.close()
 
 
+@pytest.mark.parametrize("mesh_path", [1, 2], ids=["slab_linear", "bvh"])
+@pytest.mark.parametrize("name", golden_names())
+def test_packed_kernel_matches_reference(gpu, name, mesh_path):
+    """RT_KERNEL_PACKED (two pixels per thread on FFMA2) must be the same function as the scalar kernel."""
+    if mesh_path == 2 and not load_golden_scene(name).meshes:
+        pytest.skip("scene has no triangle mesh")
+    r = make_renderer(name)
+    r.ctx.set_mesh_path(mesh_path)
+    r.ctx.set_kernel_variant(2)
+    got = r.Render()
+    r.ctx.set_kernel_variant(1)
+    assert np.array_equal(got, r.Render()), "packed and scalar kernels disagree"
+    identical, max_err, n_diff = compare_frames(got, load_golden_frame(name))
+    if name in EXACT:
+        assert n_diff == 0
+    assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB
+    r.close()
+
+
 def test_frame_matches_cpu_oracle_on_fresh_pose(gpu):
     """A pose that is in no fixture: oracle and CUDA path on the same inputs."""
     from oracle import rt_oracle

@@ -14,9 +14,9 @@ from gp1_raytracer_2223_b200 import Renderer  # noqa: E402
 
 names = [a for a in sys.argv[1:] if not a.startswith("-")] or ["bunny_4k", "bunny_640", "w3_640", "w4ref_640"]
 reps = 20
-paths = {"slab": 1, "bvh": 2}
+paths = {"slab/scalar": (1, 1), "slab/packed": (1, 2), "bvh/scalar": (2, 1), "bvh/packed": (2, 2)}
 for name in names:
-  for pname, path in paths.items():
+  for pname, (path, variant) in paths.items():
     info = MANIFEST[name]
     scene = load_golden_scene(name)
     if path == 2 and not scene.meshes:
@@ -28,10 +28,11 @@ for name in names:
         r.ToggleShadows()
     r.SetScene(scene)
     r.ctx.set_mesh_path(path)
+    r.ctx.set_kernel_variant(variant)
     for _ in range(3):
         r.render_device()
     ms = [r.render_device()["kernel_ms"] for _ in range(reps)]
     got = r.download()
     diff = int((got != load_golden_frame(name)).sum())
-    print(f"{name:24s} {pname:5s} kernel ms mean {np.mean(ms):.4f} min {np.min(ms):.4f}  diff_px {diff}")
+    print(f"{name:24s} {pname:12s} kernel ms mean {np.mean(ms):.4f} min {np.min(ms):.4f}  diff_px {diff}")
     r.close()
