@@ -215,6 +215,7 @@ namespace
 		v.bvh_nodes = d.d_mesh + d.node_offset;
 		v.n_spheres = ctx->n_spheres; v.n_planes = ctx->n_planes; v.n_lights = ctx->n_lights;
 		v.n_materials = ctx->n_materials; v.n_meshes = (int32_t)ctx->meshes.size();
+		v.k_neg0 = make_float2(-0.f, -0.f); v.k_one = make_float2(1.f, 1.f); v.k_mone = make_float2(-1.f, -1.f);
 	}
 
 	// The pinned mirrors are about to be rewritten: wait until every device has consumed them.
@@ -266,8 +267,8 @@ namespace
 		{
 			const HostMesh& hm = ctx->meshes[m];
 			const int32_t count = (int32_t)(hm.triangles.size() / 3), node_count = (int32_t)(hm.nodes.size() / 2);
-			h[3 * m + 0] = make_float4(hm.aabb_min[0], hm.aabb_min[1], hm.aabb_min[2], bits_as_float(first));
-			h[3 * m + 1] = make_float4(hm.aabb_max[0], hm.aabb_max[1], hm.aabb_max[2], bits_as_float(count));
+			h[3 * m + 0] = make_float4(hm.aabb_min[0], hm.aabb_max[0], hm.aabb_min[1], hm.aabb_max[1]);
+			h[3 * m + 1] = make_float4(hm.aabb_min[2], hm.aabb_max[2], bits_as_float(first), bits_as_float(count));
 			h[3 * m + 2] = make_float4(bits_as_float(hm.cull_mode), bits_as_float(hm.material), bits_as_float(first_node), bits_as_float(node_count));
 			if (count) memcpy(tris + 3 * (size_t)first, hm.triangles.data(), hm.triangles.size() * sizeof(float4));
 			if (node_count) memcpy(nodes + 2 * (size_t)first_node, hm.nodes.data(), hm.nodes.size() * sizeof(float4));
@@ -308,7 +309,6 @@ namespace
 		if (grid.y > 65535u) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame too tall for one launch");
 		if (stream != d.stream) RT_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_upload, 0));   // scene copies ride d.stream
 		static_assert(rt::x2::kBlockW == rt::kBlockW, "both kernels must cut the frame into the same CTA grid");
-		p.k_neg0 = make_float2(-0.f, -0.f); p.k_one = make_float2(1.f, 1.f); p.k_mone = make_float2(-1.f, -1.f);
 		const bool packed = ctx->kernel_variant == RT_KERNEL_PACKED;   // AUTO = scalar: the faster build today
 		if (packed) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::x2::kThreads, 0, stream>>>(d.view, p);
 		else pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
@@ -519,8 +519,8 @@ namespace
 				stack.push_back({ first + 1, it.escape });
 				stack.push_back({ first, first + 1 });
 			}
-			out[2 * (size_t)it.node + 0] = make_float4(nd.min_aabb[0], nd.min_aabb[1], nd.min_aabb[2], bits_as_float(first));
-			out[2 * (size_t)it.node + 1] = make_float4(nd.max_aabb[0], nd.max_aabb[1], nd.max_aabb[2],
+			out[2 * (size_t)it.node + 0] = make_float4(nd.min_aabb[0], nd.max_aabb[0], nd.min_aabb[1], nd.max_aabb[1]);
+			out[2 * (size_t)it.node + 1] = make_float4(nd.min_aabb[2], nd.max_aabb[2], bits_as_float(first),
 			                                            bits_as_float((it.escape + 1) | (leaf_tris << rt::BvhLink::kEscapeBits)));
 		}
 		if (covered != mesh->triangle_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH leaves cover %lld of %d triangles", (long long)covered, mesh->triangle_count);

@@ -47,10 +47,13 @@ namespace rt
 		const float* light_intensity;
 		const int32_t* light_type;
 		const float4* materials;       // 2 float4 per material: {tag bits, r, g, b} {p0, p1, p2, -}
-		const float4* mesh_table;      // 3 float4 per mesh: {min xyz, first triangle}, {max xyz, triangle count}, {cull, material, first BVH node, BVH node count}
+		const float4* mesh_table;      // 3 float4 per mesh: {min.x, max.x, min.y, max.y}, {min.z, max.z, first triangle, triangle count}, {cull, material, first BVH node, BVH node count}
 		const float4* triangles;       // 3 float4 per triangle: {v0 xyz, n.x} {e1 xyz, n.y} {e2 xyz, n.z}
-		const float4* bvh_nodes;       // 2 float4 per node: {min xyz, first}, {max xyz, link}; see BvhLink
+		const float4* bvh_nodes;       // 2 float4 per node: {min.x, max.x, min.y, max.y}, {min.z, max.z, first, link}; see BvhLink
 		int32_t n_spheres, n_planes, n_lights, n_materials, n_meshes;
+		// (-0,-0), (1,1), (-1,-1): third operands of the packed FFMA2 arithmetic (struct Pk).  They are
+		// kernel parameters on purpose - see rt_kernel_x2.cuh on why literals would break exactness.
+		float2 k_neg0, k_one, k_mone;
 	};
 
 	struct FrameParams
@@ -71,7 +74,6 @@ namespace rt
 		unsigned long long* counters;    // counters build only
 		unsigned int* band_done;         // progressive present: band_done[b] counts the finished CTAs of band b (NULL = off)
 		int32_t strips_per_band;
-		float2 k_neg0, k_one, k_mone;    // (-0,-0), (1,1), (-1,-1): run-time operands of the packed kernel's FFMA2 (rt_kernel_x2.cuh)
 	};
 
 	struct Ray
@@ -178,7 +180,22 @@ namespace rt
 		return false;
 	}
 
-	// SlabTest_TriangleMesh / SlabTest_BVH, Utils.h:194-216, 221-243.
+	// Packed FP32 arithmetic (Blackwell FFMA2): two independent IEEE multiplies / adds / subtracts per issue
+	// slot, each individually rounded:  a*b = fma(a, b, -0),  a+b = fma(a, 1, b),  a-b = fma(b, -1, a).
+	// The constants are run-time values (SceneDevice::k_*), never literals (rt_kernel_x2.cuh explains why).
+	struct Pk
+	{
+		float2 neg0, one, mone;
+		__device__ __forceinline__ float2 mul(float2 a, float2 b) const { return __ffma2_rn(a, b, neg0); }
+		__device__ __forceinline__ float2 add(float2 a, float2 b) const { return __ffma2_rn(a, one, b); }
+		__device__ __forceinline__ float2 sub(float2 a, float2 b) const { return __ffma2_rn(b, mone, a); }
+	};
+	__device__ __forceinline__ Pk make_pk(const SceneDevice& dev) { Pk k; k.neg0 = dev.k_neg0; k.one = dev.k_one; k.mone = dev.k_mone; return k; }
+	__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
+
+	// SlabTest_TriangleMesh / SlabTest_BVH, Utils.h:194-216, 221-243, on a box stored as
+	// b0 = {min.x, max.x, min.y, max.y}, b1 = {min.z, max.z, -, -}: the (tx1, tx2), (ty1, ty2), (tz1, tz2)
+	// pairs are six packed operations instead of twelve scalar ones.
 	//
 	// FAST = true replaces the std::min / std::max ternaries by FMNMX (fminf / fmaxf).  The two only
 	// differ when an operand is NaN (and in the sign of a zero result, which the final comparisons
@@ -186,37 +203,23 @@ namespace rt
 	// whose inverse direction is finite (Ray::nan_safe, all but axis-parallel rays) take the fast
 	// form with the same boolean result; the others take the literal one.
 	template <bool FAST>
-	__device__ __forceinline__ bool slab_test(const float4 bmin, const float4 bmax, const Ray& ray);
-
-	template <>
-	__device__ __forceinline__ bool slab_test<true>(const float4 bmin, const float4 bmax, const Ray& ray)
+	__device__ __forceinline__ bool slab_test(const Pk& K, const float4 b0, const float4 b1, const Ray& ray)
 	{
-		const float tx1 = mul(sub(bmin.x, ray.o.x), ray.inv.x);
-		const float tx2 = mul(sub(bmax.x, ray.o.x), ray.inv.x);
-		const float ty1 = mul(sub(bmin.y, ray.o.y), ray.inv.y);
-		const float ty2 = mul(sub(bmax.y, ray.o.y), ray.inv.y);
-		const float tz1 = mul(sub(bmin.z, ray.o.z), ray.inv.z);
-		const float tz2 = mul(sub(bmax.z, ray.o.z), ray.inv.z);
-		const float t_min = fmaxf(fmaxf(fminf(tx1, tx2), fminf(ty1, ty2)), fminf(tz1, tz2));
-		const float t_max = fminf(fminf(fmaxf(tx1, tx2), fmaxf(ty1, ty2)), fmaxf(tz1, tz2));
-		return t_max > 0 && t_max >= t_min;
-	}
-
-	template <>
-	__device__ __forceinline__ bool slab_test<false>(const float4 bmin, const float4 bmax, const Ray& ray)
-	{
-		const float tx1 = mul(sub(bmin.x, ray.o.x), ray.inv.x);
-		const float tx2 = mul(sub(bmax.x, ray.o.x), ray.inv.x);
-		float t_min = std_min(tx1, tx2);
-		float t_max = std_max(tx1, tx2);
-		const float ty1 = mul(sub(bmin.y, ray.o.y), ray.inv.y);
-		const float ty2 = mul(sub(bmax.y, ray.o.y), ray.inv.y);
-		t_min = std_max(t_min, std_min(ty1, ty2));
-		t_max = std_min(t_max, std_max(ty1, ty2));
-		const float tz1 = mul(sub(bmin.z, ray.o.z), ray.inv.z);
-		const float tz2 = mul(sub(bmax.z, ray.o.z), ray.inv.z);
-		t_min = std_max(t_min, std_min(tz1, tz2));
-		t_max = std_min(t_max, std_max(tz1, tz2));
+		const float2 tx = K.mul(K.sub(make_float2(b0.x, b0.y), splat(ray.o.x)), splat(ray.inv.x));
+		const float2 ty = K.mul(K.sub(make_float2(b0.z, b0.w), splat(ray.o.y)), splat(ray.inv.y));
+		const float2 tz = K.mul(K.sub(make_float2(b1.x, b1.y), splat(ray.o.z)), splat(ray.inv.z));
+		if (FAST)
+		{
+			const float t_min = fmaxf(fmaxf(fminf(tx.x, tx.y), fminf(ty.x, ty.y)), fminf(tz.x, tz.y));
+			const float t_max = fminf(fminf(fmaxf(tx.x, tx.y), fmaxf(ty.x, ty.y)), fmaxf(tz.x, tz.y));
+			return t_max > 0 && t_max >= t_min;
+		}
+		float t_min = std_min(tx.x, tx.y);
+		float t_max = std_max(tx.x, tx.y);
+		t_min = std_max(t_min, std_min(ty.x, ty.y));
+		t_max = std_min(t_max, std_max(ty.x, ty.y));
+		t_min = std_max(t_min, std_min(tz.x, tz.y));
+		t_max = std_min(t_max, std_max(tz.x, tz.y));
 		return t_max > 0 && t_max >= t_min;
 	}
 
@@ -352,7 +355,7 @@ namespace rt
 	};
 
 	template <int CULL, bool FAST, bool COUNT>
-	__device__ __forceinline__ void bvh_closest(const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	__device__ __forceinline__ void bvh_closest(const Pk& K, const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
 	{
 		int node = 0;
 		while (node >= 0)
@@ -361,9 +364,9 @@ namespace rt
 			const int link = __float_as_int(n1.w);
 			const int escape = (link & BvhLink::kEscapeMask) - 1;
 			cnt.hit(RT_CNT_BVH_P_NODE);
-			if (!slab_test<FAST>(n0, n1, ray)) { node = escape; continue; }
+			if (!slab_test<FAST>(K, n0, n1, ray)) { node = escape; continue; }
 			const int count = link >> BvhLink::kEscapeBits;
-			const int first = __float_as_int(n0.w);
+			const int first = __float_as_int(n1.z);
 			if (count == 0) { node = first; continue; }
 			for (int k = 0; k < count; ++k)
 				closest_one<CULL>(load_tri(tri + 3 * (first + k)), first + k, ray, best_t, best_tri, cnt);
@@ -372,7 +375,7 @@ namespace rt
 	}
 
 	template <int CULL, bool FAST, bool COUNT>
-	__device__ __forceinline__ bool bvh_any(const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
+	__device__ __forceinline__ bool bvh_any(const Pk& K, const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
 	{
 		int node = 0;
 		while (node >= 0)
@@ -381,9 +384,9 @@ namespace rt
 			const int link = __float_as_int(n1.w);
 			const int escape = (link & BvhLink::kEscapeMask) - 1;
 			cnt.hit(RT_CNT_BVH_S_NODE);
-			if (!slab_test<FAST>(n0, n1, ray)) { node = escape; continue; }
+			if (!slab_test<FAST>(K, n0, n1, ray)) { node = escape; continue; }
 			const int count = link >> BvhLink::kEscapeBits;
-			const int first = __float_as_int(n0.w);
+			const int first = __float_as_int(n1.z);
 			if (count == 0) { node = first; continue; }
 			for (int k = 0; k < count; ++k)
 				if (shadow_one<CULL>(load_tri(tri + 3 * (first + k)), ray, cnt)) return true;
@@ -393,20 +396,20 @@ namespace rt
 	}
 
 	template <bool FAST, bool COUNT>
-	__device__ __forceinline__ void bvh_closest_any_cull(int cull, const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	__device__ __forceinline__ void bvh_closest_any_cull(const Pk& K, int cull, const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
 	{
-		if (cull == RT_CULL_BACK_FACE) bvh_closest<RT_CULL_BACK_FACE, FAST>(nodes, tri, ray, best_t, best_tri, cnt);
-		else if (cull == RT_CULL_FRONT_FACE) bvh_closest<RT_CULL_FRONT_FACE, FAST>(nodes, tri, ray, best_t, best_tri, cnt);
-		else bvh_closest<RT_CULL_NONE, FAST>(nodes, tri, ray, best_t, best_tri, cnt);
+		if (cull == RT_CULL_BACK_FACE) bvh_closest<RT_CULL_BACK_FACE, FAST>(K, nodes, tri, ray, best_t, best_tri, cnt);
+		else if (cull == RT_CULL_FRONT_FACE) bvh_closest<RT_CULL_FRONT_FACE, FAST>(K, nodes, tri, ray, best_t, best_tri, cnt);
+		else bvh_closest<RT_CULL_NONE, FAST>(K, nodes, tri, ray, best_t, best_tri, cnt);
 	}
 
 	// Utils.h:114-127: shadow rays see the opposite cull mode
 	template <bool FAST, bool COUNT>
-	__device__ __forceinline__ bool bvh_any_any_cull(int cull, const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
+	__device__ __forceinline__ bool bvh_any_any_cull(const Pk& K, int cull, const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
 	{
-		if (cull == RT_CULL_BACK_FACE) return bvh_any<RT_CULL_FRONT_FACE, FAST>(nodes, tri, ray, cnt);
-		if (cull == RT_CULL_FRONT_FACE) return bvh_any<RT_CULL_BACK_FACE, FAST>(nodes, tri, ray, cnt);
-		return bvh_any<RT_CULL_NONE, FAST>(nodes, tri, ray, cnt);
+		if (cull == RT_CULL_BACK_FACE) return bvh_any<RT_CULL_FRONT_FACE, FAST>(K, nodes, tri, ray, cnt);
+		if (cull == RT_CULL_FRONT_FACE) return bvh_any<RT_CULL_BACK_FACE, FAST>(K, nodes, tri, ray, cnt);
+		return bvh_any<RT_CULL_NONE, FAST>(K, nodes, tri, ray, cnt);
 	}
 
 	// Scene::GetClosestHit, Scene.cpp:29-66: spheres, planes, meshes in order; strict '<' keeps
@@ -416,6 +419,7 @@ namespace rt
 	template <bool BVH, bool COUNT>
 	__device__ __forceinline__ Hit closest_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
 	{
+		const Pk K = make_pk(dev);
 		Hit best;
 		best.t = FLT_MAX; best.did = false; best.material = 0;
 		best.origin = v3(0.f, 0.f, 0.f); best.normal = v3(0.f, 0.f, 0.f);
@@ -458,8 +462,8 @@ namespace rt
 
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
-			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
-			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
+			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
 			int best_tri = -1;
@@ -467,13 +471,13 @@ namespace rt
 			{
 				if (count == 0) continue;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				if (!ray.nan_safe) bvh_closest_any_cull<false>(cull, nodes, tri, ray, best.t, best_tri, cnt);
-				else bvh_closest_any_cull<true>(cull, nodes, tri, ray, best.t, best_tri, cnt);
+				if (!ray.nan_safe) bvh_closest_any_cull<false>(K, cull, nodes, tri, ray, best.t, best_tri, cnt);
+				else bvh_closest_any_cull<true>(K, cull, nodes, tri, ray, best.t, best_tri, cnt);
 			}
 			else
 			{
 				cnt.hit(RT_CNT_SLAB_P_TEST);
-				if (!(ray.nan_safe ? slab_test<true>(bmin, bmax, ray) : slab_test<false>(bmin, bmax, ray))) continue;
+				if (!(ray.nan_safe ? slab_test<true>(K, b0, b1, ray) : slab_test<false>(K, b0, b1, ray))) continue;
 				cnt.hit(RT_CNT_SLAB_P_PASS);
 				if (cull == RT_CULL_BACK_FACE) mesh_closest<RT_CULL_BACK_FACE>(tri, count, ray, best.t, best_tri, cnt);
 				else if (cull == RT_CULL_FRONT_FACE) mesh_closest<RT_CULL_FRONT_FACE>(tri, count, ray, best.t, best_tri, cnt);
@@ -495,6 +499,7 @@ namespace rt
 	template <bool BVH, bool COUNT>
 	__device__ __forceinline__ bool does_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
 	{
+		const Pk K = make_pk(dev);
 		float t;
 		for (int i = 0; i < dev.n_spheres; ++i)
 			if (hit_sphere<true>(sc.sphere[i], ray, t, cnt)) return true;
@@ -502,8 +507,8 @@ namespace rt
 			if (hit_plane<true>(sc.plane_o[i], sc.plane_n[i], ray, t, cnt)) return true;
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
-			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
-			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
+			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
 			// Utils.h:114-127: shadow rays see the opposite cull mode
@@ -512,13 +517,13 @@ namespace rt
 			{
 				if (count == 0) continue;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				if (!ray.nan_safe) hit = bvh_any_any_cull<false>(cull, nodes, tri, ray, cnt);
-				else hit = bvh_any_any_cull<true>(cull, nodes, tri, ray, cnt);
+				if (!ray.nan_safe) hit = bvh_any_any_cull<false>(K, cull, nodes, tri, ray, cnt);
+				else hit = bvh_any_any_cull<true>(K, cull, nodes, tri, ray, cnt);
 			}
 			else
 			{
 				cnt.hit(RT_CNT_SLAB_S_TEST);
-				if (!(ray.nan_safe ? slab_test<true>(bmin, bmax, ray) : slab_test<false>(bmin, bmax, ray))) continue;
+				if (!(ray.nan_safe ? slab_test<true>(K, b0, b1, ray) : slab_test<false>(K, b0, b1, ray))) continue;
 				cnt.hit(RT_CNT_SLAB_S_PASS);
 				if (cull == RT_CULL_BACK_FACE) hit = mesh_any<RT_CULL_FRONT_FACE>(tri, count, ray, cnt);
 				else if (cull == RT_CULL_FRONT_FACE) hit = mesh_any<RT_CULL_BACK_FACE>(tri, count, ray, cnt);

@@ -47,13 +47,10 @@ namespace x2
 		float2 x, y, z;
 	};
 
-	// Packed arithmetic on run-time constants (see the header comment).
-	struct Pk
+	// Packed vector helpers on top of rt::Pk (run-time constants, see the header comment).
+	struct Pk : rt::Pk
 	{
-		float2 neg0, one, mone;
-		__device__ __forceinline__ float2 mul(float2 a, float2 b) const { return __ffma2_rn(a, b, neg0); }
-		__device__ __forceinline__ float2 add(float2 a, float2 b) const { return __ffma2_rn(a, one, b); }
-		__device__ __forceinline__ float2 sub(float2 a, float2 b) const { return __ffma2_rn(b, mone, a); }
+		using rt::Pk::mul; using rt::Pk::add; using rt::Pk::sub;
 		__device__ __forceinline__ V3x2 sub(const V3x2& a, const V3x2& b) const { V3x2 r; r.x = sub(a.x, b.x); r.y = sub(a.y, b.y); r.z = sub(a.z, b.z); return r; }
 		// Vector3::Dot, Vector3.cpp:48-51
 		__device__ __forceinline__ float2 dot(const V3x2& a, const V3x2& b) const { return add(add(mul(a.x, b.x), mul(a.y, b.y)), mul(a.z, b.z)); }
@@ -68,7 +65,7 @@ namespace x2
 		}
 	};
 
-	__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
+	using rt::splat;
 	__device__ __forceinline__ V3x2 splat3(float x, float y, float z) { V3x2 r; r.x = splat(x); r.y = splat(y); r.z = splat(z); return r; }
 	__device__ __forceinline__ V3x2 pack(V3 a, V3 b) { V3x2 r; r.x = make_float2(a.x, b.x); r.y = make_float2(a.y, b.y); r.z = make_float2(a.z, b.z); return r; }
 	__device__ __forceinline__ V3 lo(const V3x2& a) { return v3(a.x.x, a.y.x, a.z.x); }
@@ -251,14 +248,14 @@ namespace x2
 			const int link = __float_as_int(n1.w);
 			const int escape = (link & BvhLink::kEscapeMask) - 1;
 			bool h0, h1;
-			slab2<FAST>(K, n0.x, n0.y, n0.z, n1.x, n1.y, n1.z, r, h0, h1);
+			slab2<FAST>(K, n0.x, n0.z, n1.x, n0.y, n0.w, n1.y, r, h0, h1);
 			h0 = h0 && (res0 == kAwake);
 			h1 = h1 && (res1 == kAwake);
 			if (!h0 && res0 == kAwake) res0 = escape;     // this ray skips the subtree, like the early return of Utils.h:251-254
 			if (!h1 && res1 == kAwake) res1 = escape;
 			if (!(h0 | h1)) { node = escape; continue; }
 			const int count = link >> BvhLink::kEscapeBits;
-			const int first = __float_as_int(n0.w);
+			const int first = __float_as_int(n1.z);
 			if (count == 0) { node = first; continue; }
 			for (int k = 0; k < count && (h0 | h1); ++k)
 			{
@@ -318,32 +315,32 @@ namespace x2
 		}
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
-			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
-			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
+			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
-			int b0 = -1, b1 = -1;
+			int t0 = -1, t1 = -1;
 			bool dummy0 = false, dummy1 = false;
 			if (BVH)
 			{
 				if (count == 0) continue;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				if (r.fast) bvh2_cull<true, false>(cull, K, nodes, tri, r, on0, on1, best_t, b0, b1, dummy0, dummy1);
-				else bvh2_cull<false, false>(cull, K, nodes, tri, r, on0, on1, best_t, b0, b1, dummy0, dummy1);
+				if (r.fast) bvh2_cull<true, false>(cull, K, nodes, tri, r, on0, on1, best_t, t0, t1, dummy0, dummy1);
+				else bvh2_cull<false, false>(cull, K, nodes, tri, r, on0, on1, best_t, t0, t1, dummy0, dummy1);
 			}
 			else
 			{
 				bool s0, s1;
-				if (r.fast) slab2<true>(K, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, r, s0, s1);
-				else slab2<false>(K, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, r, s0, s1);
+				if (r.fast) slab2<true>(K, b0.x, b0.z, b1.x, b0.y, b0.w, b1.y, r, s0, s1);
+				else slab2<false>(K, b0.x, b0.z, b1.x, b0.y, b0.w, b1.y, r, s0, s1);
 				s0 = s0 && on0; s1 = s1 && on1;
 				if (!(s0 | s1)) continue;
-				if (cull == RT_CULL_BACK_FACE) mesh_closest2<RT_CULL_BACK_FACE>(K, tri, count, r, s0, s1, best_t, b0, b1);
-				else if (cull == RT_CULL_FRONT_FACE) mesh_closest2<RT_CULL_FRONT_FACE>(K, tri, count, r, s0, s1, best_t, b0, b1);
-				else mesh_closest2<RT_CULL_NONE>(K, tri, count, r, s0, s1, best_t, b0, b1);
+				if (cull == RT_CULL_BACK_FACE) mesh_closest2<RT_CULL_BACK_FACE>(K, tri, count, r, s0, s1, best_t, t0, t1);
+				else if (cull == RT_CULL_FRONT_FACE) mesh_closest2<RT_CULL_FRONT_FACE>(K, tri, count, r, s0, s1, best_t, t0, t1);
+				else mesh_closest2<RT_CULL_NONE>(K, tri, count, r, s0, s1, best_t, t0, t1);
 			}
-			if (b0 >= 0) id0 = kTriangle | (m << kMeshShift) | b0;
-			if (b1 >= 0) id1 = kTriangle | (m << kMeshShift) | b1;
+			if (t0 >= 0) id0 = kTriangle | (m << kMeshShift) | t0;
+			if (t1 >= 0) id1 = kTriangle | (m << kMeshShift) | t1;
 		}
 	}
 
@@ -371,8 +368,8 @@ namespace x2
 		else
 		{
 			const int m = (id & ~kKindMask) >> kMeshShift;
-			const float4 bmin = sc.mesh[3 * m], info = sc.mesh[3 * m + 2];
-			const Tri T = load_tri(dev.triangles + 3 * ((size_t)__float_as_int(bmin.w) + index));
+			const float4 b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			const Tri T = load_tri(dev.triangles + 3 * ((size_t)__float_as_int(b1.z) + index));
 			hit.material = __float_as_int(info.y);
 			hit.normal = v3(T.a0.w, T.a1.w, T.a2.w);
 		}
@@ -402,8 +399,8 @@ namespace x2
 		}
 		for (int m = 0; m < dev.n_meshes && (on0 | on1); ++m)
 		{
-			const float4 bmin = sc.mesh[3 * m], bmax = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
-			const int first = __float_as_int(bmin.w), count = __float_as_int(bmax.w);
+			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
 			int cull = __float_as_int(info.x);
 			// Utils.h:114-127: shadow rays see the opposite cull mode
 			cull = (cull == RT_CULL_FRONT_FACE) ? RT_CULL_BACK_FACE : (cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : cull);
@@ -422,8 +419,8 @@ namespace x2
 			else
 			{
 				bool s0, s1;
-				if (r.fast) slab2<true>(K, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, r, s0, s1);
-				else slab2<false>(K, bmin.x, bmin.y, bmin.z, bmax.x, bmax.y, bmax.z, r, s0, s1);
+				if (r.fast) slab2<true>(K, b0.x, b0.z, b1.x, b0.y, b0.w, b1.y, r, s0, s1);
+				else slab2<false>(K, b0.x, b0.z, b1.x, b0.y, b0.w, b1.y, r, s0, s1);
 				s0 = s0 && on0; s1 = s1 && on1;
 				if (!(s0 | s1)) continue;
 				bool o0 = false, o1 = false;
@@ -546,7 +543,7 @@ namespace x2
 		__syncthreads();
 
 		Pk K;
-		K.neg0 = p.k_neg0; K.one = p.k_one; K.mone = p.k_mone;
+		K.neg0 = dev.k_neg0; K.one = dev.k_one; K.mone = dev.k_mone;
 
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 		const int tx = lane & 7, ty = lane >> 3;
