@@ -6,7 +6,10 @@ Combined lighting, shadows on (BASELINE.json configs[4], the north-star target).
 
 A step is one frame.  Metric: Mrays/s (primary + shadow rays of the frame / time).
   value      device-timed (CUDA events on the launching stream), scene resident in HBM, frame left in
-             HBM on rank 0 (N > 1: strip render on every rank + NCCL gather + unstripe on rank 0).
+             HBM on rank 0.  N > 1: every rank renders its 8-row strips straight into rank 0's frame
+             (CUDA-IPC mapped peer memory, 128-bit stores over NVLink: render and gather are one kernel),
+             followed by a one-element NCCL all-reduce as the barrier.  RT_BENCH_GATHER=nccl selects the
+             unfused form instead (packed bands + NCCL gather + unstripe kernel).
              Headline = the library's default mesh path: the reference's shipped BVH walk over the
              reference's own nodes (source/Utils.h:246-297).  The slab + every-triangle body the north
              star names (source/Utils.h:298-325) is measured the same way and reported under
@@ -231,35 +234,64 @@ def main():
             counters = r.count_frame(mesh_path=pid)
             flop_per_frame[pname] = algorithmic_flops(counters, 3)
             assert rays(counters) == RAYS_PER_FRAME, (rays(counters), RAYS_PER_FRAME)
+    fused = world > 1 and os.environ.get("RT_BENCH_GATHER", "fused") != "nccl"
     spr = bands.strips_per_rank(HEIGHT, world)
-    band = torch.empty((spr * bands.STRIP_ROWS, WIDTH), dtype=torch.int32, device="cuda")
-    frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda") if rank == 0 else None
-    gathered = torch.empty((world,) + tuple(band.shape), dtype=torch.int32, device="cuda") if (rank == 0 and world > 1) else None
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory() if rank == 0 else None
+    band = frame_dev = gathered = None
+    frame_ptr = 0
+    token = torch.zeros(1, dtype=torch.int32, device="cuda")
+    if world == 1:
+        frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
+    elif fused:
+        handle = [r.frame_export() if rank == 0 else None]       # rank 0 owns the frame, the others map it
+        dist.broadcast_object_list(handle, src=0)
+        frame_ptr = 0 if rank == 0 else r.frame_import(handle[0])
+    else:
+        band = torch.empty((spr * bands.STRIP_ROWS, WIDTH), dtype=torch.int32, device="cuda")
+        if rank == 0:
+            frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
+            gathered = torch.empty((world,) + tuple(band.shape), dtype=torch.int32, device="cuda")
+
+    def render_step():
+        """This rank's kernel launch of one frame."""
+        if world == 1:
+            r.render_strips_device(0, 1, frame_dev.data_ptr(), stream)
+        elif fused:
+            r.render_strips_to_frame(rank, world, frame_ptr, stream)
+        else:
+            r.render_strips_device(rank, world, band.data_ptr(), stream)
+
+    def exchange_step():
+        """What makes the frame complete in rank 0's HBM."""
+        if world == 1:
+            return
+        if fused:
+            dist.all_reduce(token)                 # barrier, stream-ordered after every rank's kernel
+        elif rank == 0:
+            dist.gather(band, list(gathered.unbind(0)), dst=0)
+            r.unstripe_device(gathered.data_ptr(), frame_dev.data_ptr(), world, spr, stream)
+        else:
+            dist.gather(band, None, dst=0)
 
     def device_step():
         """Inputs resident; result = the whole frame in rank 0's HBM."""
-        if world == 1:
-            r.render_strips_device(0, 1, frame_dev.data_ptr(), stream)
-        else:
-            r.render_strips_device(rank, world, band.data_ptr(), stream)
-            if rank == 0:
-                dist.gather(band, list(gathered.unbind(0)), dst=0)
-                r.unstripe_device(gathered.data_ptr(), frame_dev.data_ptr(), world, spr, stream)
-            else:
-                dist.gather(band, None, dst=0)
+        render_step()
+        exchange_step()
 
     def e2e_step():
         """Host buffers in, host buffer out, through the C ABI."""
         r.ctx.upload_mesh(0, mesh)                                  # H2D: what UpdateTransforms produced this frame
         if world == 1:
-            r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + D2H, blocking
-        else:
-            device_step()
-            if rank == 0:
-                host_frame.copy_(frame_dev, non_blocking=True)
-            torch.cuda.synchronize()
+            r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + progressive D2H, blocking
+            return
+        device_step()
+        torch.cuda.synchronize()
+        if rank == 0:
+            if fused:
+                r.download_to(host_frame.data_ptr(), WIDTH * 4)
+            else:
+                host_frame.copy_(frame_dev)
 
     # ---- device-timed region ---------------------------------------------------------------------
     def timed_device_region(sampler):
@@ -275,21 +307,14 @@ def main():
             for i in range(args.steps):
                 flush.zero_()                      # evict the frame buffer from L2 between timed steps
                 starts[i].record()
-                if world == 1:
-                    device_step()
-                else:
-                    kstarts[i].record()
-                    r.render_strips_device(rank, world, band.data_ptr(), stream)
-                    kends[i].record()
-                    if rank == 0:
-                        dist.gather(band, list(gathered.unbind(0)), dst=0)
-                        r.unstripe_device(gathered.data_ptr(), frame_dev.data_ptr(), world, spr, stream)
-                    else:
-                        dist.gather(band, None, dst=0)
+                kstarts[i].record()
+                render_step()
+                kends[i].record()
+                exchange_step()
                 ends[i].record()
             barrier()
         step_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(starts, ends)], dtype=torch.float64, device="cuda")
-        kern_ms = step_ms.clone() if world == 1 else torch.tensor([a.elapsed_time(b) for a, b in zip(kstarts, kends)], dtype=torch.float64, device="cuda")
+        kern_ms = torch.tensor([a.elapsed_time(b) for a, b in zip(kstarts, kends)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)     # per step, the slowest rank
             dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
@@ -326,8 +351,21 @@ def main():
     if rank != 0:
         if world > 1:
             dist.barrier()
+            if fused:
+                r.frame_release(frame_ptr)
             dist.destroy_process_group()
         return 0
+
+    # ---- the frame the timed path produced, against the frame the reference rendered ----------------
+    import lzma
+    with open(os.path.join(ROOT, "tests", "golden", "bunny_4k.frame.xz"), "rb") as f:
+        planar = np.frombuffer(lzma.decompress(f.read()), dtype=np.uint8).reshape(3, HEIGHT, WIDTH).astype(np.uint32)
+    golden = (planar[0] << 16) | (planar[1] << 8) | planar[2]
+    produced = host_frame.numpy().view(np.uint32) if e2e is not None else None
+    frame_check = None
+    if produced is not None:
+        differing = int((produced != golden).sum())
+        frame_check = {"differing_pixels_vs_reference_frame": differing, "pixels": WIDTH * HEIGHT}
 
     # ---- roofline (rank 0's GPU) -----------------------------------------------------------------
     peak_nofma = r.ctx.measure_fp32_peak(False)
@@ -380,11 +418,12 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "reference scene fixture tests/golden/bunny_4k.rtsc (dumped from the reference's Scene_W4_BunnyScene::Initialize; deterministic, no RNG)",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "rays_per_frame": RAYS_PER_FRAME,
-                   "triangles": int(mesh.triangle_count), "lights": 3, "partition": f"{bands.STRIP_ROWS}-row strips round-robin over {world} rank(s), NCCL gather to rank 0",
+                   "triangles": int(mesh.triangle_count), "lights": 3, "partition": f"{bands.STRIP_ROWS}-row strips round-robin over {world} rank(s); " + ("single GPU" if world == 1 else ("peer stores into rank 0's frame over NVLink (fused gather) + NCCL barrier" if fused else "NCCL gather to rank 0 + unstripe")),
                    "l2": f"{L2_FLUSH_BYTES >> 20} MiB memset between timed steps (outside the event pairs)"},
         "clocks": sampler.summary(),
         "e2e": e2e,
-        "gpu_launches": args.steps * (world + (1 if world > 1 else 0)),
+        "frame_check": frame_check,
+        "gpu_launches": args.steps * (world + (1 if (world > 1 and not fused) else 0)),
         "mesh_path": "bvh (reference's shipped IntersectionTest_BVH over the reference's own nodes)",
         "kernel_variant": "scalar (one pixel per thread); rt_render overlaps the present copy with rendering (progressive present)",
         "roofline": roofline,

@@ -1001,6 +1001,70 @@ int rt_unstripe_device(rt_context* ctx, const void* device_src, void* device_dst
 	return RT_OK;
 }
 
+int rt_frame_export(rt_context* ctx, int32_t width, int32_t height, void* out_handle)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!out_handle || width <= 0 || height <= 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad frame export arguments");
+	static_assert(sizeof(cudaIpcMemHandle_t) <= RT_IPC_HANDLE_BYTES, "IPC handle does not fit");
+	DeviceState& d = ctx->devs[0];
+	int rc = ensure_frame(ctx, d, (size_t)width * (size_t)height);
+	if (rc != RT_OK) return rc;
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaIpcMemHandle_t h;
+	RT_CUDA(ctx, cudaIpcGetMemHandle(&h, d.d_frame));
+	memset(out_handle, 0, RT_IPC_HANDLE_BYTES);
+	memcpy(out_handle, &h, sizeof h);
+	ctx->last_width = width; ctx->last_height = height;
+	return RT_OK;
+}
+
+int rt_frame_import(rt_context* ctx, const void* handle, void** out_device_ptr)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!handle || !out_device_ptr) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad frame import arguments");
+	RT_CUDA(ctx, cudaSetDevice(ctx->devs[0].device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, sizeof h);
+	RT_CUDA(ctx, cudaIpcOpenMemHandle(out_device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return RT_OK;
+}
+
+int rt_frame_release(rt_context* ctx, void* device_ptr)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!device_ptr) return RT_OK;
+	RT_CUDA(ctx, cudaSetDevice(ctx->devs[0].device));
+	RT_CUDA(ctx, cudaIpcCloseMemHandle(device_ptr));
+	return RT_OK;
+}
+
+int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                              int32_t strip_first, int32_t strip_step, void* frame_device_ptr, void* cuda_stream)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	int rc = validate_frame(ctx, camera, frame);
+	if (rc != RT_OK) return rc;
+	if (strip_step <= 0 || strip_first < 0 || strip_first >= strip_step) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "strip_first %d / strip_step %d is not a rank / world pair", strip_first, strip_step);
+	DeviceState& d = ctx->devs[0];
+	if (!frame_device_ptr)
+	{
+		if ((rc = ensure_frame(ctx, d, (size_t)frame->width * (size_t)frame->height)) != RT_OK) return rc;
+		frame_device_ptr = d.d_frame;
+		ctx->last_width = frame->width; ctx->last_height = frame->height;
+	}
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+	const int total_strips = (frame->height + rt::kBlockH - 1) / rt::kBlockH;
+	rt::FrameParams p = make_params(camera, frame);
+	p.row_begin = 0; p.row_end = frame->height;
+	p.strip_first = strip_first; p.strip_step = strip_step; p.dst_full_frame = 1; p.dst = (uint32_t*)frame_device_ptr;
+	ctx->timing = rt_timing{};
+	rc = launch(ctx, d, p, stream, (total_strips - strip_first + strip_step - 1) / strip_step);
+	if (rc != RT_OK) return rc;
+	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
+	return RT_OK;
+}
+
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing)
 {
 	if (!ctx || !out_timing) return RT_ERR_INVALID_ARGUMENT;

@@ -176,6 +176,29 @@ class Renderer:
         self.ctx.check(self.ctx.lib.rt_unstripe_device(self.ctx.handle, src_ptr, dst_ptr, self.width, self.height, world,
                                                        strips_per_rank, stream), "rt_unstripe_device")
 
+    # -- one process per GPU, gather fused into the kernel (rt_b200.h) -----------------------------------
+    def frame_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.ctx.check(self.ctx.lib.rt_frame_export(self.ctx.handle, self.width, self.height, buf), "rt_frame_export")
+        return buf.raw
+
+    def frame_import(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self.ctx.check(self.ctx.lib.rt_frame_import(self.ctx.handle, C.c_char_p(handle), C.byref(ptr)), "rt_frame_import")
+        return int(ptr.value)
+
+    def frame_release(self, ptr: int) -> None:
+        self.ctx.check(self.ctx.lib.rt_frame_release(self.ctx.handle, ptr), "rt_frame_release")
+
+    def render_strips_to_frame(self, strip_first: int, strip_step: int, frame_ptr: int = 0, stream: int = 0, camera=None):
+        cam = camera_struct(camera if camera is not None else self.scene.camera)
+        frame = self._frame()
+        self.ctx.check(self.ctx.lib.rt_render_strips_to_frame(self.ctx.handle, C.byref(cam), C.byref(frame), strip_first,
+                                                              strip_step, frame_ptr or None, stream), "rt_render_strips_to_frame")
+
+    def download_to(self, host_ptr: int, pitch_bytes: int) -> None:
+        self.ctx.check(self.ctx.lib.rt_download_frame(self.ctx.handle, host_ptr, pitch_bytes), "rt_download_frame")
+
     def count_frame(self, camera=None, mesh_path: int = 1) -> np.ndarray:
         """Test histogram of one frame; mesh_path 1 = slab + linear (the algorithmic counts), 2 = BVH."""
         cam = camera_struct(camera if camera is not None else self.scene.camera)

@@ -337,6 +337,21 @@ int rt_render_strips_device(rt_context* ctx, const rt_camera* camera, const rt_f
 int rt_unstripe_device(rt_context* ctx, const void* device_src, void* device_dst, int32_t width, int32_t height,
                        int32_t world, int32_t strips_per_rank, void* cuda_stream);
 
+/* ---- one process per GPU, gather fused into the kernel ------------------------------------------
+ * The root rank owns the frame; the other ranks map it (CUDA IPC, NVLink peer access) and their pixel
+ * kernels store their strips straight into it: no gather step, no unstripe, only a barrier.
+ *   root:   rt_frame_export(ctx, w, h, handle)      -> send the RT_IPC_HANDLE_BYTES to the other ranks
+ *   others: rt_frame_import(ctx, handle, &ptr)      -> ptr addresses the root's frame from this process
+ *   all:    rt_render_strips_to_frame(ctx, cam, frame, rank, world, ptr_or_NULL, stream)
+ *           (NULL = this context's own frame, i.e. the root), then a barrier across ranks
+ *   root:   rt_download_frame(ctx, host, pitch)     others: rt_frame_release(ctx, ptr) when done */
+#define RT_IPC_HANDLE_BYTES 64
+int rt_frame_export(rt_context* ctx, int32_t width, int32_t height, void* out_handle);
+int rt_frame_import(rt_context* ctx, const void* handle, void** out_device_ptr);
+int rt_frame_release(rt_context* ctx, void* device_ptr);
+int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                              int32_t strip_first, int32_t strip_step, void* frame_device_ptr, void* cuda_stream);
+
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing);
 
 /* Counters build of the same kernel: fills the test histogram for one frame (slow path,
