@@ -407,9 +407,39 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         res, frames, kind = bounded_reference_run(100, 1, budget_s=15.0)
         ms = statistics.mean(res["ms"])
+        one = run_reference(1, 0, threads=1) if kind == "reference" else None     # also the 1-thread time
         cpu_baseline = {"value": RAYS_PER_FRAME / (ms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": res["threads"],
-                        "kind": kind, "ms_per_frame": ms,
+                        "kind": kind, "ms_per_frame": ms, "ms_per_frame_1_thread": one["ms_median"] if one else None,
                         "sample": f"{frames} full {WIDTH}x{HEIGHT} frames of the reference's Renderer::Render ({res.get('path')})"}
+
+    # ---- the other BASELINE.json configs (640x480), N = 1 only: parity + times, not the headline ---------
+    other = None
+    if world == 1:
+        other = {}
+        for label, fixture, mode_shadows in (("Scene_W1 640x480 no shadows", "w1_640", (3, False)), ("Scene_W3 640x480", "w3_640", (3, True)),
+                                             ("Scene_W4_ReferenceScene 640x480", "w4ref_640", (3, True)), ("Scene_W4_BunnyScene 640x480", "bunny_640", (3, True)),
+                                             ("Scene_W4_OptionalScene 320x240 (3082 triangles)", "optional_320", (3, True))):
+            sc = load_rtsc(os.path.join(ROOT, "tests", "golden", fixture + ".rtsc"))
+            rr = Renderer(sc.width, sc.height, device_ids=[local_rank])
+            if not mode_shadows[1]:
+                rr.ToggleShadows()
+            rr.SetScene(sc)
+            with open(os.path.join(ROOT, "tests", "golden", fixture + ".frame.xz"), "rb") as f:
+                pl = np.frombuffer(lzma.decompress(f.read()), dtype=np.uint8).reshape(3, sc.height, sc.width).astype(np.uint32)
+            want = (pl[0] << 16) | (pl[1] << 8) | pl[2]
+            host = torch.empty((sc.height, sc.width), dtype=torch.int32).pin_memory()
+            for _ in range(5):
+                rr.render_host_ptr(host.data_ptr(), sc.width * 4)
+            k_ms = [rr.render_device()["kernel_ms"] for _ in range(30)]
+            t0 = time.perf_counter()
+            for _ in range(30):
+                rr.render_host_ptr(host.data_ptr(), sc.width * 4)
+            e_ms = (time.perf_counter() - t0) / 30 * 1e3
+            n_rays = rays(rr.count_frame(mesh_path=1))
+            other[label] = {"kernel_ms": float(np.mean(k_ms)), "e2e_ms": e_ms, "rays_per_frame": n_rays,
+                            "Mrays_per_s_kernel": n_rays / (float(np.mean(k_ms)) * 1e-3) / 1e6,
+                            "differing_pixels_vs_reference_frame": int((host.numpy().view(np.uint32) != want).sum())}
+            rr.close()
 
     ms_per_step = total_ms / args.steps
     line = {
@@ -428,6 +458,7 @@ def main():
         "kernel_variant": "scalar (one pixel per thread); rt_render overlaps the present copy with rendering (progressive present)",
         "roofline": roofline,
         "north_star_slab_linear": north_star,
+        "other_configs": other,
         "cpu_baseline": cpu_baseline,
     }
     emit(line)
