@@ -122,10 +122,19 @@ def run_reference(frames: int, warmup: int, threads: int = 0):
     """Times Renderer::Render of the reference binary on the host cores.  Returns the driver's JSON."""
     args = [REF_BIN, "--scene", "W4_Bunny", "--width", str(WIDTH), "--height", str(HEIGHT), "--mode", "3",
             "--shadows", "1", "--frames", str(frames), "--warmup", str(warmup)]
-    if threads:
-        args += ["--threads", str(threads)]
-    out = subprocess.run(args, check=True, capture_output=True, text=True).stdout
+    # all host cores unless told otherwise: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently turn the reference's parallel loop into a serial one
+    args += ["--threads", str(threads or host_cores())]
+    env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
+    out = subprocess.run(args, check=True, capture_output=True, text=True, env=env).stdout
     return json.loads(out.strip().splitlines()[-1])
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 def run_port(frames: int, warmup: int):
@@ -136,10 +145,10 @@ def run_port(frames: int, warmup: int):
     ms = []
     for i in range(warmup + frames):
         t0 = time.perf_counter()
-        rt_oracle.render(scene, WIDTH, HEIGHT)
+        rt_oracle.render(scene, WIDTH, HEIGHT, threads=host_cores())
         if i >= warmup:
             ms.append((time.perf_counter() - t0) * 1e3)
-    return {"ms": ms, "ms_median": statistics.median(ms), "threads": os.cpu_count(),
+    return {"ms": ms, "ms_median": statistics.median(ms), "threads": host_cores(),
             "path": "C restatement, slab + linear triangle loop"}
 
 
