@@ -8,8 +8,10 @@ A step is one frame.  Metric: Mrays/s (primary + shadow rays of the frame / time
   value      device-timed (CUDA events on the launching stream), scene resident in HBM, frame left in
              HBM on rank 0.  N > 1: every rank renders its 8-row strips straight into rank 0's frame
              (CUDA-IPC mapped peer memory, 128-bit stores over NVLink: render and gather are one kernel),
-             followed by a one-element NCCL all-reduce as the barrier.  RT_BENCH_GATHER=nccl selects the
-             unfused form instead (packed bands + NCCL gather + unstripe kernel).
+             and bumps a signal word behind the frame; rank 0's stream waits on that word
+             (cuStreamWaitValue32): no collective on the data path.  RT_BENCH_GATHER=fused-barrier uses a
+             one-element NCCL all-reduce as the barrier instead, RT_BENCH_GATHER=nccl the unfused form
+             (packed bands + NCCL gather + unstripe kernel).
              Headline = the library's default mesh path: the reference's shipped BVH walk over the
              reference's own nodes (source/Utils.h:246-297).  The slab + every-triangle body the north
              star names (source/Utils.h:298-325) is measured the same way and reported under
@@ -243,7 +245,10 @@ def main():
             counters = r.count_frame(mesh_path=pid)
             flop_per_frame[pname] = algorithmic_flops(counters, 3)
             assert rays(counters) == RAYS_PER_FRAME, (rays(counters), RAYS_PER_FRAME)
-    fused = world > 1 and os.environ.get("RT_BENCH_GATHER", "fused") != "nccl"
+    gather_mode = os.environ.get("RT_BENCH_GATHER", "fused")      # fused | fused-barrier | nccl
+    fused = world > 1 and gather_mode != "nccl"
+    signals = fused and gather_mode == "fused"
+    expected = [0]
     spr = bands.strips_per_rank(HEIGHT, world)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory() if rank == 0 else None
@@ -275,7 +280,15 @@ def main():
         """What makes the frame complete in rank 0's HBM."""
         if world == 1:
             return
-        if fused:
+        if fused and signals:
+            # completion over the same peer mapping: the other ranks bump the frame's signal word after their
+            # strips, rank 0's stream waits until all of them have (no collective on the step)
+            if rank == 0:
+                expected[0] += world - 1
+                r.frame_wait(expected[0], stream)
+            else:
+                r.frame_signal(frame_ptr, stream)
+        elif fused:
             dist.all_reduce(token)                 # barrier, stream-ordered after every rank's kernel
         elif rank == 0:
             dist.gather(band, list(gathered.unbind(0)), dst=0)
@@ -457,12 +470,12 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "reference scene fixture tests/golden/bunny_4k.rtsc (dumped from the reference's Scene_W4_BunnyScene::Initialize; deterministic, no RNG)",
         "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "rays_per_frame": RAYS_PER_FRAME,
-                   "triangles": int(mesh.triangle_count), "lights": 3, "partition": f"{bands.STRIP_ROWS}-row strips round-robin over {world} rank(s); " + ("single GPU" if world == 1 else ("peer stores into rank 0's frame over NVLink (fused gather) + NCCL barrier" if fused else "NCCL gather to rank 0 + unstripe")),
+                   "triangles": int(mesh.triangle_count), "lights": 3, "partition": f"{bands.STRIP_ROWS}-row strips round-robin over {world} rank(s); " + ("single GPU" if world == 1 else ("peer stores into rank 0's frame over NVLink (fused gather), completion by peer signal word + stream wait" if signals else ("peer stores into rank 0's frame over NVLink (fused gather) + NCCL barrier" if fused else "NCCL gather to rank 0 + unstripe"))),
                    "l2": f"{L2_FLUSH_BYTES >> 20} MiB memset between timed steps (outside the event pairs)"},
         "clocks": sampler.summary(),
         "e2e": e2e,
         "frame_check": frame_check,
-        "gpu_launches": args.steps * (world + (1 if (world > 1 and not fused) else 0)),
+        "gpu_launches": args.steps * (world + ((world - 1) if signals else (0 if fused or world == 1 else 1))),
         "mesh_path": "bvh (reference's shipped IntersectionTest_BVH over the reference's own nodes)",
         "kernel_variant": "scalar (one pixel per thread); rt_render overlaps the present copy with rendering (progressive present)",
         "roofline": roofline,

@@ -186,12 +186,17 @@ namespace
 		return p;
 	}
 
+	// Byte offset of the signal word behind a frame of `pixels` pixels (same formula on every rank).
+	inline size_t signal_offset(size_t pixels) { return (pixels * sizeof(uint32_t) + 255) & ~size_t(255); }
+
 	int ensure_frame(rt_context* ctx, DeviceState& d, size_t pixels)
 	{
 		if (d.frame_capacity >= pixels) return RT_OK;
 		RT_CUDA(ctx, cudaSetDevice(d.device));
 		if (d.d_frame) { RT_CUDA(ctx, cudaStreamSynchronize(d.stream)); RT_CUDA(ctx, cudaFree(d.d_frame)); d.d_frame = nullptr; }
-		RT_CUDA(ctx, cudaMalloc(&d.d_frame, pixels * sizeof(uint32_t)));
+		// + one 256-byte trailer: the completion signal word of rt_frame_signal / rt_frame_wait
+		RT_CUDA(ctx, cudaMalloc(&d.d_frame, signal_offset(pixels) + 256));
+		RT_CUDA(ctx, cudaMemset(d.d_frame, 0, signal_offset(pixels) + 256));
 		d.frame_capacity = pixels;
 		return RT_OK;
 	}
@@ -1010,6 +1015,7 @@ int rt_frame_export(rt_context* ctx, int32_t width, int32_t height, void* out_ha
 	int rc = ensure_frame(ctx, d, (size_t)width * (size_t)height);
 	if (rc != RT_OK) return rc;
 	RT_CUDA(ctx, cudaSetDevice(d.device));
+	RT_CUDA(ctx, cudaMemset((char*)d.d_frame + signal_offset((size_t)width * (size_t)height), 0, 4));
 	cudaIpcMemHandle_t h;
 	RT_CUDA(ctx, cudaIpcGetMemHandle(&h, d.d_frame));
 	memset(out_handle, 0, RT_IPC_HANDLE_BYTES);
@@ -1062,6 +1068,35 @@ int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt
 	rc = launch(ctx, d, p, stream, (total_strips - strip_first + strip_step - 1) / strip_step);
 	if (rc != RT_OK) return rc;
 	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
+	return RT_OK;
+}
+
+int rt_frame_signal(rt_context* ctx, void* frame_device_ptr, int32_t width, int32_t height, void* cuda_stream)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!frame_device_ptr || width <= 0 || height <= 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad frame signal arguments");
+	DeviceState& d = ctx->devs[0];
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+	unsigned int* word = reinterpret_cast<unsigned int*>((char*)frame_device_ptr + signal_offset((size_t)width * (size_t)height));
+	rt::frame_signal_kernel<<<1, 1, 0, stream>>>(word);
+	RT_CUDA(ctx, cudaGetLastError());
+	ctx->timing.kernel_launches++;
+	return RT_OK;
+}
+
+int rt_frame_wait(rt_context* ctx, uint32_t expected, void* cuda_stream)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	DeviceState& d = ctx->devs[0];
+	if (!d.d_frame || ctx->last_width <= 0) return fail(ctx, RT_ERR_BAD_STATE, "rt_frame_wait needs an exported frame");
+	const WaitValue32Fn wait = wait_value32();
+	if (!wait) return fail(ctx, RT_ERR_BAD_STATE, "stream memory operations (cuStreamWaitValue32) are not available");
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+	char* word = (char*)d.d_frame + signal_offset((size_t)ctx->last_width * (size_t)ctx->last_height);
+	const CUresult cr = wait((CUstream)stream, (CUdeviceptr)(uintptr_t)word, (cuuint32_t)expected, CU_STREAM_WAIT_VALUE_GEQ);
+	if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
 	return RT_OK;
 }
 

@@ -832,4 +832,12 @@ namespace rt
 		for (int i = 0; i < 8; ++i) s += acc[i];
 		if (s == 123.456f) out[0] = s;   // never true in practice; keeps the chain alive
 	}
+
+	// One rank's "my strips are in the root's frame" signal: a system-scope fenced increment of the word
+	// behind the frame's pixels (peer memory).  Stream order puts it after the pixel kernel.
+	__global__ void frame_signal_kernel(unsigned int* word)
+	{
+		__threadfence_system();
+		atomicAdd_system(word, 1u);
+	}
 }

@@ -196,6 +196,12 @@ class Renderer:
         self.ctx.check(self.ctx.lib.rt_render_strips_to_frame(self.ctx.handle, C.byref(cam), C.byref(frame), strip_first,
                                                               strip_step, frame_ptr or None, stream), "rt_render_strips_to_frame")
 
+    def frame_signal(self, frame_ptr: int, stream: int = 0) -> None:
+        self.ctx.check(self.ctx.lib.rt_frame_signal(self.ctx.handle, frame_ptr, self.width, self.height, stream), "rt_frame_signal")
+
+    def frame_wait(self, expected: int, stream: int = 0) -> None:
+        self.ctx.check(self.ctx.lib.rt_frame_wait(self.ctx.handle, expected & 0xFFFFFFFF, stream), "rt_frame_wait")
+
     def download_to(self, host_ptr: int, pitch_bytes: int) -> None:
         self.ctx.check(self.ctx.lib.rt_download_frame(self.ctx.handle, host_ptr, pitch_bytes), "rt_download_frame")
 

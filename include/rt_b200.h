@@ -351,6 +351,13 @@ int rt_frame_import(rt_context* ctx, const void* handle, void** out_device_ptr);
 int rt_frame_release(rt_context* ctx, void* device_ptr);
 int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
                               int32_t strip_first, int32_t strip_step, void* frame_device_ptr, void* cuda_stream);
+/* Completion signalling over the same peer mapping (instead of a collective): the frame allocation carries
+ * a signal word behind its width * height pixels.  A non-root rank bumps it after its strips
+ * (rt_frame_signal, stream-ordered after rt_render_strips_to_frame); the root makes its stream wait until
+ * the word has reached `expected` (rt_frame_wait, cuStreamWaitValue32; the word only ever grows, so
+ * expected = frames so far x (world - 1)).  RT_ERR_BAD_STATE if stream memory operations are unavailable. */
+int rt_frame_signal(rt_context* ctx, void* frame_device_ptr, int32_t width, int32_t height, void* cuda_stream);
+int rt_frame_wait(rt_context* ctx, uint32_t expected, void* cuda_stream);
 
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing);
 
