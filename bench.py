@@ -230,7 +230,12 @@ def main():
     mesh = scene.meshes[0]
     r = Renderer(WIDTH, HEIGHT, device_ids=[local_rank])
     r.SetScene(scene)
-    stream = torch.cuda.current_stream().cuda_stream
+    # A real (non-default) stream: the C ABI treats a NULL stream as "use the context's own stream and block",
+    # and the timing events must sit on the stream the kernels are launched on.
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def barrier():
         if world > 1:
@@ -249,6 +254,8 @@ def main():
     fused = world > 1 and gather_mode != "nccl"
     signals = fused and gather_mode == "fused"
     expected = [0]
+    present_no = [0]
+    PRESENT_BANDS = 16
     spr = bands.strips_per_rank(HEIGHT, world)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory() if rank == 0 else None
@@ -306,6 +313,15 @@ def main():
         r.ctx.upload_mesh(0, mesh)                                  # H2D: what UpdateTransforms produced this frame
         if world == 1:
             r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + progressive D2H, blocking
+            return
+        if signals:
+            # every rank's CTAs bump per-band counters in rank 0's frame; rank 0 presents band after band
+            present_no[0] += 1
+            r.render_strips_to_frame_banded(rank, world, frame_ptr, PRESENT_BANDS, stream)
+            if rank == 0:
+                r.frame_present(host_frame.data_ptr(), WIDTH * 4, PRESENT_BANDS, present_no[0])
+            dist.all_reduce(token)            # nobody starts the next frame before the root has presented this one
+            torch.cuda.synchronize()
             return
         device_step()
         torch.cuda.synchronize()

@@ -569,7 +569,8 @@ namespace
 		ctx->timing = rt_timing{};
 		ctx->last_width = W; ctx->last_height = H;
 
-		const WaitValue32Fn wait = wait_value32();
+		const int n_dev = (int)ctx->devs.size();
+		const WaitValue32Fn wait = (n_dev == 1 || ctx->peer_stores) ? wait_value32() : nullptr;
 		static const int requested = [] { const char* e = getenv("RT_B200_PIPELINE_BANDS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 64) ? v : 0; }();
 		const int total_strips = (H + rt::kBlockH - 1) / rt::kBlockH;
 		const int grid_x = (W + rt::kBlockW - 1) / rt::kBlockW;
@@ -597,12 +598,23 @@ namespace
 			RT_CUDA(ctx, cudaMemsetAsync(d.d_band_done, 0, sizeof(unsigned int) * 64, d.stream));
 			RT_CUDA(ctx, cudaEventRecord(d.ev_band[0], d.stream));
 			RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_band[0], 0));      // counters are zero before anyone polls them
-			RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
-			rt::FrameParams p = base;
-			p.row_begin = 0; p.row_end = H; p.strip_first = 0; p.strip_step = 1; p.dst_full_frame = 1; p.dst = d.d_frame;
-			p.band_done = d.d_band_done; p.strips_per_band = strips_per_band;
-			if ((rc = launch(ctx, d, p, d.stream, total_strips)) != RT_OK) return rc;
-			RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+			// every device renders its strips (dealt round-robin) straight into device 0's frame and bumps
+			// device 0's band counters; with one device this is the plain single-launch case
+			for (int k = 0; k < n_dev; ++k)
+			{
+				DeviceState& dk = ctx->devs[k];
+				RT_CUDA(ctx, cudaSetDevice(dk.device));
+				if (k > 0) RT_CUDA(ctx, cudaStreamWaitEvent(dk.stream, d.ev_band[0], 0));   // ... nor bumps them
+				RT_CUDA(ctx, cudaEventRecord(dk.ev_begin, dk.stream));
+				rt::FrameParams p = base;
+				p.row_begin = 0; p.row_end = H; p.strip_first = k; p.strip_step = n_dev; p.dst_full_frame = 1; p.dst = d.d_frame;
+				p.band_done = d.d_band_done; p.strips_per_band = strips_per_band;
+				p.band_local = n_dev > 1 ? dk.d_band_done + 64 : nullptr;      // second half of each device's own array
+				if ((rc = launch(ctx, dk, p, dk.stream, (total_strips - k + n_dev - 1) / n_dev)) != RT_OK) return rc;
+				RT_CUDA(ctx, cudaEventRecord(dk.ev_kernel, dk.stream));
+			}
+			RT_CUDA(ctx, cudaSetDevice(d.device));
+			for (int k = 1; k < n_dev; ++k) RT_CUDA(ctx, cudaStreamWaitEvent(d.stream, ctx->devs[k].ev_kernel, 0));
 			for (int b = 0; b < bands; ++b)
 			{
 				const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
@@ -704,7 +716,8 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		RT_CREATE(cudaEventCreate(&d.ev_done));
 		RT_CREATE(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
 		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 64));
+		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 128));
+		RT_CREATE(cudaMemset(d.d_band_done, 0, sizeof(unsigned int) * 128));
 		ctx->devs.push_back(d);
 	}
 	RT_CREATE(cudaSetDevice(ids[0]));
@@ -928,7 +941,7 @@ int rt_render(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* fra
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
 	if (!host_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "host_dst must not be NULL");
-	if (ctx->devs.size() == 1) return render_pipelined(ctx, camera, frame, host_dst, pitch_bytes);
+	if (ctx->devs.size() == 1 || (ctx->peer_stores && wait_value32())) return render_pipelined(ctx, camera, frame, host_dst, pitch_bytes);
 	int rc = render_to_device0(ctx, camera, frame);
 	if (rc != RT_OK) return rc;
 	if ((rc = download(ctx, host_dst, pitch_bytes, true)) != RT_OK) return rc;
@@ -1015,7 +1028,7 @@ int rt_frame_export(rt_context* ctx, int32_t width, int32_t height, void* out_ha
 	int rc = ensure_frame(ctx, d, (size_t)width * (size_t)height);
 	if (rc != RT_OK) return rc;
 	RT_CUDA(ctx, cudaSetDevice(d.device));
-	RT_CUDA(ctx, cudaMemset((char*)d.d_frame + signal_offset((size_t)width * (size_t)height), 0, 4));
+	RT_CUDA(ctx, cudaMemset((char*)d.d_frame + signal_offset((size_t)width * (size_t)height), 0, 256));
 	cudaIpcMemHandle_t h;
 	RT_CUDA(ctx, cudaIpcGetMemHandle(&h, d.d_frame));
 	memset(out_handle, 0, RT_IPC_HANDLE_BYTES);
@@ -1068,6 +1081,83 @@ int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt
 	rc = launch(ctx, d, p, stream, (total_strips - strip_first + strip_step - 1) / strip_step);
 	if (rc != RT_OK) return rc;
 	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
+	return RT_OK;
+}
+
+int rt_render_strips_to_frame_banded(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                                     int32_t strip_first, int32_t strip_step, void* frame_device_ptr,
+                                     int32_t bands, void* cuda_stream)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	int rc = validate_frame(ctx, camera, frame);
+	if (rc != RT_OK) return rc;
+	if (strip_step <= 0 || strip_first < 0 || strip_first >= strip_step) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "strip_first %d / strip_step %d is not a rank / world pair", strip_first, strip_step);
+	if (bands < 1 || bands > RT_MAX_PRESENT_BANDS) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bands %d outside [1, %d]", bands, RT_MAX_PRESENT_BANDS);
+	DeviceState& d = ctx->devs[0];
+	const size_t pixels = (size_t)frame->width * (size_t)frame->height;
+	if (!frame_device_ptr)
+	{
+		if ((rc = ensure_frame(ctx, d, pixels)) != RT_OK) return rc;
+		frame_device_ptr = d.d_frame;
+		ctx->last_width = frame->width; ctx->last_height = frame->height;
+	}
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	cudaStream_t stream = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+	const int total_strips = (frame->height + rt::kBlockH - 1) / rt::kBlockH;
+	rt::FrameParams p = make_params(camera, frame);
+	p.row_begin = 0; p.row_end = frame->height;
+	p.strip_first = strip_first; p.strip_step = strip_step; p.dst_full_frame = 1; p.dst = (uint32_t*)frame_device_ptr;
+	// trailer word 0 is the whole-frame signal (rt_frame_signal), words 1.. are the band counters
+	p.band_done = reinterpret_cast<unsigned int*>((char*)frame_device_ptr + signal_offset(pixels)) + 1;
+	p.strips_per_band = (total_strips + bands - 1) / bands;
+	p.band_local = d.d_band_done + 64;
+	ctx->timing = rt_timing{};
+	rc = launch(ctx, d, p, stream, (total_strips - strip_first + strip_step - 1) / strip_step);
+	if (rc != RT_OK) return rc;
+	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
+	return RT_OK;
+}
+
+int rt_frame_present(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes, int32_t bands, uint32_t frame_number)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	DeviceState& d = ctx->devs[0];
+	const int W = ctx->last_width, H = ctx->last_height;
+	if (!d.d_frame || W <= 0 || H <= 0) return fail(ctx, RT_ERR_BAD_STATE, "rt_frame_present needs an exported frame");
+	if (!host_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "host_dst must not be NULL");
+	if (pitch_bytes < 4 * W || (pitch_bytes & 3)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "pitch_bytes %d too small or unaligned for width %d", pitch_bytes, W);
+	if (bands < 1 || bands > RT_MAX_PRESENT_BANDS) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bands %d outside [1, %d]", bands, RT_MAX_PRESENT_BANDS);
+	const WaitValue32Fn wait = wait_value32();
+	if (!wait) return fail(ctx, RT_ERR_BAD_STATE, "stream memory operations (cuStreamWaitValue32) are not available");
+	const size_t span = (size_t)pitch_bytes * (size_t)(H - 1) + (size_t)W * 4u;
+	void* target = nullptr;
+	int rc = prepare_host(ctx, host_dst, span, &target);
+	if (rc != RT_OK) return rc;
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	const int total_strips = (H + rt::kBlockH - 1) / rt::kBlockH, grid_x = (W + rt::kBlockW - 1) / rt::kBlockW;
+	const int strips_per_band = (total_strips + bands - 1) / bands;
+	unsigned int* counters = reinterpret_cast<unsigned int*>((char*)d.d_frame + signal_offset((size_t)W * (size_t)H)) + 1;
+	for (int b = 0; b < bands; ++b)
+	{
+		const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
+		if (s1 <= s0) break;
+		const cuuint32_t expected = (cuuint32_t)((uint64_t)frame_number * (uint64_t)((s1 - s0) * grid_x));
+		const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(counters + b), expected, CU_STREAM_WAIT_VALUE_GEQ);
+		if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
+		const int r0 = s0 * rt::kBlockH, r1 = std::min(H, s1 * rt::kBlockH);
+		char* dst = (char*)target + (size_t)r0 * (size_t)pitch_bytes;
+		const uint32_t* src = d.d_frame + (size_t)r0 * (size_t)W;
+		if (pitch_bytes == 4 * W)
+			RT_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)(r1 - r0) * W * 4u, cudaMemcpyDeviceToHost, d.copy_stream));
+		else
+			RT_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)pitch_bytes, src, (size_t)W * 4u, (size_t)W * 4u, (size_t)(r1 - r0), cudaMemcpyDeviceToHost, d.copy_stream));
+	}
+	RT_CUDA(ctx, cudaStreamSynchronize(d.copy_stream));
+	if (target != host_dst)
+	{
+		if (pitch_bytes == 4 * W) memcpy(host_dst, target, (size_t)W * H * 4u);
+		else for (int y = 0; y < H; ++y) memcpy((char*)host_dst + (size_t)y * pitch_bytes, (char*)target + (size_t)y * pitch_bytes, (size_t)W * 4u);
+	}
 	return RT_OK;
 }
 

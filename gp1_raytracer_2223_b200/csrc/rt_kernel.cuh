@@ -73,7 +73,8 @@ namespace rt
 		uint32_t* dst;
 		unsigned long long* counters;    // counters build only
 		unsigned int* band_done;         // progressive present: band_done[b] counts the finished CTAs of band b (NULL = off)
-		int32_t strips_per_band;
+		int32_t strips_per_band;         // a band = this many consecutive 8-row strips of the frame
+		unsigned int* band_local;        // multi-GPU: this GPU's own per-band CTA counters (see signal_band_done)
 	};
 
 	struct Ray
@@ -738,6 +739,40 @@ namespace rt
 		}
 	}
 
+	// Progressive present: tell the copy stream (cuStreamWaitValue32 on band_done[b]) that this CTA's pixels
+	// are in memory.  CTA barrier first, then one thread signals.
+	//  * One GPU (band_local == NULL): a release-ordered reduction on band_done[b] per CTA.  A release
+	//    (MEMBAR.ALL.GPU) is enough; __threadfence() would also invalidate the SM's L1 (CCTL.IVALL) and evict
+	//    the BVH nodes and triangles the other resident CTAs are streaming.
+	//  * Several GPUs: band_done lives on GPU 0 (peer memory) and a system-scope release per CTA is far too
+	//    expensive.  CTAs count on their own GPU (band_local[b], gpu scope); the CTA that completes this GPU's
+	//    share of a band forwards the whole share with ONE system-scope release and re-arms the local counter.
+	__device__ __forceinline__ void signal_band_done(const FrameParams& p)
+	{
+		__syncthreads();
+		if (threadIdx.x != 0) return;
+		const int strip = (int)blockIdx.y * p.strip_step + p.strip_first;      // position in the frame, whoever renders it
+		const int band = strip / p.strips_per_band;
+		if (!p.band_local)
+		{
+			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p.band_done + band) : "memory");
+			return;
+		}
+		// strips of this band that belong to this GPU: those congruent to strip_first modulo strip_step
+		const int total_strips = (p.row_end - p.row_begin + kBlockH - 1) / kBlockH;
+		const int s0 = band * p.strips_per_band, s1 = min(total_strips, s0 + p.strips_per_band);
+		const int first_mine = s0 + ((p.strip_first - s0) % p.strip_step + p.strip_step) % p.strip_step;
+		const int mine = first_mine < s1 ? (s1 - 1 - first_mine) / p.strip_step + 1 : 0;
+		const unsigned int share = (unsigned int)mine * gridDim.x;
+		unsigned int old;
+		asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.band_local + band) : "memory");
+		if (old + 1u == share)
+		{
+			p.band_local[band] = 0u;
+			asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(share) : "memory");
+		}
+	}
+
 	template <int MODE, int SHADOWS, bool BVH, bool COUNT>
 	__global__ void __launch_bounds__(kThreads)
 	render_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
@@ -774,19 +809,7 @@ namespace rt
 			row[px] = pixel;
 		}
 
-		if (p.band_done)
-		{
-			// Tell the copy stream (cuStreamWaitValue32 on band_done[b]) that this CTA's pixels are in
-			// memory: CTA barrier, then one release-ordered reduction per CTA.  A release (MEMBAR.ALL.GPU)
-			// is enough here; __threadfence() would also invalidate the SM's L1 (CCTL.IVALL) and evict the
-			// BVH nodes and triangles the other resident CTAs are streaming.
-			__syncthreads();
-			if (threadIdx.x == 0)
-			{
-				unsigned int* counter = p.band_done + blockIdx.y / p.strips_per_band;
-				asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
-			}
-		}
+		if (p.band_done) signal_band_done(p);
 	}
 
 	// Root-rank tail of the band gather: band r holds strips r, r + world, ... packed; write the

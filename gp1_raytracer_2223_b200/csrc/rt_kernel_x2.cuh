@@ -572,15 +572,7 @@ namespace x2
 			if (valid1) row[px + 1] = pixel1;
 		}
 
-		if (p.band_done)
-		{
-			__syncthreads();
-			if (threadIdx.x == 0)
-			{
-				unsigned int* counter = p.band_done + blockIdx.y / p.strips_per_band;
-				asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
-			}
-		}
+		if (p.band_done) signal_band_done(p);
 	}
 }
 }

@@ -202,6 +202,15 @@ class Renderer:
     def frame_wait(self, expected: int, stream: int = 0) -> None:
         self.ctx.check(self.ctx.lib.rt_frame_wait(self.ctx.handle, expected & 0xFFFFFFFF, stream), "rt_frame_wait")
 
+    def render_strips_to_frame_banded(self, strip_first: int, strip_step: int, frame_ptr: int, bands: int, stream: int = 0, camera=None):
+        cam = camera_struct(camera if camera is not None else self.scene.camera)
+        frame = self._frame()
+        self.ctx.check(self.ctx.lib.rt_render_strips_to_frame_banded(self.ctx.handle, C.byref(cam), C.byref(frame), strip_first, strip_step,
+                                                                     frame_ptr or None, bands, stream), "rt_render_strips_to_frame_banded")
+
+    def frame_present(self, host_ptr: int, pitch_bytes: int, bands: int, frame_number: int) -> None:
+        self.ctx.check(self.ctx.lib.rt_frame_present(self.ctx.handle, host_ptr, pitch_bytes, bands, frame_number & 0xFFFFFFFF), "rt_frame_present")
+
     def download_to(self, host_ptr: int, pitch_bytes: int) -> None:
         self.ctx.check(self.ctx.lib.rt_download_frame(self.ctx.handle, host_ptr, pitch_bytes), "rt_download_frame")
 

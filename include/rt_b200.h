@@ -358,6 +358,17 @@ int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt
  * expected = frames so far x (world - 1)).  RT_ERR_BAD_STATE if stream memory operations are unavailable. */
 int rt_frame_signal(rt_context* ctx, void* frame_device_ptr, int32_t width, int32_t height, void* cuda_stream);
 int rt_frame_wait(rt_context* ctx, uint32_t expected, void* cuda_stream);
+/* Progressive present across ranks: with bands > 0 every CTA of rt_render_strips_to_frame_banded also bumps
+ * the counter of the band (group of consecutive strips of the FRAME) it belongs to, in the root's trailer.
+ * The root's rt_frame_present copies band after band to the host surface as soon as ALL ranks' CTAs of that
+ * band are done (cuStreamWaitValue32 on a copy stream) and returns when the surface is complete.  Counters
+ * only grow: frame_number counts the banded frames rendered into this frame buffer so far, starting at 1,
+ * and must be the same on every rank's call. */
+#define RT_MAX_PRESENT_BANDS 32
+int rt_render_strips_to_frame_banded(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                                     int32_t strip_first, int32_t strip_step, void* frame_device_ptr,
+                                     int32_t bands, void* cuda_stream);
+int rt_frame_present(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes, int32_t bands, uint32_t frame_number);
 
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing);
 
