@@ -130,7 +130,7 @@ namespace rt
 	{
 		Ray r;
 		r.o = o; r.d = d;
-		r.inv = v3(quo(1.f, d.x), quo(1.f, d.y), quo(1.f, d.z));   // DataTypes.h:550-563
+		r.inv = v3(rcp(d.x), rcp(d.y), rcp(d.z));   // DataTypes.h:550-563
 		r.tmin = tmin; r.tmax = tmax;
 		r.nan_safe = (fabsf(r.inv.x) < INFINITY) && (fabsf(r.inv.y) < INFINITY) && (fabsf(r.inv.z) < INFINITY);
 		return r;
@@ -263,7 +263,7 @@ namespace rt
 		const float a = dot(e1, h);
 		if (fabsf(a) < FLT_EPSILON) { cnt.hit(base + 1); return false; }
 
-		const float f = quo(1.f, a);
+		const float f = rcp(a);
 		const float u = mul(f, dot(s, h));
 		if (u < 0.f || u > 1.f) { cnt.hit(base + 2); return false; }
 
