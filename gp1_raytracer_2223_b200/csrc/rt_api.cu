@@ -89,6 +89,7 @@ struct rt_context
 	size_t h_mesh_capacity = 0;         // in float4
 	int32_t n_spheres = 0, n_planes = 0, n_lights = 0, n_materials = 0;
 	std::vector<HostMesh> meshes;
+	bool static_dirty = true, mesh_dirty = true;   // mirrors changed since the last push (pushed lazily, once per frame)
 
 	cudaEvent_t ev_gather = nullptr, ev_d2h = nullptr;   // on device 0
 	rt_timing timing{};
@@ -158,6 +159,8 @@ namespace
 		return (all_have_nodes && !ctx->meshes.empty()) ? RT_MESH_PATH_BVH : RT_MESH_PATH_SLAB_LINEAR;
 	}
 
+	int flush_uploads(rt_context* ctx);
+
 	int validate_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame)
 	{
 		if (!camera || !frame) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "camera and frame must not be NULL");
@@ -169,7 +172,7 @@ namespace
 			return fail(ctx, RT_ERR_INVALID_ARGUMENT, "pixel format shifts out of range");
 		for (const HostMesh& m : ctx->meshes)
 			if (!m.uploaded) return fail(ctx, RT_ERR_BAD_STATE, "rt_set_mesh_count announced a mesh that was never uploaded");
-		return RT_OK;
+		return flush_uploads(ctx);
 	}
 
 	rt::FrameParams make_params(const rt_camera* c, const rt_frame_desc* f)
@@ -297,6 +300,16 @@ namespace
 			RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
 			refresh_view(ctx, d);
 		}
+		return RT_OK;
+	}
+
+	// Scene uploads only touch the pinned mirrors; the device copies happen here, once, right before the
+	// next launch (one copy per dirty block and device instead of one per rt_upload_* call).
+	int flush_uploads(rt_context* ctx)
+	{
+		int rc = RT_OK;
+		if (ctx->static_dirty) { if ((rc = push_static(ctx)) != RT_OK) return rc; ctx->static_dirty = false; }
+		if (ctx->mesh_dirty) { if ((rc = push_meshes(ctx)) != RT_OK) return rc; ctx->mesh_dirty = false; }
 		return RT_OK;
 	}
 
@@ -743,8 +756,7 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ctx->peer_stores = false;
 		cudaGetLastError();
 	}
-	int rc = push_static(ctx);
-	if (rc == RT_OK) rc = push_meshes(ctx);
+	const int rc = flush_uploads(ctx);
 	if (rc != RT_OK) return bail(rc);
 	cudaSetDevice(previous);
 	*out_ctx = ctx;
@@ -795,7 +807,8 @@ int rt_upload_spheres(rt_context* ctx, const rt_spheres_soa* s)
 		ctx->bytes[i] = s->material_index[i];
 	}
 	ctx->n_spheres = s->count;
-	return push_static(ctx);
+	ctx->static_dirty = true;
+	return RT_OK;
 }
 
 int rt_upload_planes(rt_context* ctx, const rt_planes_soa* p)
@@ -815,7 +828,8 @@ int rt_upload_planes(rt_context* ctx, const rt_planes_soa* p)
 		ctx->bytes[rt::kMaxSpheres + i] = p->material_index[i];
 	}
 	ctx->n_planes = p->count;
-	return push_static(ctx);
+	ctx->static_dirty = true;
+	return RT_OK;
 }
 
 int rt_upload_lights(rt_context* ctx, const rt_lights_soa* l)
@@ -836,7 +850,8 @@ int rt_upload_lights(rt_context* ctx, const rt_lights_soa* l)
 		ctx->light_type[i] = l->type[i];
 	}
 	ctx->n_lights = l->count;
-	return push_static(ctx);
+	ctx->static_dirty = true;
+	return RT_OK;
 }
 
 int rt_upload_materials(rt_context* ctx, const rt_material_desc* materials, int32_t count)
@@ -854,7 +869,8 @@ int rt_upload_materials(rt_context* ctx, const rt_material_desc* materials, int3
 		ctx->materials[2 * i + 1] = make_float4(m.p0, m.p1, m.p2, 0.f);
 	}
 	ctx->n_materials = count;
-	return push_static(ctx);
+	ctx->static_dirty = true;
+	return RT_OK;
 }
 
 int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count)
@@ -863,7 +879,7 @@ int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count)
 	if (mesh_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "negative mesh count");
 	if (mesh_count > rt::kMaxMeshes) return fail(ctx, RT_ERR_CAPACITY, "%d meshes exceed the capacity of %d", mesh_count, rt::kMaxMeshes);
 	ctx->meshes.resize((size_t)mesh_count);
-	if (mesh_count == 0) return push_meshes(ctx);
+	ctx->mesh_dirty = true;
 	return RT_OK;
 }
 
@@ -923,8 +939,8 @@ int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
 	const int brc = thread_bvh(ctx, mesh, hm.nodes);
 	if (brc != RT_OK) { hm.uploaded = false; return brc; }
 	hm.uploaded = true;
-	for (const HostMesh& m : ctx->meshes) if (!m.uploaded) return RT_OK;   // push once every announced mesh is there
-	return push_meshes(ctx);
+	ctx->mesh_dirty = true;
+	return RT_OK;
 }
 
 int rt_render_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame)
