@@ -426,6 +426,7 @@ namespace rt
 		best.origin = v3(0.f, 0.f, 0.f); best.normal = v3(0.f, 0.f, 0.f);
 
 		int best_sphere = -1;
+#pragma unroll 1
 		for (int i = 0; i < dev.n_spheres; ++i)
 		{
 			float t;
@@ -444,6 +445,7 @@ namespace rt
 			normalize(best.normal);                        // Scene.cpp:40
 		}
 
+#pragma unroll 1
 		for (int i = 0; i < dev.n_planes; ++i)
 		{
 			float t;
@@ -461,6 +463,7 @@ namespace rt
 			}
 		}
 
+#pragma unroll 1
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
 			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
@@ -502,10 +505,13 @@ namespace rt
 	{
 		const Pk K = make_pk(dev);
 		float t;
+#pragma unroll 1
 		for (int i = 0; i < dev.n_spheres; ++i)
 			if (hit_sphere<true>(sc.sphere[i], ray, t, cnt)) return true;
+#pragma unroll 1
 		for (int i = 0; i < dev.n_planes; ++i)
 			if (hit_plane<true>(sc.plane_o[i], sc.plane_n[i], ray, t, cnt)) return true;
+#pragma unroll 1
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
 			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
@@ -642,6 +648,7 @@ namespace rt
 			cnt.hit(RT_CNT_HIT_PIXELS);
 			const V3 origin_offset = hit.origin + hit.normal * 0.0001f;   // Renderer.cpp:126
 			const V3 view_neg = neg(d);
+#pragma unroll 1
 			for (int li = 0; li < dev.n_lights; ++li)
 			{
 				cnt.hit(RT_CNT_LIGHT_ITERATIONS);
