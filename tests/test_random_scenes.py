@@ -47,3 +47,41 @@ def test_random_scene_matches_oracle(seed, mode, shadows):
             assert n_diff == 0, (seed, gpu_path, n_diff, max_err)
         assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (seed, gpu_path, n_diff, max_err)
     r.close()
+
+
+@pytest.mark.gpu
+def test_capacity_limits_match_oracle():
+    """Largest scene the ABI takes: 64 spheres, 64 planes, 16 lights, 32 meshes (and one past each is an error)."""
+    import ctypes as C
+    from gp1_raytracer_2223_b200 import Renderer
+    from gp1_raytracer_2223_b200._abi import SceneViews
+    from oracle import rt_oracle
+    scene = random_scene(7, n_spheres=64, n_planes=64, n_meshes=32, n_triangles=6, n_lights=5, pow_materials=False)
+    # 16 lights: repeat the 5 generated ones with shifted positions
+    reps = 16
+    scene.light_origin = np.ascontiguousarray(np.tile(scene.light_origin, (1, 4))[:, :reps] + np.arange(reps, dtype=np.float32) * 0.25)
+    scene.light_direction = np.zeros((3, reps), np.float32)
+    scene.light_color = np.ascontiguousarray(np.tile(scene.light_color, (1, 4))[:, :reps] * 0.3)
+    scene.light_intensity = np.ascontiguousarray(np.tile(scene.light_intensity, 4)[:reps])
+    scene.light_type = np.ascontiguousarray(np.tile(scene.light_type, 4)[:reps])
+    W, H = 160, 96
+    r = Renderer(W, H)
+    r.SetScene(scene)
+    for gpu_path, oracle_path in ((1, rt_oracle.MESH_SLAB_LINEAR), (2, rt_oracle.MESH_BVH)):
+        r.ctx.set_mesh_path(gpu_path)
+        want = rt_oracle.render(scene, W, H, mesh_path=oracle_path)
+        for variant in (1, 2):
+            r.ctx.set_kernel_variant(variant)
+            assert np.array_equal(r.Render(), want), (gpu_path, variant)
+    # one past each capacity
+    v = SceneViews(scene)
+    lib, h = r.ctx.lib, r.ctx.handle
+    v.spheres.count = 65
+    assert lib.rt_upload_spheres(h, C.byref(v.spheres)) == 5
+    v.planes.count = 65
+    assert lib.rt_upload_planes(h, C.byref(v.planes)) == 5
+    v.lights.count = 17
+    assert lib.rt_upload_lights(h, C.byref(v.lights)) == 5
+    assert lib.rt_upload_materials(h, v.materials, 257) == 5
+    assert lib.rt_set_mesh_count(h, 33) == 5
+    r.close()
