@@ -264,11 +264,31 @@ def main():
     token = torch.zeros(1, dtype=torch.int32, device="cuda")
     if world == 1:
         frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
-    elif fused:
-        handle = [r.frame_export() if rank == 0 else None]       # rank 0 owns the frame, the others map it
+    if world > 1 and fused:
+        # rank 0 owns the frame, the others map it (CUDA IPC).  If any rank cannot (no peer access between
+        # the GPUs, IPC disabled in the container), every rank falls back to the NCCL gather together.
+        ok = torch.ones(1, dtype=torch.int32, device="cuda")
+        try:
+            handle = [r.frame_export() if rank == 0 else None]
+        except Exception as exc:                                   # noqa: BLE001
+            print(f"rank {rank}: frame export failed: {exc}", file=sys.stderr)
+            handle, ok[0] = [None], 0
         dist.broadcast_object_list(handle, src=0)
-        frame_ptr = 0 if rank == 0 else r.frame_import(handle[0])
-    else:
+        if rank != 0 and handle[0] is not None:
+            try:
+                frame_ptr = r.frame_import(handle[0])
+            except Exception as exc:                               # noqa: BLE001
+                print(f"rank {rank}: frame import failed: {exc}", file=sys.stderr)
+                ok[0] = 0
+        elif rank != 0:
+            ok[0] = 0
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok) == 0:
+            if frame_ptr:
+                r.frame_release(frame_ptr)
+                frame_ptr = 0
+            fused = signals = False
+    if world > 1 and not fused:
         band = torch.empty((spr * bands.STRIP_ROWS, WIDTH), dtype=torch.int32, device="cuda")
         if rank == 0:
             frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")

@@ -326,7 +326,9 @@ namespace
 		const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)n_strips, 1);
 		if (grid.y > 65535u) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame too tall for one launch");
 		if (stream != d.stream) RT_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_upload, 0));   // scene copies ride d.stream
+#ifndef RT_EXPERIMENT_BLOCK
 		static_assert(rt::x2::kBlockW == rt::kBlockW, "both kernels must cut the frame into the same CTA grid");
+#endif
 		const bool packed = ctx->kernel_variant == RT_KERNEL_PACKED;   // AUTO = scalar: the faster build today
 		if (packed) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::x2::kThreads, 0, stream>>>(d.view, p);
 		else pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
