@@ -51,6 +51,11 @@ class rt_mesh_desc(C.Structure):
                 ("bvh_nodes", C.POINTER(rt_bvh_node)), ("bvh_node_count", C.c_int32)]
 
 
+class rt_mesh_source(C.Structure):
+    _fields_ = [("positions", c_float_p), ("vertex_count", C.c_int32), ("indices", c_i32_p), ("normals", c_float_p),
+                ("triangle_count", C.c_int32), ("cull_mode", C.c_int32), ("material_index", C.c_uint8)]
+
+
 class rt_camera(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("fov", C.c_float), ("right", C.c_float * 3), ("up", C.c_float * 3),
                 ("forward", C.c_float * 3)]

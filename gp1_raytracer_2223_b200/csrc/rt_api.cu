@@ -30,6 +30,11 @@ namespace
 		int32_t cull_mode = RT_CULL_BACK_FACE;
 		int32_t material = 0;
 		bool uploaded = false;
+		// device-side UpdateTransforms (rt_upload_mesh_source / rt_transform_mesh)
+		std::vector<float> src_positions, src_normals;
+		std::vector<int32_t> src_indices;
+		bool has_source = false, source_dirty = false, has_transform = false, transform_dirty = false;
+		float transform[16] = {};
 	};
 
 	// Offsets (in floats) of the SoA arrays inside the per-device float arena.
@@ -60,6 +65,8 @@ namespace
 		size_t mesh_capacity = 0;          // in float4
 		size_t triangle_offset = 0, node_offset = 0;   // in float4, inside d_mesh
 		cudaEvent_t ev_upload = nullptr;   // last scene copy on this device (pinned source may be reused after it)
+		struct MeshSourceDevice { float* positions = nullptr; float* normals = nullptr; int32_t* indices = nullptr; };
+		std::vector<MeshSourceDevice> sources;   // untransformed meshes (rt_upload_mesh_source), by mesh id
 		uint32_t* d_frame = nullptr;
 		size_t frame_capacity = 0;         // in pixels
 		unsigned long long* d_counters = nullptr;
@@ -160,6 +167,7 @@ namespace
 	}
 
 	int flush_uploads(rt_context* ctx);
+	int run_device_transforms(rt_context* ctx, bool block_rewritten);
 
 	int validate_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame)
 	{
@@ -172,6 +180,8 @@ namespace
 			return fail(ctx, RT_ERR_INVALID_ARGUMENT, "pixel format shifts out of range");
 		for (const HostMesh& m : ctx->meshes)
 			if (!m.uploaded) return fail(ctx, RT_ERR_BAD_STATE, "rt_set_mesh_count announced a mesh that was never uploaded");
+		for (const HostMesh& m : ctx->meshes)
+			if (m.has_source && !m.has_transform) return fail(ctx, RT_ERR_BAD_STATE, "a mesh uploaded with rt_upload_mesh_source has no transform yet (rt_transform_mesh)");
 		return flush_uploads(ctx);
 	}
 
@@ -303,14 +313,63 @@ namespace
 		return RT_OK;
 	}
 
+	// Meshes that are transformed on the device: (re)send their untransformed source when it changed, and run
+	// transform_mesh_kernel when the transform changed or the mesh block was just rewritten from the host mirror.
+	int run_device_transforms(rt_context* ctx, bool block_rewritten)
+	{
+		for (size_t m = 0; m < ctx->meshes.size(); ++m)
+		{
+			HostMesh& hm = ctx->meshes[m];
+			if (!hm.has_source) continue;
+			const int32_t T = (int32_t)(hm.src_indices.size() / 3);
+			int32_t first = 0, first_node = 0;
+			for (size_t k = 0; k < m; ++k) { first += (int32_t)(ctx->meshes[k].triangles.size() / 3); first_node += (int32_t)(ctx->meshes[k].nodes.size() / 2); }
+			for (DeviceState& d : ctx->devs)
+			{
+				RT_CUDA(ctx, cudaSetDevice(d.device));
+				if (d.sources.size() < ctx->meshes.size()) d.sources.resize(ctx->meshes.size());
+				DeviceState::MeshSourceDevice& sd = d.sources[m];
+				if (hm.source_dirty)
+				{
+					RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+					cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices);
+					sd = DeviceState::MeshSourceDevice{};
+					RT_CUDA(ctx, cudaMalloc(&sd.positions, std::max<size_t>(hm.src_positions.size(), 1) * sizeof(float)));
+					RT_CUDA(ctx, cudaMalloc(&sd.normals, std::max<size_t>(hm.src_normals.size(), 1) * sizeof(float)));
+					RT_CUDA(ctx, cudaMalloc(&sd.indices, std::max<size_t>(hm.src_indices.size(), 1) * sizeof(int32_t)));
+					// one-off upload (pageable source: the copy is complete when the call returns)
+					RT_CUDA(ctx, cudaMemcpy(sd.positions, hm.src_positions.data(), hm.src_positions.size() * sizeof(float), cudaMemcpyHostToDevice));
+					RT_CUDA(ctx, cudaMemcpy(sd.normals, hm.src_normals.data(), hm.src_normals.size() * sizeof(float), cudaMemcpyHostToDevice));
+					RT_CUDA(ctx, cudaMemcpy(sd.indices, hm.src_indices.data(), hm.src_indices.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+				}
+				if (hm.has_transform && (hm.transform_dirty || hm.source_dirty || block_rewritten) && T > 0)
+				{
+					rt::TransformParams tp{};
+					memcpy(tp.m, hm.transform, sizeof tp.m);
+					tp.positions = sd.positions; tp.indices = sd.indices; tp.normals = sd.normals;
+					tp.triangle_count = T;
+					tp.triangles = d.d_mesh + d.triangle_offset + 3 * (size_t)first;
+					tp.table = d.d_mesh + 3 * m;
+					tp.first_triangle = first;
+					rt::transform_mesh_kernel<<<1, 256, 0, d.stream>>>(tp);
+					RT_CUDA(ctx, cudaGetLastError());
+					RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
+				}
+			}
+			hm.source_dirty = false; hm.transform_dirty = false;
+		}
+		return RT_OK;
+	}
+
 	// Scene uploads only touch the pinned mirrors; the device copies happen here, once, right before the
 	// next launch (one copy per dirty block and device instead of one per rt_upload_* call).
 	int flush_uploads(rt_context* ctx)
 	{
 		int rc = RT_OK;
 		if (ctx->static_dirty) { if ((rc = push_static(ctx)) != RT_OK) return rc; ctx->static_dirty = false; }
-		if (ctx->mesh_dirty) { if ((rc = push_meshes(ctx)) != RT_OK) return rc; ctx->mesh_dirty = false; }
-		return RT_OK;
+		bool pushed = false;
+		if (ctx->mesh_dirty) { if ((rc = push_meshes(ctx)) != RT_OK) return rc; ctx->mesh_dirty = false; pushed = true; }
+		return run_device_transforms(ctx, pushed);
 	}
 
 	inline float std_min_f(float a, float b) { return (b < a) ? b : a; }
@@ -775,6 +834,7 @@ int rt_destroy(rt_context* ctx)
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
+		for (auto& sd : d.sources) { cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices); }
 		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
 		if (d.ev_kernel) cudaEventDestroy(d.ev_kernel);
 		if (d.ev_done) cudaEventDestroy(d.ev_done);
@@ -893,6 +953,43 @@ int rt_set_mesh_path(rt_context* ctx, int32_t mesh_path)
 	return RT_OK;
 }
 
+int rt_upload_mesh_source(rt_context* ctx, int32_t mesh_id, const rt_mesh_source* src)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (mesh_id < 0 || mesh_id >= (int32_t)ctx->meshes.size()) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "mesh id %d outside the announced count %d", mesh_id, (int)ctx->meshes.size());
+	if (!src || src->triangle_count < 0 || src->vertex_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad mesh source descriptor");
+	if (src->triangle_count > 0 && (!src->positions || !src->indices || !src->normals)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "mesh source has a NULL array");
+	if (src->cull_mode < RT_CULL_FRONT_FACE || src->cull_mode > RT_CULL_NONE) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown cull mode %d", src->cull_mode);
+	for (int i = 0; i < 3 * src->triangle_count; ++i)
+		if (src->indices[i] < 0 || src->indices[i] >= src->vertex_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "index %d of mesh %d is out of range", i, mesh_id);
+	HostMesh& hm = ctx->meshes[(size_t)mesh_id];
+	hm.src_positions.assign(src->positions, src->positions + 3 * (size_t)src->vertex_count);
+	hm.src_indices.assign(src->indices, src->indices + 3 * (size_t)src->triangle_count);
+	hm.src_normals.assign(src->normals, src->normals + 3 * (size_t)src->triangle_count);
+	// the stream slice is sized now and filled by transform_mesh_kernel; no BVH -> slab + linear body
+	hm.triangles.assign(3 * (size_t)src->triangle_count, make_float4(0.f, 0.f, 0.f, 0.f));
+	hm.nodes.clear();
+	for (int k = 0; k < 3; ++k) { hm.aabb_min[k] = 0.f; hm.aabb_max[k] = 0.f; }
+	hm.cull_mode = src->cull_mode;
+	hm.material = src->material_index;
+	hm.uploaded = true;
+	hm.has_source = true; hm.source_dirty = true; hm.has_transform = false;
+	ctx->mesh_dirty = true;
+	return RT_OK;
+}
+
+int rt_transform_mesh(rt_context* ctx, int32_t mesh_id, const float* transform)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (mesh_id < 0 || mesh_id >= (int32_t)ctx->meshes.size()) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "mesh id %d outside the announced count %d", mesh_id, (int)ctx->meshes.size());
+	if (!transform) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "transform must not be NULL");
+	HostMesh& hm = ctx->meshes[(size_t)mesh_id];
+	if (!hm.has_source) return fail(ctx, RT_ERR_BAD_STATE, "mesh %d was not uploaded with rt_upload_mesh_source", mesh_id);
+	memcpy(hm.transform, transform, sizeof hm.transform);
+	hm.has_transform = true; hm.transform_dirty = true;
+	return RT_OK;
+}
+
 int rt_set_kernel_variant(rt_context* ctx, int32_t variant)
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
@@ -912,6 +1009,7 @@ int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
 		if (mesh->indices[i] < 0 || mesh->indices[i] >= mesh->vertex_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "index %d of mesh %d is out of range", i, mesh_id);
 
 	HostMesh& hm = ctx->meshes[(size_t)mesh_id];
+	hm.has_source = false; hm.has_transform = false;
 	hm.triangles.resize(3 * (size_t)mesh->triangle_count);
 	// Bounds of the indexed vertices, started like a BVH root box (reference
 	// source/DataTypes.h:310-321 with MaxVector / MinVector of source/Vector3.cpp:13-14).

@@ -11,7 +11,9 @@
 //
 // Renderer.h fixes the class layout, so the device context lives in a side table keyed by the
 // Renderer (created on the first Render, released at process exit).  Devices: environment variable
-// RT_B200_DEVICES="0,1,2,3" (default: the current device).  Errors have no channel in the reference
+// RT_B200_DEVICES="0,1,2,3" (default: the current device).  RT_B200_DEVICE_TRANSFORM=1 moves
+// TriangleMesh::UpdateTransforms' vertex / normal transform to the device as well (mesh source uploaded once,
+// 64 bytes per mesh and frame; rendered by the slab + linear body).  Errors have no channel in the reference
 // API (Render returns void): they are printed to stderr and the frame is left untouched; there is
 // no CPU fallback.
 #include "SDL.h"
@@ -74,6 +76,7 @@ namespace
 			std::fprintf(stderr, "rt_b200: rt_create failed (%d): %s\n", rc, rt_last_error(nullptr));
 			side->ctx = nullptr;
 		}
+		if (const char* env = std::getenv("RT_B200_DEVICE_TRANSFORM")) side->scratch.device_transform = std::atoi(env) != 0;
 		DeviceSide* raw = side.get();
 		g_devices.emplace(renderer, std::move(side));
 		return raw;

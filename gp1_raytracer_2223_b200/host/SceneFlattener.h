@@ -31,6 +31,9 @@ namespace rt_host
 		std::vector<float> light[10];          // ox, oy, oz, dx, dy, dz, r, g, b, intensity
 		std::vector<int32_t> light_type;
 		std::vector<rt_material_desc> materials;
+		// device-side UpdateTransforms (RT_B200_DEVICE_TRANSFORM=1): what was last sent as mesh source
+		bool device_transform = false;
+		std::vector<size_t> source_vertices, source_triangles;
 	};
 
 	inline bool DescribeMaterial(dae::Material* material, rt_material_desc& out)
@@ -130,6 +133,38 @@ namespace rt_host
 		static_assert(sizeof(dae::BVHNode) == sizeof(rt_bvh_node), "BVHNode layout differs from rt_bvh_node");
 		auto& meshes = pScene->m_TriangleMeshGeometries;
 		if ((rc = rt_set_mesh_count(ctx, (int32_t)meshes.size())) != RT_OK) return fail(rc, "rt_set_mesh_count");
+		if (scratch.device_transform)
+		{
+			// the untransformed mesh crosses once, each frame only finalTransform = S * R * T
+			// (source/DataTypes.h:213); TransformPoint / TransformVector().Normalized() run on the device and the
+			// mesh is rendered by the slab + linear body (no BVH upload).  BuildBVH keeps permuting `indices` and
+			// `normals` together on the host; any such order is the same triangle set, so the first one is kept.
+			scratch.source_vertices.resize(meshes.size(), (size_t)-1);
+			scratch.source_triangles.resize(meshes.size(), (size_t)-1);
+			for (size_t i = 0; i < meshes.size(); ++i)
+			{
+				const dae::TriangleMesh& m = meshes[i];
+				if (scratch.source_vertices[i] != m.positions.size() || scratch.source_triangles[i] != m.indices.size() / 3)
+				{
+					rt_mesh_source src{};
+					src.positions = m.positions.empty() ? nullptr : &m.positions[0].x;
+					src.vertex_count = (int32_t)m.positions.size();
+					src.indices = m.indices.data();
+					src.normals = m.normals.empty() ? nullptr : &m.normals[0].x;
+					src.triangle_count = (int32_t)(m.indices.size() / 3);
+					src.cull_mode = (int32_t)m.cullMode;
+					src.material_index = m.materialIndex;
+					if ((rc = rt_upload_mesh_source(ctx, (int32_t)i, &src)) != RT_OK) return fail(rc, "rt_upload_mesh_source");
+					scratch.source_vertices[i] = m.positions.size();
+					scratch.source_triangles[i] = m.indices.size() / 3;
+				}
+				const dae::Matrix finalTransform = m.scaleTransform * m.rotationTransform * m.translationTransform;
+				float t[16];
+				for (int r = 0; r < 4; ++r) { const dae::Vector4 row = finalTransform[r]; t[4 * r] = row.x; t[4 * r + 1] = row.y; t[4 * r + 2] = row.z; t[4 * r + 3] = row.w; }
+				if ((rc = rt_transform_mesh(ctx, (int32_t)i, t)) != RT_OK) return fail(rc, "rt_transform_mesh");
+			}
+			return RT_OK;
+		}
 		for (size_t i = 0; i < meshes.size(); ++i)
 		{
 			const dae::TriangleMesh& m = meshes[i];

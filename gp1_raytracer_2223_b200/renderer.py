@@ -73,6 +73,21 @@ class Context:
         """The reference's compile-time `#define BVH` as a run-time choice (0 auto, 1 slab + linear, 2 BVH)."""
         self.check(self.lib.rt_set_mesh_path(self.handle, int(mesh_path)), "rt_set_mesh_path")
 
+    def upload_mesh_source(self, mesh_id: int, positions, indices, normals, cull_mode: int, material_index: int) -> None:
+        """Untransformed mesh, once (device-side TriangleMesh::UpdateTransforms, reference source/DataTypes.h:210-230)."""
+        from ._abi import rt_mesh_source, c_float_p, c_i32_p
+        pos = np.ascontiguousarray(positions, dtype=np.float32)
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        nrm = np.ascontiguousarray(normals, dtype=np.float32)
+        src = rt_mesh_source(pos.ctypes.data_as(c_float_p), int(pos.shape[0]), idx.ctypes.data_as(c_i32_p), nrm.ctypes.data_as(c_float_p),
+                             int(idx.shape[0]), int(cull_mode), int(material_index))
+        self.check(self.lib.rt_upload_mesh_source(self.handle, mesh_id, C.byref(src)), "rt_upload_mesh_source")
+
+    def transform_mesh(self, mesh_id: int, transform) -> None:
+        """finalTransform = scale * rotation * translation as the 16 floats of Matrix::data (per frame: 64 bytes)."""
+        m = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+        self.check(self.lib.rt_transform_mesh(self.handle, mesh_id, m.ctypes.data_as(C.POINTER(C.c_float))), "rt_transform_mesh")
+
     def set_kernel_variant(self, variant: int) -> None:
         """0 auto (= scalar today), 1 scalar one-pixel kernel, 2 packed two-pixel FFMA2 kernel."""
         self.check(self.lib.rt_set_kernel_variant(self.handle, int(variant)), "rt_set_kernel_variant")

@@ -155,3 +155,33 @@ def load_rtsc(path) -> FlatScene:
         light_intensity=np.ascontiguousarray(lig["i"], dtype=np.float32), light_type=lig["t"].astype(np.int32),
         materials=mats, meshes=meshes, camera=camera, width=width, height=height, aspect_ratio=aspect,
         lighting_mode=mode, shadows_enabled=shadows)
+
+
+@dataclasses.dataclass
+class MeshSource:
+    """What TriangleMesh::UpdateTransforms consumes (reference source/DataTypes.h:210-230)."""
+    positions: np.ndarray     # (V, 3) float32, untransformed
+    indices: np.ndarray       # (T, 3) int32
+    normals: np.ndarray       # (T, 3) float32, untransformed face normals
+    transform: np.ndarray     # (4, 4) float32: Matrix::data rows of finalTransform = S * R * T
+
+
+def load_rtms(path) -> List[MeshSource]:
+    """"RTMS0001": i32 n_meshes, then per mesh i32 n_vertices, n_triangles, f32 positions, i32 indices,
+    f32 normals, f32[16] finalTransform (written by oracle/ref_driver.cpp --dump-mesh-source)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:8] != b"RTMS0001":
+        raise ValueError(f"{path}: not an RTMS0001 file")
+    r = _Reader(data)
+    r.pos = 8
+    out = []
+    for _ in range(int(r.i32(1)[0])):
+        n_v, n_t = (int(v) for v in r.i32(2))
+        pos = r.f32(3 * n_v).reshape(n_v, 3)
+        idx = r.i32(3 * n_t).reshape(n_t, 3)
+        nrm = r.f32(3 * n_t).reshape(n_t, 3)
+        out.append(MeshSource(pos, idx, nrm, r.f32(16).reshape(4, 4)))
+    if r.pos != len(data):
+        raise ValueError(f"{path}: trailing bytes")
+    return out

@@ -289,6 +289,27 @@ int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count);
 int rt_set_mesh_path(rt_context* ctx, int32_t mesh_path);
 int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh);
 
+/* ---- N1 of SURVEY.md 8(f): TriangleMesh::UpdateTransforms on the device ---------------------------------
+ * Instead of re-uploading transformedPositions / transformedNormals every frame (rt_upload_mesh), upload the
+ * UNtransformed mesh once (positions, indices, normals: source/DataTypes.h:133-135) and send only the final
+ * transform each frame.  rt_transform_mesh runs source/DataTypes.h:216-230 on the device -
+ * TransformPoint (source/Matrix.cpp:49-56) per vertex, TransformVector().Normalized()
+ * (source/Matrix.cpp:35-42, source/Vector3.cpp:42-46) per face normal, same operation order - and rebuilds the
+ * triangle stream and the mesh box there.  No BVH is built: such a mesh is rendered by the slab + linear body.
+ * transform = the 16 floats of Matrix::data[0..3] of finalTransform = scale * rotation * translation. */
+typedef struct rt_mesh_source
+{
+	const float* positions;     /* 3 * vertex_count, untransformed */
+	int32_t vertex_count;
+	const int32_t* indices;     /* 3 * triangle_count */
+	const float* normals;       /* 3 * triangle_count floats, untransformed face normals */
+	int32_t triangle_count;
+	int32_t cull_mode;          /* rt_cull_mode */
+	uint8_t material_index;
+} rt_mesh_source;
+int rt_upload_mesh_source(rt_context* ctx, int32_t mesh_id, const rt_mesh_source* source);
+int rt_transform_mesh(rt_context* ctx, int32_t mesh_id, const float* transform);
+
 /* Which build of the pixel kernel renders frames.  Both compute the same function, bit for bit.
  *   RT_KERNEL_SCALAR  one pixel per thread (default; also what rt_count_frame instruments)
  *   RT_KERNEL_PACKED  two pixels per thread on Blackwell's packed FP32 (FFMA2) */

@@ -568,6 +568,28 @@ int rto_render_rows(const rto_scene* scene, const rt_camera* camera, const rt_fr
 	return 0;
 }
 
+void rto_transform_mesh(const float* positions, int32_t vertex_count, const float* normals, int32_t triangle_count,
+                        const float* m, float* out_positions, float* out_normals)
+{
+	/* rows: m[0..3] = data[0] (x axis), m[4..7] = data[1], m[8..11] = data[2], m[12..15] = data[3] (translation) */
+	for (int i = 0; i < vertex_count; ++i)
+	{
+		const float x = positions[3 * i], y = positions[3 * i + 1], z = positions[3 * i + 2];
+		/* Matrix::TransformPoint, Matrix.cpp:49-56 */
+		out_positions[3 * i + 0] = m[0] * x + m[4] * y + m[8] * z + m[12];
+		out_positions[3 * i + 1] = m[1] * x + m[5] * y + m[9] * z + m[13];
+		out_positions[3 * i + 2] = m[2] * x + m[6] * y + m[10] * z + m[14];
+	}
+	for (int i = 0; i < triangle_count; ++i)
+	{
+		const float x = normals[3 * i], y = normals[3 * i + 1], z = normals[3 * i + 2];
+		/* Matrix::TransformVector, Matrix.cpp:35-42, then Vector3::Normalized, Vector3.cpp:42-46 */
+		v3 n = v3_make(m[0] * x + m[4] * y + m[8] * z, m[1] * x + m[5] * y + m[9] * z, m[2] * x + m[6] * y + m[10] * z);
+		v3_normalize(&n);
+		out_normals[3 * i] = n.x; out_normals[3 * i + 1] = n.y; out_normals[3 * i + 2] = n.z;
+	}
+}
+
 uint64_t rto_fnv1a64(const void* data, uint64_t bytes)
 {
 	const unsigned char* p = (const unsigned char*)data;

@@ -60,6 +60,13 @@ int rto_render_rows(const rto_scene* scene, const rt_camera* camera, const rt_fr
  * source/Vector3.cpp:13-14), so that it equals the shipped build's root-node box. */
 void rto_mesh_bounds(const rt_mesh_desc* mesh, float out_min[3], float out_max[3]);
 
+/* TriangleMesh::UpdateTransforms without the BVH build (reference source/DataTypes.h:210-230):
+ * out_positions[v] = finalTransform.TransformPoint(positions[v])                (source/Matrix.cpp:49-56)
+ * out_normals[t]   = finalTransform.TransformVector(normals[t]).Normalized()    (source/Matrix.cpp:35-42)
+ * transform = the 16 floats of Matrix::data[0..3] (x, y, z, w per row). */
+void rto_transform_mesh(const float* positions, int32_t vertex_count, const float* normals, int32_t triangle_count,
+                        const float* transform, float* out_positions, float* out_normals);
+
 uint64_t rto_fnv1a64(const void* data, uint64_t bytes);
 
 #ifdef __cplusplus

@@ -63,6 +63,7 @@ namespace
 		float fovAngle = 45.f;
 		std::string out;
 		std::string dump;
+		std::string dumpSource;   // untransformed meshes + their final transform ("RTMS0001")
 		std::string resources; // directory that CONTAINS "Resources/"
 	};
 
@@ -73,7 +74,7 @@ namespace
 			"usage: ref_render --scene {W1|W2|W3|W3_Test|W4_Reference|W4_Bunny|W4_Optional}\n"
 			"  [--width W --height H] [--mode 0..3] [--shadows 0|1] [--frames N] [--warmup N]\n"
 			"  [--threads T] [--time SECONDS] [--mesh-yaw RAD] [--cam-origin X Y Z]\n"
-			"  [--cam-rot PITCH YAW] [--fov DEGREES] [--out FILE] [--dump-scene FILE]\n"
+			"  [--cam-rot PITCH YAW] [--fov DEGREES] [--out FILE] [--dump-scene FILE] [--dump-mesh-source FILE]\n"
 			"  [--resources DIR]\n", why);
 		std::exit(2);
 	}
@@ -100,6 +101,7 @@ namespace
 			else if (a == "--fov") { need(i, 1); o.haveFov = true; o.fovAngle = std::strtof(argv[++i], nullptr); }
 			else if (a == "--out") { need(i, 1); o.out = argv[++i]; }
 			else if (a == "--dump-scene") { need(i, 1); o.dump = argv[++i]; }
+			else if (a == "--dump-mesh-source") { need(i, 1); o.dumpSource = argv[++i]; }
 			else if (a == "--resources") { need(i, 1); o.resources = argv[++i]; }
 			else Usage(("unknown argument " + a).c_str());
 		}
@@ -197,6 +199,31 @@ namespace
 	}
 }
 
+namespace
+{
+	// What TriangleMesh::UpdateTransforms consumes (source/DataTypes.h:210-230): the untransformed positions
+	// and face normals (in their current order), the indices, and finalTransform = S * R * T.
+	void DumpMeshSources(Scene* pScene, const char* path)
+	{
+		FILE* f = std::fopen(path, "wb");
+		if (!f) { std::perror(path); std::exit(1); }
+		Writer w{ f };
+		std::fwrite("RTMS0001", 1, 8, f);
+		const auto& meshes = pScene->m_TriangleMeshGeometries;
+		w.I32((int32_t)meshes.size());
+		for (const TriangleMesh& m : meshes)
+		{
+			w.I32((int32_t)m.positions.size()); w.I32((int32_t)(m.indices.size() / 3));
+			for (const Vector3& p : m.positions) w.V3(p);
+			for (int idx : m.indices) w.I32(idx);
+			for (const Vector3& n : m.normals) w.V3(n);
+			const Matrix finalTransform = m.scaleTransform * m.rotationTransform * m.translationTransform;   // DataTypes.h:213
+			for (int r = 0; r < 4; ++r) { w.F32(finalTransform.data[r].x); w.F32(finalTransform.data[r].y); w.F32(finalTransform.data[r].z); w.F32(finalTransform.data[r].w); }
+		}
+		std::fclose(f);
+	}
+}
+
 int main(int argc, char** argv)
 {
 	const Options o = Parse(argc, argv);
@@ -209,12 +236,12 @@ int main(int argc, char** argv)
 		const ssize_t n = readlink("/proc/self/exe", exe, sizeof(exe) - 1);
 		if (n > 0) { exe[n] = 0; res = exe; res = res.substr(0, res.find_last_of('/')); }
 	}
-	std::string out = o.out, dump = o.dump;
+	std::string out = o.out, dump = o.dump, dumpSource = o.dumpSource;
 	auto absolutise = [](std::string& p)
 	{
 		if (!p.empty() && p[0] != '/') { char cwd[4096]; if (getcwd(cwd, sizeof cwd)) p = std::string(cwd) + "/" + p; }
 	};
-	absolutise(out); absolutise(dump);
+	absolutise(out); absolutise(dump); absolutise(dumpSource);
 	if (!res.empty() && chdir(res.c_str()) != 0) { std::perror(res.c_str()); return 1; }
 
 	if (o.threads > 0) omp_set_num_threads(o.threads);
@@ -269,6 +296,7 @@ int main(int argc, char** argv)
 		std::fclose(f);
 	}
 	if (!dump.empty()) DumpScene(o, pScene, pRenderer->m_AspectRatio, dump.c_str());
+	if (!dumpSource.empty()) DumpMeshSources(pScene, dumpSource.c_str());
 
 	std::vector<double> sorted = ms;
 	std::sort(sorted.begin(), sorted.end());

@@ -53,6 +53,8 @@ def lib():
         _lib.rto_render_rows.argtypes = [C.POINTER(rto_scene), C.POINTER(rt_camera), C.POINTER(rt_frame_desc),
                                          C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                          C.POINTER(rt_counters)]
+        _lib.rto_transform_mesh.restype = None
+        _lib.rto_transform_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.rto_fnv1a64.restype = C.c_uint64
         _lib.rto_fnv1a64.argtypes = [C.c_void_p, C.c_uint64]
     return _lib
@@ -95,3 +97,13 @@ def render(scene: FlatScene, width: int, height: int, lighting_mode: int = 3, sh
     if counters:
         return out, np.array(list(cnt.slot), dtype=np.uint64)
     return out
+
+
+def transform_mesh(positions: np.ndarray, normals: np.ndarray, transform: np.ndarray):
+    """CPU restatement of TransformPoint / TransformVector().Normalized() over a mesh.  Returns (positions, normals)."""
+    pos = np.ascontiguousarray(positions, dtype=np.float32)
+    nrm = np.ascontiguousarray(normals, dtype=np.float32)
+    m = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+    out_p, out_n = np.empty_like(pos), np.empty_like(nrm)
+    lib().rto_transform_mesh(pos.ctypes.data, pos.shape[0], nrm.ctypes.data, nrm.shape[0], m.ctypes.data, out_p.ctypes.data, out_n.ctypes.data)
+    return out_p, out_n

@@ -68,6 +68,11 @@ CASES = {
 }
 
 
+# cases that also get <case>.rtms: the untransformed meshes + finalTransform (input of the device-side
+# TriangleMesh::UpdateTransforms)
+MESH_SOURCES = {"bunny_320_yaw05", "bunny_320_yaw10", "bunny_320_time2", "w4ref_320_time13", "optional_320"}
+
+
 def pack_frame(frame_u32: np.ndarray) -> bytes:
     b = frame_u32.view(np.uint8).reshape(-1, 4)          # little-endian XRGB8888: B, G, R, X
     assert not b[:, 3].any(), "X byte must be 0 for XRGB8888"
@@ -85,7 +90,8 @@ def main():
             rtsc = os.path.join(HERE, name + ".rtsc")
             args = ["--scene", scene, "--width", str(w), "--height", str(h), "--mode", str(mode),
                     "--shadows", str(shadows)] + extra
-            out = subprocess.run([REF] + args + ["--out", raw, "--dump-scene", rtsc], check=True,
+            extra_out = ["--dump-mesh-source", os.path.join(HERE, name + ".rtms")] if name in MESH_SOURCES else []
+            out = subprocess.run([REF] + args + ["--out", raw, "--dump-scene", rtsc] + extra_out, check=True,
                                  capture_output=True, text=True).stdout
             info = json.loads(out)
             frame = np.fromfile(raw, dtype=np.uint32)

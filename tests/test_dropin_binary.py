@@ -29,8 +29,9 @@ CASES = [
 ]
 
 
-def run(binary, args, out):
-    res = subprocess.run([binary] + args + ["--out", out], check=True, capture_output=True, text=True)
+def run(binary, args, out, env=None):
+    res = subprocess.run([binary] + args + ["--out", out], check=True, capture_output=True, text=True,
+                         env=dict(os.environ, **(env or {})))
     assert "rt_b200:" not in res.stderr, res.stderr
     return json.loads(res.stdout.strip().splitlines()[-1])
 
@@ -50,3 +51,21 @@ def test_dropin_renders_what_the_reference_renders(tmp_path, args, exact):
         assert info_ref["fnv1a64"] == info_gpu["fnv1a64"] and n_diff == 0
     assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (n_diff, max_err)
     assert "B200" in info_gpu["path"]
+
+
+@pytest.mark.parametrize("args", [c[0] for c in CASES if c[0][1].startswith("W4")], ids=[" ".join(c[0][1:2] + c[0][6:]) for c in CASES if c[0][1].startswith("W4")])
+def test_dropin_with_device_side_update_transforms(tmp_path, args):
+    """RT_B200_DEVICE_TRANSFORM=1: the drop-in sends the untransformed mesh once and finalTransform per frame
+    (SURVEY.md 8(f) N1); frames must still be the reference's."""
+    if not (os.path.exists(REF) and os.path.exists(DROPIN)):
+        pytest.skip("oracle/_ref binaries are not built (they need /root/reference at build time)")
+    a, b = str(tmp_path / "ref.bin"), str(tmp_path / "b200.bin")
+    info_ref = run(REF, args, a)
+    run(DROPIN, args + ["--frames", "3"], b, env={"RT_B200_DEVICE_TRANSFORM": "1"})
+    w, h = info_ref["width"], info_ref["height"]
+    want = np.fromfile(a, dtype=np.uint32).reshape(h, w)
+    got = np.fromfile(b, dtype=np.uint32).reshape(h, w)
+    identical, max_err, n_diff = compare_frames(got, want)
+    if "W4_Bunny" in args:
+        assert n_diff == 0
+    assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (n_diff, max_err)

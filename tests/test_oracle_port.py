@@ -63,3 +63,20 @@ def test_counters_match_survey_table():
     assert c[29] == 3 * 307200                                   # one shadow ray per light per hit pixel
     rays = int(c[0] + c[29])
     assert rays == 1228800
+
+
+@pytest.mark.parametrize("name", ["bunny_320_yaw05", "bunny_320_yaw10", "bunny_320_time2", "w4ref_320_time13", "optional_320"])
+def test_port_transform_matches_reference_update_transforms(name):
+    """rto_transform_mesh against what the reference's own TriangleMesh::UpdateTransforms produced
+    (source/DataTypes.h:210-230): transformedPositions / transformedNormals of the same run, bit for bit."""
+    import os
+    from conftest import GOLDEN
+    from gp1_raytracer_2223_b200.scene_file import load_rtms
+    sources = load_rtms(os.path.join(GOLDEN, name + ".rtms"))
+    scene = load_golden_scene(name)
+    assert len(sources) == len(scene.meshes)
+    for src, mesh in zip(sources, scene.meshes):
+        pos, nrm = rt_oracle.transform_mesh(src.positions, src.normals, src.transform)
+        assert np.array_equal(src.indices, mesh.indices)
+        assert np.array_equal(pos.view(np.uint32), mesh.positions.view(np.uint32))
+        assert np.array_equal(nrm.view(np.uint32), mesh.normals.view(np.uint32))
