@@ -499,6 +499,29 @@ def main():
                             "differing_pixels_vs_reference_frame": int((host.numpy().view(np.uint32) != want).sum())}
             rr.close()
 
+        # N1: untransformed mesh uploaded once, 64 bytes of transform per frame, vertices / normals
+        # transformed on the device, slab + linear body (no BVH)
+        try:
+            from gp1_raytracer_2223_b200.scene_file import load_rtms
+            sc = load_rtsc(os.path.join(ROOT, "tests", "golden", "bunny_320_yaw10.rtsc"))
+            src = load_rtms(os.path.join(ROOT, "tests", "golden", "bunny_320_yaw10.rtms"))[0]
+            rr = Renderer(WIDTH, HEIGHT, device_ids=[local_rank])
+            rr.SetScene(sc)
+            rr.ctx.upload_mesh_source(0, src.positions, src.indices, src.normals, sc.meshes[0].cull_mode, sc.meshes[0].material_index)
+            host = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
+            for _ in range(5):
+                rr.ctx.transform_mesh(0, src.transform)
+                rr.render_host_ptr(host.data_ptr(), WIDTH * 4)
+            t0 = time.perf_counter()
+            for _ in range(30):
+                rr.ctx.transform_mesh(0, src.transform)
+                tm = rr.render_host_ptr(host.data_ptr(), WIDTH * 4)
+            other["device-side UpdateTransforms, bunny 3840x2160 (pose yaw 1.0), slab + linear body"] = {
+                "e2e_ms": (time.perf_counter() - t0) / 30 * 1e3, "kernel_ms": tm["kernel_ms"], "h2d_bytes_per_frame": 64}
+            rr.close()
+        except Exception as exc:                       # noqa: BLE001  (reported, not fatal for the headline)
+            other["device-side UpdateTransforms"] = {"error": str(exc)}
+
     ms_per_step = total_ms / args.steps
     line = {
         "metric": "Mrays/s", "value": RAYS_PER_FRAME / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s",
