@@ -224,7 +224,7 @@ def main():
 
     from gp1_raytracer_2223_b200 import Renderer, bands, build, load_rtsc
     from gp1_raytracer_2223_b200.flops import algorithmic_flops, rays
-    build.build()
+    build.ensure()
 
     scene = load_rtsc(FIXTURE)
     mesh = scene.meshes[0]

@@ -61,5 +61,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def ensure() -> str:
+    """Build only when the library is missing.  Used by bench.py and the tests: on the GPU box the snapshot's
+    file times say nothing about freshness, and N ranks must not start N concurrent nvcc runs over one file.
+    (`__graft_entry__.build()` / `python -m gp1_raytracer_2223_b200.build` are what rebuild after an edit.)"""
+    if os.path.exists(LIB):
+        return LIB
+    return build(force=True)
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))

@@ -11,7 +11,7 @@ from gp1_raytracer_2223_b200 import _abi, _lib, build
 
 @pytest.fixture(scope="module")
 def lib():
-    build.build()
+    build.ensure()
     return _lib.load()
 
 

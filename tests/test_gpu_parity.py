@@ -24,7 +24,7 @@ def gpu():
     import torch
     assert torch.cuda.is_available(), "these tests need the B200"
     from gp1_raytracer_2223_b200 import build
-    build.build()
+    build.ensure()
     return torch
 
 
