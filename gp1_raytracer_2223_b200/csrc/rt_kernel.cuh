@@ -2,7 +2,8 @@
 // 32x8 pixel strip segment.  Replaces Renderer::RenderPixel (reference
 // source/Renderer.cpp:100-182) and everything it calls:
 //   Scene::GetClosestHit / DoesHit        source/Scene.cpp:29-96
-//   GeometryUtils::HitTest_* / SlabTest   source/Utils.h:15-216, 290-327 (#else branch)
+//   GeometryUtils::HitTest_* / SlabTest   source/Utils.h:15-216, 290-327 (both bodies of HitTest_TriangleMesh:
+//                                         the #else slab + linear loop and the shipped BVH walk, Utils.h:221-288)
 //   LightUtils                            source/Utils.h:341-369
 //   Material::Shade x4, BRDF::*           source/Material.h:34-129, source/BRDFs.h:14-99
 //   ColorRGB::MaxToOne + pack             source/ColorRGB.h:12-17, source/Renderer.cpp:176-181
@@ -10,7 +11,9 @@
 // Data movement: spheres, planes, lights, materials and the mesh table are staged from the
 // SoA upload buffers into shared memory once per CTA; triangles are streamed as three float4
 // per triangle (v0|nx, e1|ny, e2|nz) with warp-uniform 128-bit loads that live in L1/L2; the
-// only HBM traffic is the 4 B/pixel result, written with 128-bit stores.
+// only HBM traffic is the 4 B/pixel result, written with 128-bit stores.  This file also holds the small
+// kernels around it: unstripe (multi-process gather tail), the FP32 peak probe, the frame completion
+// signal and the device-side TriangleMesh::UpdateTransforms.
 #pragma once
 
 #include "rt_device.cuh"
