@@ -452,13 +452,13 @@ def main():
                     "peak_gbs": _measured_peaks().get("hbm_gbs")},
         }
 
-    roofline = roofline_of("bvh", kernel_ms, "rt::render_kernel<Combined, shadows, BVH>")
+    roofline = roofline_of("bvh", kernel_ms, "rt::render_kernel_persistent<Combined, shadows, BVH>")
     # the same kernel time against the north-star algorithm's FLOP count (what a brute-force kernel would have to do)
     roofline["survey_algorithmic_gflop_per_frame"] = flop_per_frame["slab_linear"] / 1e9
     roofline["survey_algorithmic_tflops_equivalent"] = flop_per_frame["slab_linear"] / world / (kernel_ms * 1e-3) / 1e12
     slab_ms_per_step = slab_total_ms / args.steps
     north_star = {"value": RAYS_PER_FRAME / (slab_ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": slab_ms_per_step,
-                  "roofline": roofline_of("slab_linear", slab_kernel_ms, "rt::render_kernel<Combined, shadows, slab + linear>")}
+                  "roofline": roofline_of("slab_linear", slab_kernel_ms, "rt::render_kernel_persistent<Combined, shadows, slab + linear>")}
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
     cpu_baseline = None
@@ -536,7 +536,7 @@ def main():
         "frame_check": frame_check,
         "gpu_launches": args.steps * (world + ((world - 1) if signals else (0 if fused or world == 1 else 1))),
         "mesh_path": "bvh (reference's shipped IntersectionTest_BVH over the reference's own nodes)",
-        "kernel_variant": "scalar (one pixel per thread); rt_render overlaps the present copy with rendering (progressive present)",
+        "kernel_variant": "persistent warps (one pixel per thread, 8x4 warp tiles pulled off a device queue; 128-thread CTAs, 9 per SM); rt_render overlaps the present copy with rendering (progressive present)",
         "roofline": roofline,
         "north_star_slab_linear": north_star,
         "other_configs": other,

@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,6 +58,8 @@ namespace
 		static constexpr size_t total = (bytes + rt::kMaxSpheres + rt::kMaxPlanes + 15) & ~size_t(15);
 	};
 
+	constexpr unsigned int kQueueRing = 256;
+
 	struct DeviceState
 	{
 		int device = -1;
@@ -74,6 +78,9 @@ namespace
 		cudaStream_t copy_stream = nullptr;                 // device-to-host copies that overlap the next band's kernel
 		cudaEvent_t ev_band[16] = {};
 		unsigned int* d_band_done = nullptr;                // kMaxBands counters for the single-launch progressive present
+		unsigned int* d_queues = nullptr;                   // kQueueRing work queues {next, finished} of the persistent kernel (self re-arming)
+		unsigned int queue_cursor = 0;
+		int sm_count = 0;
 		rt::SceneDevice view{};
 	};
 }
@@ -150,6 +157,30 @@ namespace
 		};
 #undef RT_ROW
 		return table[mode][bvh ? 1 : 0][shadows ? 1 : 0];
+	}
+
+	KernelFn pick_kernel_persistent(int mode, int shadows, bool bvh)
+	{
+#define RT_ROW(M) { { rt::render_kernel_persistent<M, 0, false>, rt::render_kernel_persistent<M, 1, false> }, { rt::render_kernel_persistent<M, 0, true>, rt::render_kernel_persistent<M, 1, true> } }
+		static const KernelFn table[4][2][2] = {
+			RT_ROW(RT_LIGHTING_OBSERVED_AREA), RT_ROW(RT_LIGHTING_RADIANCE), RT_ROW(RT_LIGHTING_BRDF), RT_ROW(RT_LIGHTING_COMBINED),
+		};
+#undef RT_ROW
+		return table[mode][bvh ? 1 : 0][shadows ? 1 : 0];
+	}
+
+	// One wave of the persistent kernel: SMs x CTAs resident per SM (asked of the runtime once per kernel).
+	int persistent_ctas_per_sm(KernelFn fn)
+	{
+		static std::map<KernelFn, int> cache;
+		static std::mutex lock;
+		std::lock_guard<std::mutex> guard(lock);
+		auto it = cache.find(fn);
+		if (it != cache.end()) return it->second;
+		int n = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, rt::kPersistentThreads, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+		cache[fn] = n;
+		return n;
 	}
 
 	// The mesh body a frame runs (the reference's `#ifdef BVH`), or -1 with the error set.
@@ -388,9 +419,35 @@ namespace
 #ifndef RT_EXPERIMENT_BLOCK
 		static_assert(rt::x2::kBlockW == rt::kBlockW, "both kernels must cut the frame into the same CTA grid");
 #endif
-		const bool packed = ctx->kernel_variant == RT_KERNEL_PACKED;   // AUTO = scalar: the faster build today
-		if (packed) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::x2::kThreads, 0, stream>>>(d.view, p);
-		else pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
+		p.grid_x = (int32_t)grid.x; p.n_strips = n_strips;
+		p.grid_x_magic = (uint32_t)((1ull << 32) / grid.x) + 1u;
+		// the persistent kernel decodes tile -> (strip, column) with one multiply; exact while tile * grid_x < 2^32
+		const bool decodable = grid.x > 1u && (unsigned long long)grid.x * grid.y * grid.x < (1ull << 32);
+		int variant = ctx->kernel_variant;
+		const long long tiles = (long long)grid.x * (long long)grid.y;
+		KernelFn persistent = nullptr;
+		int wave = 0;
+		if (variant == RT_KERNEL_AUTO || variant == RT_KERNEL_PERSISTENT)
+		{
+			persistent = pick_kernel_persistent(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH);
+			wave = d.sm_count * persistent_ctas_per_sm(persistent);
+			// AUTO: persistent warps pay off once the frame is many waves deep; small frames keep one CTA per tile
+			if (variant == RT_KERNEL_AUTO)
+				variant = (tiles * rt::kSignalsPerTile >= 8ll * wave * (rt::kPersistentThreads / 32)) ? RT_KERNEL_PERSISTENT : RT_KERNEL_SCALAR;
+			if (!decodable) variant = RT_KERNEL_SCALAR;
+		}
+		if (variant == RT_KERNEL_PACKED) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::x2::kThreads, 0, stream>>>(d.view, p);
+		else if (variant == RT_KERNEL_SCALAR) pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
+		else
+		{
+			// persistent warps: one wave of CTAs, never more than the launch has tiles; every launch takes the
+			// next queue of the ring (a queue is all zeros again when its kernel ends, and launches that could
+			// overlap - other streams - are far fewer than the ring is long)
+			const KernelFn fn = persistent;
+			p.queue = d.d_queues + 2 * (d.queue_cursor++ % kQueueRing);
+			const long long ctas_of_work = (tiles * rt::kSignalsPerTile + rt::kPersistentThreads / 32 - 1) / (rt::kPersistentThreads / 32);
+			fn<<<(unsigned)std::min<long long>(wave, ctas_of_work), rt::kPersistentThreads, 0, stream>>>(d.view, p);
+		}
 		RT_CUDA(ctx, cudaGetLastError());
 		ctx->timing.kernel_launches++;
 		return RT_OK;
@@ -693,7 +750,7 @@ namespace
 			{
 				const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
 				if (s1 <= s0) break;
-				const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)((s1 - s0) * grid_x), CU_STREAM_WAIT_VALUE_GEQ);
+				const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)((s1 - s0) * grid_x * rt::kSignalsPerTile), CU_STREAM_WAIT_VALUE_GEQ);
 				if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
 				if ((rc = copy_band(s0 * rt::kBlockH, std::min(H, s1 * rt::kBlockH))) != RT_OK) return rc;
 			}
@@ -792,6 +849,9 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 128));
 		RT_CREATE(cudaMemset(d.d_band_done, 0, sizeof(unsigned int) * 128));
+		RT_CREATE(cudaMalloc(&d.d_queues, sizeof(unsigned int) * 2 * kQueueRing));
+		RT_CREATE(cudaMemset(d.d_queues, 0, sizeof(unsigned int) * 2 * kQueueRing));
+		d.sm_count = prop.multiProcessorCount;
 		ctx->devs.push_back(d);
 	}
 	RT_CREATE(cudaSetDevice(ids[0]));
@@ -832,7 +892,7 @@ int rt_destroy(rt_context* ctx)
 	{
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
-		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done);
+		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
 		for (auto& sd : d.sources) { cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices); }
 		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
@@ -993,7 +1053,7 @@ int rt_transform_mesh(rt_context* ctx, int32_t mesh_id, const float* transform)
 int rt_set_kernel_variant(rt_context* ctx, int32_t variant)
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
-	if (variant < RT_KERNEL_AUTO || variant > RT_KERNEL_PACKED) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", variant);
+	if (variant < RT_KERNEL_AUTO || variant > RT_KERNEL_PERSISTENT) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", variant);
 	ctx->kernel_variant = variant;
 	return RT_OK;
 }
@@ -1257,7 +1317,7 @@ int rt_frame_present(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes, i
 	{
 		const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
 		if (s1 <= s0) break;
-		const cuuint32_t expected = (cuuint32_t)((uint64_t)frame_number * (uint64_t)((s1 - s0) * grid_x));
+		const cuuint32_t expected = (cuuint32_t)((uint64_t)frame_number * (uint64_t)((s1 - s0) * grid_x * rt::kSignalsPerTile));
 		const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(counters + b), expected, CU_STREAM_WAIT_VALUE_GEQ);
 		if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
 		const int r0 = s0 * rt::kBlockH, r1 = std::min(H, s1 * rt::kBlockH);

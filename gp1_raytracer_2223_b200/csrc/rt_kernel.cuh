@@ -77,7 +77,10 @@ namespace rt
 		unsigned long long* counters;    // counters build only
 		unsigned int* band_done;         // progressive present: band_done[b] counts the finished CTAs of band b (NULL = off)
 		int32_t strips_per_band;         // a band = this many consecutive 8-row strips of the frame
-		unsigned int* band_local;        // multi-GPU: this GPU's own per-band CTA counters (see signal_band_done)
+		unsigned int* band_local;        // multi-GPU: this GPU's own per-band counters (see signal_band_done)
+		int32_t grid_x, n_strips;        // the launch's tile grid: 32-pixel columns x 8-row strips (set by launch())
+		unsigned int* queue;             // persistent kernel: {next work item, finished warps}, both zero between launches
+		uint32_t grid_x_magic;           // floor(2^32 / grid_x) + 1: tile / grid_x == __umulhi(tile, magic) while tile * grid_x < 2^32
 	};
 
 	struct Ray
@@ -99,11 +102,12 @@ namespace rt
 	{
 		float4 sphere[kMaxSpheres];          // {ox, oy, oz, radius}
 		float4 plane_o[kMaxPlanes];          // {ox, oy, oz, material bits}
-		float4 plane_n[kMaxPlanes];          // {nx, ny, nz, -}
+		float4 plane_n[kMaxPlanes];          // {nx, ny, nz, (plane origin - camera origin) . n: HitTest_Plane's numerator for view rays}
 		float4 light_a[kMaxLights];          // {ox, oy, oz, intensity}
 		float4 light_b[kMaxLights];          // {r, g, b, type bits}
 		float4 mesh[3 * kMaxMeshes];
 		float4 material[2 * kMaxMaterials];
+		float4 sphere_view[kMaxSpheres];     // {c - camera origin, |c - camera origin|^2}: HitTest_Sphere's ray-independent part for view rays
 		uint8_t sphere_mat[kMaxSpheres];
 	};
 
@@ -139,21 +143,27 @@ namespace rt
 		return r;
 	}
 
-	// HitTest_Sphere, Utils.h:52-71.  Returns t through `t_out`.
+	// HitTest_Sphere, Utils.h:52-71.  Returns t through `t_out`.  `ov` = centre - ray origin and `ov2` = ov . ov
+	// are passed in: every view ray of a frame shares them (staged once per CTA), shadow rays compute them here.
 	template <bool SHADOW, bool COUNT>
-	__device__ __forceinline__ bool hit_sphere(const float4 s, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	__device__ __forceinline__ bool hit_sphere_from(const V3 ov, const float ov2, const float radius, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
 	{
-		const V3 ov = v3(s) - ray.o;
-		const float ov2 = dot(ov, ov);
 		const float p = dot(ray.d, ov);
 		const float perp = sub(ov2, mul(p, p));
-		const float r2 = mul(s.w, s.w);
+		const float r2 = mul(radius, radius);
 		if (r2 < perp) { cnt.hit(SHADOW ? RT_CNT_SPHERE_S_DISC : RT_CNT_SPHERE_P_DISC); return false; }
 		const float t = sub(p, root(sub(r2, perp)));
 		if (t < ray.tmin || t > ray.tmax) { cnt.hit(SHADOW ? RT_CNT_SPHERE_S_TREJ : RT_CNT_SPHERE_P_TREJ); return false; }
 		cnt.hit(SHADOW ? RT_CNT_SPHERE_S_HIT : RT_CNT_SPHERE_P_HIT);
 		t_out = t;
 		return true;
+	}
+
+	template <bool SHADOW, bool COUNT>
+	__device__ __forceinline__ bool hit_sphere(const float4 s, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	{
+		const V3 ov = v3(s) - ray.o;
+		return hit_sphere_from<SHADOW>(ov, dot(ov, ov), s.w, ray, t_out, cnt);
 	}
 
 	// Can t = RN(num / den) satisfy tmin <= t < tmax (tmin = 1e-4)?  Returns false only when that is
@@ -171,17 +181,22 @@ namespace rt
 		return true;
 	}
 
-	// HitTest_Plane, Utils.h:82-98.
+	// HitTest_Plane, Utils.h:82-98.  `num` = (plane origin - ray origin) . n is passed in for the same reason.
 	template <bool SHADOW, bool COUNT>
-	__device__ __forceinline__ bool hit_plane(const float4 po, const float4 pn, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	__device__ __forceinline__ bool hit_plane_from(const float num, const float4 pn, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
 	{
-		const V3 n = v3(pn);
-		const float num = dot(v3(po) - ray.o, n), den = dot(ray.d, n);
+		const float den = dot(ray.d, v3(pn));
 		cnt.hit(SHADOW ? RT_CNT_PLANE_S_TEST : RT_CNT_PLANE_P_TEST);
 		if (!plane_may_hit(num, den, ray.tmax)) return false;
 		const float t = quo(num, den);
 		if (t >= ray.tmin && t < ray.tmax) { t_out = t; return true; }
 		return false;
+	}
+
+	template <bool SHADOW, bool COUNT>
+	__device__ __forceinline__ bool hit_plane(const float4 po, const float4 pn, const Ray& ray, float& t_out, Counters<COUNT>& cnt)
+	{
+		return hit_plane_from<SHADOW>(dot(v3(po) - ray.o, v3(pn)), pn, ray, t_out, cnt);
 	}
 
 	// Packed FP32 arithmetic (Blackwell FFMA2): two independent IEEE multiplies / adds / subtracts per issue
@@ -209,9 +224,13 @@ namespace rt
 	template <bool FAST>
 	__device__ __forceinline__ bool slab_test(const Pk& K, const float4 b0, const float4 b1, const Ray& ray)
 	{
-		const float2 tx = K.mul(K.sub(make_float2(b0.x, b0.y), splat(ray.o.x)), splat(ray.inv.x));
-		const float2 ty = K.mul(K.sub(make_float2(b0.z, b0.w), splat(ray.o.y)), splat(ray.inv.y));
-		const float2 tz = K.mul(K.sub(make_float2(b1.x, b1.y), splat(ray.o.z)), splat(ray.inv.z));
+		// The products are a * b + (+0) here, not a * b + (-0): the two differ only in the sign of a zero
+		// product, and the t values only meet comparisons and min / max below, which cannot see it.  +0 is the
+		// zero register, so the loop carries one constant pair less.
+		const float2 zero = make_float2(0.f, 0.f);
+		const float2 tx = __ffma2_rn(K.sub(make_float2(b0.x, b0.y), splat(ray.o.x)), splat(ray.inv.x), zero);
+		const float2 ty = __ffma2_rn(K.sub(make_float2(b0.z, b0.w), splat(ray.o.y)), splat(ray.inv.y), zero);
+		const float2 tz = __ffma2_rn(K.sub(make_float2(b1.x, b1.y), splat(ray.o.z)), splat(ray.inv.z), zero);
 		if (FAST)
 		{
 			const float t_min = fmaxf(fmaxf(fminf(tx.x, tx.y), fminf(ty.x, ty.y)), fminf(tz.x, tz.y));
@@ -433,7 +452,8 @@ namespace rt
 		for (int i = 0; i < dev.n_spheres; ++i)
 		{
 			float t;
-			if (hit_sphere<false>(sc.sphere[i], ray, t, cnt))
+			const float4 sv = sc.sphere_view[i];
+			if (hit_sphere_from<false>(v3(sv), sv.w, sc.sphere[i].w, ray, t, cnt))
 			{
 				if (t < best.t) { best.t = t; best_sphere = i; cnt.hit(RT_CNT_SPHERE_P_CLOSEST); }
 			}
@@ -453,7 +473,7 @@ namespace rt
 		{
 			float t;
 			const float4 po = sc.plane_o[i], pn = sc.plane_n[i];
-			if (hit_plane<false>(po, pn, ray, t, cnt))
+			if (hit_plane_from<false>(pn.w, pn, ray, t, cnt))
 			{
 				cnt.hit(RT_CNT_PLANE_P_HIT);
 				if (t < best.t)
@@ -646,10 +666,74 @@ namespace rt
 
 		float shadow_factor = 1.f;
 		V3 color = v3(0.f, 0.f, 0.f);
+#ifdef RT_MASK_FIRST
 		if (hit.did)
 		{
 			cnt.hit(RT_CNT_HIT_PIXELS);
 			const V3 origin_offset = hit.origin + hit.normal * 0.0001f;   // Renderer.cpp:126
+			// Pass 1: the shadow rays of every light (Renderer.cpp:131-141).  Only the occlusion bit of each
+			// light leaves this loop, so the colour state is not live across the traversals.
+			unsigned int occluded = 0u;
+			if (shadows)
+			{
+#pragma unroll 1
+				for (int li = 0; li < dev.n_lights; ++li)
+				{
+					const float4 la = sc.light_a[li];
+					const int ltype = __float_as_int(sc.light_b[li].w);
+					V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
+					const float mag = normalize(l);
+					cnt.hit(RT_CNT_SHADOW_RAYS);
+					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);   // Renderer.cpp:136
+					if (does_hit<BVH>(sc, dev, shadow_ray, cnt)) { occluded |= 1u << li; cnt.hit(RT_CNT_OCCLUDED); }
+				}
+			}
+			// Pass 2: the lights that are not occluded, in light order (same accumulation order as the
+			// reference's single loop); every occluded light scales shadowFactor by 0.95f (Renderer.cpp:139-140;
+			// the factor is the same for each of them, so their position in the order does not matter).
+			const V3 view_neg = neg(d);
+#pragma unroll 1
+			for (int li = 0; li < dev.n_lights; ++li)
+			{
+				cnt.hit(RT_CNT_LIGHT_ITERATIONS);
+				if ((occluded >> li) & 1u) { shadow_factor = mul(shadow_factor, 0.95f); continue; }
+				cnt.hit(RT_CNT_LIT);
+				const float4 la = sc.light_a[li], lb = sc.light_b[li];
+				const int ltype = __float_as_int(lb.w);
+				V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
+				normalize(l);
+				if (mode == RT_LIGHTING_COMBINED)
+				{
+					const float oa = std_max(dot(hit.normal, l), 0.f);
+					const V3 e = radiance(la, lb, hit.origin);
+					const V3 brdf = shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+					// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
+					color = color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
+				}
+				else if (mode == RT_LIGHTING_OBSERVED_AREA)
+				{
+					const float oa = std_max(dot(hit.normal, l), 0.f);
+					color = color + v3(oa, oa, oa);
+				}
+				else if (mode == RT_LIGHTING_RADIANCE)
+				{
+					color = color + radiance(la, lb, hit.origin);
+				}
+				else if (mode == RT_LIGHTING_BRDF)
+				{
+					color = color + shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+				}
+			}
+			color = color * shadow_factor;                                  // Renderer.cpp:173
+		}
+#else
+		if (hit.did)
+		{
+			cnt.hit(RT_CNT_HIT_PIXELS);
+			V3 origin_offset = hit.origin + hit.normal * 0.0001f;   // Renderer.cpp:126
+			// keep it in registers: under register pressure ptxas would otherwise re-evaluate the three
+			// multiply-adds inside the shadow traversal loops (once per BVH node)
+			asm volatile("" : "+f"(origin_offset.x), "+f"(origin_offset.y), "+f"(origin_offset.z));
 			const V3 view_neg = neg(d);
 #pragma unroll 1
 			for (int li = 0; li < dev.n_lights; ++li)
@@ -699,6 +783,8 @@ namespace rt
 			color = color * shadow_factor;                                  // Renderer.cpp:173
 		}
 
+#endif
+
 		// ColorRGB::MaxToOne, ColorRGB.h:12-17
 		const float max_value = std_max(color.x, std_max(color.y, color.z));
 		if (max_value > 1.f) { color.x = quo(color.x, max_value); color.y = quo(color.y, max_value); color.z = quo(color.z, max_value); }
@@ -711,19 +797,27 @@ namespace rt
 		return (R << p.r_shift) | (G << p.g_shift) | (B << p.b_shift) | p.alpha_mask;
 	}
 
+	// `cam` is the origin every view ray of the frame starts from: the parts of HitTest_Sphere / HitTest_Plane
+	// that depend on the ray origin only (Utils.h:54-55, 86) are evaluated here once per CTA for those rays,
+	// with the same operations in the same order as the per-ray code.
 	template <int THREADS>
-	__device__ __forceinline__ void stage_scene(SharedScene& sc, const SceneDevice& dev)
+	__device__ __forceinline__ void stage_scene(SharedScene& sc, const SceneDevice& dev, const V3 cam)
 	{
 		const int tid = threadIdx.x;
 		for (int i = tid; i < dev.n_spheres; i += THREADS)
 		{
-			sc.sphere[i] = make_float4(dev.sphere_ox[i], dev.sphere_oy[i], dev.sphere_oz[i], dev.sphere_r[i]);
+			const float4 s = make_float4(dev.sphere_ox[i], dev.sphere_oy[i], dev.sphere_oz[i], dev.sphere_r[i]);
+			const V3 ov = v3(s) - cam;
+			sc.sphere[i] = s;
+			sc.sphere_view[i] = make_float4(ov.x, ov.y, ov.z, dot(ov, ov));
 			sc.sphere_mat[i] = dev.sphere_mat[i];
 		}
 		for (int i = tid; i < dev.n_planes; i += THREADS)
 		{
-			sc.plane_o[i] = make_float4(dev.plane_ox[i], dev.plane_oy[i], dev.plane_oz[i], __int_as_float((int)dev.plane_mat[i]));
-			sc.plane_n[i] = make_float4(dev.plane_nx[i], dev.plane_ny[i], dev.plane_nz[i], 0.f);
+			const float4 po = make_float4(dev.plane_ox[i], dev.plane_oy[i], dev.plane_oz[i], __int_as_float((int)dev.plane_mat[i]));
+			const V3 n = v3(dev.plane_nx[i], dev.plane_ny[i], dev.plane_nz[i]);
+			sc.plane_o[i] = po;
+			sc.plane_n[i] = make_float4(n.x, n.y, n.z, dot(v3(po) - cam, n));
 		}
 		for (int i = tid; i < dev.n_lights; i += THREADS)
 		{
@@ -749,23 +843,24 @@ namespace rt
 		}
 	}
 
-	// Progressive present: tell the copy stream (cuStreamWaitValue32 on band_done[b]) that this CTA's pixels
-	// are in memory.  CTA barrier first, then one thread signals.
-	//  * One GPU (band_local == NULL): a release-ordered reduction on band_done[b] per CTA.  A release
+	// Progressive present: tell the copy stream (cuStreamWaitValue32 on band_done[b]) that pixels are in
+	// memory.  Counters run in warp tiles (8x4 pixels): a 32x8 CTA tile is kSignalsPerTile of them.  The
+	// caller has synchronised the threads whose stores it reports (CTA barrier / __syncwarp) and calls this
+	// from ONE thread with the strip index `k` of the launch and the number of warp tiles finished.
+	//  * One GPU (band_local == NULL): a release-ordered reduction on band_done[b].  A release
 	//    (MEMBAR.ALL.GPU) is enough; __threadfence() would also invalidate the SM's L1 (CCTL.IVALL) and evict
-	//    the BVH nodes and triangles the other resident CTAs are streaming.
-	//  * Several GPUs: band_done lives on GPU 0 (peer memory) and a system-scope release per CTA is far too
-	//    expensive.  CTAs count on their own GPU (band_local[b], gpu scope); the CTA that completes this GPU's
+	//    the BVH nodes and triangles the other resident warps are streaming.
+	//  * Several GPUs: band_done lives on GPU 0 (peer memory) and a system-scope release per tile is far too
+	//    expensive.  Tiles count on their own GPU (band_local[b], gpu scope); the one that completes this GPU's
 	//    share of a band forwards the whole share with ONE system-scope release and re-arms the local counter.
-	__device__ __forceinline__ void signal_band_done(const FrameParams& p)
+	constexpr int kSignalsPerTile = kThreads / 32;
+	__device__ __forceinline__ void signal_band_done(const FrameParams& p, int k, unsigned int units)
 	{
-		__syncthreads();
-		if (threadIdx.x != 0) return;
-		const int strip = (int)blockIdx.y * p.strip_step + p.strip_first;      // position in the frame, whoever renders it
+		const int strip = k * p.strip_step + p.strip_first;      // position in the frame, whoever renders it
 		const int band = strip / p.strips_per_band;
 		if (!p.band_local)
 		{
-			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(p.band_done + band) : "memory");
+			asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(units) : "memory");
 			return;
 		}
 		// strips of this band that belong to this GPU: those congruent to strip_first modulo strip_step
@@ -773,14 +868,21 @@ namespace rt
 		const int s0 = band * p.strips_per_band, s1 = min(total_strips, s0 + p.strips_per_band);
 		const int first_mine = s0 + ((p.strip_first - s0) % p.strip_step + p.strip_step) % p.strip_step;
 		const int mine = first_mine < s1 ? (s1 - 1 - first_mine) / p.strip_step + 1 : 0;
-		const unsigned int share = (unsigned int)mine * gridDim.x;
+		const unsigned int share = (unsigned int)mine * (unsigned int)p.grid_x * (unsigned int)kSignalsPerTile;
 		unsigned int old;
-		asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(p.band_local + band) : "memory");
-		if (old + 1u == share)
+		asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p.band_local + band), "r"(units) : "memory");
+		if (old + units == share)
 		{
 			p.band_local[band] = 0u;
 			asm volatile("red.release.sys.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(share) : "memory");
 		}
+	}
+
+	// CTA-tile form: the whole 32x8 tile of this CTA is in memory.
+	__device__ __forceinline__ void signal_band_done(const FrameParams& p)
+	{
+		__syncthreads();
+		if (threadIdx.x == 0) signal_band_done(p, (int)blockIdx.y, (unsigned int)kSignalsPerTile);
 	}
 
 	template <int MODE, int SHADOWS, bool BVH, bool COUNT>
@@ -788,7 +890,7 @@ namespace rt
 	render_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
 		__shared__ SharedScene sc;
-		stage_scene<kThreads>(sc, dev);
+		stage_scene<kThreads>(sc, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
 
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -820,6 +922,109 @@ namespace rt
 		}
 
 		if (p.band_done) signal_band_done(p);
+	}
+
+	// The shipped form of the pixel kernel: persistent warps.  The grid is one wave (SMs x resident CTAs);
+	// the scene is staged into shared memory once per CTA, then every warp pulls 8x4 warp tiles off a
+	// device-wide queue (ids run through the launch's tiles in the order the tiled kernel's CTAs would be
+	// scheduled: neighbouring warps work on neighbouring pixels, bands finish in order) until the queue is
+	// empty.  Against the tiled form (render_kernel, one CTA per 32x8 tile) this removes the per-tile
+	// staging + barrier and the idle warp slots of a CTA waiting for its slowest warp.  The next id is
+	// fetched before the current tile is rendered, so the atomic's latency is never exposed.  The queue
+	// re-arms itself: the last warp to see it empty zeroes both words for the next launch.
+	__device__ __forceinline__ int next_work_item(unsigned int* queue, int lane)
+	{
+		unsigned int id = 0;
+		if (lane == 0) id = atomicAdd(queue, 1u);
+		return (int)__shfl_sync(0xffffffffu, id, 0);
+	}
+
+	struct TileCoords { int k, px, py, local_y; bool valid; };
+	__device__ __forceinline__ TileCoords decode_work_item(const FrameParams& p, int item, int lane)
+	{
+		TileCoords c;
+		const unsigned int tile = (unsigned int)item / kSignalsPerTile, warp = (unsigned int)item % kSignalsPerTile;
+		c.k = (int)__umulhi(tile, p.grid_x_magic);
+		const int bx = (int)tile - c.k * p.grid_x;
+		const int wx = warp % kWarpsX, wy = warp / kWarpsX;
+		c.px = bx * kBlockW + wx * kTileW + (lane & (kTileW - 1));
+		c.local_y = wy * kTileH + (lane >> 3);
+		c.py = p.row_begin + (c.k * p.strip_step + p.strip_first) * kBlockH + c.local_y;
+		c.valid = (c.px < p.width) && (c.py < p.row_end);
+		return c;
+	}
+
+	// 128-thread CTAs, 9 per SM: 56 registers, 36 warps per SM (measured best on the 4K bunny frame: 64
+	// registers / 32 warps +1.4 %, 48 registers / 40 warps +6 %, 80 registers / 24 warps +13 %)
+#ifndef RT_PERSISTENT_MIN_CTAS
+#define RT_PERSISTENT_MIN_CTAS 9
+#endif
+#ifndef RT_PERSISTENT_THREADS
+#define RT_PERSISTENT_THREADS 128
+#endif
+	constexpr int kPersistentThreads = RT_PERSISTENT_THREADS;   // CTA size is free here: warps are the workers
+	template <int MODE, int SHADOWS, bool BVH>
+	__global__ void __launch_bounds__(kPersistentThreads, RT_PERSISTENT_MIN_CTAS)
+	render_kernel_persistent(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
+	{
+		__shared__ SharedScene sc;
+		stage_scene<kPersistentThreads>(sc, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
+		__syncthreads();
+
+		const int lane = threadIdx.x & 31;
+		const int total = p.grid_x * p.n_strips * kSignalsPerTile;
+		Counters<false> cnt;
+
+		int item = next_work_item(p.queue, lane);
+		while (item < total)
+		{
+#ifdef RT_PERSIST_PREFETCH
+			const int upcoming = next_work_item(p.queue, lane);
+#endif
+			uint32_t pixel = 0;
+			{
+				const TileCoords c = decode_work_item(p, item, lane);
+				if (c.valid) pixel = render_pixel<MODE, SHADOWS, BVH, false>(sc, dev, p, c.px, c.py, cnt);
+			}
+			// Only `item` is carried across the pixel: its coordinates are decoded again (a handful of integer
+			// instructions) instead of occupying registers during the traversals.
+			asm volatile("" : "+r"(item));
+			const TileCoords c = decode_work_item(p, item, lane);
+			const int dst_row = p.dst_full_frame ? c.py : (c.k * kBlockH + c.local_y);
+			uint32_t* row = p.dst + (size_t)dst_row * (size_t)p.width;
+			if (p.vector_store)
+			{
+				const uint32_t p1 = __shfl_down_sync(0xffffffffu, pixel, 1);
+				const uint32_t p2 = __shfl_down_sync(0xffffffffu, pixel, 2);
+				const uint32_t p3 = __shfl_down_sync(0xffffffffu, pixel, 3);
+				if (c.valid && (lane & 3) == 0) *reinterpret_cast<uint4*>(row + c.px) = make_uint4(pixel, p1, p2, p3);
+			}
+			else if (c.valid)
+			{
+				row[c.px] = pixel;
+			}
+			if (p.band_done)
+			{
+				__syncwarp();
+				if (lane == 0) signal_band_done(p, c.k, 1u);
+			}
+#ifdef RT_PERSIST_PREFETCH
+			item = upcoming;
+#else
+			item = next_work_item(p.queue, lane);
+#endif
+		}
+
+		// every warp of the grid arrives here exactly once, after its last fetch
+		if (lane == 0)
+		{
+			const unsigned int warps = gridDim.x * (unsigned int)(kPersistentThreads / 32);
+			if (atomicAdd(p.queue + 1, 1u) + 1u == warps)
+			{
+				p.queue[0] = 0u;
+				p.queue[1] = 0u;
+			}
+		}
 	}
 
 	// Root-rank tail of the band gather: band r holds strips r, r + world, ... packed; write the

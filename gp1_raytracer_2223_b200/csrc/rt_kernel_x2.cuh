@@ -539,7 +539,7 @@ namespace x2
 	render_kernel_x2(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
 		__shared__ SharedScene sc;
-		stage_scene<kThreads>(sc, dev);
+		stage_scene<kThreads>(sc, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
 
 		Pk K;

@@ -310,14 +310,17 @@ typedef struct rt_mesh_source
 int rt_upload_mesh_source(rt_context* ctx, int32_t mesh_id, const rt_mesh_source* source);
 int rt_transform_mesh(rt_context* ctx, int32_t mesh_id, const float* transform);
 
-/* Which build of the pixel kernel renders frames.  Both compute the same function, bit for bit.
- *   RT_KERNEL_SCALAR  one pixel per thread (default; also what rt_count_frame instruments)
- *   RT_KERNEL_PACKED  two pixels per thread on Blackwell's packed FP32 (FFMA2) */
+/* Which build of the pixel kernel renders frames.  All compute the same function, bit for bit.
+ *   RT_KERNEL_SCALAR      one pixel per thread, one CTA per 32x8 pixel tile (also what rt_count_frame instruments)
+ *   RT_KERNEL_PACKED      two pixels per thread on Blackwell's packed FP32 (FFMA2), one CTA per tile
+ *   RT_KERNEL_PERSISTENT  one pixel per thread, persistent warps pulling 8x4 warp tiles off a device queue
+ *                         (default: what RT_KERNEL_AUTO selects) */
 enum rt_kernel_variant
 {
 	RT_KERNEL_AUTO = 0,
 	RT_KERNEL_SCALAR = 1,
-	RT_KERNEL_PACKED = 2
+	RT_KERNEL_PACKED = 2,
+	RT_KERNEL_PERSISTENT = 3
 };
 int rt_set_kernel_variant(rt_context* ctx, int32_t variant);
 

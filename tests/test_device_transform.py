@@ -33,7 +33,7 @@ def test_device_transform_renders_the_reference_frame(name):
         r.Render()
     for i, src in enumerate(sources):
         r.ctx.transform_mesh(i, src.transform)
-    for variant in (1, 2):
+    for variant in (1, 2, 3):
         r.ctx.set_kernel_variant(variant)
         got = r.Render()
         identical, max_err, n_diff = compare_frames(got, load_golden_frame(name))

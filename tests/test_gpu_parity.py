@@ -67,9 +67,11 @@ def test_packed_kernel_matches_reference(gpu, name, mesh_path):
     r = make_renderer(name)
     r.ctx.set_mesh_path(mesh_path)
     r.ctx.set_kernel_variant(2)
-    got = r.Render()
+    got = r.Render().copy()
     r.ctx.set_kernel_variant(1)
     assert np.array_equal(got, r.Render()), "packed and scalar kernels disagree"
+    r.ctx.set_kernel_variant(3)
+    assert np.array_equal(got, r.Render()), "persistent and tiled kernels disagree"
     identical, max_err, n_diff = compare_frames(got, load_golden_frame(name))
     if name in EXACT:
         assert n_diff == 0

@@ -39,9 +39,12 @@ def test_random_scene_matches_oracle(seed, mode, shadows):
         want = rt_oracle.render(scene, W, H, mode, shadows, mesh_path=oracle_path)
         r.ctx.set_kernel_variant(2)
         packed = r.Render().copy()
+        r.ctx.set_kernel_variant(3)
+        persistent = r.Render().copy()
         r.ctx.set_kernel_variant(1)
         got = r.Render()
         assert np.array_equal(packed, got), (seed, gpu_path, "packed kernel differs from scalar kernel")
+        assert np.array_equal(persistent, got), (seed, gpu_path, "persistent kernel differs from tiled kernel")
         identical, max_err, n_diff = compare_frames(got, want)
         if not pow_materials or mode in (0, 1):
             assert n_diff == 0, (seed, gpu_path, n_diff, max_err)
@@ -70,7 +73,7 @@ def test_capacity_limits_match_oracle():
     for gpu_path, oracle_path in ((1, rt_oracle.MESH_SLAB_LINEAR), (2, rt_oracle.MESH_BVH)):
         r.ctx.set_mesh_path(gpu_path)
         want = rt_oracle.render(scene, W, H, mesh_path=oracle_path)
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             r.ctx.set_kernel_variant(variant)
             assert np.array_equal(r.Render(), want), (gpu_path, variant)
     # one past each capacity

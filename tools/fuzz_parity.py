@@ -28,7 +28,7 @@ for seed in range(first, first + count):
     for gpu_path, oracle_path in ((1, rt_oracle.MESH_SLAB_LINEAR), (2, rt_oracle.MESH_BVH)):
         if gpu_path == 2 and not scene.meshes: continue
         want = rt_oracle.render(scene, W, H, mode, shadows, mesh_path=oracle_path)
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             r.ctx.set_mesh_path(gpu_path); r.ctx.set_kernel_variant(variant)
             got = r.Render()
             total += 1

@@ -14,7 +14,7 @@ from gp1_raytracer_2223_b200 import Renderer  # noqa: E402
 
 names = [a for a in sys.argv[1:] if not a.startswith("-")] or ["bunny_4k", "bunny_640", "w3_640", "w4ref_640"]
 reps = 20
-paths = {"slab/scalar": (1, 1), "slab/packed": (1, 2), "bvh/scalar": (2, 1), "bvh/packed": (2, 2)}
+paths = {"slab/scalar": (1, 1), "slab/persist": (1, 3), "bvh/scalar": (2, 1), "bvh/persist": (2, 3)}
 for name in names:
   for pname, (path, variant) in paths.items():
     info = MANIFEST[name]
