@@ -185,3 +185,36 @@ def load_rtms(path) -> List[MeshSource]:
     if r.pos != len(data):
         raise ValueError(f"{path}: trailing bytes")
     return out
+
+
+@dataclasses.dataclass
+class MeshSteps:
+    """Input of a sequence of TriangleMesh::UpdateTransforms calls with BuildBVH (reference
+    source/DataTypes.h:210-236, 294-389): the mesh as it is BEFORE the first call (BuildBVH reorders indices and
+    normals in place, so every build starts from the order the previous one left) and one finalTransform per call."""
+    positions: np.ndarray     # (V, 3) float32, untransformed
+    indices: np.ndarray       # (T, 3) int32, order before the first call
+    normals: np.ndarray       # (T, 3) float32, untransformed face normals, same order
+    transforms: np.ndarray    # (n_steps, 4, 4) float32
+
+
+def load_rtmp(path) -> List[MeshSteps]:
+    """"RTMP0001": i32 n_meshes, n_steps, then per mesh i32 n_vertices, n_triangles, f32 positions, i32 indices,
+    f32 normals, n_steps x f32[16] finalTransform (written by oracle/ref_driver.cpp --yaw-steps --dump-mesh-steps)."""
+    with open(path, "rb") as f:
+        data = f.read()
+    if data[:8] != b"RTMP0001":
+        raise ValueError(f"{path}: not an RTMP0001 file")
+    r = _Reader(data)
+    r.pos = 8
+    n_meshes, n_steps = (int(v) for v in r.i32(2))
+    out = []
+    for _ in range(n_meshes):
+        n_v, n_t = (int(v) for v in r.i32(2))
+        pos = r.f32(3 * n_v).reshape(n_v, 3)
+        idx = r.i32(3 * n_t).reshape(n_t, 3)
+        nrm = r.f32(3 * n_t).reshape(n_t, 3)
+        out.append(MeshSteps(pos, idx, nrm, r.f32(16 * n_steps).reshape(n_steps, 4, 4)))
+    if r.pos != len(data):
+        raise ValueError(f"{path}: trailing bytes")
+    return out

@@ -590,6 +590,191 @@ void rto_transform_mesh(const float* positions, int32_t vertex_count, const floa
 	}
 }
 
+/* ---- TriangleMesh::BuildBVH, source/DataTypes.h:294-483 (the shipped configuration: BVH + USE_BINS) ---- */
+
+typedef struct bvh_build
+{
+	const float* tp;        /* transformedPositions */
+	int32_t* indices;       /* reordered in place, DataTypes.h:358-360 */
+	float* normals;         /* reordered in place, DataTypes.h:355 */
+	float* tnormals;        /* transformedNormals, reordered in place, DataTypes.h:356 */
+	rto_bvh_node* nodes;
+	int32_t capacity;
+	int32_t used;
+	int overflow;
+} bvh_build;
+
+static v3 bb_position(const bvh_build* b, int32_t index) { return v3_make(b->tp[3 * index], b->tp[3 * index + 1], b->tp[3 * index + 2]); }
+static float v3_axis(v3 v, int axis) { return axis == 0 ? v.x : (axis == 1 ? v.y : v.z); }
+static float std_minf(float a, float b) { return (b < a) ? b : a; }   /* std::min */
+static float std_maxf(float a, float b) { return (a < b) ? b : a; }   /* std::max */
+
+/* centroid of the triangle whose first index sits at `i`, DataTypes.h:349, 412-416, 432-435 */
+static v3 bb_centroid(const bvh_build* b, uint32_t i)
+{
+	const v3 sum = v3_add(v3_add(bb_position(b, b->indices[i]), bb_position(b, b->indices[i + 1])), bb_position(b, b->indices[i + 2]));
+	return v3_scale(sum, 0.3333f);
+}
+
+/* AABB, DataTypes.h:56-80 */
+typedef struct aabb { v3 mn, mx; } aabb;
+static aabb aabb_empty(void) { aabb a; a.mn = v3_make(FLT_MAX, FLT_MAX, FLT_MAX); a.mx = v3_make(FLT_MIN, FLT_MIN, FLT_MIN); return a; }   /* Vector3.cpp:13-14 */
+static void aabb_grow(aabb* a, v3 p)
+{
+	a->mn = v3_make(std_minf(a->mn.x, p.x), std_minf(a->mn.y, p.y), std_minf(a->mn.z, p.z));
+	a->mx = v3_make(std_maxf(a->mx.x, p.x), std_maxf(a->mx.y, p.y), std_maxf(a->mx.z, p.z));
+}
+static void aabb_grow_box(aabb* a, const aabb* o)
+{
+	a->mn = v3_make(std_minf(a->mn.x, o->mn.x), std_minf(a->mn.y, o->mn.y), std_minf(a->mn.z, o->mn.z));
+	a->mx = v3_make(std_maxf(a->mx.x, o->mx.x), std_maxf(a->mx.y, o->mx.y), std_maxf(a->mx.z, o->mx.z));
+}
+static float aabb_area(const aabb* a)
+{
+	const v3 e = v3_sub(a->mx, a->mn);
+	return e.x * e.y + e.y * e.z + e.z * e.x;
+}
+
+/* UpdateNodeBounds, DataTypes.h:310-321 */
+static void bb_update_bounds(bvh_build* b, uint32_t node_index)
+{
+	rto_bvh_node* n = &b->nodes[node_index];
+	aabb box = aabb_empty();
+	for (uint32_t i = n->first_idx; i < n->first_idx + n->idx_count; ++i) aabb_grow(&box, bb_position(b, b->indices[i]));
+	n->min_aabb[0] = box.mn.x; n->min_aabb[1] = box.mn.y; n->min_aabb[2] = box.mn.z;
+	n->max_aabb[0] = box.mx.x; n->max_aabb[1] = box.mx.y; n->max_aabb[2] = box.mx.z;
+}
+
+/* FindBestSplitPlane, DataTypes.h:398-483 */
+static float bb_best_split(const bvh_build* b, const rto_bvh_node* n, int* axis, float* split_pos)
+{
+	float best = FLT_MAX;
+	for (int a = 0; a < 3; ++a)
+	{
+		float lo = FLT_MAX, hi = FLT_MIN;
+		for (uint32_t k = 0; k < n->idx_count; k += 3)
+		{
+			const float c = v3_axis(bb_centroid(b, n->first_idx + k), a);
+			lo = std_minf(lo, c);
+			hi = std_maxf(hi, c);
+		}
+		const float diff = hi - lo;
+		if (fabsf(diff) < FLT_EPSILON) continue;
+
+		aabb bin_box[8];
+		uint32_t bin_count[8];
+		for (int i = 0; i < 8; ++i) { bin_box[i] = aabb_empty(); bin_count[i] = 0; }
+		float scale = 8 / diff;
+		for (uint32_t k = 0; k < n->idx_count; k += 3)
+		{
+			const uint32_t at = n->first_idx + k;
+			const float c = v3_axis(bb_centroid(b, at), a);
+			int bin = (int)((c - lo) * scale);
+			if (7 < bin) bin = 7;                                                     /* std::min(amountOfPlaneBins, ...) */
+			bin_count[bin] += 3;
+			aabb_grow(&bin_box[bin], bb_position(b, b->indices[at]));
+			aabb_grow(&bin_box[bin], bb_position(b, b->indices[at + 1]));
+			aabb_grow(&bin_box[bin], bb_position(b, b->indices[at + 2]));
+		}
+
+		float left_area[7], right_area[7];
+		int left_count[7], right_count[7];
+		int left_sum = 0, right_sum = 0;
+		aabb left_box = aabb_empty(), right_box = aabb_empty();
+		for (int i = 0; i < 7; ++i)
+		{
+			left_sum += (int)bin_count[i];
+			left_count[i] = left_sum;
+			aabb_grow_box(&left_box, &bin_box[i]);
+			left_area[i] = aabb_area(&left_box);
+			right_sum += (int)bin_count[7 - i];
+			right_count[7 - i - 1] = right_sum;
+			aabb_grow_box(&right_box, &bin_box[7 - i]);
+			right_area[7 - i - 1] = aabb_area(&right_box);
+		}
+		scale = diff / 8;
+		for (int i = 0; i < 7; ++i)
+		{
+			const float cost = left_count[i] * left_area[i] + right_count[i] * right_area[i];
+			if (cost < best)
+			{
+				*axis = a;
+				*split_pos = lo + scale * (i + 1);
+				best = cost;
+			}
+		}
+	}
+	return best;
+}
+
+static void swap_v3_at(float* v, uint32_t a, uint32_t b)
+{
+	for (int k = 0; k < 3; ++k) { const float t = v[3 * a + k]; v[3 * a + k] = v[3 * b + k]; v[3 * b + k] = t; }
+}
+
+/* Subdivide, DataTypes.h:323-389 */
+static void bb_subdivide(bvh_build* b, uint32_t node_index)
+{
+	rto_bvh_node* n = &b->nodes[node_index];
+	if (n->idx_count <= 8) return;
+
+	int axis = 0;
+	float split_pos = 0.f;
+	const float split_cost = bb_best_split(b, n, &axis, &split_pos);
+	aabb box; box.mn = v3_make(n->min_aabb[0], n->min_aabb[1], n->min_aabb[2]); box.mx = v3_make(n->max_aabb[0], n->max_aabb[1], n->max_aabb[2]);
+	const float no_split_cost = (float)n->idx_count * aabb_area(&box);                /* CalculateNodeCost, DataTypes.h:391-396 */
+	if (split_cost >= no_split_cost) return;
+
+	int i = (int)n->first_idx;
+	int j = i + (int)n->idx_count - 1;
+	while (i <= j)
+	{
+		if (v3_axis(bb_centroid(b, (uint32_t)i), axis) < split_pos) i += 3;
+		else
+		{
+			swap_v3_at(b->normals, (uint32_t)(i / 3), (uint32_t)((j - 2) / 3));
+			swap_v3_at(b->tnormals, (uint32_t)(i / 3), (uint32_t)((j - 2) / 3));
+			for (int k = 0; k < 3; ++k) { const int32_t t = b->indices[i + k]; b->indices[i + k] = b->indices[j - 2 + k]; b->indices[j - 2 + k] = t; }
+			j -= 3;
+		}
+	}
+	const int left_count = i - (int)n->first_idx;
+	if (left_count == 0 || left_count == (int)n->idx_count) return;
+	if (b->used + 2 > b->capacity) { b->overflow = 1; return; }
+
+	const uint32_t left = (uint32_t)b->used++, right = (uint32_t)b->used++;
+	n->left_node = left;
+	b->nodes[left].first_idx = n->first_idx;
+	b->nodes[left].idx_count = (uint32_t)left_count;
+	b->nodes[left].left_node = 0;
+	b->nodes[right].first_idx = (uint32_t)i;
+	b->nodes[right].idx_count = n->idx_count - (uint32_t)left_count;
+	b->nodes[right].left_node = 0;
+	n->idx_count = 0;
+	bb_update_bounds(b, left);
+	bb_update_bounds(b, right);
+	bb_subdivide(b, left);
+	bb_subdivide(b, right);
+}
+
+int32_t rto_update_transforms_bvh(const float* positions, int32_t vertex_count, int32_t* indices, float* normals,
+                                  int32_t triangle_count, const float* transform, float* out_positions,
+                                  float* out_normals, rto_bvh_node* out_nodes, int32_t node_capacity)
+{
+	if (node_capacity < 1) return -1;
+	rto_transform_mesh(positions, vertex_count, normals, triangle_count, transform, out_positions, out_normals);
+	bvh_build b;
+	b.tp = out_positions; b.indices = indices; b.normals = normals; b.tnormals = out_normals;
+	b.nodes = out_nodes; b.capacity = node_capacity; b.used = 1; b.overflow = 0;
+	/* BuildBVH, DataTypes.h:294-308 */
+	out_nodes[0].left_node = 0;
+	out_nodes[0].first_idx = 0;
+	out_nodes[0].idx_count = (uint32_t)(3 * triangle_count);
+	bb_update_bounds(&b, 0);
+	bb_subdivide(&b, 0);
+	return b.overflow ? -1 : b.used;
+}
+
 uint64_t rto_fnv1a64(const void* data, uint64_t bytes)
 {
 	const unsigned char* p = (const unsigned char*)data;

@@ -67,6 +67,16 @@ void rto_mesh_bounds(const rt_mesh_desc* mesh, float out_min[3], float out_max[3
 void rto_transform_mesh(const float* positions, int32_t vertex_count, const float* normals, int32_t triangle_count,
                         const float* transform, float* out_positions, float* out_normals);
 
+/* TriangleMesh::UpdateTransforms as the reference ships it, BuildBVH included (reference source/DataTypes.h:210-236,
+ * 294-483, with BVH and USE_BINS defined, DataTypes.h:8-9).  `indices` (3 * T) and `normals` (3 * T floats) are
+ * reordered IN PLACE exactly as the reference reorders TriangleMesh::indices / normals (DataTypes.h:344-363): the
+ * next call starts from the order this one leaves, as in the reference.  out_positions (3 * V) and out_normals
+ * (3 * T, final order) receive transformedPositions / transformedNormals, out_nodes the BVHNode array (capacity
+ * node_capacity >= 2 * T is always enough).  Returns nodesUsed, or -1 when out_nodes is too small. */
+int32_t rto_update_transforms_bvh(const float* positions, int32_t vertex_count, int32_t* indices, float* normals,
+                                  int32_t triangle_count, const float* transform, float* out_positions,
+                                  float* out_normals, rto_bvh_node* out_nodes, int32_t node_capacity);
+
 uint64_t rto_fnv1a64(const void* data, uint64_t bytes);
 
 #ifdef __cplusplus

@@ -64,6 +64,8 @@ namespace
 		std::string out;
 		std::string dump;
 		std::string dumpSource;   // untransformed meshes + their final transform ("RTMS0001")
+		std::vector<float> yawSteps;  // --yaw-steps a,b,c: RotateY(a); UpdateTransforms(); RotateY(b); UpdateTransforms(); ...
+		std::string dumpSteps;    // the mesh state BEFORE those steps + the final transform of each step ("RTMP0001")
 		std::string resources; // directory that CONTAINS "Resources/"
 	};
 
@@ -75,6 +77,7 @@ namespace
 			"  [--width W --height H] [--mode 0..3] [--shadows 0|1] [--frames N] [--warmup N]\n"
 			"  [--threads T] [--time SECONDS] [--mesh-yaw RAD] [--cam-origin X Y Z]\n"
 			"  [--cam-rot PITCH YAW] [--fov DEGREES] [--out FILE] [--dump-scene FILE] [--dump-mesh-source FILE]\n"
+			"  [--yaw-steps A,B,... [--dump-mesh-steps FILE]]\n"
 			"  [--resources DIR]\n", why);
 		std::exit(2);
 	}
@@ -102,6 +105,21 @@ namespace
 			else if (a == "--out") { need(i, 1); o.out = argv[++i]; }
 			else if (a == "--dump-scene") { need(i, 1); o.dump = argv[++i]; }
 			else if (a == "--dump-mesh-source") { need(i, 1); o.dumpSource = argv[++i]; }
+			else if (a == "--dump-mesh-steps") { need(i, 1); o.dumpSteps = argv[++i]; }
+			else if (a == "--yaw-steps")
+			{
+				need(i, 1);
+				const std::string list = argv[++i];
+				size_t pos = 0;
+				while (pos <= list.size())
+				{
+					const size_t comma = list.find(',', pos);
+					const std::string item = list.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+					if (!item.empty()) o.yawSteps.push_back((float)std::atof(item.c_str()));
+					if (comma == std::string::npos) break;
+					pos = comma + 1;
+				}
+			}
 			else if (a == "--resources") { need(i, 1); o.resources = argv[++i]; }
 			else Usage(("unknown argument " + a).c_str());
 		}
@@ -224,6 +242,52 @@ namespace
 	}
 }
 
+namespace
+{
+	// Input of a sequence of TriangleMesh::UpdateTransforms calls (source/DataTypes.h:210-236, BuildBVH
+	// included): the meshes as they are BEFORE the first call - BuildBVH reorders indices and normals in
+	// place (DataTypes.h:344-363), so every build starts from the order the previous one left - and the
+	// finalTransform of every call.  The matching output is the --dump-scene of the same run.
+	struct StepRecorder
+	{
+		struct MeshBefore { std::vector<Vector3> positions, normals; std::vector<int> indices; };
+		std::vector<MeshBefore> before;
+		std::vector<std::vector<Matrix>> transforms;   // [step][mesh]
+		void Capture(Scene* pScene)
+		{
+			for (const TriangleMesh& m : pScene->m_TriangleMeshGeometries) before.push_back({ m.positions, m.normals, m.indices });
+		}
+		void Step(Scene* pScene)
+		{
+			transforms.emplace_back();
+			for (const TriangleMesh& m : pScene->m_TriangleMeshGeometries)
+				transforms.back().push_back(m.scaleTransform * m.rotationTransform * m.translationTransform);   // DataTypes.h:213
+		}
+		void Write(const char* path) const
+		{
+			FILE* f = std::fopen(path, "wb");
+			if (!f) { std::perror(path); std::exit(1); }
+			Writer w{ f };
+			std::fwrite("RTMP0001", 1, 8, f);
+			w.I32((int32_t)before.size()); w.I32((int32_t)transforms.size());
+			for (size_t k = 0; k < before.size(); ++k)
+			{
+				const MeshBefore& m = before[k];
+				w.I32((int32_t)m.positions.size()); w.I32((int32_t)(m.indices.size() / 3));
+				for (const Vector3& p : m.positions) w.V3(p);
+				for (int idx : m.indices) w.I32(idx);
+				for (const Vector3& n : m.normals) w.V3(n);
+				for (size_t s = 0; s < transforms.size(); ++s)
+				{
+					const Matrix& t = transforms[s][k];
+					for (int r = 0; r < 4; ++r) { w.F32(t.data[r].x); w.F32(t.data[r].y); w.F32(t.data[r].z); w.F32(t.data[r].w); }
+				}
+			}
+			std::fclose(f);
+		}
+	};
+}
+
 int main(int argc, char** argv)
 {
 	const Options o = Parse(argc, argv);
@@ -236,12 +300,12 @@ int main(int argc, char** argv)
 		const ssize_t n = readlink("/proc/self/exe", exe, sizeof(exe) - 1);
 		if (n > 0) { exe[n] = 0; res = exe; res = res.substr(0, res.find_last_of('/')); }
 	}
-	std::string out = o.out, dump = o.dump, dumpSource = o.dumpSource;
+	std::string out = o.out, dump = o.dump, dumpSource = o.dumpSource, dumpSteps = o.dumpSteps;
 	auto absolutise = [](std::string& p)
 	{
 		if (!p.empty() && p[0] != '/') { char cwd[4096]; if (getcwd(cwd, sizeof cwd)) p = std::string(cwd) + "/" + p; }
 	};
-	absolutise(out); absolutise(dump); absolutise(dumpSource);
+	absolutise(out); absolutise(dump); absolutise(dumpSource); absolutise(dumpSteps);
 	if (!res.empty() && chdir(res.c_str()) != 0) { std::perror(res.c_str()); return 1; }
 
 	if (o.threads > 0) omp_set_num_threads(o.threads);
@@ -268,6 +332,17 @@ int main(int argc, char** argv)
 	if (o.haveMeshYaw)
 	{
 		for (TriangleMesh& m : pScene->m_TriangleMeshGeometries) { m.RotateY(o.meshYaw); m.UpdateTransforms(); }
+	}
+	if (!o.yawSteps.empty())
+	{
+		StepRecorder rec;
+		rec.Capture(pScene);
+		for (float yaw : o.yawSteps)
+		{
+			for (TriangleMesh& m : pScene->m_TriangleMeshGeometries) { m.RotateY(yaw); m.UpdateTransforms(); }
+			rec.Step(pScene);
+		}
+		if (!dumpSteps.empty()) rec.Write(dumpSteps.c_str());
 	}
 	if (o.haveCamOrigin) cam.origin = { o.camOrigin[0], o.camOrigin[1], o.camOrigin[2] };
 	if (o.haveCamRot)

@@ -55,6 +55,9 @@ def lib():
                                          C.POINTER(rt_counters)]
         _lib.rto_transform_mesh.restype = None
         _lib.rto_transform_mesh.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.rto_update_transforms_bvh.restype = C.c_int32
+        _lib.rto_update_transforms_bvh.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
         _lib.rto_fnv1a64.restype = C.c_uint64
         _lib.rto_fnv1a64.argtypes = [C.c_void_p, C.c_uint64]
     return _lib
@@ -107,3 +110,22 @@ def transform_mesh(positions: np.ndarray, normals: np.ndarray, transform: np.nda
     out_p, out_n = np.empty_like(pos), np.empty_like(nrm)
     lib().rto_transform_mesh(pos.ctypes.data, pos.shape[0], nrm.ctypes.data, nrm.shape[0], m.ctypes.data, out_p.ctypes.data, out_n.ctypes.data)
     return out_p, out_n
+
+
+def update_transforms_bvh(positions: np.ndarray, indices: np.ndarray, normals: np.ndarray, transform: np.ndarray):
+    """CPU restatement of TriangleMesh::UpdateTransforms with BuildBVH (reference source/DataTypes.h:210-236, 294-483).
+    `indices` (T, 3) int32 and `normals` (T, 3) float32 are REORDERED IN PLACE like the reference's members (they
+    must be C-contiguous arrays of exactly those dtypes).  Returns (transformed positions, transformed normals in
+    the new order, BVH nodes as a BVH_NODE_DTYPE array)."""
+    from gp1_raytracer_2223_b200.scene_file import BVH_NODE_DTYPE
+    pos = np.ascontiguousarray(positions, dtype=np.float32)
+    assert indices.dtype == np.int32 and indices.flags.c_contiguous and normals.dtype == np.float32 and normals.flags.c_contiguous
+    m = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
+    n_t = indices.shape[0]
+    out_p, out_n = np.empty_like(pos), np.empty_like(normals)
+    nodes = np.zeros(max(2 * n_t, 1), dtype=BVH_NODE_DTYPE)
+    used = lib().rto_update_transforms_bvh(pos.ctypes.data, pos.shape[0], indices.ctypes.data, normals.ctypes.data, n_t,
+                                           m.ctypes.data, out_p.ctypes.data, out_n.ctypes.data, nodes.ctypes.data, len(nodes))
+    if used < 0:
+        raise RuntimeError("rto_update_transforms_bvh: node array too small")
+    return out_p, out_n, nodes[:used].copy()

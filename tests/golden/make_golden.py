@@ -63,6 +63,11 @@ CASES = {
     "w4ref_101x203": ("W4_Reference", (101, 203), 3, 1, []),
     # next row N3: 3082-triangle mesh, Cook-Torrance
     "optional_320": ("W4_Optional", SMALL, 3, 1, []),
+    # sequences of UpdateTransforms + BuildBVH calls (every build starts from the triangle order the previous one
+    # left): pin the BuildBVH restatement and the device-side build
+    "bunny_320_steps3": ("W4_Bunny", SMALL, 3, 1, ["--yaw-steps", "0.5,1.0,1.7"]),
+    "w4ref_320_steps2": ("W4_Reference", SMALL, 3, 1, ["--yaw-steps", "0.7,2.1"]),
+    "optional_320_steps2": ("W4_Optional", SMALL, 3, 1, ["--yaw-steps", "0.3,0.9"]),
     # BASELINE.json configs[4]: the headline frame
     "bunny_4k": ("W4_Bunny", L, 3, 1, []),
 }
@@ -70,6 +75,9 @@ CASES = {
 
 # cases that also get <case>.rtms: the untransformed meshes + finalTransform (input of the device-side
 # TriangleMesh::UpdateTransforms)
+# cases that also get <case>.rtmp: the meshes before the --yaw-steps sequence + the transform of every step
+MESH_STEPS = {"bunny_320_steps3", "w4ref_320_steps2", "optional_320_steps2"}
+
 MESH_SOURCES = {"bunny_320_yaw05", "bunny_320_yaw10", "bunny_320_time2", "w4ref_320_time13", "optional_320"}
 
 
@@ -84,13 +92,21 @@ def main():
     if not os.path.exists(REF):
         sys.exit("oracle/_ref/ref_render missing: run `make -C oracle ref` first")
     manifest = {}
+    only = set(sys.argv[1:])            # `make_golden.py case ...` regenerates just those cases
+    if only:
+        with open(os.path.join(HERE, "manifest.json")) as f:
+            manifest.update(json.load(f))
     for name, (scene, (w, h), mode, shadows, extra) in CASES.items():
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as tmp:
             raw = os.path.join(tmp, "frame.bin")
             rtsc = os.path.join(HERE, name + ".rtsc")
             args = ["--scene", scene, "--width", str(w), "--height", str(h), "--mode", str(mode),
                     "--shadows", str(shadows)] + extra
             extra_out = ["--dump-mesh-source", os.path.join(HERE, name + ".rtms")] if name in MESH_SOURCES else []
+            if name in MESH_STEPS:
+                extra_out += ["--dump-mesh-steps", os.path.join(HERE, name + ".rtmp")]
             out = subprocess.run([REF] + args + ["--out", raw, "--dump-scene", rtsc] + extra_out, check=True,
                                  capture_output=True, text=True).stdout
             info = json.loads(out)
