@@ -56,6 +56,11 @@ class rt_mesh_source(C.Structure):
                 ("triangle_count", C.c_int32), ("cull_mode", C.c_int32), ("material_index", C.c_uint8)]
 
 
+class rt_built_node(C.Structure):
+    _fields_ = [("min_aabb", C.c_float * 3), ("max_aabb", C.c_float * 3), ("first", C.c_int32), ("triangle_count", C.c_int32),
+                ("escape", C.c_int32)]
+
+
 class rt_camera(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("fov", C.c_float), ("right", C.c_float * 3), ("up", C.c_float * 3),
                 ("forward", C.c_float * 3)]

@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from ._abi import (rt_mesh_source, rt_camera, rt_counters, rt_frame_desc, rt_lights_soa, rt_material_desc, rt_mesh_desc,
+from ._abi import (rt_built_node, rt_mesh_source, rt_camera, rt_counters, rt_frame_desc, rt_lights_soa, rt_material_desc, rt_mesh_desc,
                    rt_planes_soa, rt_spheres_soa, rt_timing)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -29,6 +29,9 @@ SYMBOLS = {
     "rt_set_mesh_path": (C.c_int, [_ctx, C.c_int32]),
     "rt_upload_mesh_source": (C.c_int, [_ctx, C.c_int32, C.POINTER(rt_mesh_source)]),
     "rt_transform_mesh": (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_float)]),
+    "rt_set_mesh_device_bvh": (C.c_int, [_ctx, C.c_int32, C.c_int32]),
+    "rt_read_mesh_build": (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(rt_built_node), C.c_int32,
+                                     C.POINTER(C.c_int32)]),
     "rt_set_kernel_variant": (C.c_int, [_ctx, C.c_int32]),
     "rt_upload_mesh": (C.c_int, [_ctx, C.c_int32, C.POINTER(rt_mesh_desc)]),
     "rt_render": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_void_p, C.c_int32]),

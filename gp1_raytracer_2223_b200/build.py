@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librt_b200.so")
 SOURCES = ["rt_api.cu"]
-HEADERS = ["rt_kernel.cuh", "rt_kernel_x2.cuh", "rt_device.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
+HEADERS = ["rt_kernel.cuh", "rt_kernel_x2.cuh", "rt_device.cuh", "rt_bvh_build.cuh", os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -5,11 +5,13 @@
 // CUDA is not there.
 #include "rt_kernel.cuh"
 #include "rt_kernel_x2.cuh"
+#include "rt_bvh_build.cuh"
 
 #include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +39,10 @@ namespace
 		std::vector<int32_t> src_indices;
 		bool has_source = false, source_dirty = false, has_transform = false, transform_dirty = false;
 		float transform[16] = {};
+		// device-side BuildBVH (rt_set_mesh_device_bvh): every rt_transform_mesh is one UpdateTransforms call of the
+		// reference, build included; the builds are history-dependent, so none may be skipped or repeated
+		bool device_bvh = false;
+		std::vector<std::array<float, 16>> pending_builds;
 	};
 
 	// Offsets (in floats) of the SoA arrays inside the per-device float arena.
@@ -69,7 +75,15 @@ namespace
 		size_t mesh_capacity = 0;          // in float4
 		size_t triangle_offset = 0, node_offset = 0;   // in float4, inside d_mesh
 		cudaEvent_t ev_upload = nullptr;   // last scene copy on this device (pinned source may be reused after it)
-		struct MeshSourceDevice { float* positions = nullptr; float* normals = nullptr; int32_t* indices = nullptr; };
+		struct MeshSourceDevice
+		{
+			float* positions = nullptr; float* normals = nullptr; int32_t* indices = nullptr;
+			// device-side BuildBVH: the other half of the indices / normals ping-pong pair, scratch and results
+			float* normals_alt = nullptr; int32_t* indices_alt = nullptr;
+			void* build_block = nullptr;
+			rt::BuildParams build{};           // pointers into build_block, filled once per source upload
+			bool built = false;                // build results are valid (emit_mesh_kernel may copy them)
+		};
 		std::vector<MeshSourceDevice> sources;   // untransformed meshes (rt_upload_mesh_source), by mesh id
 		uint32_t* d_frame = nullptr;
 		size_t frame_capacity = 0;         // in pixels
@@ -108,6 +122,8 @@ struct rt_context
 	cudaEvent_t ev_gather = nullptr, ev_d2h = nullptr;   // on device 0
 	rt_timing timing{};
 	int32_t last_width = 0, last_height = 0;
+
+	int32_t* h_build_status = nullptr;  // pinned, one word per mesh: status of the last device-side BVH build (device 0)
 
 	void* registered_host = nullptr;    // host surface we pinned ourselves
 	size_t registered_bytes = 0;
@@ -344,15 +360,44 @@ namespace
 		return RT_OK;
 	}
 
-	// Meshes that are transformed on the device: (re)send their untransformed source when it changed, and run
-	// transform_mesh_kernel when the transform changed or the mesh block was just rewritten from the host mirror.
+	// Carves the scratch / result arrays of update_transforms_bvh_kernel out of one allocation.
+	int allocate_build_block(rt_context* ctx, DeviceState::MeshSourceDevice& sd, int32_t V, int32_t T)
+	{
+		const size_t N = (size_t)std::max(2 * T - 1, 1);
+		size_t offset = 0;
+		auto take = [&](size_t bytes) { const size_t at = offset; offset = (offset + bytes + 15) & ~size_t(15); return at; };
+		const size_t o_tpos = take(12 * (size_t)std::max(V, 1)), o_cen = take(12 * (size_t)std::max(T, 1)), o_min = take(12 * (size_t)std::max(T, 1)),
+		             o_max = take(12 * (size_t)std::max(T, 1)), o_tn = take(12 * (size_t)std::max(T, 1)), o_order = take(4 * (size_t)std::max(T, 1)),
+		             o_flag = take((size_t)std::max(T, 1)), o_first = take(4 * N), o_count = take(4 * N), o_escape = take(4 * N), o_box = take(24 * N),
+		             o_qa = take(4 * (size_t)std::max(T, 1)), o_qb = take(4 * (size_t)std::max(T, 1)), o_tris = take(48 * (size_t)std::max(T, 1)),
+		             o_nodes = take(32 * N), o_info = take(32);
+		RT_CUDA(ctx, cudaMalloc(&sd.build_block, offset));
+		RT_CUDA(ctx, cudaMemset(sd.build_block, 0, offset));
+		char* base = (char*)sd.build_block;
+		rt::BuildParams& b = sd.build;
+		b = rt::BuildParams{};
+		b.positions = sd.positions; b.vertex_count = V; b.triangle_count = T;
+		b.tpos = (float*)(base + o_tpos); b.centroid = (float*)(base + o_cen); b.tri_min = (float*)(base + o_min); b.tri_max = (float*)(base + o_max);
+		b.tnormal = (float*)(base + o_tn); b.order = (int32_t*)(base + o_order); b.left_flag = (uint8_t*)(base + o_flag);
+		b.node_first = (int32_t*)(base + o_first); b.node_count = (int32_t*)(base + o_count); b.node_escape = (int32_t*)(base + o_escape);
+		b.node_box = (float*)(base + o_box); b.queue_a = (int32_t*)(base + o_qa); b.queue_b = (int32_t*)(base + o_qb);
+		b.result_triangles = (float4*)(base + o_tris); b.result_nodes = (float4*)(base + o_nodes); b.result_info = (int32_t*)(base + o_info);
+		return RT_OK;
+	}
+
+	// Meshes that are transformed on the device: (re)send their untransformed source when it changed, then
+	//  * without device BVH: run transform_mesh_kernel when the transform changed or the mesh block was just
+	//    rewritten from the host mirror (idempotent);
+	//  * with device BVH: run update_transforms_bvh_kernel once per rt_transform_mesh call since the last frame, in
+	//    call order (each build starts from the triangle order the previous one left), then copy the last build
+	//    into the block (emit_mesh_kernel) - also when only the block was rewritten.
 	int run_device_transforms(rt_context* ctx, bool block_rewritten)
 	{
 		for (size_t m = 0; m < ctx->meshes.size(); ++m)
 		{
 			HostMesh& hm = ctx->meshes[m];
 			if (!hm.has_source) continue;
-			const int32_t T = (int32_t)(hm.src_indices.size() / 3);
+			const int32_t T = (int32_t)(hm.src_indices.size() / 3), V = (int32_t)(hm.src_positions.size() / 3);
 			int32_t first = 0, first_node = 0;
 			for (size_t k = 0; k < m; ++k) { first += (int32_t)(ctx->meshes[k].triangles.size() / 3); first_node += (int32_t)(ctx->meshes[k].nodes.size() / 2); }
 			for (DeviceState& d : ctx->devs)
@@ -363,7 +408,7 @@ namespace
 				if (hm.source_dirty)
 				{
 					RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
-					cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices);
+					cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices); cudaFree(sd.normals_alt); cudaFree(sd.indices_alt); cudaFree(sd.build_block);
 					sd = DeviceState::MeshSourceDevice{};
 					RT_CUDA(ctx, cudaMalloc(&sd.positions, std::max<size_t>(hm.src_positions.size(), 1) * sizeof(float)));
 					RT_CUDA(ctx, cudaMalloc(&sd.normals, std::max<size_t>(hm.src_normals.size(), 1) * sizeof(float)));
@@ -372,8 +417,42 @@ namespace
 					RT_CUDA(ctx, cudaMemcpy(sd.positions, hm.src_positions.data(), hm.src_positions.size() * sizeof(float), cudaMemcpyHostToDevice));
 					RT_CUDA(ctx, cudaMemcpy(sd.normals, hm.src_normals.data(), hm.src_normals.size() * sizeof(float), cudaMemcpyHostToDevice));
 					RT_CUDA(ctx, cudaMemcpy(sd.indices, hm.src_indices.data(), hm.src_indices.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+					if (hm.device_bvh)
+					{
+						RT_CUDA(ctx, cudaMalloc(&sd.normals_alt, std::max<size_t>(hm.src_normals.size(), 1) * sizeof(float)));
+						RT_CUDA(ctx, cudaMalloc(&sd.indices_alt, std::max<size_t>(hm.src_indices.size(), 1) * sizeof(int32_t)));
+						const int rc = allocate_build_block(ctx, sd, V, T);
+						if (rc != RT_OK) return rc;
+					}
 				}
-				if (hm.has_transform && (hm.transform_dirty || hm.source_dirty || block_rewritten) && T > 0)
+				if (hm.device_bvh)
+				{
+					for (const std::array<float, 16>& transform : hm.pending_builds)
+					{
+						rt::BuildParams& b = sd.build;
+						memcpy(b.m, transform.data(), sizeof b.m);
+						b.indices_in = sd.indices; b.normals_in = sd.normals; b.indices_out = sd.indices_alt; b.normals_out = sd.normals_alt;
+						rt::update_transforms_bvh_kernel<<<1, rt::kBuildThreads, 0, d.stream>>>(b);
+						RT_CUDA(ctx, cudaGetLastError());
+						std::swap(sd.indices, sd.indices_alt); std::swap(sd.normals, sd.normals_alt);     // the order the build left
+						sd.built = true;
+						if (&d == &ctx->devs[0]) RT_CUDA(ctx, cudaMemcpyAsync(ctx->h_build_status + m, b.result_info + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
+						ctx->timing.kernel_launches++;
+					}
+					if (sd.built && (!hm.pending_builds.empty() || block_rewritten) && T > 0)
+					{
+						rt::EmitParams e{};
+						e.result_triangles = sd.build.result_triangles; e.result_nodes = sd.build.result_nodes; e.result_info = sd.build.result_info;
+						e.triangle_count = T;
+						e.triangles = d.d_mesh + d.triangle_offset + 3 * (size_t)first;
+						e.nodes = d.d_mesh + d.node_offset + 2 * (size_t)first_node;
+						e.table = d.d_mesh + 3 * m;
+						rt::emit_mesh_kernel<<<1, 256, 0, d.stream>>>(e);
+						RT_CUDA(ctx, cudaGetLastError());
+						RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
+					}
+				}
+				else if (hm.has_transform && (hm.transform_dirty || hm.source_dirty || block_rewritten) && T > 0)
 				{
 					rt::TransformParams tp{};
 					memcpy(tp.m, hm.transform, sizeof tp.m);
@@ -387,7 +466,16 @@ namespace
 					RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
 				}
 			}
-			hm.source_dirty = false; hm.transform_dirty = false;
+			// a leaf wider than the link's triangle field can only come out of a mesh that large: only then is the
+			// status word worth a host synchronisation
+			const bool check_status = hm.device_bvh && !hm.pending_builds.empty() && T > rt::BvhLink::kMaxLeafTriangles;
+			hm.source_dirty = false; hm.transform_dirty = false; hm.pending_builds.clear();
+			if (check_status)
+			{
+				RT_CUDA(ctx, cudaStreamSynchronize(ctx->devs[0].stream));
+				if (ctx->h_build_status[m] != 0)
+					return fail(ctx, RT_ERR_CAPACITY, "the device-side BVH build of mesh %d produced a leaf wider than %d triangles", (int)m, rt::BvhLink::kMaxLeafTriangles);
+			}
 		}
 		return RT_OK;
 	}
@@ -855,6 +943,8 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		ctx->devs.push_back(d);
 	}
 	RT_CREATE(cudaSetDevice(ids[0]));
+	RT_CREATE(cudaHostAlloc(&ctx->h_build_status, sizeof(int32_t) * rt::kMaxMeshes, cudaHostAllocPortable));
+	memset(ctx->h_build_status, 0, sizeof(int32_t) * rt::kMaxMeshes);
 	RT_CREATE(cudaHostAlloc(&ctx->h_static, StaticBlock::total, cudaHostAllocPortable));
 	memset(ctx->h_static, 0, StaticBlock::total);
 	ctx->arena = reinterpret_cast<float*>(ctx->h_static + StaticBlock::arena);
@@ -894,7 +984,7 @@ int rt_destroy(rt_context* ctx)
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
-		for (auto& sd : d.sources) { cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices); }
+		for (auto& sd : d.sources) { cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices); cudaFree(sd.normals_alt); cudaFree(sd.indices_alt); cudaFree(sd.build_block); }
 		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
 		if (d.ev_kernel) cudaEventDestroy(d.ev_kernel);
 		if (d.ev_done) cudaEventDestroy(d.ev_done);
@@ -1027,8 +1117,10 @@ int rt_upload_mesh_source(rt_context* ctx, int32_t mesh_id, const rt_mesh_source
 	hm.src_indices.assign(src->indices, src->indices + 3 * (size_t)src->triangle_count);
 	hm.src_normals.assign(src->normals, src->normals + 3 * (size_t)src->triangle_count);
 	// the stream slice is sized now and filled by transform_mesh_kernel; no BVH -> slab + linear body
+	// (rt_set_mesh_device_bvh reserves the node slice and switches to update_transforms_bvh_kernel)
 	hm.triangles.assign(3 * (size_t)src->triangle_count, make_float4(0.f, 0.f, 0.f, 0.f));
 	hm.nodes.clear();
+	hm.device_bvh = false; hm.pending_builds.clear();
 	for (int k = 0; k < 3; ++k) { hm.aabb_min[k] = 0.f; hm.aabb_max[k] = 0.f; }
 	hm.cull_mode = src->cull_mode;
 	hm.material = src->material_index;
@@ -1047,6 +1139,29 @@ int rt_transform_mesh(rt_context* ctx, int32_t mesh_id, const float* transform)
 	if (!hm.has_source) return fail(ctx, RT_ERR_BAD_STATE, "mesh %d was not uploaded with rt_upload_mesh_source", mesh_id);
 	memcpy(hm.transform, transform, sizeof hm.transform);
 	hm.has_transform = true; hm.transform_dirty = true;
+	if (hm.device_bvh)
+	{
+		std::array<float, 16> t;
+		memcpy(t.data(), transform, sizeof hm.transform);
+		hm.pending_builds.push_back(t);
+	}
+	return RT_OK;
+}
+
+int rt_set_mesh_device_bvh(rt_context* ctx, int32_t mesh_id, int32_t enable)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (mesh_id < 0 || mesh_id >= (int32_t)ctx->meshes.size()) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "mesh id %d outside the announced count %d", mesh_id, (int)ctx->meshes.size());
+	HostMesh& hm = ctx->meshes[(size_t)mesh_id];
+	if (!hm.has_source) return fail(ctx, RT_ERR_BAD_STATE, "mesh %d was not uploaded with rt_upload_mesh_source", mesh_id);
+	if (hm.has_transform) return fail(ctx, RT_ERR_BAD_STATE, "rt_set_mesh_device_bvh must be called before the first rt_transform_mesh of mesh %d", mesh_id);
+	const size_t T = hm.src_indices.size() / 3;
+	if (enable && 2 * T > (size_t)rt::BvhLink::kEscapeMask) return fail(ctx, RT_ERR_CAPACITY, "%zu triangles exceed what the BVH node links can address", T);
+	hm.device_bvh = enable != 0;
+	// node slice: 2T - 1 nodes at most, written by emit_mesh_kernel
+	if (hm.device_bvh && T > 0) hm.nodes.assign(2 * (2 * T - 1), make_float4(0.f, 0.f, 0.f, 0.f)); else hm.nodes.clear();
+	hm.source_dirty = true;      // (re)allocate the device-side build buffers
+	ctx->mesh_dirty = true;
 	return RT_OK;
 }
 
@@ -1370,6 +1485,46 @@ int rt_get_timing(const rt_context* ctx, rt_timing* out_timing)
 {
 	if (!ctx || !out_timing) return RT_ERR_INVALID_ARGUMENT;
 	*out_timing = ctx->timing;
+	return RT_OK;
+}
+
+int rt_read_mesh_build(rt_context* ctx, int32_t mesh_id, int32_t* indices, float* normals, rt_built_node* nodes, int32_t node_capacity, int32_t* out_node_count)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (mesh_id < 0 || mesh_id >= (int32_t)ctx->meshes.size()) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "mesh id %d outside the announced count %d", mesh_id, (int)ctx->meshes.size());
+	HostMesh& hm = ctx->meshes[(size_t)mesh_id];
+	if (!hm.device_bvh) return fail(ctx, RT_ERR_BAD_STATE, "mesh %d is not built on the device (rt_set_mesh_device_bvh)", mesh_id);
+	if (!hm.has_transform) return fail(ctx, RT_ERR_BAD_STATE, "mesh %d has not been transformed yet (rt_transform_mesh)", mesh_id);
+	if (nodes && node_capacity < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "negative node capacity");
+	int rc = flush_uploads(ctx);       // runs the builds that are still pending, in call order
+	if (rc != RT_OK) return rc;
+	DeviceState& d = ctx->devs[0];
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+	const DeviceState::MeshSourceDevice& sd = d.sources[(size_t)mesh_id];
+	const size_t T = hm.src_indices.size() / 3;
+	if (indices && T) RT_CUDA(ctx, cudaMemcpy(indices, sd.indices, 3 * T * sizeof(int32_t), cudaMemcpyDeviceToHost));
+	if (normals && T) RT_CUDA(ctx, cudaMemcpy(normals, sd.normals, 3 * T * sizeof(float), cudaMemcpyDeviceToHost));
+	int32_t info[8] = {};
+	RT_CUDA(ctx, cudaMemcpy(info, sd.build.result_info, sizeof info, cudaMemcpyDeviceToHost));
+	if (out_node_count) *out_node_count = info[0];
+	if (nodes)
+	{
+		if (info[0] > node_capacity) return fail(ctx, RT_ERR_CAPACITY, "the build has %d nodes, the caller's array holds %d", info[0], node_capacity);
+		std::vector<float4> records(2 * (size_t)info[0]);
+		if (info[0]) RT_CUDA(ctx, cudaMemcpy(records.data(), sd.build.result_nodes, records.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+		for (int32_t n = 0; n < info[0]; ++n)
+		{
+			const float4 a = records[2 * (size_t)n], b = records[2 * (size_t)n + 1];
+			int32_t first, link;
+			memcpy(&first, &b.z, sizeof first); memcpy(&link, &b.w, sizeof link);
+			rt_built_node& out = nodes[n];
+			out.min_aabb[0] = a.x; out.max_aabb[0] = a.y; out.min_aabb[1] = a.z; out.max_aabb[1] = a.w; out.min_aabb[2] = b.x; out.max_aabb[2] = b.y;
+			out.first = first;
+			out.triangle_count = link >> rt::BvhLink::kEscapeBits;
+			out.escape = (link & rt::BvhLink::kEscapeMask) - 1;
+		}
+	}
 	return RT_OK;
 }
 

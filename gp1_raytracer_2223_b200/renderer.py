@@ -88,8 +88,29 @@ class Context:
         m = np.ascontiguousarray(transform, dtype=np.float32).reshape(16)
         self.check(self.lib.rt_transform_mesh(self.handle, mesh_id, m.ctypes.data_as(C.POINTER(C.c_float))), "rt_transform_mesh")
 
+    def set_mesh_device_bvh(self, mesh_id: int, enable: bool = True) -> None:
+        """Every later transform_mesh is a full TriangleMesh::UpdateTransforms of the reference, BuildBVH included
+        (reference source/DataTypes.h:210-236, 294-483), run on the device; the mesh is rendered by the BVH body."""
+        self.check(self.lib.rt_set_mesh_device_bvh(self.handle, mesh_id, 1 if enable else 0), "rt_set_mesh_device_bvh")
+
+    def read_mesh_build(self, mesh_id: int, triangle_count: int):
+        """(indices, normals, nodes) the device-side builds left behind: TriangleMesh::indices / normals in their new
+        order and the tree as a structured array (min_aabb, max_aabb, first, triangle_count, escape)."""
+        from ._abi import rt_built_node, c_float_p, c_i32_p
+        idx = np.zeros(3 * triangle_count, dtype=np.int32)
+        nrm = np.zeros((triangle_count, 3), dtype=np.float32)
+        capacity = max(2 * triangle_count - 1, 1)
+        nodes = (rt_built_node * capacity)()
+        count = C.c_int32(0)
+        self.check(self.lib.rt_read_mesh_build(self.handle, mesh_id, idx.ctypes.data_as(c_i32_p), nrm.ctypes.data_as(c_float_p), nodes, capacity,
+                                               C.byref(count)), "rt_read_mesh_build")
+        dt = np.dtype([("min_aabb", np.float32, 3), ("max_aabb", np.float32, 3), ("first", np.int32), ("triangle_count", np.int32),
+                       ("escape", np.int32)])
+        return idx, nrm, np.frombuffer(nodes, dtype=dt, count=count.value).copy()
+
     def set_kernel_variant(self, variant: int) -> None:
-        """0 auto (= scalar today), 1 scalar one-pixel kernel, 2 packed two-pixel FFMA2 kernel."""
+        """0 auto (persistent warps on deep frames, else tiled), 1 tiled one-pixel kernel, 2 packed two-pixel FFMA2
+        kernel, 3 persistent warps."""
         self.check(self.lib.rt_set_kernel_variant(self.handle, int(variant)), "rt_set_kernel_variant")
 
     def upload_mesh(self, mesh_id: int, mesh) -> None:

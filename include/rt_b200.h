@@ -310,6 +310,39 @@ typedef struct rt_mesh_source
 int rt_upload_mesh_source(rt_context* ctx, int32_t mesh_id, const rt_mesh_source* source);
 int rt_transform_mesh(rt_context* ctx, int32_t mesh_id, const float* transform);
 
+/* The reference ships TriangleMesh::UpdateTransforms WITH BuildBVH (source/DataTypes.h:8-9, 231-232, 294-483).
+ * rt_set_mesh_device_bvh(ctx, mesh, 1) - after rt_upload_mesh_source, before the mesh's first rt_transform_mesh -
+ * moves that build to the device as well: from then on EVERY rt_transform_mesh call is one UpdateTransforms call
+ * of the reference (transform + binned-SAH build + the in-place reordering of indices / normals,
+ * DataTypes.h:344-363), executed in call order before the next frame, and the mesh is rendered by the BVH body.
+ * The build is history-dependent exactly like the reference's (each one starts from the triangle order the
+ * previous one left), so the source must be uploaded in the order TriangleMesh::indices / normals have at that
+ * moment and calls must mirror the reference's one for one.  Node numbering is the device's own (pairs are
+ * handed out in parallel); boxes, leaves, triangle order and the walk order are the reference's.
+ * Errors: RT_ERR_BAD_STATE after the first transform, RT_ERR_CAPACITY beyond what node links can address; a leaf
+ * wider than the link's triangle field fails the render that runs the build (RT_ERR_CAPACITY). */
+int rt_set_mesh_device_bvh(rt_context* ctx, int32_t mesh_id, int32_t enable);
+
+/* What the device-side builds left behind, for the caller that owns the TriangleMesh (its indices / normals
+ * vectors go stale while the device runs UpdateTransforms; copy them back before handing the mesh to host code
+ * again) and for the parity tests.  Pending rt_transform_mesh calls are executed first.
+ *   indices  3 * triangle_count, TriangleMesh::indices after the last build        (may be NULL)
+ *   normals  3 * triangle_count, TriangleMesh::normals (untransformed) in that order (may be NULL)
+ *   nodes    the tree in the device's numbering (may be NULL); RT_ERR_CAPACITY when node_capacity is too small
+ * A node is a leaf iff triangle_count > 0 (BVHNode::IsLeaf, source/DataTypes.h:50-53): then `first` is its first
+ * TRIANGLE (BVHNode::firstIdx / 3); otherwise `first` is the left child and first + 1 the right one
+ * (BVHNode::leftNode).  `escape` is the node IntersectionTest_BVH (source/Utils.h:246-288) visits after this
+ * subtree, -1 at the end of the walk. */
+typedef struct rt_built_node
+{
+	float min_aabb[3];
+	float max_aabb[3];
+	int32_t first;
+	int32_t triangle_count;
+	int32_t escape;
+} rt_built_node;
+int rt_read_mesh_build(rt_context* ctx, int32_t mesh_id, int32_t* indices, float* normals, rt_built_node* nodes, int32_t node_capacity, int32_t* out_node_count);
+
 /* Which build of the pixel kernel renders frames.  All compute the same function, bit for bit.
  *   RT_KERNEL_SCALAR      one pixel per thread, one CTA per 32x8 pixel tile (also what rt_count_frame instruments)
  *   RT_KERNEL_PACKED      two pixels per thread on Blackwell's packed FP32 (FFMA2), one CTA per tile
