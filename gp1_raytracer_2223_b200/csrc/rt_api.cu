@@ -85,6 +85,7 @@ namespace
 			bool built = false;                // build results are valid (emit_mesh_kernel may copy them)
 		};
 		std::vector<MeshSourceDevice> sources;   // untransformed meshes (rt_upload_mesh_source), by mesh id
+		long long build_shared_limit = -1;       // dynamic shared memory the build kernel may use here; -1 = not asked yet
 		uint32_t* d_frame = nullptr;
 		size_t frame_capacity = 0;         // in pixels
 		unsigned long long* d_counters = nullptr;
@@ -123,6 +124,7 @@ struct rt_context
 	rt_timing timing{};
 	int32_t last_width = 0, last_height = 0;
 
+	int32_t build_local_triangles = 0;  // rt::BuildParams::local_triangles (RT_B200_BUILD_LOCAL overrides: measurement)
 	int32_t* h_build_status = nullptr;  // pinned, one word per mesh: status of the last device-side BVH build (device 0)
 
 	void* registered_host = nullptr;    // host surface we pinned ourselves
@@ -360,17 +362,36 @@ namespace
 		return RT_OK;
 	}
 
+	// Dynamic shared memory update_transforms_bvh_kernel may use on this device (opt-in limit minus its static part);
+	// raises the kernel's limit the first time.  0 when the attribute cannot be set: the build then works in global memory.
+	size_t build_shared_limit(rt_context* ctx, DeviceState& d)
+	{
+		if (d.build_shared_limit >= 0) return (size_t)d.build_shared_limit;
+		d.build_shared_limit = 0;
+		if (getenv("RT_B200_BUILD_GLOBAL")) return 0;     // measurement: force the global-memory work arrays
+		int optin = 0;
+		cudaFuncAttributes attr{};
+		if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.device) != cudaSuccess ||
+		    cudaFuncGetAttributes(&attr, rt::update_transforms_bvh_kernel) != cudaSuccess) { cudaGetLastError(); return 0; }
+		const long long room = (long long)optin - (long long)attr.sharedSizeBytes - 1024;
+		if (room <= 0) return 0;
+		if (cudaFuncSetAttribute(rt::update_transforms_bvh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room) != cudaSuccess) { cudaGetLastError(); return 0; }
+		(void)ctx;
+		d.build_shared_limit = room;
+		return (size_t)room;
+	}
+
 	// Carves the scratch / result arrays of update_transforms_bvh_kernel out of one allocation.
 	int allocate_build_block(rt_context* ctx, DeviceState::MeshSourceDevice& sd, int32_t V, int32_t T)
 	{
 		const size_t N = (size_t)std::max(2 * T - 1, 1);
 		size_t offset = 0;
 		auto take = [&](size_t bytes) { const size_t at = offset; offset = (offset + bytes + 15) & ~size_t(15); return at; };
-		const size_t o_tpos = take(12 * (size_t)std::max(V, 1)), o_cen = take(12 * (size_t)std::max(T, 1)), o_min = take(12 * (size_t)std::max(T, 1)),
-		             o_max = take(12 * (size_t)std::max(T, 1)), o_tn = take(12 * (size_t)std::max(T, 1)), o_order = take(4 * (size_t)std::max(T, 1)),
-		             o_flag = take((size_t)std::max(T, 1)), o_first = take(4 * N), o_count = take(4 * N), o_escape = take(4 * N), o_box = take(24 * N),
-		             o_qa = take(4 * (size_t)std::max(T, 1)), o_qb = take(4 * (size_t)std::max(T, 1)), o_tris = take(48 * (size_t)std::max(T, 1)),
-		             o_nodes = take(32 * N), o_info = take(32);
+		const size_t Tn = (size_t)std::max(T, 1);
+		const size_t o_tpos = take(12 * (size_t)std::max(V, 1)), o_cen = take(12 * Tn), o_min = take(12 * Tn), o_max = take(12 * Tn), o_tn = take(12 * Tn),
+		             o_order = take(4 * Tn), o_tmp = take(4 * Tn), o_rb = take(4 * Tn), o_fr = take(4 * Tn), o_bl = take(4 * Tn),
+		             o_first = take(4 * N), o_count = take(4 * N), o_escape = take(4 * N), o_box = take(24 * N),
+		             o_qa = take(4 * Tn), o_qb = take(4 * Tn), o_tris = take(48 * Tn), o_nodes = take(32 * N), o_info = take(32);
 		RT_CUDA(ctx, cudaMalloc(&sd.build_block, offset));
 		RT_CUDA(ctx, cudaMemset(sd.build_block, 0, offset));
 		char* base = (char*)sd.build_block;
@@ -378,7 +399,8 @@ namespace
 		b = rt::BuildParams{};
 		b.positions = sd.positions; b.vertex_count = V; b.triangle_count = T;
 		b.tpos = (float*)(base + o_tpos); b.centroid = (float*)(base + o_cen); b.tri_min = (float*)(base + o_min); b.tri_max = (float*)(base + o_max);
-		b.tnormal = (float*)(base + o_tn); b.order = (int32_t*)(base + o_order); b.left_flag = (uint8_t*)(base + o_flag);
+		b.tnormal = (float*)(base + o_tn); b.order = (int32_t*)(base + o_order); b.order_tmp = (int32_t*)(base + o_tmp);
+		b.rights_before = (int32_t*)(base + o_rb); b.front_right = (int32_t*)(base + o_fr); b.back_left = (int32_t*)(base + o_bl);
 		b.node_first = (int32_t*)(base + o_first); b.node_count = (int32_t*)(base + o_count); b.node_escape = (int32_t*)(base + o_escape);
 		b.node_box = (float*)(base + o_box); b.queue_a = (int32_t*)(base + o_qa); b.queue_b = (int32_t*)(base + o_qb);
 		b.result_triangles = (float4*)(base + o_tris); b.result_nodes = (float4*)(base + o_nodes); b.result_info = (int32_t*)(base + o_info);
@@ -389,8 +411,8 @@ namespace
 	//  * without device BVH: run transform_mesh_kernel when the transform changed or the mesh block was just
 	//    rewritten from the host mirror (idempotent);
 	//  * with device BVH: run update_transforms_bvh_kernel once per rt_transform_mesh call since the last frame, in
-	//    call order (each build starts from the triangle order the previous one left), then copy the last build
-	//    into the block (emit_mesh_kernel) - also when only the block was rewritten.
+	//    call order (each build starts from the triangle order the previous one left; each writes its result into
+	//    the block as well); when only the block was rewritten, emit_mesh_kernel copies the last build back.
 	int run_device_transforms(rt_context* ctx, bool block_rewritten)
 	{
 		for (size_t m = 0; m < ctx->meshes.size(); ++m)
@@ -432,14 +454,23 @@ namespace
 						rt::BuildParams& b = sd.build;
 						memcpy(b.m, transform.data(), sizeof b.m);
 						b.indices_in = sd.indices; b.normals_in = sd.normals; b.indices_out = sd.indices_alt; b.normals_out = sd.normals_alt;
-						rt::update_transforms_bvh_kernel<<<1, rt::kBuildThreads, 0, d.stream>>>(b);
+						// the build also writes the mesh's slices of the scene block (the last one of the frame is what stays)
+						b.scene_triangles = T > 0 ? d.d_mesh + d.triangle_offset + 3 * (size_t)first : nullptr;     // an empty mesh owns no slices
+						b.scene_nodes = T > 0 ? d.d_mesh + d.node_offset + 2 * (size_t)first_node : nullptr;
+						b.scene_table = T > 0 ? d.d_mesh + 3 * m : nullptr;
+						size_t work_bytes = sizeof(float) * rt::kBuildWorkWordsPerTriangle * (size_t)std::max(T, 1);
+						b.work_in_shared = work_bytes <= build_shared_limit(ctx, d) ? 1 : 0;
+						if (!b.work_in_shared) work_bytes = 0;
+						b.local_triangles = ctx->build_local_triangles;
+						rt::update_transforms_bvh_kernel<<<1, rt::kBuildThreads, work_bytes, d.stream>>>(b);
 						RT_CUDA(ctx, cudaGetLastError());
 						std::swap(sd.indices, sd.indices_alt); std::swap(sd.normals, sd.normals_alt);     // the order the build left
 						sd.built = true;
 						if (&d == &ctx->devs[0]) RT_CUDA(ctx, cudaMemcpyAsync(ctx->h_build_status + m, b.result_info + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
 						ctx->timing.kernel_launches++;
 					}
-					if (sd.built && (!hm.pending_builds.empty() || block_rewritten) && T > 0)
+					if (!hm.pending_builds.empty()) RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
+					if (sd.built && hm.pending_builds.empty() && block_rewritten && T > 0)
 					{
 						rt::EmitParams e{};
 						e.result_triangles = sd.build.result_triangles; e.result_nodes = sd.build.result_nodes; e.result_info = sd.build.result_info;
@@ -943,6 +974,7 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		ctx->devs.push_back(d);
 	}
 	RT_CREATE(cudaSetDevice(ids[0]));
+	if (const char* e = getenv("RT_B200_BUILD_LOCAL")) ctx->build_local_triangles = std::max(0, std::min(rt::kLocalTriangles, atoi(e)));
 	RT_CREATE(cudaHostAlloc(&ctx->h_build_status, sizeof(int32_t) * rt::kMaxMeshes, cudaHostAllocPortable));
 	memset(ctx->h_build_status, 0, sizeof(int32_t) * rt::kMaxMeshes);
 	RT_CREATE(cudaHostAlloc(&ctx->h_static, StaticBlock::total, cudaHostAllocPortable));

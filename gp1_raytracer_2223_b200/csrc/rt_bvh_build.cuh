@@ -1,21 +1,27 @@
 // TriangleMesh::UpdateTransforms as the reference ships it - vertex / normal transform AND BuildBVH - on the
 // device (reference source/DataTypes.h:210-236, 294-483 with BVH and USE_BINS defined,
-// DataTypes.h:8-9).  One CTA per mesh.
+// DataTypes.h:8-9).  One CTA of 32 warps per mesh.
 //
 // What has to be reproduced, and how:
 //  * the tree: per node the binned SAH split of FindBestSplitPlane (DataTypes.h:398-483: centroid bounds, 8 bins,
 //    7 planes, 3 axes, first strictly smaller cost wins), the no-split test of Subdivide (DataTypes.h:333-336)
 //    and the leaf rule idxCount <= 8 (DataTypes.h:327) - every float operation in the reference's order
-//    (rt_device.cuh arithmetic), minima / maxima in any order (exact and commutative);
+//    (rt_device.cuh arithmetic), minima / maxima in any order (exact and commutative; the one observable
+//    difference is which of -0.0f / +0.0f a bound keeps when both occur);
 //  * the triangle order: Subdivide partitions indices / normals IN PLACE with a two-pointer sweep
 //    (DataTypes.h:344-363) and the next UpdateTransforms starts from the order the last one left, so the mesh
-//    state lives on the device between calls (indices / normals ping-pong buffers) and the sweep is run
-//    literally (one lane per node over a precomputed predicate);
+//    state lives on the device between calls (indices / normals ping-pong buffers).  The sweep's result has a
+//    closed form (partition_range below), so it runs as scans and scatters instead of a serial loop;
 //  * the walk order of IntersectionTest_BVH (Utils.h:246-288: left child, then left + 1): children are a pair,
 //    every node gets the "escape" link of rt::BvhLink when it is created (left -> right sibling, right ->
 //    parent's escape).  Node NUMBERS are free (the walk never compares them): pairs are handed out by an atomic
-//    counter instead of the reference's depth-first nodesUsed++, which is what lets a whole tree level be built
-//    in parallel, one warp per node.
+//    counter instead of the reference's depth-first nodesUsed++, which is what lets independent subtrees be
+//    built concurrently.
+//
+// Work distribution: the tree is built level by level while a level has few, large nodes - the CTA splits into
+// 1 / 2 / 4 / 8 teams of warps (named barriers), one node per team - and by one warp per node after that; a warp
+// that reaches a node of at most kLocalTriangles triangles finishes that whole subtree itself from a private
+// stack, so the deep, narrow part of the tree costs no CTA-wide barriers.
 #pragma once
 
 #include "rt_kernel.cuh"
@@ -39,7 +45,10 @@ namespace rt
 		float* tri_max;                 // 3T
 		float* tnormal;                 // 3T   transformedNormals per slot
 		int32_t* order;                 // T    order[k] = slot that sits at position k
-		uint8_t* left_flag;             // T    partition predicate per position
+		int32_t* order_tmp;             // T    partition output before it is copied back
+		int32_t* rights_before;         // T    partition: right-hand elements in front of position k, inside its node
+		int32_t* front_right;           // T    partition: position of the node's k-th right-hand element from the front
+		int32_t* back_left;             // T    partition: distance from the node's end of its k-th left-hand element from the back
 		int32_t* node_first;            // N    first triangle position
 		int32_t* node_count;            // N    triangles
 		int32_t* node_escape;           // N
@@ -50,12 +59,37 @@ namespace rt
 		float4* result_triangles;       // 3T   {v0|nx}{e1|ny}{e2|nz} in the new order
 		float4* result_nodes;           // 2N   device node records (rt::BvhLink)
 		int32_t* result_info;           // [0] nodes used, [1] status (0 ok, 1 leaf too large for BvhLink), [2..7] root box bits
+		// the mesh's slices of the scene's mesh block: written at the end of the build as well (NULL: not)
+		float4* scene_triangles;
+		float4* scene_nodes;
+		float4* scene_table;
+		int32_t work_in_shared;         // the per-triangle work arrays (14 words per triangle) live in dynamic shared memory
+		int32_t local_triangles;        // a warp finishes subtrees of at most this many triangles on its own (<= kLocalTriangles)
 	};
 
-	constexpr int kBuildThreads = 512;
-	constexpr int kBuildWarps = kBuildThreads / 32;
+	// The arrays every pass of the build reads and writes.  Shared memory when the mesh fits (latency of a pass is a few
+	// dependent accesses: ~30 cycles each there, an L2 round trip each in global memory), else the host's scratch.
+	struct BuildWork
+	{
+		float* centroid;                // 3T   per triangle slot
+		float* tri_min;                 // 3T
+		float* tri_max;                 // 3T
+		int32_t* order;                 // T    order[k] = slot that sits at position k
+		int32_t* order_tmp;             // T
+		int32_t* rights_before;         // T
+		int32_t* front_right;           // T
+		int32_t* back_left;             // T
+	};
+	constexpr int kBuildWorkWordsPerTriangle = 14;
 
-	// order-preserving map float -> unsigned for shared-memory atomicMin / atomicMax (no NaN can reach it)
+	constexpr int kBuildThreads = 1024;
+	constexpr int kBuildWarps = kBuildThreads / 32;
+	constexpr int kMaxTeams = 8;             // teams of more than one warp: named barriers 1..8
+	constexpr int kLocalTriangles = 32;      // upper limit of BuildParams::local_triangles
+	constexpr int kLocalStack = kLocalTriangles + 4;
+	constexpr int kAtomicBinTriangles = 64;  // nodes up to this size bin with plain shared-memory atomics
+
+	// order-preserving map float -> unsigned for integer min / max (REDUX, shared-memory atomics); no NaN reaches it
 	__device__ __forceinline__ unsigned int float_key(float f)
 	{
 		const unsigned int b = __float_as_uint(f);
@@ -66,17 +100,6 @@ namespace rt
 		return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 	}
 
-	__device__ __forceinline__ float warp_min(float v)
-	{
-		for (int s = 16; s > 0; s >>= 1) v = std_min(v, __shfl_xor_sync(0xffffffffu, v, s));
-		return v;
-	}
-	__device__ __forceinline__ float warp_max(float v)
-	{
-		for (int s = 16; s > 0; s >>= 1) v = std_max(v, __shfl_xor_sync(0xffffffffu, v, s));
-		return v;
-	}
-
 	// AABB::Area, DataTypes.h:75-79
 	__device__ __forceinline__ float box_area(const float mn[3], const float mx[3])
 	{
@@ -84,21 +107,36 @@ namespace rt
 		return add(add(mul(ex, ey), mul(ey, ez)), mul(ez, ex));
 	}
 
-	// UpdateNodeBounds, DataTypes.h:310-321, over positions [first, first + count) of `order`: one warp.
-	// Starts from +FLT_MAX / +FLT_MIN like the reference (Vector3.cpp:13-14).  Every lane returns the box.
-	__device__ __forceinline__ void warp_range_bounds(const BuildParams& p, int first, int count, int lane, float mn[3], float mx[3])
+	// Per team (and per warp once teams are single warps): reduction slots, bins of the three axes, the split that
+	// was chosen, and the private node stack of a warp.
+	struct TeamScratch
 	{
-		for (int k = 0; k < 3; ++k) { mn[k] = FLT_MAX; mx[k] = FLT_MIN; }
-		for (int t = lane; t < count; t += 32)
-		{
-			const int slot = p.order[first + t];
-			for (int k = 0; k < 3; ++k)
-			{
-				mn[k] = std_min(mn[k], p.tri_min[3 * slot + k]);
-				mx[k] = std_max(mx[k], p.tri_max[3 * slot + k]);
-			}
-		}
-		for (int k = 0; k < 3; ++k) { mn[k] = warp_min(mn[k]); mx[k] = warp_max(mx[k]); }
+		unsigned int centroid_lo[3], centroid_hi[3];
+		unsigned int bin_count[3][8];
+		unsigned int bin_lo[3][8][3];           // float_key of the bin box
+		unsigned int bin_hi[3][8][3];
+		unsigned int child_lo[2][3], child_hi[2][3];
+		int warp_total[kBuildWarps];
+		float best, split_pos;
+		int axis, pair;
+		int stack[kLocalStack];
+		int top;
+	};
+
+	struct Team
+	{
+		int threads;       // 32 * warps
+		int warps;
+		int tid;           // thread within the team
+		int warp;          // warp within the team
+		int barrier;       // named barrier of the team (teams of more than one warp)
+		TeamScratch* s;
+	};
+
+	__device__ __forceinline__ void team_sync(const Team& t)
+	{
+		if (t.threads == 32) __syncwarp();
+		else asm volatile("bar.sync %0, %1;" :: "r"(t.barrier), "r"(t.threads) : "memory");
 	}
 
 	// The device record of a finished node (SceneDevice::bvh_nodes): box, first child / first triangle, link.
@@ -111,173 +149,303 @@ namespace rt
 		p.result_nodes[2 * node + 1] = make_float4(b[2], b[5], __int_as_float(first_or_child), __int_as_float(link));
 	}
 
-	struct BinScratch
+	// The in-place partition of Subdivide (DataTypes.h:344-363) over positions [first, first + count):
+	//     i = first, j = last;  while (i <= j)  left(i) ? ++i : (swap(i, j), --j)
+	// Each element is examined exactly once, always at position i: elements come from the front while the last
+	// one examined was left-hand and from the back while it was right-hand.  Hence, with k a position relative
+	// to `first`, R(k) the right-hand elements in front of k and L(k) the left-hand elements behind k:
+	//   * an element is reached from the front iff  k + B(k) < count,  B(k) = 0 if R(k) == 0, else 1 + the
+	//     distance from the end of the R(k)-th left-hand element counted from the back (count if there is none);
+	//     then a left-hand element stays where it is and a right-hand one ends at  count - 1 - B(k);
+	//   * otherwise it is reached from the back: a left-hand element fills the hole of the (L(k) + 1)-th
+	//     right-hand element counted from the front, a right-hand one moves down by one position.
+	// (Checked against the literal loop for every flag pattern up to 14 elements and random ones up to 4000.)
+	// Returns the left count; `order` holds the result.  Also reorders when everything is right-hand, like the loop.
+	__device__ __forceinline__ int partition_range(const BuildWork& p, const Team& t, int first, int count, int axis, float split_pos)
 	{
-		unsigned int count[8];
-		unsigned int lo[8][3];      // float_key of the bin box minimum
-		unsigned int hi[8][3];
-	};
-
-	// Subdivide (DataTypes.h:323-389) of one node by one warp.  Children are appended to `next`.
-	__device__ __forceinline__ void subdivide_node(const BuildParams& p, int node, int lane, BinScratch& bins,
-	                                               int* nodes_used, int* next, int* next_count)
-	{
-		const int first = p.node_first[node], count = p.node_count[node];
-		const unsigned int idx_count = 3u * (unsigned int)count;
-
-		// ---- FindBestSplitPlane, DataTypes.h:398-483 ----
-		float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { FLT_MIN, FLT_MIN, FLT_MIN };
-		for (int t = lane; t < count; t += 32)
+		TeamScratch& s = *t.s;
+		const int lane = threadIdx.x & 31;
+		int running = 0;
+		for (int base = 0; base < count; base += t.threads)
 		{
-			const int slot = p.order[first + t];
-			for (int k = 0; k < 3; ++k)
+			const int k = base + t.tid;
+			const bool active = k < count;
+			const bool right = active && !(p.centroid[3 * p.order[first + k] + axis] < split_pos);
+			const unsigned int ballot = __ballot_sync(0xffffffffu, right);
+			int before = running + __popc(ballot & ((1u << lane) - 1u));
+			if (t.threads > 32)
 			{
-				const float c = p.centroid[3 * slot + k];
-				lo[k] = std_min(lo[k], c);
-				hi[k] = std_max(hi[k], c);
+				if (lane == 0) s.warp_total[t.warp] = __popc(ballot);
+				team_sync(t);
+				for (int w = 0; w < t.warps; ++w)
+				{
+					const int c = s.warp_total[w];
+					if (w < t.warp) before += c;
+					running += c;
+				}
+				team_sync(t);
+			}
+			else running += __popc(ballot);
+			if (active)
+			{
+				p.rights_before[first + k] = before;
+				if (right) p.front_right[first + before] = k;
 			}
 		}
-		for (int k = 0; k < 3; ++k) { lo[k] = warp_min(lo[k]); hi[k] = warp_max(hi[k]); }
-
-		float best = FLT_MAX, split_pos = 0.f;
-		int axis = 0;
-		for (int a = 0; a < 3; ++a)
+		const int n_left = count - running;
+		if (n_left == count) return n_left;                      // nothing moves
+		for (int k = t.tid; k < count; k += t.threads)
 		{
-			const float diff = sub(hi[a], lo[a]);
-			if (fabsf(diff) < FLT_EPSILON) continue;                                   // DataTypes.h:421-422 (warp-uniform)
-
-			// bins, DataTypes.h:425-441: counts and boxes through shared-memory atomics
-			__syncwarp();
-			if (lane < 8)
+			const bool left = p.centroid[3 * p.order[first + k] + axis] < split_pos;
+			if (left) p.back_left[first + n_left - (k - p.rights_before[first + k]) - 1] = count - 1 - k;
+		}
+		team_sync(t);
+		for (int k = t.tid; k < count; k += t.threads)
+		{
+			const int slot = p.order[first + k];
+			const bool left = p.centroid[3 * slot + axis] < split_pos;
+			const int r = p.rights_before[first + k];
+			const int from_back = (r == 0) ? 0 : (r > n_left ? count : p.back_left[first + r - 1] + 1);
+			int final_position;
+			if (k + from_back < count) final_position = left ? k : count - 1 - from_back;
+			else
 			{
-				bins.count[lane] = 0u;
-				for (int k = 0; k < 3; ++k) { bins.lo[lane][k] = float_key(FLT_MAX); bins.hi[lane][k] = float_key(FLT_MIN); }
+				const int lefts_behind = n_left - (k - r) - (left ? 1 : 0);
+				final_position = left ? p.front_right[first + lefts_behind] : k - 1;
 			}
-			__syncwarp();
-			const float scale = quo(8.f, diff);
-			for (int t = lane; t < count; t += 32)
+			p.order_tmp[first + final_position] = slot;
+		}
+		team_sync(t);
+		for (int k = t.tid; k < count; k += t.threads) p.order[first + k] = p.order_tmp[first + k];
+		team_sync(t);
+		return n_left;
+	}
+
+	// Subdivide (DataTypes.h:323-389) of one node by one team.  Children that need splitting go to the team's private
+	// stack (single-warp teams, small children) or to the next level's queue.
+	__device__ __forceinline__ void subdivide_node(const BuildParams& p, const BuildWork& w, int node, const Team& t, int* nodes_used, int* next, int* next_count)
+	{
+		TeamScratch& s = *t.s;
+		const int lane = threadIdx.x & 31;
+		const int first = p.node_first[node], count = p.node_count[node];
+		const unsigned int idx_count = 3u * (unsigned int)count;
+		const unsigned int key_max = float_key(FLT_MAX), key_min = float_key(FLT_MIN);
+
+		// every reduction starts like the reference's boxes: +FLT_MAX / +FLT_MIN (Vector3.cpp:13-14)
+		if (t.tid < 3) { s.centroid_lo[t.tid] = key_max; s.centroid_hi[t.tid] = key_min; }
+		if (t.tid < 6) { (&s.child_lo[0][0])[t.tid] = key_max; (&s.child_hi[0][0])[t.tid] = key_min; }
+		for (int k = t.tid; k < 24; k += t.threads) (&s.bin_count[0][0])[k] = 0u;
+		for (int k = t.tid; k < 72; k += t.threads) { (&s.bin_lo[0][0][0])[k] = key_max; (&s.bin_hi[0][0][0])[k] = key_min; }
+		team_sync(t);
+
+		// ---- FindBestSplitPlane, DataTypes.h:398-483; centroid bounds of the three axes in one pass ----
+		{
+			unsigned int lo[3] = { key_max, key_max, key_max }, hi[3] = { key_min, key_min, key_min };
+			for (int k = t.tid; k < count; k += t.threads)
 			{
-				const int slot = p.order[first + t];
-				int bin = __float2int_rz(mul(sub(p.centroid[3 * slot + a], lo[a]), scale));
-				bin = min(7, bin);
-				atomicAdd(&bins.count[bin], 3u);
-				for (int k = 0; k < 3; ++k)
+				const int slot = w.order[first + k];
+				for (int a = 0; a < 3; ++a)
 				{
-					atomicMin(&bins.lo[bin][k], float_key(p.tri_min[3 * slot + k]));
-					atomicMax(&bins.hi[bin][k], float_key(p.tri_max[3 * slot + k]));
+					const unsigned int c = float_key(w.centroid[3 * slot + a]);
+					lo[a] = min(lo[a], c);
+					hi[a] = max(hi[a], c);
 				}
 			}
-			__syncwarp();
+			for (int a = 0; a < 3; ++a)
+			{
+				lo[a] = __reduce_min_sync(0xffffffffu, lo[a]);
+				hi[a] = __reduce_max_sync(0xffffffffu, hi[a]);
+			}
+			if (lane == 0)
+				for (int a = 0; a < 3; ++a) { atomicMin(&s.centroid_lo[a], lo[a]); atomicMax(&s.centroid_hi[a], hi[a]); }
+		}
+		team_sync(t);
+		float lo[3], diff[3], scale[3];
+		bool use_axis[3];
+		for (int a = 0; a < 3; ++a)
+		{
+			lo[a] = key_float(s.centroid_lo[a]);
+			diff[a] = sub(key_float(s.centroid_hi[a]), lo[a]);
+			use_axis[a] = !(fabsf(diff[a]) < FLT_EPSILON);                             // DataTypes.h:421-422
+			scale[a] = quo(8.f, diff[a]);
+		}
 
-			// the 7 planes, DataTypes.h:443-466: lane i owns plane i (left = bins 0..i, right = bins i+1..7)
+		// bins of the three axes, DataTypes.h:425-441: lanes that share a bin reduce among themselves (REDUX), one of
+		// them adds the group to the team's bins
+		for (int base = 0; base < count; base += t.threads)
+		{
+			const int k = base + t.tid;
+			const bool active = k < count;
+			int slot = 0;
+			float c[3] = { 0.f, 0.f, 0.f };
+			unsigned int mn[3] = { key_max, key_max, key_max }, mx[3] = { key_min, key_min, key_min };
+			if (active)
+			{
+				slot = w.order[first + k];
+				for (int a = 0; a < 3; ++a)
+				{
+					c[a] = w.centroid[3 * slot + a];
+					mn[a] = float_key(w.tri_min[3 * slot + a]);
+					mx[a] = float_key(w.tri_max[3 * slot + a]);
+				}
+			}
+			for (int a = 0; a < 3; ++a)
+			{
+				if (!use_axis[a]) continue;                                              // uniform over the team
+				const int bin = active ? min(7, __float2int_rz(mul(sub(c[a], lo[a]), scale[a]))) : -1;
+				if (count <= kAtomicBinTriangles)                                        // uniform over the team
+				{
+					if (active)
+					{
+						atomicAdd(&s.bin_count[a][bin], 3u);
+						for (int d = 0; d < 3; ++d) { atomicMin(&s.bin_lo[a][bin][d], mn[d]); atomicMax(&s.bin_hi[a][bin][d], mx[d]); }
+					}
+					continue;
+				}
+				const unsigned int peers = __match_any_sync(0xffffffffu, bin);
+				if (active)
+				{
+					unsigned int gmn[3], gmx[3];
+					for (int d = 0; d < 3; ++d) { gmn[d] = __reduce_min_sync(peers, mn[d]); gmx[d] = __reduce_max_sync(peers, mx[d]); }
+					if (lane == __ffs(peers) - 1)
+					{
+						atomicAdd(&s.bin_count[a][bin], 3u * (unsigned int)__popc(peers));
+						for (int d = 0; d < 3; ++d) { atomicMin(&s.bin_lo[a][bin][d], gmn[d]); atomicMax(&s.bin_hi[a][bin][d], gmx[d]); }
+					}
+				}
+			}
+		}
+		team_sync(t);
+
+		// the 7 planes of the 3 axes, DataTypes.h:443-479: lane 7a + i of the team's first warp owns plane i of axis a
+		// (left = bins 0..i, right = bins i + 1..7).  The reference walks axis 0..2, plane 0..6 and keeps the first
+		// strictly smaller cost: that is the lowest lane holding the minimum.
+		if (t.warp == 0)
+		{
+			const int a = lane / 7, plane = lane - 7 * a;
 			float cost = 0.f;
 			bool candidate = false;
-			if (lane < 7)
+			if (lane < 21 && (a == 0 ? use_axis[0] : (a == 1 ? use_axis[1] : use_axis[2])))
 			{
 				float lmn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, lmx[3] = { FLT_MIN, FLT_MIN, FLT_MIN };
 				float rmn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, rmx[3] = { FLT_MIN, FLT_MIN, FLT_MIN };
 				int left_count = 0, right_count = 0;
 				for (int b = 0; b < 8; ++b)
 				{
-					const bool is_left = b <= lane;
-					const int c = (int)bins.count[b];
+					const bool is_left = b <= plane;
+					const int c = (int)s.bin_count[a][b];
 					if (is_left) left_count += c; else right_count += c;
-					for (int k = 0; k < 3; ++k)
+					for (int d = 0; d < 3; ++d)
 					{
-						const float bl = key_float(bins.lo[b][k]), bh = key_float(bins.hi[b][k]);
-						if (is_left) { lmn[k] = std_min(lmn[k], bl); lmx[k] = std_max(lmx[k], bh); }
-						else { rmn[k] = std_min(rmn[k], bl); rmx[k] = std_max(rmx[k], bh); }
+						const float bl = key_float(s.bin_lo[a][b][d]), bh = key_float(s.bin_hi[a][b][d]);
+						if (is_left) { lmn[d] = std_min(lmn[d], bl); lmx[d] = std_max(lmx[d], bh); }
+						else { rmn[d] = std_min(rmn[d], bl); rmx[d] = std_max(rmx[d], bh); }
 					}
 				}
 				// DataTypes.h:472: leftCount[i] * leftArea[i] + rightCount[i] * rightArea[i]
 				cost = add(mul((float)left_count, box_area(lmn, lmx)), mul((float)right_count, box_area(rmn, rmx)));
-				candidate = cost < best;                                              // false for NaN (an empty side: 0 * inf)
+				candidate = cost < FLT_MAX;                                              // bestCost starts at FLT_MAX; false for NaN
 			}
-			// "first strictly smaller cost wins" over planes 0..6 == the lowest plane that holds the minimum of the
-			// costs below the running best
 			float m = candidate ? cost : INFINITY;
-			for (int s = 4; s > 0; s >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, s, 8));
-			m = __shfl_sync(0xffffffffu, m, 0);
+			for (int sh = 16; sh > 0; sh >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, sh));
 			const unsigned int winners = __ballot_sync(0xffffffffu, candidate && cost == m);
-			if (winners)
+			if (lane == 0)
 			{
-				const int plane = __ffs(winners) - 1;
-				axis = a;
-				split_pos = add(lo[a], mul(quo(diff, 8.f), (float)(plane + 1)));           // DataTypes.h:469, 476
-				best = m;
+				if (winners)
+				{
+					const int win = __ffs(winners) - 1, wa = win / 7, wp = win - 7 * wa;
+					const float wlo = wa == 0 ? lo[0] : (wa == 1 ? lo[1] : lo[2]), wdiff = wa == 0 ? diff[0] : (wa == 1 ? diff[1] : diff[2]);
+					s.axis = wa;
+					s.split_pos = add(wlo, mul(quo(wdiff, 8.f), (float)(wp + 1)));            // DataTypes.h:469, 476
+					s.best = m;
+				}
+				else { s.axis = 0; s.split_pos = 0.f; s.best = FLT_MAX; }
 			}
 		}
+		team_sync(t);
+		const float best = s.best, split_pos = s.split_pos;
+		const int axis = s.axis;
 
 		// ---- Subdivide, DataTypes.h:333-336: keep the node as a leaf if splitting is not cheaper ----
 		const float no_split = mul((float)idx_count, box_area(p.node_box + 6 * node, p.node_box + 6 * node + 3));
 		bool leaf = best >= no_split;
-
 		int left_count = 0;
 		if (!leaf)
 		{
-			// ---- the in-place partition, DataTypes.h:344-363: predicate in parallel, sweep by one lane ----
-			for (int t = lane; t < count; t += 32)
-				p.left_flag[first + t] = p.centroid[3 * p.order[first + t] + axis] < split_pos ? 1 : 0;
-			__syncwarp();
-			if (lane == 0)
-			{
-				int i = first, j = first + count - 1;
-				while (i <= j)
-				{
-					if (p.left_flag[i]) ++i;
-					else
-					{
-						const int oi = p.order[i], oj = p.order[j];
-						p.order[i] = oj; p.order[j] = oi;
-						p.left_flag[i] = p.left_flag[j];
-						--j;
-					}
-				}
-				left_count = i - first;
-			}
-			left_count = __shfl_sync(0xffffffffu, left_count, 0);
-			__syncwarp();
+			left_count = partition_range(w, t, first, count, axis, split_pos);          // DataTypes.h:344-363
 			leaf = (left_count == 0 || left_count == count);                           // DataTypes.h:366-369
 		}
-
 		if (leaf)
 		{
-			if (lane == 0) write_node_record(p, node, true, first, count);
+			if (t.tid == 0) write_node_record(p, node, true, first, count);
+			team_sync(t);                                                                // scratch is reused by the next node
 			return;
 		}
 
-		// ---- children, DataTypes.h:371-388 ----
-		int pair = 0;
-		if (lane == 0) pair = atomicAdd(nodes_used, 2);
-		pair = __shfl_sync(0xffffffffu, pair, 0);
-		const int child[2] = { pair, pair + 1 };
-		const int child_first[2] = { first, first + left_count };
-		const int child_count[2] = { left_count, count - left_count };
-		for (int c = 0; c < 2; ++c)
+		// ---- children, DataTypes.h:371-388: both boxes in one pass (UpdateNodeBounds, DataTypes.h:310-321) ----
+		if (t.tid == 0) s.pair = atomicAdd(nodes_used, 2);
+		for (int base = 0; base < count; base += t.threads)
 		{
-			float mn[3], mx[3];
-			warp_range_bounds(p, child_first[c], child_count[c], lane, mn, mx);
-			if (lane == 0)
+			const int k = base + t.tid;
+			const bool active = k < count;
+			const int side = (k < left_count) ? 0 : 1;
+			const unsigned int in_left = __ballot_sync(0xffffffffu, active && side == 0), in_right = __ballot_sync(0xffffffffu, active && side == 1);
+			if (active)
+			{
+				const int slot = w.order[first + k];
+				const unsigned int peers = side ? in_right : in_left;
+				unsigned int gmn[3], gmx[3];
+				for (int d = 0; d < 3; ++d)
+				{
+					gmn[d] = __reduce_min_sync(peers, float_key(w.tri_min[3 * slot + d]));
+					gmx[d] = __reduce_max_sync(peers, float_key(w.tri_max[3 * slot + d]));
+				}
+				if (lane == __ffs(peers) - 1)
+					for (int d = 0; d < 3; ++d) { atomicMin(&s.child_lo[side][d], gmn[d]); atomicMax(&s.child_hi[side][d], gmx[d]); }
+			}
+		}
+		team_sync(t);
+		if (t.tid == 0)
+		{
+			const int pair = s.pair;
+			const int child[2] = { pair, pair + 1 };
+			const int child_first[2] = { first, first + left_count };
+			const int child_count[2] = { left_count, count - left_count };
+			for (int c = 0; c < 2; ++c)
 			{
 				p.node_first[child[c]] = child_first[c];
 				p.node_count[child[c]] = child_count[c];
 				p.node_escape[child[c]] = (c == 0) ? child[1] : p.node_escape[node];
-				for (int k = 0; k < 3; ++k) { p.node_box[6 * child[c] + k] = mn[k]; p.node_box[6 * child[c] + 3 + k] = mx[k]; }
+				for (int d = 0; d < 3; ++d) { p.node_box[6 * child[c] + d] = key_float(s.child_lo[c][d]); p.node_box[6 * child[c] + 3 + d] = key_float(s.child_hi[c][d]); }
 				if (3 * child_count[c] <= 8) write_node_record(p, child[c], true, child_first[c], child_count[c]);   // DataTypes.h:327
+				else if (t.threads == 32 && child_count[c] <= p.local_triangles) s.stack[s.top++] = child[c];
 				else next[atomicAdd(next_count, 1)] = child[c];
 			}
+			write_node_record(p, node, false, child[0], 0);
 		}
-		if (lane == 0) write_node_record(p, node, false, child[0], 0);
-		__syncwarp();
+		team_sync(t);
 	}
 
 	__global__ void __launch_bounds__(kBuildThreads)
 	update_transforms_bvh_kernel(const __grid_constant__ BuildParams p)
 	{
-		__shared__ BinScratch bins[kBuildWarps];
+		__shared__ TeamScratch scratch[kBuildWarps];
 		__shared__ int nodes_used, level_count[2];
+		extern __shared__ __align__(16) float dynamic_shared[];
 		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 		const int T = p.triangle_count;
+		BuildWork w;
+		if (p.work_in_shared)
+		{
+			w.centroid = dynamic_shared; w.tri_min = w.centroid + 3 * T; w.tri_max = w.tri_min + 3 * T;
+			w.order = reinterpret_cast<int32_t*>(w.tri_max + 3 * T); w.order_tmp = w.order + T; w.rights_before = w.order_tmp + T;
+			w.front_right = w.rights_before + T; w.back_left = w.front_right + T;
+		}
+		else
+		{
+			w.centroid = p.centroid; w.tri_min = p.tri_min; w.tri_max = p.tri_max; w.order = p.order; w.order_tmp = p.order_tmp;
+			w.rights_before = p.rights_before; w.front_right = p.front_right; w.back_left = p.back_left;
+		}
 
 		// transformedPositions, DataTypes.h:216-222 (Matrix::TransformPoint, Matrix.cpp:49-56)
 		for (int v = tid; v < p.vertex_count; v += kBuildThreads)
@@ -286,6 +454,7 @@ namespace rt
 			p.tpos[3 * v] = q.x; p.tpos[3 * v + 1] = q.y; p.tpos[3 * v + 2] = q.z;
 		}
 		if (tid == 0) { nodes_used = 1; level_count[0] = 0; level_count[1] = 0; p.result_info[1] = 0; }
+		if (lane == 0) scratch[warp].top = 0;
 		__syncthreads();
 
 		// per triangle slot: transformedNormals (DataTypes.h:224-230), centroid (DataTypes.h:349), vertex min / max
@@ -298,40 +467,49 @@ namespace rt
 				v[k] = v3(p.tpos[3 * vi], p.tpos[3 * vi + 1], p.tpos[3 * vi + 2]);
 			}
 			const V3 c = ((v[0] + v[1]) + v[2]) * 0.3333f;
-			p.centroid[3 * t] = c.x; p.centroid[3 * t + 1] = c.y; p.centroid[3 * t + 2] = c.z;
-			p.tri_min[3 * t] = std_min(std_min(v[0].x, v[1].x), v[2].x); p.tri_max[3 * t] = std_max(std_max(v[0].x, v[1].x), v[2].x);
-			p.tri_min[3 * t + 1] = std_min(std_min(v[0].y, v[1].y), v[2].y); p.tri_max[3 * t + 1] = std_max(std_max(v[0].y, v[1].y), v[2].y);
-			p.tri_min[3 * t + 2] = std_min(std_min(v[0].z, v[1].z), v[2].z); p.tri_max[3 * t + 2] = std_max(std_max(v[0].z, v[1].z), v[2].z);
+			w.centroid[3 * t] = c.x; w.centroid[3 * t + 1] = c.y; w.centroid[3 * t + 2] = c.z;
+			w.tri_min[3 * t] = std_min(std_min(v[0].x, v[1].x), v[2].x); w.tri_max[3 * t] = std_max(std_max(v[0].x, v[1].x), v[2].x);
+			w.tri_min[3 * t + 1] = std_min(std_min(v[0].y, v[1].y), v[2].y); w.tri_max[3 * t + 1] = std_max(std_max(v[0].y, v[1].y), v[2].y);
+			w.tri_min[3 * t + 2] = std_min(std_min(v[0].z, v[1].z), v[2].z); w.tri_max[3 * t + 2] = std_max(std_max(v[0].z, v[1].z), v[2].z);
 			const float nx = p.normals_in[3 * t], ny = p.normals_in[3 * t + 1], nz = p.normals_in[3 * t + 2];
 			V3 n = v3(add(add(mul(p.m[0], nx), mul(p.m[4], ny)), mul(p.m[8], nz)),
 			          add(add(mul(p.m[1], nx), mul(p.m[5], ny)), mul(p.m[9], nz)),
 			          add(add(mul(p.m[2], nx), mul(p.m[6], ny)), mul(p.m[10], nz)));
 			normalize(n);
 			p.tnormal[3 * t] = n.x; p.tnormal[3 * t + 1] = n.y; p.tnormal[3 * t + 2] = n.z;
-			p.order[t] = t;
+			w.order[t] = t;
 		}
 		__syncthreads();
 
-		// BuildBVH, DataTypes.h:294-308: the root owns everything
-		if (warp == 0)
+		// BuildBVH, DataTypes.h:294-308: the root owns everything; its box (UpdateNodeBounds) by the whole CTA
 		{
-			float mn[3], mx[3];
-			warp_range_bounds(p, 0, T, lane, mn, mx);
+			TeamScratch& s = scratch[0];
+			const unsigned int key_max = float_key(FLT_MAX), key_min = float_key(FLT_MIN);
+			if (tid < 3) { s.child_lo[0][tid] = key_max; s.child_hi[0][tid] = key_min; }
+			__syncthreads();
+			unsigned int mn[3] = { key_max, key_max, key_max }, mx[3] = { key_min, key_min, key_min };
+			for (int t = tid; t < T; t += kBuildThreads)
+				for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], float_key(w.tri_min[3 * t + d])); mx[d] = max(mx[d], float_key(w.tri_max[3 * t + d])); }
+			for (int d = 0; d < 3; ++d) { mn[d] = __reduce_min_sync(0xffffffffu, mn[d]); mx[d] = __reduce_max_sync(0xffffffffu, mx[d]); }
 			if (lane == 0)
+				for (int d = 0; d < 3; ++d) { atomicMin(&s.child_lo[0][d], mn[d]); atomicMax(&s.child_hi[0][d], mx[d]); }
+			__syncthreads();
+			if (tid == 0)
 			{
 				p.node_first[0] = 0; p.node_count[0] = T; p.node_escape[0] = -1;
-				for (int k = 0; k < 3; ++k)
+				for (int d = 0; d < 3; ++d)
 				{
-					p.node_box[k] = mn[k]; p.node_box[3 + k] = mx[k];
-					p.result_info[2 + k] = __float_as_int(mn[k]); p.result_info[5 + k] = __float_as_int(mx[k]);
+					const float lo = key_float(s.child_lo[0][d]), hi = key_float(s.child_hi[0][d]);
+					p.node_box[d] = lo; p.node_box[3 + d] = hi;
+					p.result_info[2 + d] = __float_as_int(lo); p.result_info[5 + d] = __float_as_int(hi);
 				}
 				if (3 * T <= 8) write_node_record(p, 0, true, 0, T);
 				else { p.queue_a[0] = 0; level_count[0] = 1; }
 			}
+			__syncthreads();
 		}
-		__syncthreads();
 
-		// one tree level per round, one warp per node
+		// one tree level per round
 		int* cur = p.queue_a;
 		int* nxt = p.queue_b;
 		int parity = 0;
@@ -339,8 +517,30 @@ namespace rt
 		{
 			const int n = level_count[parity];
 			if (n == 0) break;
-			for (int q = warp; q < n; q += kBuildWarps)
-				subdivide_node(p, cur[q], lane, bins[warp], &nodes_used, nxt, &level_count[parity ^ 1]);
+			Team t;
+			int n_teams;
+			if (n > kMaxTeams) { n_teams = kBuildWarps; t.warps = 1; }
+			else { n_teams = n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8)); t.warps = kBuildWarps / n_teams; }
+			t.threads = 32 * t.warps;
+			const int team = warp / t.warps;
+			t.warp = warp - team * t.warps;
+			t.tid = tid - team * t.threads;
+			t.barrier = 1 + team;
+			t.s = &scratch[team];
+			for (int q = team; q < n; q += n_teams)
+			{
+				subdivide_node(p, w, cur[q], t, &nodes_used, nxt, &level_count[parity ^ 1]);
+				while (t.threads == 32)                     // this warp's own subtrees, to the bottom
+				{
+					const int top = t.s->top;
+					if (top == 0) break;
+					const int node = t.s->stack[top - 1];
+					__syncwarp();
+					if (lane == 0) t.s->top = top - 1;
+					__syncwarp();
+					subdivide_node(p, w, node, t, &nodes_used, nxt, &level_count[parity ^ 1]);
+				}
+			}
 			__syncthreads();
 			if (tid == 0) level_count[parity] = 0;
 			int* swap = cur; cur = nxt; nxt = swap;
@@ -352,7 +552,7 @@ namespace rt
 		// pixel kernel ({v0|nx}{e1|ny}{e2|nz}, e1 = v1 - v0, e2 = v2 - v0: Utils.h:143-144)
 		for (int k = tid; k < T; k += kBuildThreads)
 		{
-			const int slot = p.order[k];
+			const int slot = w.order[k];
 			V3 v[3];
 			for (int c = 0; c < 3; ++c)
 			{
@@ -362,15 +562,29 @@ namespace rt
 				v[c] = v3(p.tpos[3 * vi], p.tpos[3 * vi + 1], p.tpos[3 * vi + 2]);
 			}
 			const V3 e1 = v[1] - v[0], e2 = v[2] - v[0];
-			p.result_triangles[3 * k + 0] = make_float4(v[0].x, v[0].y, v[0].z, p.tnormal[3 * slot]);
-			p.result_triangles[3 * k + 1] = make_float4(e1.x, e1.y, e1.z, p.tnormal[3 * slot + 1]);
-			p.result_triangles[3 * k + 2] = make_float4(e2.x, e2.y, e2.z, p.tnormal[3 * slot + 2]);
+			const float4 r0 = make_float4(v[0].x, v[0].y, v[0].z, p.tnormal[3 * slot]);
+			const float4 r1 = make_float4(e1.x, e1.y, e1.z, p.tnormal[3 * slot + 1]);
+			const float4 r2 = make_float4(e2.x, e2.y, e2.z, p.tnormal[3 * slot + 2]);
+			p.result_triangles[3 * k + 0] = r0; p.result_triangles[3 * k + 1] = r1; p.result_triangles[3 * k + 2] = r2;
+			if (p.scene_triangles) { p.scene_triangles[3 * k + 0] = r0; p.scene_triangles[3 * k + 1] = r1; p.scene_triangles[3 * k + 2] = r2; }
 		}
-		if (tid == 0) p.result_info[0] = nodes_used;
+		const int n_nodes = nodes_used;
+		if (tid == 0) p.result_info[0] = n_nodes;
+		if (p.scene_nodes)
+		{
+			for (int i = tid; i < 2 * n_nodes; i += kBuildThreads) p.scene_nodes[i] = p.result_nodes[i];
+			if (tid == 0)
+			{
+				const float4 keep1 = p.scene_table[1], keep2 = p.scene_table[2];
+				p.scene_table[0] = make_float4(p.node_box[0], p.node_box[3], p.node_box[1], p.node_box[4]);
+				p.scene_table[1] = make_float4(p.node_box[2], p.node_box[5], keep1.z, keep1.w);
+				p.scene_table[2] = make_float4(keep2.x, keep2.y, keep2.z, __int_as_float(n_nodes));
+			}
+		}
 	}
 
 	// Copies a mesh's last build into the scene's mesh block: triangle stream slice, node slice, and the mesh
-	// table's box / node rows.  Runs after every build and whenever the block was rewritten from the host mirror
+	// table's box / node rows.  Runs when the block was rewritten from the host mirror and no new build is due
 	// (a rebuild there would advance the triangle order a second time).
 	struct EmitParams
 	{

@@ -145,3 +145,59 @@ def test_device_bvh_must_be_chosen_before_the_first_transform():
     with pytest.raises(RtError, match="before the first rt_transform_mesh"):
         r.ctx.set_mesh_device_bvh(0, True)
     r.close()
+
+
+def made_up_mesh(rng, n_triangles, kind):
+    """Triangle soups that stress the builder: sizes around the team / warp / leaf limits, flat and repeated geometry."""
+    n_vertices = max(3, (n_triangles * 2) // 3 + 3)
+    pos = rng.uniform(-1.0, 1.0, size=(n_vertices, 3)).astype(np.float32)
+    if kind == "flat":
+        pos[:, 2] = np.float32(0.25)                 # one axis without extent: skipped by FindBestSplitPlane
+    if kind == "grid":
+        pos = np.round(pos * 4).astype(np.float32) / 4   # many equal centroids and ties between planes
+    idx = rng.integers(0, n_vertices, size=(n_triangles, 3)).astype(np.int32)
+    if kind == "repeated":
+        idx[:] = idx[0]                                 # every centroid the same: no axis splits, one wide leaf
+    e1, e2 = pos[idx[:, 1]] - pos[idx[:, 0]], pos[idx[:, 2]] - pos[idx[:, 0]]
+    nrm = np.cross(e1, e2).astype(np.float32)
+    length = np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm = np.where(length > 0, nrm / np.maximum(length, 1e-30), np.float32([0, 1, 0])).astype(np.float32)
+    return pos, idx, nrm
+
+
+MADE_UP = [(1, "soup"), (2, "soup"), (3, "soup"), (9, "soup"), (33, "soup"), (64, "grid"), (65, "soup"), (257, "flat"), (300, "repeated"),
+           (1025, "soup"), (1500, "grid"), (2600, "soup"), (5000, "soup")]
+
+
+@pytest.mark.parametrize("n_triangles,kind", MADE_UP)
+def test_device_build_matches_the_oracle_on_made_up_meshes(n_triangles, kind):
+    """Three successive builds (each starts from the order the last one left) of a made-up mesh: triangle order, normals
+    order and tree against the oracle's restatement after every one, and the frame after the last."""
+    from gp1_raytracer_2223_b200 import Renderer
+    from oracle import rt_oracle
+    rng = np.random.default_rng(1000 + n_triangles)
+    scene = load_golden_scene("bunny_320_yaw10")
+    pos, idx, nrm = made_up_mesh(rng, n_triangles, kind)
+    w, h = 96, 72
+    scene.width, scene.height = w, h
+    r = Renderer(w, h)
+    r.SetScene(scene)
+    mesh = scene.meshes[0]
+    r.ctx.upload_mesh_source(0, pos, idx, nrm, mesh.cull_mode, mesh.material_index)
+    r.ctx.set_mesh_device_bvh(0, True)
+    idx, nrm = idx.copy(), nrm.copy()
+    for step in range(3):
+        a = np.float32(0.7 * step + 0.2)
+        c, s_ = np.float32(np.cos(a)), np.float32(np.sin(a))
+        m = np.array([[2 * c, 0, -2 * s_, 0], [0, 2, 0, 0], [2 * s_, 0, 2 * c, 0], [0.1 * step, 1.5, 0, 1]], dtype=np.float32)
+        r.ctx.transform_mesh(0, m)
+        tpos, tnrm, nodes = rt_oracle.update_transforms_bvh(pos, idx, nrm, m)
+        got_idx, got_nrm, got_nodes = r.ctx.read_mesh_build(0, n_triangles)
+        assert np.array_equal(got_idx.reshape(-1, 3), idx), f"triangle order differs after build {step}"
+        assert np.array_equal(got_nrm.view(np.uint32), nrm.view(np.uint32))
+        assert len(got_nodes) == len(nodes)
+        assert assert_same_tree(got_nodes, nodes) == len(nodes)
+    mesh.positions, mesh.indices, mesh.normals, mesh.bvh_nodes = tpos, idx, tnrm, nodes
+    r.ctx.set_mesh_path(2)
+    assert np.array_equal(r.Render(), rt_oracle.render(scene, w, h))
+    r.close()
