@@ -398,7 +398,7 @@ namespace
 		rt::BuildParams& b = sd.build;
 		b = rt::BuildParams{};
 		b.positions = sd.positions; b.vertex_count = V; b.triangle_count = T;
-		b.tpos = (float*)(base + o_tpos); b.centroid = (float*)(base + o_cen); b.tri_min = (float*)(base + o_min); b.tri_max = (float*)(base + o_max);
+		b.tpos = (float*)(base + o_tpos); b.centroid = (float*)(base + o_cen); b.tri_min = (unsigned int*)(base + o_min); b.tri_max = (unsigned int*)(base + o_max);
 		b.tnormal = (float*)(base + o_tn); b.order = (int32_t*)(base + o_order); b.order_tmp = (int32_t*)(base + o_tmp);
 		b.rights_before = (int32_t*)(base + o_rb); b.front_right = (int32_t*)(base + o_fr); b.back_left = (int32_t*)(base + o_bl);
 		b.node_first = (int32_t*)(base + o_first); b.node_count = (int32_t*)(base + o_count); b.node_escape = (int32_t*)(base + o_escape);

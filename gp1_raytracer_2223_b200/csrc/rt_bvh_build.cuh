@@ -41,8 +41,8 @@ namespace rt
 		// scratch, all sized by the host (T = triangles, N = 2T - 1 nodes at most)
 		float* tpos;                    // 3V   transformedPositions
 		float* centroid;                // 3T   per triangle slot
-		float* tri_min;                 // 3T   min / max over the slot's three vertices
-		float* tri_max;                 // 3T
+		unsigned int* tri_min;          // 3T   float_key of the min / max over the slot's three vertices
+		unsigned int* tri_max;          // 3T
 		float* tnormal;                 // 3T   transformedNormals per slot
 		int32_t* order;                 // T    order[k] = slot that sits at position k
 		int32_t* order_tmp;             // T    partition output before it is copied back
@@ -72,8 +72,8 @@ namespace rt
 	struct BuildWork
 	{
 		float* centroid;                // 3T   per triangle slot
-		float* tri_min;                 // 3T
-		float* tri_max;                 // 3T
+		unsigned int* tri_min;          // 3T   float_key of the triangle's box
+		unsigned int* tri_max;          // 3T
 		int32_t* order;                 // T    order[k] = slot that sits at position k
 		int32_t* order_tmp;             // T
 		int32_t* rights_before;         // T
@@ -285,8 +285,8 @@ namespace rt
 				for (int a = 0; a < 3; ++a)
 				{
 					c[a] = w.centroid[3 * slot + a];
-					mn[a] = float_key(w.tri_min[3 * slot + a]);
-					mx[a] = float_key(w.tri_max[3 * slot + a]);
+					mn[a] = w.tri_min[3 * slot + a];
+					mx[a] = w.tri_max[3 * slot + a];
 				}
 			}
 			for (int a = 0; a < 3; ++a)
@@ -317,33 +317,47 @@ namespace rt
 		}
 		team_sync(t);
 
-		// the 7 planes of the 3 axes, DataTypes.h:443-479: lane 7a + i of the team's first warp owns plane i of axis a
-		// (left = bins 0..i, right = bins i + 1..7).  The reference walks axis 0..2, plane 0..6 and keeps the first
-		// strictly smaller cost: that is the lowest lane holding the minimum.
+		// the 7 planes of the 3 axes, DataTypes.h:443-479.  Lane 8a + b of the team's first warp loads bin b of axis a;
+		// an inclusive scan up the 8 lanes gives "bins 0..b" (leftBox / leftCount of plane b), one down the lanes gives
+		// "bins b..7", whose neighbour b + 1 is rightBox / rightCount of plane b.  Boxes stay float_keys until the areas.
+		// The reference walks axis 0..2, plane 0..6 and keeps the first strictly smaller cost: the lowest lane holding
+		// the minimum.
 		if (t.warp == 0)
 		{
-			const int a = lane / 7, plane = lane - 7 * a;
+			const int a = lane >> 3, b = lane & 7;
+			const bool holds_bin = lane < 24;
+			unsigned int llo[3] = { key_max, key_max, key_max }, lhi[3] = { key_min, key_min, key_min };
+			int lcount = 0;
+			if (holds_bin)
+			{
+				lcount = (int)s.bin_count[a][b];
+				for (int d = 0; d < 3; ++d) { llo[d] = s.bin_lo[a][b][d]; lhi[d] = s.bin_hi[a][b][d]; }
+			}
+			unsigned int rlo[3] = { llo[0], llo[1], llo[2] }, rhi[3] = { lhi[0], lhi[1], lhi[2] };
+			int rcount = lcount;
+			for (int off = 1; off < 8; off <<= 1)
+			{
+				const int uc = __shfl_up_sync(0xffffffffu, lcount, off, 8), dc = __shfl_down_sync(0xffffffffu, rcount, off, 8);
+				unsigned int ulo[3], uhi[3], dlo[3], dhi[3];
+				for (int d = 0; d < 3; ++d)
+				{
+					ulo[d] = __shfl_up_sync(0xffffffffu, llo[d], off, 8); uhi[d] = __shfl_up_sync(0xffffffffu, lhi[d], off, 8);
+					dlo[d] = __shfl_down_sync(0xffffffffu, rlo[d], off, 8); dhi[d] = __shfl_down_sync(0xffffffffu, rhi[d], off, 8);
+				}
+				if (b >= off) { lcount += uc; for (int d = 0; d < 3; ++d) { llo[d] = min(llo[d], ulo[d]); lhi[d] = max(lhi[d], uhi[d]); } }
+				if (b + off < 8) { rcount += dc; for (int d = 0; d < 3; ++d) { rlo[d] = min(rlo[d], dlo[d]); rhi[d] = max(rhi[d], dhi[d]); } }
+			}
+			// plane b: right side = bins b + 1..7 = the lane above
+			rcount = __shfl_down_sync(0xffffffffu, rcount, 1, 8);
+			for (int d = 0; d < 3; ++d) { rlo[d] = __shfl_down_sync(0xffffffffu, rlo[d], 1, 8); rhi[d] = __shfl_down_sync(0xffffffffu, rhi[d], 1, 8); }
 			float cost = 0.f;
 			bool candidate = false;
-			if (lane < 21 && (a == 0 ? use_axis[0] : (a == 1 ? use_axis[1] : use_axis[2])))
+			if (holds_bin && b < 7 && (a == 0 ? use_axis[0] : (a == 1 ? use_axis[1] : use_axis[2])))
 			{
-				float lmn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, lmx[3] = { FLT_MIN, FLT_MIN, FLT_MIN };
-				float rmn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, rmx[3] = { FLT_MIN, FLT_MIN, FLT_MIN };
-				int left_count = 0, right_count = 0;
-				for (int b = 0; b < 8; ++b)
-				{
-					const bool is_left = b <= plane;
-					const int c = (int)s.bin_count[a][b];
-					if (is_left) left_count += c; else right_count += c;
-					for (int d = 0; d < 3; ++d)
-					{
-						const float bl = key_float(s.bin_lo[a][b][d]), bh = key_float(s.bin_hi[a][b][d]);
-						if (is_left) { lmn[d] = std_min(lmn[d], bl); lmx[d] = std_max(lmx[d], bh); }
-						else { rmn[d] = std_min(rmn[d], bl); rmx[d] = std_max(rmx[d], bh); }
-					}
-				}
+				float lmn[3], lmx[3], rmn[3], rmx[3];
+				for (int d = 0; d < 3; ++d) { lmn[d] = key_float(llo[d]); lmx[d] = key_float(lhi[d]); rmn[d] = key_float(rlo[d]); rmx[d] = key_float(rhi[d]); }
 				// DataTypes.h:472: leftCount[i] * leftArea[i] + rightCount[i] * rightArea[i]
-				cost = add(mul((float)left_count, box_area(lmn, lmx)), mul((float)right_count, box_area(rmn, rmx)));
+				cost = add(mul((float)lcount, box_area(lmn, lmx)), mul((float)rcount, box_area(rmn, rmx)));
 				candidate = cost < FLT_MAX;                                              // bestCost starts at FLT_MAX; false for NaN
 			}
 			float m = candidate ? cost : INFINITY;
@@ -353,7 +367,7 @@ namespace rt
 			{
 				if (winners)
 				{
-					const int win = __ffs(winners) - 1, wa = win / 7, wp = win - 7 * wa;
+					const int win = __ffs(winners) - 1, wa = win >> 3, wp = win & 7;
 					const float wlo = wa == 0 ? lo[0] : (wa == 1 ? lo[1] : lo[2]), wdiff = wa == 0 ? diff[0] : (wa == 1 ? diff[1] : diff[2]);
 					s.axis = wa;
 					s.split_pos = add(wlo, mul(quo(wdiff, 8.f), (float)(wp + 1)));            // DataTypes.h:469, 476
@@ -397,8 +411,8 @@ namespace rt
 				unsigned int gmn[3], gmx[3];
 				for (int d = 0; d < 3; ++d)
 				{
-					gmn[d] = __reduce_min_sync(peers, float_key(w.tri_min[3 * slot + d]));
-					gmx[d] = __reduce_max_sync(peers, float_key(w.tri_max[3 * slot + d]));
+					gmn[d] = __reduce_min_sync(peers, w.tri_min[3 * slot + d]);
+					gmx[d] = __reduce_max_sync(peers, w.tri_max[3 * slot + d]);
 				}
 				if (lane == __ffs(peers) - 1)
 					for (int d = 0; d < 3; ++d) { atomicMin(&s.child_lo[side][d], gmn[d]); atomicMax(&s.child_hi[side][d], gmx[d]); }
@@ -437,7 +451,7 @@ namespace rt
 		BuildWork w;
 		if (p.work_in_shared)
 		{
-			w.centroid = dynamic_shared; w.tri_min = w.centroid + 3 * T; w.tri_max = w.tri_min + 3 * T;
+			w.centroid = dynamic_shared; w.tri_min = reinterpret_cast<unsigned int*>(w.centroid + 3 * T); w.tri_max = w.tri_min + 3 * T;
 			w.order = reinterpret_cast<int32_t*>(w.tri_max + 3 * T); w.order_tmp = w.order + T; w.rights_before = w.order_tmp + T;
 			w.front_right = w.rights_before + T; w.back_left = w.front_right + T;
 		}
@@ -468,9 +482,9 @@ namespace rt
 			}
 			const V3 c = ((v[0] + v[1]) + v[2]) * 0.3333f;
 			w.centroid[3 * t] = c.x; w.centroid[3 * t + 1] = c.y; w.centroid[3 * t + 2] = c.z;
-			w.tri_min[3 * t] = std_min(std_min(v[0].x, v[1].x), v[2].x); w.tri_max[3 * t] = std_max(std_max(v[0].x, v[1].x), v[2].x);
-			w.tri_min[3 * t + 1] = std_min(std_min(v[0].y, v[1].y), v[2].y); w.tri_max[3 * t + 1] = std_max(std_max(v[0].y, v[1].y), v[2].y);
-			w.tri_min[3 * t + 2] = std_min(std_min(v[0].z, v[1].z), v[2].z); w.tri_max[3 * t + 2] = std_max(std_max(v[0].z, v[1].z), v[2].z);
+			w.tri_min[3 * t] = float_key(std_min(std_min(v[0].x, v[1].x), v[2].x)); w.tri_max[3 * t] = float_key(std_max(std_max(v[0].x, v[1].x), v[2].x));
+			w.tri_min[3 * t + 1] = float_key(std_min(std_min(v[0].y, v[1].y), v[2].y)); w.tri_max[3 * t + 1] = float_key(std_max(std_max(v[0].y, v[1].y), v[2].y));
+			w.tri_min[3 * t + 2] = float_key(std_min(std_min(v[0].z, v[1].z), v[2].z)); w.tri_max[3 * t + 2] = float_key(std_max(std_max(v[0].z, v[1].z), v[2].z));
 			const float nx = p.normals_in[3 * t], ny = p.normals_in[3 * t + 1], nz = p.normals_in[3 * t + 2];
 			V3 n = v3(add(add(mul(p.m[0], nx), mul(p.m[4], ny)), mul(p.m[8], nz)),
 			          add(add(mul(p.m[1], nx), mul(p.m[5], ny)), mul(p.m[9], nz)),
@@ -489,7 +503,7 @@ namespace rt
 			__syncthreads();
 			unsigned int mn[3] = { key_max, key_max, key_max }, mx[3] = { key_min, key_min, key_min };
 			for (int t = tid; t < T; t += kBuildThreads)
-				for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], float_key(w.tri_min[3 * t + d])); mx[d] = max(mx[d], float_key(w.tri_max[3 * t + d])); }
+				for (int d = 0; d < 3; ++d) { mn[d] = min(mn[d], w.tri_min[3 * t + d]); mx[d] = max(mx[d], w.tri_max[3 * t + d]); }
 			for (int d = 0; d < 3; ++d) { mn[d] = __reduce_min_sync(0xffffffffu, mn[d]); mx[d] = __reduce_max_sync(0xffffffffu, mx[d]); }
 			if (lane == 0)
 				for (int d = 0; d < 3; ++d) { atomicMin(&s.child_lo[0][d], mn[d]); atomicMax(&s.child_hi[0][d], mx[d]); }

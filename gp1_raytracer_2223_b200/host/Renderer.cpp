@@ -13,7 +13,8 @@
 // Renderer (created on the first Render, released at process exit).  Devices: environment variable
 // RT_B200_DEVICES="0,1,2,3" (default: the current device).  RT_B200_DEVICE_TRANSFORM=1 moves
 // TriangleMesh::UpdateTransforms' vertex / normal transform to the device as well (mesh source uploaded once,
-// 64 bytes per mesh and frame; rendered by the slab + linear body).  Errors have no channel in the reference
+// 64 bytes per mesh and frame; rendered by the slab + linear body); RT_B200_DEVICE_TRANSFORM=2 moves BuildBVH there
+// too (one build per change of pose; rendered by the BVH body).  Errors have no channel in the reference
 // API (Render returns void): they are printed to stderr and the frame is left untouched; there is
 // no CPU fallback.
 #include "SDL.h"
@@ -28,6 +29,7 @@
 
 #include "SceneFlattener.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
@@ -76,7 +78,7 @@ namespace
 			std::fprintf(stderr, "rt_b200: rt_create failed (%d): %s\n", rc, rt_last_error(nullptr));
 			side->ctx = nullptr;
 		}
-		if (const char* env = std::getenv("RT_B200_DEVICE_TRANSFORM")) side->scratch.device_transform = std::atoi(env) != 0;
+		if (const char* env = std::getenv("RT_B200_DEVICE_TRANSFORM")) side->scratch.device_transform = std::max(0, std::min(2, std::atoi(env)));
 		DeviceSide* raw = side.get();
 		g_devices.emplace(renderer, std::move(side));
 		return raw;

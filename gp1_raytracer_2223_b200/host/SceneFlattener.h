@@ -17,6 +17,9 @@
 
 #include <cstdint>
 #include <string>
+#include <array>
+#include <cstring>
+#include <limits>
 #include <vector>
 
 namespace rt_host
@@ -31,9 +34,11 @@ namespace rt_host
 		std::vector<float> light[10];          // ox, oy, oz, dx, dy, dz, r, g, b, intensity
 		std::vector<int32_t> light_type;
 		std::vector<rt_material_desc> materials;
-		// device-side UpdateTransforms (RT_B200_DEVICE_TRANSFORM=1): what was last sent as mesh source
-		bool device_transform = false;
+		// device-side UpdateTransforms (RT_B200_DEVICE_TRANSFORM): 0 = host (upload its results), 1 = transform on the
+		// device, 2 = transform + BuildBVH on the device; what was last sent as mesh source / transform
+		int device_transform = 0;
 		std::vector<size_t> source_vertices, source_triangles;
+		std::vector<std::array<float, 16>> sent_transform;
 	};
 
 	inline bool DescribeMaterial(dae::Material* material, rt_material_desc& out)
@@ -139,8 +144,15 @@ namespace rt_host
 			// (source/DataTypes.h:213); TransformPoint / TransformVector().Normalized() run on the device and the
 			// mesh is rendered by the slab + linear body (no BVH upload).  BuildBVH keeps permuting `indices` and
 			// `normals` together on the host; any such order is the same triangle set, so the first one is kept.
+			//
+			// Mode 2 moves BuildBVH along (rt_set_mesh_device_bvh): the mesh is rendered by the BVH body, and every
+			// CHANGE of finalTransform is one UpdateTransforms call of the reference, run on the device from the
+			// triangle order the previous one left.  That is the reference's own sequence of builds when the host's
+			// Scene::Update only sets the pose (RotateY / Translate / Scale) and leaves UpdateTransforms to this path
+			// (INTEGRATION.md); the source is taken in the order TriangleMesh::indices has at the first Render.
 			scratch.source_vertices.resize(meshes.size(), (size_t)-1);
 			scratch.source_triangles.resize(meshes.size(), (size_t)-1);
+			scratch.sent_transform.resize(meshes.size());
 			for (size_t i = 0; i < meshes.size(); ++i)
 			{
 				const dae::TriangleMesh& m = meshes[i];
@@ -155,12 +167,19 @@ namespace rt_host
 					src.cull_mode = (int32_t)m.cullMode;
 					src.material_index = m.materialIndex;
 					if ((rc = rt_upload_mesh_source(ctx, (int32_t)i, &src)) != RT_OK) return fail(rc, "rt_upload_mesh_source");
+					if (scratch.device_transform == 2 && (rc = rt_set_mesh_device_bvh(ctx, (int32_t)i, 1)) != RT_OK) return fail(rc, "rt_set_mesh_device_bvh");
 					scratch.source_vertices[i] = m.positions.size();
 					scratch.source_triangles[i] = m.indices.size() / 3;
+					scratch.sent_transform[i].fill(std::numeric_limits<float>::quiet_NaN());     // differs from every transform
 				}
 				const dae::Matrix finalTransform = m.scaleTransform * m.rotationTransform * m.translationTransform;
 				float t[16];
 				for (int r = 0; r < 4; ++r) { const dae::Vector4 row = finalTransform[r]; t[4 * r] = row.x; t[4 * r + 1] = row.y; t[4 * r + 2] = row.z; t[4 * r + 3] = row.w; }
+				if (scratch.device_transform == 2)
+				{
+					if (std::memcmp(t, scratch.sent_transform[i].data(), sizeof t) == 0) continue;    // same pose: no new build
+					std::memcpy(scratch.sent_transform[i].data(), t, sizeof t);
+				}
 				if ((rc = rt_transform_mesh(ctx, (int32_t)i, t)) != RT_OK) return fail(rc, "rt_transform_mesh");
 			}
 			return RT_OK;

@@ -66,6 +66,8 @@ namespace
 		std::string dumpSource;   // untransformed meshes + their final transform ("RTMS0001")
 		std::vector<float> yawSteps;  // --yaw-steps a,b,c: RotateY(a); UpdateTransforms(); RotateY(b); UpdateTransforms(); ...
 		std::string dumpSteps;    // the mesh state BEFORE those steps + the final transform of each step ("RTMP0001")
+		bool stepsOnDevice = false; // --steps-on-device (drop-in build only): RotateY(a); Render(); RotateY(b); Render(); ... -
+		                            // the host never runs UpdateTransforms for the steps, the drop-in's device side does
 		std::string resources; // directory that CONTAINS "Resources/"
 	};
 
@@ -77,7 +79,7 @@ namespace
 			"  [--width W --height H] [--mode 0..3] [--shadows 0|1] [--frames N] [--warmup N]\n"
 			"  [--threads T] [--time SECONDS] [--mesh-yaw RAD] [--cam-origin X Y Z]\n"
 			"  [--cam-rot PITCH YAW] [--fov DEGREES] [--out FILE] [--dump-scene FILE] [--dump-mesh-source FILE]\n"
-			"  [--yaw-steps A,B,... [--dump-mesh-steps FILE]]\n"
+			"  [--yaw-steps A,B,... [--dump-mesh-steps FILE] [--steps-on-device]]\n"
 			"  [--resources DIR]\n", why);
 		std::exit(2);
 	}
@@ -121,6 +123,7 @@ namespace
 				}
 			}
 			else if (a == "--resources") { need(i, 1); o.resources = argv[++i]; }
+			else if (a == "--steps-on-device") o.stepsOnDevice = true;
 			else Usage(("unknown argument " + a).c_str());
 		}
 		if (o.width <= 0 || o.height <= 0 || o.frames < 0 || o.mode < 0 || o.mode > 3) Usage("bad value");
@@ -339,6 +342,16 @@ int main(int argc, char** argv)
 		rec.Capture(pScene);
 		for (float yaw : o.yawSteps)
 		{
+#ifdef GP1_DROPIN
+			if (o.stepsOnDevice)
+			{
+				// what a host whose Scene::Update no longer calls UpdateTransforms does: set the pose, render
+				// (RT_B200_DEVICE_TRANSFORM=2: the drop-in runs UpdateTransforms + BuildBVH on the device)
+				for (TriangleMesh& m : pScene->m_TriangleMeshGeometries) m.RotateY(yaw);
+				pRenderer->Render(pScene);
+				continue;
+			}
+#endif
 			for (TriangleMesh& m : pScene->m_TriangleMeshGeometries) { m.RotateY(yaw); m.UpdateTransforms(); }
 			rec.Step(pScene);
 		}

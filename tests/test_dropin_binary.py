@@ -69,3 +69,30 @@ def test_dropin_with_device_side_update_transforms(tmp_path, args):
     if "W4_Bunny" in args:
         assert n_diff == 0
     assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (n_diff, max_err)
+
+
+STEP_RUNS = [
+    ["--scene", "W4_Bunny", "--width", "320", "--height", "240", "--yaw-steps", "0.4,1.3,2.9"],
+    ["--scene", "W4_Reference", "--width", "320", "--height", "240", "--yaw-steps", "0.7,2.2"],
+    ["--scene", "W4_Optional", "--width", "320", "--height", "240", "--yaw-steps", "0.5,1.0"],
+]
+
+
+@pytest.mark.parametrize("args", STEP_RUNS, ids=[a[1] for a in STEP_RUNS])
+def test_dropin_with_device_side_bvh_builds(tmp_path, args):
+    """RT_B200_DEVICE_TRANSFORM=2: UpdateTransforms WITH BuildBVH on the device.  The reference poses the meshes and
+    runs UpdateTransforms on the host after every pose (--yaw-steps); the drop-in's host only poses them and renders
+    (--steps-on-device), every change of pose being one build on the device.  Same frame at the end - also when more
+    frames follow without a new pose (no further build may run)."""
+    if not (os.path.exists(REF) and os.path.exists(DROPIN)):
+        pytest.skip("oracle/_ref binaries are not built (they need /root/reference at build time)")
+    a, b = str(tmp_path / "ref.bin"), str(tmp_path / "b200.bin")
+    info_ref = run(REF, args, a)
+    info_gpu = run(DROPIN, args + ["--steps-on-device", "--frames", "3"], b, env={"RT_B200_DEVICE_TRANSFORM": "2"})
+    w, h = info_ref["width"], info_ref["height"]
+    want = np.fromfile(a, dtype=np.uint32).reshape(h, w)
+    got = np.fromfile(b, dtype=np.uint32).reshape(h, w)
+    identical, max_err, n_diff = compare_frames(got, want)
+    if "W4_Bunny" in args:
+        assert info_ref["fnv1a64"] == info_gpu["fnv1a64"] and n_diff == 0
+    assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (n_diff, max_err)
