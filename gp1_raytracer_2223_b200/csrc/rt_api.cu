@@ -85,7 +85,7 @@ namespace
 			bool built = false;                // build results are valid (emit_mesh_kernel may copy them)
 		};
 		std::vector<MeshSourceDevice> sources;   // untransformed meshes (rt_upload_mesh_source), by mesh id
-		long long build_shared_limit = -1;       // dynamic shared memory the build kernel may use here; -1 = not asked yet
+		long long build_shared_limit = -1, subtree_shared_limit = -1;   // dynamic shared memory the build kernels may use here; -1 = not asked yet
 		uint32_t* d_frame = nullptr;
 		size_t frame_capacity = 0;         // in pixels
 		unsigned long long* d_counters = nullptr;
@@ -124,7 +124,6 @@ struct rt_context
 	rt_timing timing{};
 	int32_t last_width = 0, last_height = 0;
 
-	int32_t build_local_triangles = 0;  // rt::BuildParams::local_triangles (RT_B200_BUILD_LOCAL overrides: measurement)
 	int32_t* h_build_status = nullptr;  // pinned, one word per mesh: status of the last device-side BVH build (device 0)
 
 	void* registered_host = nullptr;    // host surface we pinned ourselves
@@ -362,23 +361,28 @@ namespace
 		return RT_OK;
 	}
 
-	// Dynamic shared memory update_transforms_bvh_kernel may use on this device (opt-in limit minus its static part);
-	// raises the kernel's limit the first time.  0 when the attribute cannot be set: the build then works in global memory.
-	size_t build_shared_limit(rt_context* ctx, DeviceState& d)
+	// Dynamic shared memory the two build kernels may use on this device (opt-in limit minus their static part);
+	// raises the kernels' limits the first time.  0 when an attribute cannot be set: the build then works in global memory.
+	template <typename Kernel>
+	long long raise_shared_limit(Kernel kernel, int device)
 	{
-		if (d.build_shared_limit >= 0) return (size_t)d.build_shared_limit;
-		d.build_shared_limit = 0;
-		if (getenv("RT_B200_BUILD_GLOBAL")) return 0;     // measurement: force the global-memory work arrays
 		int optin = 0;
 		cudaFuncAttributes attr{};
-		if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.device) != cudaSuccess ||
-		    cudaFuncGetAttributes(&attr, rt::update_transforms_bvh_kernel) != cudaSuccess) { cudaGetLastError(); return 0; }
+		if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
+		    cudaFuncGetAttributes(&attr, kernel) != cudaSuccess) { cudaGetLastError(); return 0; }
 		const long long room = (long long)optin - (long long)attr.sharedSizeBytes - 1024;
 		if (room <= 0) return 0;
-		if (cudaFuncSetAttribute(rt::update_transforms_bvh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room) != cudaSuccess) { cudaGetLastError(); return 0; }
-		(void)ctx;
-		d.build_shared_limit = room;
-		return (size_t)room;
+		if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room) != cudaSuccess) { cudaGetLastError(); return 0; }
+		return room;
+	}
+
+	void query_build_shared_limits(DeviceState& d)
+	{
+		if (d.build_shared_limit >= 0) return;
+		d.build_shared_limit = 0; d.subtree_shared_limit = 0;
+		if (getenv("RT_B200_BUILD_GLOBAL")) return;       // measurement: force the global-memory work arrays
+		d.build_shared_limit = raise_shared_limit(rt::update_transforms_bvh_kernel, d.device);
+		d.subtree_shared_limit = raise_shared_limit(rt::build_subtrees_kernel, d.device);
 	}
 
 	// Carves the scratch / result arrays of update_transforms_bvh_kernel out of one allocation.
@@ -391,7 +395,7 @@ namespace
 		const size_t o_tpos = take(12 * (size_t)std::max(V, 1)), o_cen = take(12 * Tn), o_min = take(12 * Tn), o_max = take(12 * Tn), o_tn = take(12 * Tn),
 		             o_order = take(4 * Tn), o_tmp = take(4 * Tn), o_rb = take(4 * Tn), o_fr = take(4 * Tn), o_bl = take(4 * Tn),
 		             o_first = take(4 * N), o_count = take(4 * N), o_escape = take(4 * N), o_box = take(24 * N),
-		             o_qa = take(4 * Tn), o_qb = take(4 * Tn), o_tris = take(48 * Tn), o_nodes = take(32 * N), o_info = take(32);
+		             o_qa = take(4 * Tn), o_qb = take(4 * Tn), o_tris = take(48 * Tn), o_nodes = take(32 * N), o_info = take(sizeof(int32_t) * rt::kInfoWords);
 		RT_CUDA(ctx, cudaMalloc(&sd.build_block, offset));
 		RT_CUDA(ctx, cudaMemset(sd.build_block, 0, offset));
 		char* base = (char*)sd.build_block;
@@ -458,15 +462,22 @@ namespace
 						b.scene_triangles = T > 0 ? d.d_mesh + d.triangle_offset + 3 * (size_t)first : nullptr;     // an empty mesh owns no slices
 						b.scene_nodes = T > 0 ? d.d_mesh + d.node_offset + 2 * (size_t)first_node : nullptr;
 						b.scene_table = T > 0 ? d.d_mesh + 3 * m : nullptr;
+						query_build_shared_limits(d);
 						size_t work_bytes = sizeof(float) * rt::kBuildWorkWordsPerTriangle * (size_t)std::max(T, 1);
-						b.work_in_shared = work_bytes <= build_shared_limit(ctx, d) ? 1 : 0;
+						b.work_in_shared = (long long)work_bytes <= d.build_shared_limit ? 1 : 0;
 						if (!b.work_in_shared) work_bytes = 0;
-						b.local_triangles = ctx->build_local_triangles;
+						// subtrees are at most the whole mesh; what does not fit works in the global scratch
+						const long long fit = d.subtree_shared_limit / (long long)(sizeof(int32_t) * rt::kSubtreeWordsPerTriangle);
+						b.subtree_shared_triangles = (int32_t)std::min<long long>(fit, std::min(T, 4096));
+						const size_t subtree_bytes = sizeof(int32_t) * rt::kSubtreeWordsPerTriangle * (size_t)b.subtree_shared_triangles;
 						rt::update_transforms_bvh_kernel<<<1, rt::kBuildThreads, work_bytes, d.stream>>>(b);
+						RT_CUDA(ctx, cudaGetLastError());
+						rt::build_subtrees_kernel<<<rt::kSubtreeCtas, rt::kSubtreeThreads, subtree_bytes, d.stream>>>(b);
+						ctx->timing.kernel_launches++;
 						RT_CUDA(ctx, cudaGetLastError());
 						std::swap(sd.indices, sd.indices_alt); std::swap(sd.normals, sd.normals_alt);     // the order the build left
 						sd.built = true;
-						if (&d == &ctx->devs[0]) RT_CUDA(ctx, cudaMemcpyAsync(ctx->h_build_status + m, b.result_info + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
+						if (&d == &ctx->devs[0] && T > rt::BvhLink::kMaxLeafTriangles) RT_CUDA(ctx, cudaMemcpyAsync(ctx->h_build_status + m, b.result_info + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, d.stream));
 						ctx->timing.kernel_launches++;
 					}
 					if (!hm.pending_builds.empty()) RT_CUDA(ctx, cudaEventRecord(d.ev_upload, d.stream));
@@ -974,7 +985,6 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		ctx->devs.push_back(d);
 	}
 	RT_CREATE(cudaSetDevice(ids[0]));
-	if (const char* e = getenv("RT_B200_BUILD_LOCAL")) ctx->build_local_triangles = std::max(0, std::min(rt::kLocalTriangles, atoi(e)));
 	RT_CREATE(cudaHostAlloc(&ctx->h_build_status, sizeof(int32_t) * rt::kMaxMeshes, cudaHostAllocPortable));
 	memset(ctx->h_build_status, 0, sizeof(int32_t) * rt::kMaxMeshes);
 	RT_CREATE(cudaHostAlloc(&ctx->h_static, StaticBlock::total, cudaHostAllocPortable));

@@ -18,10 +18,17 @@
 //    counter instead of the reference's depth-first nodesUsed++, which is what lets independent subtrees be
 //    built concurrently.
 //
-// Work distribution: the tree is built level by level while a level has few, large nodes - the CTA splits into
-// 1 / 2 / 4 / 8 teams of warps (named barriers), one node per team - and by one warp per node after that; a warp
-// that reaches a node of at most kLocalTriangles triangles finishes that whole subtree itself from a private
-// stack, so the deep, narrow part of the tree costs no CTA-wide barriers.
+// Work distribution, two launches per UpdateTransforms call:
+//  * update_transforms_bvh_kernel, one CTA of 32 warps: transform, per-triangle data, root, then the tree level by
+//    level while a level has at most 8 nodes - the CTA splits into 1 / 2 / 4 / 8 teams of warps (named barriers),
+//    one node per team (one warp per node once the nodes are small).  The first level with more than 8 nodes (at
+//    most 16) is handed over;
+//  * build_subtrees_kernel, 16 CTAs of 16 warps: every CTA takes handed-over nodes off a ticket counter and builds
+//    their subtrees to the bottom the same way (teams, then one warp per node), position-indexed scratch in its
+//    shared memory.  The last CTA to finish writes what the build leaves behind: indices / normals for the next
+//    call, the triangle stream and the node records of the pixel kernel, into the results and into the scene block.
+// A build is instruction-issue bound per SM (about 1.4 k warp instructions per inner node), which is why the wide
+// part of the tree goes to several SMs instead of more warps of one.
 #pragma once
 
 #include "rt_kernel.cuh"
@@ -58,14 +65,18 @@ namespace rt
 		// results (persistent per mesh: copied into the scene's mesh block by emit_mesh_kernel)
 		float4* result_triangles;       // 3T   {v0|nx}{e1|ny}{e2|nz} in the new order
 		float4* result_nodes;           // 2N   device node records (rt::BvhLink)
-		int32_t* result_info;           // [0] nodes used, [1] status (0 ok, 1 leaf too large for BvhLink), [2..7] root box bits
+		int32_t* result_info;           // kInfoWords: [0] nodes used, [1] status (0 ok, 1 leaf too large for BvhLink), [2..7] root box bits, hand-over
 		// the mesh's slices of the scene's mesh block: written at the end of the build as well (NULL: not)
 		float4* scene_triangles;
 		float4* scene_nodes;
 		float4* scene_table;
-		int32_t work_in_shared;         // the per-triangle work arrays (14 words per triangle) live in dynamic shared memory
-		int32_t local_triangles;        // a warp finishes subtrees of at most this many triangles on its own (<= kLocalTriangles)
+		int32_t work_in_shared;         // top kernel: the per-triangle work arrays (14 words per triangle) live in dynamic shared memory
+		int32_t subtree_shared_triangles;   // subtree kernel: subtrees up to this size keep their position-indexed scratch in shared memory
 	};
+
+	// result_info words beyond the results proper: the hand-over between the two kernels
+	enum : int { kInfoNodesUsed = 0, kInfoStatus = 1, kInfoRootBox = 2, kInfoSubtrees = 8, kInfoTicket = 9, kInfoFinished = 10,
+	             kInfoSubtreeList = 16, kInfoWords = 32 };
 
 	// The arrays every pass of the build reads and writes.  Shared memory when the mesh fits (latency of a pass is a few
 	// dependent accesses: ~30 cycles each there, an L2 round trip each in global memory), else the host's scratch.
@@ -82,12 +93,14 @@ namespace rt
 	};
 	constexpr int kBuildWorkWordsPerTriangle = 14;
 
-	constexpr int kBuildThreads = 1024;
+	constexpr int kBuildThreads = 1024;         // top kernel
 	constexpr int kBuildWarps = kBuildThreads / 32;
-	constexpr int kMaxTeams = 8;             // teams of more than one warp: named barriers 1..8
-	constexpr int kLocalTriangles = 32;      // upper limit of BuildParams::local_triangles
-	constexpr int kLocalStack = kLocalTriangles + 4;
-	constexpr int kAtomicBinTriangles = 64;  // nodes up to this size bin with plain shared-memory atomics
+	constexpr int kSubtreeThreads = 512;        // subtree kernel
+	constexpr int kSubtreeCtas = 16;            // a handed-over level has at most 2 * kMaxTeams nodes
+	constexpr int kMaxTeams = 8;                // teams of more than one warp: named barriers 1..8
+	constexpr int kWarpNodeTriangles = 96;      // levels whose nodes are all this small go to one warp per node
+	constexpr int kAtomicBinTriangles = 64;     // nodes up to this size bin with plain shared-memory atomics
+	constexpr int kSubtreeWordsPerTriangle = 5; // order, order_tmp, rights_before, front_right, back_left
 
 	// order-preserving map float -> unsigned for integer min / max (REDUX, shared-memory atomics); no NaN reaches it
 	__device__ __forceinline__ unsigned int float_key(float f)
@@ -108,7 +121,7 @@ namespace rt
 	}
 
 	// Per team (and per warp once teams are single warps): reduction slots, bins of the three axes, the split that
-	// was chosen, and the private node stack of a warp.
+	// was chosen.
 	struct TeamScratch
 	{
 		unsigned int centroid_lo[3], centroid_hi[3];
@@ -119,8 +132,6 @@ namespace rt
 		int warp_total[kBuildWarps];
 		float best, split_pos;
 		int axis, pair;
-		int stack[kLocalStack];
-		int top;
 	};
 
 	struct Team
@@ -221,9 +232,8 @@ namespace rt
 		return n_left;
 	}
 
-	// Subdivide (DataTypes.h:323-389) of one node by one team.  Children that need splitting go to the team's private
-	// stack (single-warp teams, small children) or to the next level's queue.
-	__device__ __forceinline__ void subdivide_node(const BuildParams& p, const BuildWork& w, int node, const Team& t, int* nodes_used, int* next, int* next_count)
+	// Subdivide (DataTypes.h:323-389) of one node by one team.  Children that need splitting go to the next level's queue.
+	__device__ __forceinline__ void subdivide_node(const BuildParams& p, const BuildWork& w, int node, const Team& t, int* nodes_used, int* next, int* next_count, int* next_big)
 	{
 		TeamScratch& s = *t.s;
 		const int lane = threadIdx.x & 31;
@@ -432,21 +442,62 @@ namespace rt
 				p.node_escape[child[c]] = (c == 0) ? child[1] : p.node_escape[node];
 				for (int d = 0; d < 3; ++d) { p.node_box[6 * child[c] + d] = key_float(s.child_lo[c][d]); p.node_box[6 * child[c] + 3 + d] = key_float(s.child_hi[c][d]); }
 				if (3 * child_count[c] <= 8) write_node_record(p, child[c], true, child_first[c], child_count[c]);   // DataTypes.h:327
-				else if (t.threads == 32 && child_count[c] <= p.local_triangles) s.stack[s.top++] = child[c];
-				else next[atomicAdd(next_count, 1)] = child[c];
+				else { next[atomicAdd(next_count, 1)] = child[c]; atomicMax(next_big, child_count[c]); }
 			}
 			write_node_record(p, node, false, child[0], 0);
 		}
 		team_sync(t);
 	}
 
+	// Level state of one CTA: node counts and the largest node of the current and the next level.
+	struct LevelState
+	{
+		int count[2];
+		int big[2];
+	};
+
+	// Builds level after level from the nodes in `cur` (level.count[0] of them, the largest level.big[0] triangles).
+	// HAND_OVER: stops in front of the first level with more than kMaxTeams nodes and returns its size (the nodes are
+	// in *handed); 0 when the tree was finished.
+	template <bool HAND_OVER>
+	__device__ __forceinline__ int run_levels(const BuildParams& p, const BuildWork& w, TeamScratch* scratch, LevelState& level, int* nodes_used,
+	                                          int* cur, int* nxt, int** handed)
+	{
+		const int tid = threadIdx.x, warp = tid >> 5, n_warps = blockDim.x >> 5;
+		int parity = 0;
+		while (true)
+		{
+			const int n = level.count[parity], big = level.big[parity];
+			if (n == 0) return 0;
+			if (HAND_OVER && n > kMaxTeams) { *handed = cur; return n; }
+			Team t;
+			int n_teams;
+			if (n > kMaxTeams || big <= kWarpNodeTriangles) { n_teams = n_warps; t.warps = 1; }
+			else { n_teams = n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8)); t.warps = n_warps / n_teams; }
+			t.threads = 32 * t.warps;
+			const int team = warp / t.warps;
+			t.warp = warp - team * t.warps;
+			t.tid = tid - team * t.threads;
+			t.barrier = 1 + team;
+			t.s = &scratch[team];
+			for (int q = team; q < n; q += n_teams)
+				subdivide_node(p, w, cur[q], t, nodes_used, nxt, &level.count[parity ^ 1], &level.big[parity ^ 1]);
+			__syncthreads();
+			if (tid == 0) { level.count[parity] = 0; level.big[parity] = 0; }
+			int* swap = cur; cur = nxt; nxt = swap;
+			parity ^= 1;
+			__syncthreads();
+		}
+	}
+
 	__global__ void __launch_bounds__(kBuildThreads)
 	update_transforms_bvh_kernel(const __grid_constant__ BuildParams p)
 	{
-		__shared__ TeamScratch scratch[kBuildWarps];
-		__shared__ int nodes_used, level_count[2];
 		extern __shared__ __align__(16) float dynamic_shared[];
-		const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+		__shared__ TeamScratch scratch[kBuildWarps];
+		__shared__ LevelState level;
+		__shared__ int nodes_used;
+		const int tid = threadIdx.x, lane = tid & 31;
 		const int T = p.triangle_count;
 		BuildWork w;
 		if (p.work_in_shared)
@@ -467,11 +518,15 @@ namespace rt
 			const V3 q = transform_point(p.m, p.positions[3 * v], p.positions[3 * v + 1], p.positions[3 * v + 2]);
 			p.tpos[3 * v] = q.x; p.tpos[3 * v + 1] = q.y; p.tpos[3 * v + 2] = q.z;
 		}
-		if (tid == 0) { nodes_used = 1; level_count[0] = 0; level_count[1] = 0; p.result_info[1] = 0; }
-		if (lane == 0) scratch[warp].top = 0;
+		if (tid == 0)
+		{
+			nodes_used = 1; level.count[0] = 0; level.count[1] = 0; level.big[0] = 0; level.big[1] = 0;
+			p.result_info[kInfoStatus] = 0; p.result_info[kInfoSubtrees] = 0; p.result_info[kInfoTicket] = 0; p.result_info[kInfoFinished] = 0;
+		}
 		__syncthreads();
 
-		// per triangle slot: transformedNormals (DataTypes.h:224-230), centroid (DataTypes.h:349), vertex min / max
+		// per triangle slot: transformedNormals (DataTypes.h:224-230), centroid (DataTypes.h:349), vertex min / max.
+		// The slot-indexed arrays also go to global memory: the subtree kernel reads them there.
 		for (int t = tid; t < T; t += kBuildThreads)
 		{
 			V3 v[3];
@@ -481,10 +536,16 @@ namespace rt
 				v[k] = v3(p.tpos[3 * vi], p.tpos[3 * vi + 1], p.tpos[3 * vi + 2]);
 			}
 			const V3 c = ((v[0] + v[1]) + v[2]) * 0.3333f;
-			w.centroid[3 * t] = c.x; w.centroid[3 * t + 1] = c.y; w.centroid[3 * t + 2] = c.z;
-			w.tri_min[3 * t] = float_key(std_min(std_min(v[0].x, v[1].x), v[2].x)); w.tri_max[3 * t] = float_key(std_max(std_max(v[0].x, v[1].x), v[2].x));
-			w.tri_min[3 * t + 1] = float_key(std_min(std_min(v[0].y, v[1].y), v[2].y)); w.tri_max[3 * t + 1] = float_key(std_max(std_max(v[0].y, v[1].y), v[2].y));
-			w.tri_min[3 * t + 2] = float_key(std_min(std_min(v[0].z, v[1].z), v[2].z)); w.tri_max[3 * t + 2] = float_key(std_max(std_max(v[0].z, v[1].z), v[2].z));
+			const float cc[3] = { c.x, c.y, c.z };
+			const unsigned int mn[3] = { float_key(std_min(std_min(v[0].x, v[1].x), v[2].x)), float_key(std_min(std_min(v[0].y, v[1].y), v[2].y)),
+			                             float_key(std_min(std_min(v[0].z, v[1].z), v[2].z)) };
+			const unsigned int mx[3] = { float_key(std_max(std_max(v[0].x, v[1].x), v[2].x)), float_key(std_max(std_max(v[0].y, v[1].y), v[2].y)),
+			                             float_key(std_max(std_max(v[0].z, v[1].z), v[2].z)) };
+			for (int d = 0; d < 3; ++d)
+			{
+				w.centroid[3 * t + d] = cc[d]; w.tri_min[3 * t + d] = mn[d]; w.tri_max[3 * t + d] = mx[d];
+				if (p.work_in_shared) { p.centroid[3 * t + d] = cc[d]; p.tri_min[3 * t + d] = mn[d]; p.tri_max[3 * t + d] = mx[d]; }
+			}
 			const float nx = p.normals_in[3 * t], ny = p.normals_in[3 * t + 1], nz = p.normals_in[3 * t + 2];
 			V3 n = v3(add(add(mul(p.m[0], nx), mul(p.m[4], ny)), mul(p.m[8], nz)),
 			          add(add(mul(p.m[1], nx), mul(p.m[5], ny)), mul(p.m[9], nz)),
@@ -515,58 +576,33 @@ namespace rt
 				{
 					const float lo = key_float(s.child_lo[0][d]), hi = key_float(s.child_hi[0][d]);
 					p.node_box[d] = lo; p.node_box[3 + d] = hi;
-					p.result_info[2 + d] = __float_as_int(lo); p.result_info[5 + d] = __float_as_int(hi);
+					p.result_info[kInfoRootBox + d] = __float_as_int(lo); p.result_info[kInfoRootBox + 3 + d] = __float_as_int(hi);
 				}
 				if (3 * T <= 8) write_node_record(p, 0, true, 0, T);
-				else { p.queue_a[0] = 0; level_count[0] = 1; }
+				else { p.queue_a[0] = 0; level.count[0] = 1; level.big[0] = T; }
 			}
 			__syncthreads();
 		}
 
-		// one tree level per round
-		int* cur = p.queue_a;
-		int* nxt = p.queue_b;
-		int parity = 0;
-		while (true)
-		{
-			const int n = level_count[parity];
-			if (n == 0) break;
-			Team t;
-			int n_teams;
-			if (n > kMaxTeams) { n_teams = kBuildWarps; t.warps = 1; }
-			else { n_teams = n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8)); t.warps = kBuildWarps / n_teams; }
-			t.threads = 32 * t.warps;
-			const int team = warp / t.warps;
-			t.warp = warp - team * t.warps;
-			t.tid = tid - team * t.threads;
-			t.barrier = 1 + team;
-			t.s = &scratch[team];
-			for (int q = team; q < n; q += n_teams)
-			{
-				subdivide_node(p, w, cur[q], t, &nodes_used, nxt, &level_count[parity ^ 1]);
-				while (t.threads == 32)                     // this warp's own subtrees, to the bottom
-				{
-					const int top = t.s->top;
-					if (top == 0) break;
-					const int node = t.s->stack[top - 1];
-					__syncwarp();
-					if (lane == 0) t.s->top = top - 1;
-					__syncwarp();
-					subdivide_node(p, w, node, t, &nodes_used, nxt, &level_count[parity ^ 1]);
-				}
-			}
-			__syncthreads();
-			if (tid == 0) level_count[parity] = 0;
-			int* swap = cur; cur = nxt; nxt = swap;
-			parity ^= 1;
-			__syncthreads();
-		}
+		int* handed = nullptr;
+		const int n_handed = run_levels<true>(p, w, scratch, level, &nodes_used, p.queue_a, p.queue_b, &handed);
 
-		// the order the build leaves behind: indices / normals for the next call, the triangle stream for the
-		// pixel kernel ({v0|nx}{e1|ny}{e2|nz}, e1 = v1 - v0, e2 = v2 - v0: Utils.h:143-144)
-		for (int k = tid; k < T; k += kBuildThreads)
+		// what the subtree kernel needs: the order so far, the node counter, the handed-over nodes
+		if (p.work_in_shared)
+			for (int k = tid; k < T; k += kBuildThreads) p.order[k] = w.order[k];
+		if (tid < n_handed) p.result_info[kInfoSubtreeList + tid] = handed[tid];
+		if (tid == 0) { p.result_info[kInfoNodesUsed] = nodes_used; p.result_info[kInfoSubtrees] = n_handed; }
+	}
+
+	// The order the build leaves behind: indices / normals for the next call, the triangle stream for the pixel kernel
+	// ({v0|nx}{e1|ny}{e2|nz}, e1 = v1 - v0, e2 = v2 - v0: Utils.h:143-144), node records and the mesh table's rows.
+	__device__ __forceinline__ void write_build_results(const BuildParams& p)
+	{
+		const int tid = threadIdx.x, n_threads = blockDim.x;
+		const int T = p.triangle_count;
+		for (int k = tid; k < T; k += n_threads)
 		{
-			const int slot = w.order[k];
+			const int slot = p.order[k];
 			V3 v[3];
 			for (int c = 0; c < 3; ++c)
 			{
@@ -582,11 +618,10 @@ namespace rt
 			p.result_triangles[3 * k + 0] = r0; p.result_triangles[3 * k + 1] = r1; p.result_triangles[3 * k + 2] = r2;
 			if (p.scene_triangles) { p.scene_triangles[3 * k + 0] = r0; p.scene_triangles[3 * k + 1] = r1; p.scene_triangles[3 * k + 2] = r2; }
 		}
-		const int n_nodes = nodes_used;
-		if (tid == 0) p.result_info[0] = n_nodes;
 		if (p.scene_nodes)
 		{
-			for (int i = tid; i < 2 * n_nodes; i += kBuildThreads) p.scene_nodes[i] = p.result_nodes[i];
+			const int n_nodes = p.result_info[kInfoNodesUsed];
+			for (int i = tid; i < 2 * n_nodes; i += n_threads) p.scene_nodes[i] = p.result_nodes[i];
 			if (tid == 0)
 			{
 				const float4 keep1 = p.scene_table[1], keep2 = p.scene_table[2];
@@ -595,6 +630,61 @@ namespace rt
 				p.scene_table[2] = make_float4(keep2.x, keep2.y, keep2.z, __int_as_float(n_nodes));
 			}
 		}
+	}
+
+	__global__ void __launch_bounds__(kSubtreeThreads)
+	build_subtrees_kernel(const __grid_constant__ BuildParams p)
+	{
+		extern __shared__ __align__(16) float dynamic_shared[];
+		__shared__ TeamScratch scratch[kSubtreeThreads / 32];
+		__shared__ LevelState level;
+		__shared__ int ticket, last_cta;
+		const int tid = threadIdx.x;
+		const int n_subtrees = p.result_info[kInfoSubtrees];
+		int* nodes_used = p.result_info + kInfoNodesUsed;
+
+		while (true)
+		{
+			if (tid == 0) ticket = atomicAdd(p.result_info + kInfoTicket, 1);
+			__syncthreads();
+			const int mine = ticket;
+			if (mine >= n_subtrees) break;                                  // uniform
+			const int root = p.result_info[kInfoSubtreeList + mine];
+			const int first = p.node_first[root], count = p.node_count[root];
+
+			// slot-indexed arrays are read-only here; position-indexed scratch of [first, first + count) in shared memory
+			BuildWork w;
+			w.centroid = p.centroid; w.tri_min = p.tri_min; w.tri_max = p.tri_max;
+			const bool in_shared = count <= p.subtree_shared_triangles;
+			if (in_shared)
+			{
+				int32_t* base = reinterpret_cast<int32_t*>(dynamic_shared) - first;
+				w.order = base; w.order_tmp = base + count; w.rights_before = base + 2 * count; w.front_right = base + 3 * count; w.back_left = base + 4 * count;
+				for (int k = tid; k < count; k += kSubtreeThreads) w.order[first + k] = p.order[first + k];
+			}
+			else
+			{
+				w.order = p.order; w.order_tmp = p.order_tmp; w.rights_before = p.rights_before; w.front_right = p.front_right; w.back_left = p.back_left;
+			}
+			int* cur = p.queue_a + first;                                   // a level of this subtree has fewer than `count` nodes
+			int* nxt = p.queue_b + first;
+			if (tid == 0) { cur[0] = root; level.count[0] = 1; level.big[0] = count; level.count[1] = 0; level.big[1] = 0; }
+			__syncthreads();
+			int* unused = nullptr;
+			run_levels<false>(p, w, scratch, level, nodes_used, cur, nxt, &unused);
+			if (in_shared)
+				for (int k = tid; k < count; k += kSubtreeThreads) p.order[first + k] = w.order[first + k];
+			__syncthreads();                                                // before `ticket` and the scratch are reused
+		}
+
+		// the last CTA to get here writes the results: everything the others wrote is visible to it
+		__threadfence();
+		__syncthreads();
+		if (tid == 0) last_cta = (atomicAdd(p.result_info + kInfoFinished, 1) == (int)gridDim.x - 1) ? 1 : 0;
+		__syncthreads();
+		if (!last_cta) return;
+		__threadfence();
+		write_build_results(p);
 	}
 
 	// Copies a mesh's last build into the scene's mesh block: triangle stream slice, node slice, and the mesh
