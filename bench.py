@@ -259,6 +259,29 @@ def main():
     spr = bands.strips_per_rank(HEIGHT, world)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory() if rank == 0 else None
+    # N > 1, end to end: the host surface is one shared-memory mapping (rank 0 owns it, like the window surface of the
+    # reference's process); every rank copies the strips it rendered into it over its own PCIe link
+    # (rt_render_strips_to_host).  RT_BENCH_PRESENT=gather: all strips to GPU 0 over NVLink, GPU 0 presents (one link).
+    present_mode = os.environ.get("RT_BENCH_PRESENT", "direct") if world > 1 else "single"
+    shared_surface = None
+    if present_mode == "direct":
+        import mmap
+        name = [f"/dev/shm/rt_b200_surface_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}" if rank == 0 else None]
+        surface_bytes = WIDTH * HEIGHT * 4
+        if rank == 0:
+            with open(name[0], "wb") as f:
+                f.truncate(surface_bytes + 64 * world)
+        dist.broadcast_object_list(name, src=0)
+        shm_file = open(name[0], "r+b")
+        shm_map = mmap.mmap(shm_file.fileno(), surface_bytes + 64 * world)
+        shared_surface = np.frombuffer(shm_map, dtype=np.uint32, count=WIDTH * HEIGHT).reshape(HEIGHT, WIDTH)
+        # "my strips of frame k are in the surface": one word per rank (own cache line, single writer), next to the surface.
+        # The frame is complete when every word has reached k - a host-side handshake, no collective on this leg.
+        arrived = np.frombuffer(shm_map, dtype=np.int64, offset=surface_bytes, count=8 * world)[::8]
+        frames_presented = [0]
+        dist.barrier()
+        if rank == 0:
+            os.unlink(name[0])                      # the mappings keep it alive; nothing is left behind
     band = frame_dev = gathered = None
     frame_ptr = 0
     token = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -333,6 +356,13 @@ def main():
         r.ctx.upload_mesh(0, mesh)                                  # H2D: what UpdateTransforms produced this frame
         if world == 1:
             r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + progressive D2H, blocking
+            return
+        if present_mode == "direct":
+            r.render_strips_to_host(rank, world, shared_surface.ctypes.data, WIDTH * 4)   # blocking: this rank's strips are in host memory
+            frames_presented[0] += 1
+            arrived[rank] = frames_presented[0]
+            while int(arrived.min()) < frames_presented[0]:      # surface complete; nobody starts the next frame earlier
+                pass
             return
         if signals:
             # every rank's CTAs bump per-band counters in rank 0's frame; rank 0 presents band after band
@@ -419,7 +449,7 @@ def main():
     with open(os.path.join(ROOT, "tests", "golden", "bunny_4k.frame.xz"), "rb") as f:
         planar = np.frombuffer(lzma.decompress(f.read()), dtype=np.uint8).reshape(3, HEIGHT, WIDTH).astype(np.uint32)
     golden = (planar[0] << 16) | (planar[1] << 8) | planar[2]
-    produced = host_frame.numpy().view(np.uint32) if e2e is not None else None
+    produced = (shared_surface if shared_surface is not None else host_frame.numpy().view(np.uint32)) if e2e is not None else None
     frame_check = None
     if produced is not None:
         differing = int((produced != golden).sum())
@@ -570,6 +600,9 @@ def main():
                    "l2": f"{L2_FLUSH_BYTES >> 20} MiB memset between timed steps (outside the event pairs)"},
         "clocks": sampler.summary(),
         "e2e": e2e,
+        "e2e_present": {"single": "one GPU: progressive present (copy follows the kernel band by band)",
+                        "direct": "every rank copies its own strips into the shared host surface over its own PCIe link (rt_render_strips_to_host), band by band behind its kernel; completion by one flag word per rank in the same mapping; no peer traffic and no collective on this leg",
+                        "gather": "strips stored into GPU 0's frame over NVLink, GPU 0 presents band by band (one PCIe link)"}[present_mode],
         "frame_check": frame_check,
         "gpu_launches": args.steps * (world + ((world - 1) if signals else (0 if fused or world == 1 else 1))),
         "mesh_path": "bvh (reference's shipped IntersectionTest_BVH over the reference's own nodes)",

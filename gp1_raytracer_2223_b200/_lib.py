@@ -48,6 +48,8 @@ SYMBOLS = {
     "rt_frame_release": (C.c_int, [_ctx, C.c_void_p]),
     "rt_render_strips_to_frame": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32, C.c_int32,
                                             C.c_void_p, C.c_void_p]),
+    "rt_render_strips_to_host": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32, C.c_int32,
+                                           C.c_void_p, C.c_int32]),
     "rt_frame_signal": (C.c_int, [_ctx, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "rt_frame_wait": (C.c_int, [_ctx, C.c_uint32, C.c_void_p]),
     "rt_render_strips_to_frame_banded": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32, C.c_int32,

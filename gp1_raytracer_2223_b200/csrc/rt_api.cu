@@ -912,6 +912,145 @@ namespace
 		}
 		return collect_timing(ctx, true);
 	}
+
+	// ---- direct present: every device copies the strips it rendered straight into the host surface ----------------
+	// The gather-to-device-0 flow moves the whole frame through ONE PCIe link.  When the destination is host memory
+	// anyway, each device presents its own strips over its own link: device k renders strips k, k + n, ... into its
+	// own frame buffer (full-frame layout) and its copy stream follows the kernel band by band (the single-device
+	// counters of signal_band_done; one strided 2-D copy per band).  No peer traffic, no collective.
+
+	// Strips first, first + step, ... (count of them) of device d's frame buffer -> host target.
+	int copy_strips_to_host(rt_context* ctx, DeviceState& d, int W, int H, int first, int step, int count, void* target, int32_t pitch_bytes)
+	{
+		if (count <= 0) return RT_OK;
+		const int total_strips = (H + rt::kBlockH - 1) / rt::kBlockH;
+		const int last = first + (count - 1) * step;
+		int full = count;
+		const int tail_rows = H - (total_strips - 1) * rt::kBlockH;          // rows of the frame's last strip
+		if (last == total_strips - 1 && tail_rows != rt::kBlockH) --full;
+		const size_t row_bytes = (size_t)W * 4u;
+		if (pitch_bytes == 4 * W)
+		{
+			if (full > 0)
+				RT_CUDA(ctx, cudaMemcpy2DAsync((char*)target + (size_t)first * rt::kBlockH * row_bytes, (size_t)step * rt::kBlockH * row_bytes,
+				                               d.d_frame + (size_t)first * rt::kBlockH * W, (size_t)step * rt::kBlockH * row_bytes,
+				                               (size_t)rt::kBlockH * row_bytes, (size_t)full, cudaMemcpyDeviceToHost, d.copy_stream));
+		}
+		else
+		{
+			for (int j = 0; j < full; ++j)
+			{
+				const size_t r0 = (size_t)(first + j * step) * rt::kBlockH;
+				RT_CUDA(ctx, cudaMemcpy2DAsync((char*)target + r0 * (size_t)pitch_bytes, (size_t)pitch_bytes, d.d_frame + r0 * W, row_bytes, row_bytes,
+				                               (size_t)rt::kBlockH, cudaMemcpyDeviceToHost, d.copy_stream));
+			}
+		}
+		if (full < count)
+		{
+			const size_t r0 = (size_t)last * rt::kBlockH;
+			RT_CUDA(ctx, cudaMemcpy2DAsync((char*)target + r0 * (size_t)pitch_bytes, (size_t)pitch_bytes, d.d_frame + r0 * W, row_bytes, row_bytes,
+			                               (size_t)tail_rows, cudaMemcpyDeviceToHost, d.copy_stream));
+		}
+		return RT_OK;
+	}
+
+	// Enqueues kernel + copies of one device's share; the caller synchronises d.copy_stream (ev_done is its last event).
+	int enqueue_direct_present(rt_context* ctx, DeviceState& d, const rt::FrameParams& base, int strip_first, int strip_step, void* target, int32_t pitch_bytes)
+	{
+		const int W = base.width, H = base.height;
+		int rc = ensure_frame(ctx, d, (size_t)W * (size_t)H);
+		if (rc != RT_OK) return rc;
+		const int total_strips = (H + rt::kBlockH - 1) / rt::kBlockH;
+		const int grid_x = (W + rt::kBlockW - 1) / rt::kBlockW;
+		const int my_strips = strip_first < total_strips ? (total_strips - strip_first + strip_step - 1) / strip_step : 0;
+		const WaitValue32Fn wait = wait_value32();
+		static const int requested = [] { const char* e = getenv("RT_B200_PIPELINE_BANDS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 64) ? v : 0; }();
+		// a band should hold enough of THIS device's CTAs to be worth a copy of its own
+		const int max_bands = std::max(1, (int)(((long long)my_strips * grid_x) / 512));
+		const int bands = std::max(1, std::min(std::min(requested ? requested : 16, max_bands), total_strips));
+		const int strips_per_band = (total_strips + bands - 1) / bands;
+
+		RT_CUDA(ctx, cudaSetDevice(d.device));
+		rt::FrameParams p = base;
+		p.row_begin = 0; p.row_end = H; p.strip_first = strip_first; p.strip_step = strip_step; p.dst_full_frame = 1; p.dst = d.d_frame;
+		if (wait && my_strips > 0)
+		{
+			RT_CUDA(ctx, cudaMemsetAsync(d.d_band_done, 0, sizeof(unsigned int) * 64, d.stream));
+			RT_CUDA(ctx, cudaEventRecord(d.ev_band[0], d.stream));
+			RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_band[0], 0));      // counters are zero before anyone polls them
+			RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
+			p.band_done = d.d_band_done; p.strips_per_band = strips_per_band; p.band_local = nullptr;
+			if ((rc = launch(ctx, d, p, d.stream, my_strips)) != RT_OK) return rc;
+			RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+			for (int b = 0; b < bands; ++b)
+			{
+				const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
+				if (s1 <= s0) break;
+				// this device's strips of the band: those congruent to strip_first modulo strip_step (as signal_band_done counts them)
+				const int first_mine = s0 + ((strip_first - s0) % strip_step + strip_step) % strip_step;
+				const int mine = first_mine < s1 ? (s1 - 1 - first_mine) / strip_step + 1 : 0;
+				if (mine == 0) continue;
+				const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)(mine * grid_x * rt::kSignalsPerTile), CU_STREAM_WAIT_VALUE_GEQ);
+				if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
+				if ((rc = copy_strips_to_host(ctx, d, W, H, first_mine, strip_step, mine, target, pitch_bytes)) != RT_OK) return rc;
+			}
+		}
+		else
+		{
+			RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
+			if ((rc = launch(ctx, d, p, d.stream, my_strips)) != RT_OK) return rc;
+			RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+			RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_kernel, 0));
+			if ((rc = copy_strips_to_host(ctx, d, W, H, strip_first, strip_step, my_strips, target, pitch_bytes)) != RT_OK) return rc;
+		}
+		RT_CUDA(ctx, cudaEventRecord(d.ev_done, d.copy_stream));
+		return RT_OK;
+	}
+
+	// Bounce-buffer case of prepare_host: only the strips this call produced may be copied back.
+	void unbounce_strips(void* host_dst, const void* target, int W, int H, int32_t pitch_bytes, int strip_first, int strip_step)
+	{
+		const int total_strips = (H + rt::kBlockH - 1) / rt::kBlockH;
+		for (int s = strip_first; s < total_strips; s += strip_step)
+			for (int y = s * rt::kBlockH; y < std::min(H, (s + 1) * rt::kBlockH); ++y)
+				memcpy((char*)host_dst + (size_t)y * pitch_bytes, (const char*)target + (size_t)y * pitch_bytes, (size_t)W * 4u);
+	}
+
+	// Devices [0, n_present) of the context present strips strip_first + k * strip_step_per_device ... : in-process
+	// (all devices, device k takes strips k, k + n, ...) or one process per GPU (one device, its rank / world pair).
+	int render_direct(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame, uint32_t* host_dst, int32_t pitch_bytes,
+	                  int n_present, int strip_first, int strip_step)
+	{
+		int rc = validate_frame(ctx, camera, frame);
+		if (rc != RT_OK) return rc;
+		const int W = frame->width, H = frame->height;
+		if (pitch_bytes < 4 * W || (pitch_bytes & 3)) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "pitch_bytes %d too small or unaligned for width %d", pitch_bytes, W);
+		const size_t span = (size_t)pitch_bytes * (size_t)(H - 1) + (size_t)W * 4u;
+		void* target = nullptr;
+		if ((rc = prepare_host(ctx, host_dst, span, &target)) != RT_OK) return rc;
+		ctx->timing = rt_timing{};
+		ctx->last_width = W; ctx->last_height = H;
+		const rt::FrameParams base = make_params(camera, frame);
+		for (int k = 0; k < n_present; ++k)
+			if ((rc = enqueue_direct_present(ctx, ctx->devs[k], base, strip_first + k, strip_step, target, pitch_bytes)) != RT_OK) return rc;
+		float kernel_ms = 0.f, total_ms = 0.f;
+		for (int k = 0; k < n_present; ++k)
+		{
+			DeviceState& d = ctx->devs[k];
+			RT_CUDA(ctx, cudaSetDevice(d.device));
+			RT_CUDA(ctx, cudaStreamSynchronize(d.copy_stream));
+			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+			float k_ms = 0.f, t_ms = 0.f;
+			RT_CUDA(ctx, cudaEventElapsedTime(&k_ms, d.ev_begin, d.ev_kernel));
+			RT_CUDA(ctx, cudaEventElapsedTime(&t_ms, d.ev_begin, d.ev_done));
+			kernel_ms = std::max(kernel_ms, k_ms); total_ms = std::max(total_ms, t_ms);
+		}
+		RT_CUDA(ctx, cudaSetDevice(ctx->devs[0].device));
+		if (target != host_dst)
+			for (int k = 0; k < n_present; ++k) unbounce_strips(host_dst, target, W, H, pitch_bytes, strip_first + k, strip_step);
+		ctx->timing.kernel_ms = kernel_ms; ctx->timing.gather_ms = 0.f; ctx->timing.d2h_ms = std::max(0.f, total_ms - kernel_ms); ctx->timing.total_ms = total_ms;
+		return RT_OK;
+	}
 }
 
 extern "C" {
@@ -1274,6 +1413,10 @@ int rt_render(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* fra
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
 	if (!host_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "host_dst must not be NULL");
+	// several devices and a host destination: every device presents its own strips over its own PCIe link
+	// (RT_B200_PRESENT=gather keeps the flow through device 0's frame buffer, e.g. to compare)
+	static const bool gather_first = [] { const char* e = getenv("RT_B200_PRESENT"); return e && strcmp(e, "gather") == 0; }();
+	if (ctx->devs.size() > 1 && !gather_first) return render_direct(ctx, camera, frame, host_dst, pitch_bytes, (int)ctx->devs.size(), 0, (int)ctx->devs.size());
 	if (ctx->devs.size() == 1 || (ctx->peer_stores && wait_value32())) return render_pipelined(ctx, camera, frame, host_dst, pitch_bytes);
 	int rc = render_to_device0(ctx, camera, frame);
 	if (rc != RT_OK) return rc;
@@ -1415,6 +1558,15 @@ int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt
 	if (rc != RT_OK) return rc;
 	if (!cuda_stream) RT_CUDA(ctx, cudaStreamSynchronize(stream));
 	return RT_OK;
+}
+
+int rt_render_strips_to_host(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                             int32_t strip_first, int32_t strip_step, uint32_t* host_dst, int32_t pitch_bytes)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!host_dst) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "host_dst must not be NULL");
+	if (strip_step <= 0 || strip_first < 0 || strip_first >= strip_step) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "strip_first %d / strip_step %d is not a rank / world pair", strip_first, strip_step);
+	return render_direct(ctx, camera, frame, host_dst, pitch_bytes, 1, strip_first, strip_step);
 }
 
 int rt_render_strips_to_frame_banded(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,

@@ -232,6 +232,14 @@ class Renderer:
         self.ctx.check(self.ctx.lib.rt_render_strips_to_frame(self.ctx.handle, C.byref(cam), C.byref(frame), strip_first,
                                                               strip_step, frame_ptr or None, stream), "rt_render_strips_to_frame")
 
+    def render_strips_to_host(self, strip_first: int, strip_step: int, host_ptr: int, pitch_bytes: int, camera=None) -> dict:
+        """This rank's strips rendered and copied into the (shared) host surface over this GPU's own PCIe link."""
+        cam = camera_struct(camera if camera is not None else self.scene.camera)
+        frame = self._frame()
+        self.ctx.check(self.ctx.lib.rt_render_strips_to_host(self.ctx.handle, C.byref(cam), C.byref(frame), strip_first, strip_step,
+                                                             host_ptr, pitch_bytes), "rt_render_strips_to_host")
+        return self.ctx.timing()
+
     def frame_signal(self, frame_ptr: int, stream: int = 0) -> None:
         self.ctx.check(self.ctx.lib.rt_frame_signal(self.ctx.handle, frame_ptr, self.width, self.height, stream), "rt_frame_signal")
 

@@ -415,6 +415,16 @@ int rt_render_strips_to_frame(rt_context* ctx, const rt_camera* camera, const rt
  * expected = frames so far x (world - 1)).  RT_ERR_BAD_STATE if stream memory operations are unavailable. */
 int rt_frame_signal(rt_context* ctx, void* frame_device_ptr, int32_t width, int32_t height, void* cuda_stream);
 int rt_frame_wait(rt_context* ctx, uint32_t expected, void* cuda_stream);
+/* Direct present for one process per GPU: this context's device renders strips strip_first, strip_first +
+ * strip_step, ... (rank / world) and copies exactly those strips into the host surface, following its kernel band by
+ * band over its OWN PCIe link; blocking.  host_dst is the whole surface (source/Renderer.cpp:27-29: the SDL surface's
+ * pixels), e.g. a shared-memory mapping every rank opened: rows of other ranks' strips are not touched.  With N ranks
+ * the frame crosses N links at once instead of all of it crossing GPU 0's (rt_frame_present).  In-process contexts
+ * over several devices do the same inside rt_render.  Replaces nothing in the reference (it has one device: the CPU);
+ * it is the multi-GPU form of the present at source/Renderer.cpp:97. */
+int rt_render_strips_to_host(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
+                             int32_t strip_first, int32_t strip_step, uint32_t* host_dst, int32_t pitch_bytes);
+
 /* Progressive present across ranks: with bands > 0 every CTA of rt_render_strips_to_frame_banded also bumps
  * the counter of the band (group of consecutive strips of the FRAME) it belongs to, in the root's trailer.
  * The root's rt_frame_present copies band after band to the host surface as soon as ALL ranks' CTAs of that

@@ -282,6 +282,49 @@ def test_in_process_multi_device_matches_single(gpu):
     r.close()
 
 
+@pytest.mark.parametrize("name,world,extra_pitch", [("bunny_640", 3, 0), ("bunny_333x77", 2, 0), ("bunny_333x77", 5, 64), ("w4ref_101x203", 4, 0),
+                                                    ("bunny_4k", 8, 0)])
+def test_direct_present_of_rank_strips(gpu, name, world, extra_pitch):
+    """rt_render_strips_to_host: every rank copies exactly the strips it rendered into the shared host surface.  The
+    ranks run one after the other on this GPU here; together they must produce the reference frame, and a rank must
+    not touch the rows of the others (surface pre-filled with a marker; pitch wider than the rows included)."""
+    r = make_renderer(name)
+    info = MANIFEST[name]
+    w, h = info["width"], info["height"]
+    pitch = 4 * w + extra_pitch
+    surface = np.full((h, pitch // 4), 0xDEADBEEF, dtype=np.uint32)
+    want = load_golden_frame(name)
+    for rank in range(world):
+        before = surface.copy()
+        r.render_strips_to_host(rank, world, surface.ctypes.data, pitch)
+        mine = np.zeros(h, dtype=bool)
+        for s0 in range(rank * 8, h, world * 8):
+            mine[s0:s0 + 8] = True
+        assert np.array_equal(surface[~mine], before[~mine]), f"rank {rank} wrote outside its strips"
+        assert np.array_equal(surface[mine, :w], want[mine]), f"rank {rank}: its strips differ from the reference frame"
+        assert np.all(surface[:, w:] == 0xDEADBEEF)
+    assert np.array_equal(surface[:, :w], want)
+    r.close()
+
+
+def test_in_process_multi_device_presents(gpu):
+    """Several devices in one context, host destination: direct present (default) and the gather through device 0
+    (RT_B200_PRESENT=gather is read once per process, so the gather flow is exercised through rt_render_device +
+    rt_download_frame).  Odd frame sizes included."""
+    torch = gpu
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    for name in ("bunny_333x77", "w4ref_101x203", "bunny_4k"):
+        want = load_golden_frame(name)
+        r = make_renderer(name, device_ids=list(range(n)))
+        assert np.array_equal(r.Render(), want), name
+        r.render_device()
+        assert np.array_equal(r.download(), want), name
+        print(name, "direct present timing", r.ctx.timing())
+        r.close()
+
+
 def test_axis_parallel_rays_take_the_literal_slab_test(gpu):
     """Rays with a zero direction component have an infinite 1/dir; on a box face through the ray origin the
     slab products are 0 * inf = NaN and std::min/max semantics decide (reference source/Utils.h:197-215).
