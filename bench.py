@@ -265,23 +265,16 @@ def main():
     present_mode = os.environ.get("RT_BENCH_PRESENT", "direct") if world > 1 else "single"
     shared_surface = None
     if present_mode == "direct":
-        import mmap
         name = [f"/dev/shm/rt_b200_surface_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}" if rank == 0 else None]
-        surface_bytes = WIDTH * HEIGHT * 4
         if rank == 0:
-            with open(name[0], "wb") as f:
-                f.truncate(surface_bytes + 64 * world)
+            surface = bands.SharedSurface(WIDTH, HEIGHT, world, rank, name[0], create=True)
         dist.broadcast_object_list(name, src=0)
-        shm_file = open(name[0], "r+b")
-        shm_map = mmap.mmap(shm_file.fileno(), surface_bytes + 64 * world)
-        shared_surface = np.frombuffer(shm_map, dtype=np.uint32, count=WIDTH * HEIGHT).reshape(HEIGHT, WIDTH)
-        # "my strips of frame k are in the surface": one word per rank (own cache line, single writer), next to the surface.
-        # The frame is complete when every word has reached k - a host-side handshake, no collective on this leg.
-        arrived = np.frombuffer(shm_map, dtype=np.int64, offset=surface_bytes, count=8 * world)[::8]
-        frames_presented = [0]
+        if rank != 0:
+            surface = bands.SharedSurface(WIDTH, HEIGHT, world, rank, name[0], create=False)
+        shared_surface = surface.frame
         dist.barrier()
         if rank == 0:
-            os.unlink(name[0])                      # the mappings keep it alive; nothing is left behind
+            surface.unlink()                        # the mappings keep it alive; nothing is left behind
     band = frame_dev = gathered = None
     frame_ptr = 0
     token = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -358,11 +351,8 @@ def main():
             r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + progressive D2H, blocking
             return
         if present_mode == "direct":
-            r.render_strips_to_host(rank, world, shared_surface.ctypes.data, WIDTH * 4)   # blocking: this rank's strips are in host memory
-            frames_presented[0] += 1
-            arrived[rank] = frames_presented[0]
-            while int(arrived.min()) < frames_presented[0]:      # surface complete; nobody starts the next frame earlier
-                pass
+            r.render_strips_to_host(rank, world, surface.ptr, surface.pitch_bytes)   # blocking: this rank's strips are in host memory
+            surface.arrive_and_wait()             # surface complete; nobody starts the next frame earlier
             return
         if signals:
             # every rank's CTAs bump per-band counters in rank 0's frame; rank 0 presents band after band

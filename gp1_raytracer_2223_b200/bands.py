@@ -68,3 +68,54 @@ def gather_bands(band, rank: int, world: int, dst: int = 0, group=None):
         return out
     dist.gather(band, None, dst=dst, group=group)
     return None
+
+
+class SharedSurface:
+    """The host surface of a one-process-per-GPU launch: one shared-memory mapping that rank 0 owns (like the window
+    surface of the reference's process, source/Renderer.cpp:27-29) and every rank opens, so that each rank can copy the
+    strips it rendered straight into it (rt_render_strips_to_host) - N PCIe links instead of GPU 0's one.
+
+    Next to the pixels sits one arrival word per rank (own cache line, written only by that rank): rank r stores k
+    once its strips of frame k are in the surface; the frame is complete when every word has reached k.  That is the
+    whole exchange of this leg: host memory, no collective.
+    """
+
+    def __init__(self, width: int, height: int, world: int, rank: int, path: str, create: bool):
+        import mmap
+        self.width, self.height, self.world, self.rank, self.path = width, height, world, rank, path
+        self.surface_bytes = width * height * 4
+        total = self.surface_bytes + 64 * world
+        if create:
+            with open(path, "wb") as f:
+                f.truncate(total)
+        self._file = open(path, "r+b")
+        self._map = mmap.mmap(self._file.fileno(), total)
+        self.frame = np.frombuffer(self._map, dtype=np.uint32, count=width * height).reshape(height, width)
+        self.arrived = np.frombuffer(self._map, dtype=np.int64, offset=self.surface_bytes, count=8 * world)[::8]
+        self.presented = 0
+
+    @property
+    def ptr(self) -> int:
+        return self.frame.ctypes.data
+
+    @property
+    def pitch_bytes(self) -> int:
+        return 4 * self.width
+
+    def unlink(self) -> None:
+        """Rank 0, once every rank has opened the mapping: the name goes, the mappings keep the memory alive."""
+        import os
+        os.unlink(self.path)
+
+    def arrive_and_wait(self, timeout_s: float = 60.0) -> int:
+        """This rank's strips of the next frame are in the surface; returns when everybody's are."""
+        import time
+        self.presented += 1
+        self.arrived[self.rank] = self.presented
+        deadline = time.monotonic() + timeout_s
+        spins = 0
+        while int(self.arrived.min()) < self.presented:
+            spins += 1
+            if (spins & 0xFFF) == 0 and time.monotonic() > deadline:
+                raise TimeoutError(f"rank {self.rank}: frame {self.presented} incomplete, arrivals {self.arrived.tolist()}")
+        return self.presented

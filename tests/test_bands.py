@@ -76,3 +76,64 @@ def test_gloo_world2_gather_matches_reference():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert np.array_equal(frame, load_golden_frame("w4ref_101x203"))
+
+
+def _surface_worker(rank, world, port, path, frames, q):
+    """One rank of the direct present, the CPU oracle standing in for the GPU: its strips go straight into the shared
+    surface, completion by the arrival words (gloo only carries the rendezvous and the surface's name)."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        name = [path if rank == 0 else None]
+        if rank == 0:
+            surface = bands.SharedSurface(101, 203, world, rank, path, create=True)
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            surface = bands.SharedSurface(101, 203, world, rank, name[0], create=False)
+        dist.barrier()
+        if rank == 0:
+            surface.unlink()
+        scene = load_golden_scene("w4ref_101x203")
+        for k in range(frames):
+            for strip in bands.strips_of_rank(203, world, rank):
+                y0 = strip * bands.STRIP_ROWS
+                n = min(bands.STRIP_ROWS, 203 - y0)
+                surface.frame[y0:y0 + n] = rt_oracle.render(scene, 101, 203, row_begin=y0, row_count=n)
+            assert surface.arrive_and_wait() == k + 1
+            if rank == 0:
+                q.put(surface.frame.copy())
+            dist.barrier()                              # the test's own pacing: rank 0 has copied before anyone overwrites
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_direct_present_into_shared_surface(tmp_path):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path)
+    path = os.path.join(shm_dir, f"rt_b200_test_surface_{os.getpid()}")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    frames = 2
+    procs = [ctx.Process(target=_surface_worker, args=(r, 2, port, path, frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(frames)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert not os.path.exists(path)
+    want = load_golden_frame("w4ref_101x203")
+    for frame in got:
+        assert np.array_equal(frame, want)
+
+
+def test_shared_surface_handshake_times_out_instead_of_hanging(tmp_path):
+    path = str(tmp_path / "surface")
+    s = bands.SharedSurface(16, 16, 2, 0, path, create=True)
+    with pytest.raises(TimeoutError):
+        s.arrive_and_wait(timeout_s=0.05)            # rank 1 never arrives
