@@ -344,15 +344,23 @@ def main():
         render_step()
         exchange_step()
 
+    e2e_parts = [0.0] * 6      # host seconds in upload / render call / handshake, device seconds kernel / kernel + copies, steps
+
     def e2e_step():
         """Host buffers in, host buffer out, through the C ABI."""
+        t_a = time.perf_counter()
         r.ctx.upload_mesh(0, mesh)                                  # H2D: what UpdateTransforms produced this frame
+        t_b = time.perf_counter()
+        e2e_parts[0] += t_b - t_a
         if world == 1:
             r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + progressive D2H, blocking
             return
         if present_mode == "direct":
-            r.render_strips_to_host(rank, world, surface.ptr, surface.pitch_bytes)   # blocking: this rank's strips are in host memory
+            tm = r.render_strips_to_host(rank, world, surface.ptr, surface.pitch_bytes)   # blocking: this rank's strips are in host memory
+            t_c = time.perf_counter()
             surface.arrive_and_wait()             # surface complete; nobody starts the next frame earlier
+            e2e_parts[1] += t_c - t_b; e2e_parts[2] += time.perf_counter() - t_c
+            e2e_parts[3] += tm["kernel_ms"] * 1e-3; e2e_parts[4] += tm["total_ms"] * 1e-3; e2e_parts[5] += 1
             return
         if signals:
             # every rank's CTAs bump per-band counters in rank 0's frame; rank 0 presents band after band
@@ -425,6 +433,12 @@ def main():
         h2d = int(mesh.positions.nbytes + mesh.indices.nbytes + mesh.normals.nbytes) * world
         e2e = {"value": RAYS_PER_FRAME / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": WIDTH * HEIGHT * 4}
+        if present_mode == "direct" and e2e_parts[5] > 0:
+            # where a step's time goes, slowest rank per component (warm-up steps included in the averages)
+            parts = torch.tensor([x / e2e_parts[5] * 1e3 for x in e2e_parts[:5]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(parts, op=dist.ReduceOp.MAX)
+            e2e["breakdown_ms_max_over_ranks"] = dict(zip(["host_upload_mesh", "host_render_strips_to_host_call", "host_wait_for_all_ranks",
+                                                           "device_kernel", "device_kernel_and_copies"], [float(x) for x in parts]))
 
     if rank != 0:
         if world > 1:
