@@ -6,3 +6,4 @@ the CPU.
 """
 from .scene_file import FlatScene, Camera, Mesh, load_rtsc  # noqa: F401
 from .renderer import Renderer, Context, RtError  # noqa: F401
+from .obj_file import ObjMesh, parse_obj  # noqa: F401
