@@ -693,13 +693,14 @@ namespace
 	// to copy into (host itself, or the pinned bounce buffer) through `target`.
 	int prepare_host(rt_context* ctx, void* host, size_t bytes, void** target)
 	{
+		static const bool force_bounce = getenv("RT_B200_FORCE_STAGING") != nullptr;     // tests: take the bounce-buffer path
 		cudaPointerAttributes attr{};
 		const cudaError_t e = cudaPointerGetAttributes(&attr, host);
-		if (e == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged)) { *target = host; return RT_OK; }
+		if (!force_bounce && e == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged)) { *target = host; return RT_OK; }
 		cudaGetLastError();
-		if (ctx->registered_host == host && ctx->registered_bytes >= bytes) { *target = host; return RT_OK; }
+		if (!force_bounce && ctx->registered_host == host && ctx->registered_bytes >= bytes) { *target = host; return RT_OK; }
 		if (ctx->registered_host) { cudaHostUnregister(ctx->registered_host); ctx->registered_host = nullptr; ctx->registered_bytes = 0; }
-		if (cudaHostRegister(host, bytes, cudaHostRegisterPortable) == cudaSuccess)
+		if (!force_bounce && cudaHostRegister(host, bytes, cudaHostRegisterPortable) == cudaSuccess)
 		{
 			ctx->registered_host = host; ctx->registered_bytes = bytes; *target = host; return RT_OK;
 		}
@@ -707,8 +708,6 @@ namespace
 		if (ctx->staging_bytes < bytes)
 		{
 			if (ctx->staging) cudaFreeHost(ctx->staging);
-	if (ctx->h_static) cudaFreeHost(ctx->h_static);
-	if (ctx->h_mesh) cudaFreeHost(ctx->h_mesh);
 			ctx->staging = nullptr; ctx->staging_bytes = 0;
 			RT_CUDA(ctx, cudaHostAlloc(&ctx->staging, bytes, cudaHostAllocPortable));
 			ctx->staging_bytes = bytes;
@@ -1179,6 +1178,7 @@ int rt_destroy(rt_context* ctx)
 	if (ctx->staging) cudaFreeHost(ctx->staging);
 	if (ctx->h_static) cudaFreeHost(ctx->h_static);
 	if (ctx->h_mesh) cudaFreeHost(ctx->h_mesh);
+	if (ctx->h_build_status) cudaFreeHost(ctx->h_build_status);
 	cudaGetLastError();
 	delete ctx;
 	return RT_OK;

@@ -473,15 +473,23 @@ namespace rt
 			Team t;
 			int n_teams;
 			if (n > kMaxTeams || big <= kWarpNodeTriangles) { n_teams = n_warps; t.warps = 1; }
-			else { n_teams = n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8)); t.warps = n_warps / n_teams; }
+			else
+			{
+				// a team is as many warps as the level's largest node has triangles per lane, no more: warps that would
+				// only run the passes with every lane idle cost issue slots the others need (the rest of the CTA sits out)
+				n_teams = n <= 1 ? 1 : (n <= 2 ? 2 : (n <= 4 ? 4 : 8));
+				t.warps = n_warps / n_teams;
+				while (t.warps > 1 && 32 * (t.warps / 2) >= big) t.warps /= 2;
+			}
 			t.threads = 32 * t.warps;
 			const int team = warp / t.warps;
 			t.warp = warp - team * t.warps;
 			t.tid = tid - team * t.threads;
 			t.barrier = 1 + team;
-			t.s = &scratch[team];
-			for (int q = team; q < n; q += n_teams)
-				subdivide_node(p, w, cur[q], t, nodes_used, nxt, &level.count[parity ^ 1], &level.big[parity ^ 1]);
+			t.s = &scratch[team < n_teams ? team : 0];
+			if (team < n_teams)
+				for (int q = team; q < n; q += n_teams)
+					subdivide_node(p, w, cur[q], t, nodes_used, nxt, &level.count[parity ^ 1], &level.big[parity ^ 1]);
 			__syncthreads();
 			if (tid == 0) { level.count[parity] = 0; level.big[parity] = 0; }
 			int* swap = cur; cur = nxt; nxt = swap;

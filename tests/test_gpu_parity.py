@@ -344,3 +344,38 @@ def test_axis_parallel_rays_take_the_literal_slab_test(gpu):
             identical, max_err, n_diff = compare_frames(got, want)
             assert n_diff == 0 or (identical >= MIN_IDENTICAL and max_err <= MAX_LSB), (origin, fov, gpu_path, n_diff, max_err)
         r.close()
+
+
+def test_bounce_buffer_path_when_the_surface_cannot_be_pinned(gpu, tmp_path):
+    """RT_B200_FORCE_STAGING makes prepare_host behave as if cudaHostRegister had failed: frames go through the pinned
+    bounce buffer and are copied into the caller's surface by the CPU - whole frames (rt_render) and a rank's strips only
+    (rt_render_strips_to_host).  The switch is read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = '''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from conftest import load_golden_frame
+from test_gpu_parity import make_renderer
+r = make_renderer("bunny_333x77")
+want = load_golden_frame("bunny_333x77")
+assert np.array_equal(r.Render(), want)
+assert np.array_equal(r.Render(), want)
+surface = np.full((77, 333), 0xDEADBEEF, dtype=np.uint32)
+for rank in range(3):
+    r.render_strips_to_host(rank, 3, surface.ctypes.data, 333 * 4)
+    rows = np.zeros(77, dtype=bool)
+    for s0 in range(rank * 8, 77, 24):
+        rows[s0:s0 + 8] = True
+    assert np.array_equal(surface[rows], want[rows])
+    if rank < 2:
+        assert (surface[~rows] == 0xDEADBEEF).any()
+assert np.array_equal(surface, want)
+r.close()
+print("ok")
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, RT_B200_FORCE_STAGING="1"), timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr

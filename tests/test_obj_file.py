@@ -81,9 +81,9 @@ def test_loader_semantics_on_a_made_up_file(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("obj,scale,name", [("lowpoly_bunny2.obj", 2.0, "bunny_640"), ("lowpoly_bunny2.obj", 2.0, "bunny_320_yaw05"),
-                                            ("Assignment3D1.obj", 0.03, "optional_320")])
-def test_obj_file_to_frame_on_the_device(obj, scale, name):
+@pytest.mark.parametrize("obj,scale,name,posed", [("lowpoly_bunny2.obj", 2.0, "bunny_640", False), ("lowpoly_bunny2.obj", 2.0, "bunny_320_yaw05", True),
+                                                  ("Assignment3D1.obj", 0.03, "optional_320", False), ("Assignment3D1.obj", 0.03, "optional_320_steps2", True)])
+def test_obj_file_to_frame_on_the_device(obj, scale, name, posed):
     """File -> parse_obj -> rt_upload_mesh_source -> device UpdateTransforms + BuildBVH -> frame, with nothing of the
     mesh taken from the reference: the first build is the one of Initialize() (scale only, source/Scene.cpp:413-417,
     450-454), posed fixtures add the build of their pose.  Must be the frame the reference rendered."""
@@ -97,9 +97,11 @@ def test_obj_file_to_frame_on_the_device(obj, scale, name):
     r.ctx.set_mesh_device_bvh(0, True)
     s = np.float32(scale)
     r.ctx.transform_mesh(0, np.diag([s, s, s, np.float32(1)]).astype(np.float32))          # Initialize(): Scale + UpdateTransforms
-    posed = os.path.join(GOLDEN, name + ".rtms")
-    if os.path.exists(posed):
-        r.ctx.transform_mesh(0, load_rtms(posed)[0].transform)                                # the fixture's pose: one more UpdateTransforms
+    if posed and os.path.exists(os.path.join(GOLDEN, name + ".rtmp")):
+        for transform in load_rtmp(os.path.join(GOLDEN, name + ".rtmp"))[0].transforms:       # the fixture's poses, one UpdateTransforms each
+            r.ctx.transform_mesh(0, transform)
+    elif posed:
+        r.ctx.transform_mesh(0, load_rtms(os.path.join(GOLDEN, name + ".rtms"))[0].transform)   # the fixture's pose: one more UpdateTransforms
     got = r.Render()
     identical, max_err, n_diff = compare_frames(got, load_golden_frame(name))
     if name.startswith("bunny"):
