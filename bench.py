@@ -265,16 +265,35 @@ def main():
     present_mode = os.environ.get("RT_BENCH_PRESENT", "direct") if world > 1 else "single"
     shared_surface = None
     if present_mode == "direct":
-        name = [f"/dev/shm/rt_b200_surface_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}" if rank == 0 else None]
+        # any rank that cannot create / open / map the surface sends everybody back to the gather flow together
+        import tempfile
+        name, surface = [None], None
         if rank == 0:
-            surface = bands.SharedSurface(WIDTH, HEIGHT, world, rank, name[0], create=True)
+            for folder in ("/dev/shm", tempfile.gettempdir()):
+                try:
+                    candidate = os.path.join(folder, f"rt_b200_surface_{os.environ.get('MASTER_PORT', '0')}_{os.getpid()}")
+                    surface = bands.SharedSurface(WIDTH, HEIGHT, world, rank, candidate, create=True)
+                    name = [candidate]
+                    break
+                except OSError as exc:
+                    print(f"rank 0: no shared surface in {folder}: {exc}", file=sys.stderr)
         dist.broadcast_object_list(name, src=0)
-        if rank != 0:
-            surface = bands.SharedSurface(WIDTH, HEIGHT, world, rank, name[0], create=False)
-        shared_surface = surface.frame
-        dist.barrier()
-        if rank == 0:
+        opened = torch.ones(1, dtype=torch.int32, device="cuda")
+        if name[0] is None:
+            opened[0] = 0
+        elif rank != 0:
+            try:
+                surface = bands.SharedSurface(WIDTH, HEIGHT, world, rank, name[0], create=False)
+            except OSError as exc:
+                print(f"rank {rank}: cannot open the shared surface: {exc}", file=sys.stderr)
+                opened[0] = 0
+        dist.all_reduce(opened, op=dist.ReduceOp.MIN)
+        if rank == 0 and name[0] is not None:
             surface.unlink()                        # the mappings keep it alive; nothing is left behind
+        if int(opened) == 1:
+            shared_surface = surface.frame
+        else:
+            present_mode, surface = "gather", None
     band = frame_dev = gathered = None
     frame_ptr = 0
     token = torch.zeros(1, dtype=torch.int32, device="cuda")
