@@ -288,9 +288,10 @@ def main():
                 print(f"rank {rank}: cannot open the shared surface: {exc}", file=sys.stderr)
                 opened[0] = 0
         dist.all_reduce(opened, op=dist.ReduceOp.MIN)
+        everybody_opened = int(opened) == 1         # reading the value waits for the collective: every rank has tried by now
         if rank == 0 and name[0] is not None:
             surface.unlink()                        # the mappings keep it alive; nothing is left behind
-        if int(opened) == 1:
+        if everybody_opened:
             shared_surface = surface.frame
         else:
             present_mode, surface = "gather", None
