@@ -437,6 +437,7 @@ def main():
     if not args.no_e2e:
         for _ in range(3):
             e2e_step()
+        e2e_parts[:] = [0.0] * 6                  # the first call pins the surface: not part of the per-step picture
         barrier()
         sampler2 = ClockSampler(local_rank)
         with sampler2:
@@ -454,7 +455,7 @@ def main():
         e2e = {"value": RAYS_PER_FRAME / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": WIDTH * HEIGHT * 4}
         if present_mode == "direct" and e2e_parts[5] > 0:
-            # where a step's time goes, slowest rank per component (warm-up steps included in the averages)
+            # where a step's time goes, slowest rank per component, averaged over the timed steps
             parts = torch.tensor([x / e2e_parts[5] * 1e3 for x in e2e_parts[:5]], dtype=torch.float64, device="cuda")
             dist.all_reduce(parts, op=dist.ReduceOp.MAX)
             e2e["breakdown_ms_max_over_ranks"] = dict(zip(["host_upload_mesh", "host_render_strips_to_host_call", "host_wait_for_all_ranks",
