@@ -578,10 +578,10 @@ def main():
             other["device-side UpdateTransforms"] = {"error": str(exc)}
 
         # N1, second half: UpdateTransforms WITH BuildBVH on the device (rt_set_mesh_device_bvh): a new pose every frame,
-        # one build per frame (two launches), BVH body; checked against the CPU restatement's build + frame at the end
+        # one build per frame (two launches), BVH body.  Self-check without the CPU oracle: the last frame must equal the
+        # frame of the transform-only path (slab + linear body) for the same pose, bit for bit.
         try:
             from gp1_raytracer_2223_b200.scene_file import load_rtmp
-            from oracle import rt_oracle
             sc = load_rtsc(os.path.join(ROOT, "tests", "golden", "bunny_320_steps3.rtsc"))
             steps = load_rtmp(os.path.join(ROOT, "tests", "golden", "bunny_320_steps3.rtmp"))[0]
             rr = Renderer(WIDTH, HEIGHT, device_ids=[local_rank])
@@ -589,8 +589,6 @@ def main():
             rr.ctx.upload_mesh_source(0, steps.positions, steps.indices, steps.normals, sc.meshes[0].cull_mode, sc.meshes[0].material_index)
             rr.ctx.set_mesh_device_bvh(0, True)
             host = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
-            idx = np.ascontiguousarray(steps.indices, dtype=np.int32).copy()
-            nrm = np.ascontiguousarray(steps.normals, dtype=np.float32).copy()
 
             def pose(k):
                 a = np.float32(0.05 * (k + 1))
@@ -605,11 +603,16 @@ def main():
                 tm = rr.render_host_ptr(host.data_ptr(), WIDTH * 4)
                 if k >= 5:
                     t_total += time.perf_counter() - t0
-                pos, tnrm, nodes = rt_oracle.update_transforms_bvh(steps.positions, idx, nrm, m)     # the checker's copy of the mesh state
-            got_idx = rr.ctx.read_mesh_build(0, idx.shape[0])[0]
+            built = host.numpy().view(np.uint32).copy()
+            rr.close()
+            rr = Renderer(WIDTH, HEIGHT, device_ids=[local_rank])
+            rr.SetScene(sc)
+            rr.ctx.upload_mesh_source(0, steps.positions, steps.indices, steps.normals, sc.meshes[0].cull_mode, sc.meshes[0].material_index)
+            rr.ctx.transform_mesh(0, pose(n_frames - 1))
+            rr.render_host_ptr(host.data_ptr(), WIDTH * 4)
             other["device-side UpdateTransforms + BuildBVH, bunny 3840x2160, new pose every frame, BVH body"] = {
                 "e2e_ms": t_total / (n_frames - 5) * 1e3, "kernel_ms": tm["kernel_ms"], "h2d_bytes_per_frame": 64,
-                "triangle_order_equals_cpu_restatement_after_35_builds": bool(np.array_equal(got_idx.reshape(-1, 3), idx))}
+                "differing_pixels_vs_slab_body_after_35_builds": int((built != host.numpy().view(np.uint32)).sum())}
             rr.close()
         except Exception as exc:                       # noqa: BLE001
             other["device-side UpdateTransforms + BuildBVH"] = {"error": str(exc)}

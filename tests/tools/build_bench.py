@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Animated bunny at 3840x2160: one TriangleMesh::UpdateTransforms per frame, three ways.
+"""TEST TOOLING (lives under tests/ because its host arm runs the CPU oracle as a stand-in for the reference's host code).
+
+Animated bunny at 3840x2160: one TriangleMesh::UpdateTransforms per frame, three ways.
 
   host     UpdateTransforms + BuildBVH on the host (the oracle's C restatement standing in for the reference's own
            host code), rt_upload_mesh of the result, BVH body
@@ -13,7 +15,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Differential fuzzing: seeded random scenes (tests/random_scenes.py) rendered by the CUDA path (both mesh bodies,
-both kernel variants) and by the CPU oracle; reports every differing pixel.  Usage: python tools/fuzz_parity.py [first_seed] [count]"""
+both kernel variants) and by the CPU oracle; reports every differing pixel.  Usage: python tests/tools/fuzz_parity.py [first_seed] [count]"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 from random_scenes import random_scene
