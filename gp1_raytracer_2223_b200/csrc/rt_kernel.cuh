@@ -81,6 +81,12 @@ namespace rt
 		int32_t grid_x, n_strips;        // the launch's tile grid: 32-pixel columns x 8-row strips (set by launch())
 		unsigned int* queue;             // persistent kernel: {next work item, finished warps}, both zero between launches
 		uint32_t grid_x_magic;           // floor(2^32 / grid_x) + 1: tile / grid_x == __umulhi(tile, magic) while tile * grid_x < 2^32
+		// persistent kernel, scheduling only: the tiles of the rectangle [first_x0, first_x1) x [first_k0, first_k1)
+		// (tile columns x strips of this launch) are handed out before all others (first_tiles == 0: plain order)
+		int32_t first_x0, first_x1, first_k0, first_k1;
+		int32_t first_tiles;             // (first_x1 - first_x0) * (first_k1 - first_k0)
+		uint32_t first_w_magic;          // floor(2^32 / (first_x1 - first_x0)) + 1
+		uint32_t rest_w_magic;           // floor(2^32 / (grid_x - (first_x1 - first_x0))) + 1 (unused when the rectangle spans the width)
 	};
 
 	struct Ray
@@ -944,8 +950,48 @@ namespace rt
 	{
 		TileCoords c;
 		const unsigned int tile = (unsigned int)item / kSignalsPerTile, warp = (unsigned int)item % kSignalsPerTile;
-		c.k = (int)__umulhi(tile, p.grid_x_magic);
-		const int bx = (int)tile - c.k * p.grid_x;
+		int bx;
+		if (p.first_tiles == 0)
+		{
+			c.k = (int)__umulhi(tile, p.grid_x_magic);
+			bx = (int)tile - c.k * p.grid_x;
+		}
+		else if ((int)tile < p.first_tiles)
+		{
+			// inside the rectangle, row by row
+			const int w = p.first_x1 - p.first_x0;
+			const int row = (int)__umulhi(tile, p.first_w_magic);
+			c.k = p.first_k0 + row;
+			bx = p.first_x0 + ((int)tile - row * w);
+		}
+		else
+		{
+			// everything else in the plain order: full rows above, the two side pieces of the rectangle's rows, full rows below
+			const int w = p.first_x1 - p.first_x0;
+			unsigned int j = tile - (unsigned int)p.first_tiles;
+			const unsigned int above = (unsigned int)(p.first_k0 * p.grid_x);
+			const unsigned int beside = (unsigned int)((p.first_k1 - p.first_k0) * (p.grid_x - w));
+			if (j < above)
+			{
+				c.k = (int)__umulhi(j, p.grid_x_magic);
+				bx = (int)j - c.k * p.grid_x;
+			}
+			else if (j - above < beside)
+			{
+				j -= above;
+				const int row = (int)__umulhi(j, p.rest_w_magic);
+				const int col = (int)j - row * (p.grid_x - w);
+				c.k = p.first_k0 + row;
+				bx = col < p.first_x0 ? col : col + w;
+			}
+			else
+			{
+				j -= above + beside;
+				const int row = (int)__umulhi(j, p.grid_x_magic);
+				c.k = p.first_k1 + row;
+				bx = (int)j - row * p.grid_x;
+			}
+		}
 		const int wx = warp % kWarpsX, wy = warp / kWarpsX;
 		c.px = bx * kBlockW + wx * kTileW + (lane & (kTileW - 1));
 		c.local_y = wy * kTileH + (lane >> 3);
@@ -975,6 +1021,12 @@ namespace rt
 		const int total = p.grid_x * p.n_strips * kSignalsPerTile;
 		Counters<false> cnt;
 
+#ifdef RT_DRAIN_PROBE
+		// experiment: p.counters = {first warp start, first warp that found the queue empty, last warp out} in globaltimer ns
+		unsigned long long probe_t;
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(probe_t));
+		if (p.counters && lane == 0) atomicMin(p.counters, probe_t);
+#endif
 		int item = next_work_item(p.queue, lane);
 		while (item < total)
 		{
@@ -1015,6 +1067,10 @@ namespace rt
 #endif
 		}
 
+#ifdef RT_DRAIN_PROBE
+		asm volatile("mov.u64 %0, %globaltimer;" : "=l"(probe_t));
+		if (p.counters && lane == 0) { atomicMin(p.counters + 1, probe_t); atomicMax(p.counters + 2, probe_t); }
+#endif
 		// every warp of the grid arrives here exactly once, after its last fetch
 		if (lane == 0)
 		{
