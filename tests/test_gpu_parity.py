@@ -153,6 +153,40 @@ def test_strips_on_torch_stream_vector_path(gpu):
     r.close()
 
 
+@pytest.mark.parametrize("name,world,origin", [("bunny_4k", 8, None), ("bunny_4k", 4, None), ("bunny_640", 4, None), ("bunny_640", 3, (2.5, 3.0, -9.0)),
+                                               ("bunny_640", 2, (0.0, 6.5, -7.0)), ("bunny_333x77", 2, None), ("w4ref_101x203", 3, None), ("optional_320", 4, None)])
+def test_mesh_rectangle_first_order_of_the_persistent_kernel(gpu, name, world, origin):
+    """Device-only launches of the persistent kernel hand out the tiles under the meshes' screen rectangle first
+    (tiles_to_render_first): every queue position must still mean exactly one tile.  Shares of a rank / world split,
+    cameras that push the rectangle partly out of the frame, odd frame sizes; against the same frame rendered in
+    the plain order by the tiled kernel (and the reference frame where the camera is the fixture's)."""
+    torch = gpu
+    from gp1_raytracer_2223_b200 import bands
+    r = make_renderer(name)
+    scene = load_golden_scene(name)
+    if origin is not None:
+        scene.camera.origin[:] = origin
+        r.SetScene(scene)
+    info = MANIFEST[name]
+    W, H = info["width"], info["height"]
+    spr = bands.strips_per_rank(H, world)
+    frames = {}
+    for variant in (1, 3):
+        r.ctx.set_kernel_variant(variant)
+        packed = torch.full((world, spr * bands.STRIP_ROWS, W), -1, dtype=torch.int32, device="cuda")
+        for rank in range(world):
+            r.render_strips_device(rank, world, packed[rank].data_ptr())
+        torch.cuda.synchronize()
+        frames[variant] = bands.unstripe_numpy(packed.cpu().numpy().view(np.uint32), W, H, world)
+    assert np.array_equal(frames[1], frames[3])
+    if origin is None:
+        identical, max_err, n_diff = compare_frames(frames[3], load_golden_frame(name))
+        if name.startswith("bunny"):
+            assert n_diff == 0
+        assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB
+    r.close()
+
+
 def test_pixel_format_and_pitch(gpu):
     """Other SDL surface formats: BGR shifts + alpha mask, and a surface pitch wider than 4*W."""
     from oracle import rt_oracle
