@@ -96,6 +96,24 @@ namespace
 		unsigned int* d_band_done = nullptr;                // kMaxBands counters for the single-launch progressive present
 		unsigned int* d_queues = nullptr;                   // kQueueRing work queues {next, finished} of the persistent kernel (self re-arming)
 		unsigned int queue_cursor = 0;
+		// Cost feedback for the persistent kernel's tile order on small shares (see prepare_cell_order)
+		struct CellSchedule
+		{
+			static constexpr int kSlots = 4, kMaxCells = 256;
+			// the launch geometry the costs belong to; anything else starts over
+			int n_strips = 0, grid_x = 0, strip_first = -1, strip_step = -1, row_begin = -1, row_end = -1, cells_x = 0, cell_h_log2 = 0, n_cells = 0;
+			cudaStream_t stream = nullptr;
+			unsigned int* d_cost = nullptr;                 // kSlots x kMaxCells, one slice per launch in flight
+			unsigned int* h_cost = nullptr;                 // pinned read-back, same shape
+			uint8_t* d_order = nullptr;                     // kSlots x kMaxCells order tables
+			uint8_t* h_order = nullptr;                     // pinned sources of their uploads
+			cudaEvent_t ev_cost[kSlots] = {}, ev_order[kSlots] = {};
+			cudaEvent_t ev_last = nullptr;                  // after the newest launch that read a table / wrote costs
+			bool cost_pending[kSlots] = {}, order_used[kSlots] = {};
+			int cost_cursor = 0, order_cursor = 0;
+			int orders_made = 0, launches_since_measured = 0;
+			const uint8_t* current = nullptr;               // the table the next launch walks (NULL: none learned yet)
+		} cells;
 		int sm_count = 0;
 		rt::SceneDevice view{};
 	};
@@ -614,6 +632,132 @@ namespace
 		p.rest_w_magic = p.grid_x > w ? (uint32_t)((1ull << 32) / (unsigned)(p.grid_x - w)) + 1u : 0u;
 	}
 
+	// ---- ... and, from the second launch of the same geometry on, the cells that WERE expensive first -----------------
+	// The rectangle above is a guess made before anything is known; it misses, for instance, the floor in front of the
+	// bunny, whose shadow rays climb through the mesh's box.  The kernel therefore also measures: every warp tile adds
+	// its SM clocks to the counter of its cell (8 tile columns x 2^h strips, at most 256 cells per launch), the
+	// counters are read back asynchronously, and the next launch of the same geometry on the same stream walks the
+	// cells in descending cost (longest processing time first).  Nothing here waits: a read-back that has not
+	// finished is simply not used yet.  Same conditions as the rectangle (small shares, no progressive present).
+	int ensure_cell_buffers(rt_context* ctx, DeviceState& d)
+	{
+		DeviceState::CellSchedule& cs = d.cells;
+		if (cs.d_cost) return RT_OK;
+		constexpr size_t n = (size_t)DeviceState::CellSchedule::kSlots * DeviceState::CellSchedule::kMaxCells;
+		RT_CUDA(ctx, cudaMalloc(&cs.d_cost, n * sizeof(unsigned int)));
+		RT_CUDA(ctx, cudaMalloc(&cs.d_order, n));
+		RT_CUDA(ctx, cudaHostAlloc(&cs.h_cost, n * sizeof(unsigned int), cudaHostAllocPortable));
+		RT_CUDA(ctx, cudaHostAlloc(&cs.h_order, n, cudaHostAllocPortable));
+		for (int i = 0; i < DeviceState::CellSchedule::kSlots; ++i)
+		{
+			RT_CUDA(ctx, cudaEventCreateWithFlags(&cs.ev_cost[i], cudaEventDisableTiming));
+			RT_CUDA(ctx, cudaEventCreateWithFlags(&cs.ev_order[i], cudaEventDisableTiming));
+		}
+		RT_CUDA(ctx, cudaEventCreateWithFlags(&cs.ev_last, cudaEventDisableTiming));
+		return RT_OK;
+	}
+
+	// Before a persistent launch.  Sets p.cell_* (order and / or cost slice); *cost_slot = the slice to read back after
+	// the launch, or -1.
+	int prepare_cell_order(rt_context* ctx, DeviceState& d, rt::FrameParams& p, cudaStream_t stream, int n_strips, int resident_warps, int* cost_slot)
+	{
+		static const bool off = getenv("RT_B200_PLAIN_ORDER") != nullptr || getenv("RT_B200_NO_COST_FEEDBACK") != nullptr;
+		*cost_slot = -1;
+		p.cell_order = nullptr; p.cell_cost = nullptr; p.total_items = 0; p.cells_x = 1; p.cell_h_log2 = 0; p.cells_x_magic = 0;
+		if (off || p.band_done || p.grid_x < 2 || n_strips < 2) return RT_OK;
+		// measured on the 4K bunny frame against the plain order: whole frame -1.6 %, a half -4 %, a quarter -5 %, an
+		// eighth -12 % (RT_B200_ORDER_GATE = n: only launches with fewer than n warp tiles per resident warp)
+		static const long long gate = [] { const char* e = getenv("RT_B200_ORDER_GATE"); const int v = e ? atoi(e) : 0; return (long long)(v > 0 ? v : (1 << 20)); }();
+		if ((long long)p.grid_x * n_strips * rt::kSignalsPerTile >= gate * resident_warps) return RT_OK;
+		constexpr int kSlots = DeviceState::CellSchedule::kSlots, kMaxCells = DeviceState::CellSchedule::kMaxCells;
+		const int cells_x = (p.grid_x + (1 << rt::kCellWLog2) - 1) >> rt::kCellWLog2;
+		if (cells_x < 2 || cells_x > kMaxCells / 2) return RT_OK;
+		int h = 0;
+		while ((((n_strips + (1 << h) - 1) >> h) * cells_x) > kMaxCells) ++h;
+		const int cells_y = (n_strips + (1 << h) - 1) >> h, n_cells = cells_x * cells_y;
+		if (n_cells < 4) return RT_OK;
+		int rc = ensure_cell_buffers(ctx, d);
+		if (rc != RT_OK) return rc;
+		DeviceState::CellSchedule& cs = d.cells;
+		if (cs.n_strips != n_strips || cs.grid_x != p.grid_x || cs.strip_first != p.strip_first || cs.strip_step != p.strip_step ||
+		    cs.row_begin != p.row_begin || cs.row_end != p.row_end || cs.stream != stream)
+		{
+			// tables and counters of the old stream may still be in use there: the new stream queues up behind it
+			if (cs.stream && cs.stream != stream) RT_CUDA(ctx, cudaStreamWaitEvent(stream, cs.ev_last, 0));
+			cs.current = nullptr; cs.orders_made = 0; cs.launches_since_measured = 0;
+			for (bool& b : cs.cost_pending) b = false;           // late read-backs of the old geometry are ignored
+			cs.n_strips = n_strips; cs.grid_x = p.grid_x; cs.strip_first = p.strip_first; cs.strip_step = p.strip_step;
+			cs.row_begin = p.row_begin; cs.row_end = p.row_end; cs.stream = stream;
+			cs.cells_x = cells_x; cs.cell_h_log2 = h; cs.n_cells = n_cells;
+		}
+		p.cells_x = cells_x; p.cell_h_log2 = h; p.cells_x_magic = (uint32_t)((1ull << 32) / (unsigned)cells_x) + 1u;
+		// newest finished read-back -> a new order table
+		int fresh = -1;
+		for (int i = 0; i < kSlots; ++i)
+		{
+			const int slot = (cs.cost_cursor + kSlots - 1 - i) % kSlots;
+			if (!cs.cost_pending[slot] || cudaEventQuery(cs.ev_cost[slot]) != cudaSuccess) continue;
+			if (fresh < 0) fresh = slot;
+			cs.cost_pending[slot] = false;
+		}
+		cudaGetLastError();      // cudaErrorNotReady of the queries above
+		if (fresh >= 0)
+		{
+			const int oslot = cs.order_cursor % kSlots;
+			if (!cs.order_used[oslot] || cudaEventQuery(cs.ev_order[oslot]) == cudaSuccess)
+			{
+				const unsigned int* cost = cs.h_cost + (size_t)fresh * kMaxCells;
+				uint8_t* order = cs.h_order + (size_t)oslot * kMaxCells;
+				int idx[kMaxCells];
+				for (int c = 0; c < n_cells; ++c) idx[c] = c;
+				std::stable_sort(idx, idx + n_cells, [&](int a, int b) { return cost[a] > cost[b]; });
+				for (int c = 0; c < n_cells; ++c) order[c] = (uint8_t)idx[c];
+				RT_CUDA(ctx, cudaMemcpyAsync(cs.d_order + (size_t)oslot * kMaxCells, order, (size_t)n_cells, cudaMemcpyHostToDevice, stream));
+				RT_CUDA(ctx, cudaEventRecord(cs.ev_order[oslot], stream));
+				cs.order_used[oslot] = true; cs.order_cursor++; cs.orders_made++;
+				cs.current = cs.d_order + (size_t)oslot * kMaxCells;
+			}
+			else cudaGetLastError();
+		}
+		if (cs.current)
+		{
+			p.cell_order = cs.current;
+			p.total_items = (n_cells << (rt::kCellWLog2 + h)) * rt::kSignalsPerTile;
+			p.first_tiles = 0;                                // the measured order replaces the guessed rectangle
+		}
+		// Measuring costs three stream operations around the kernel (clear, read back, and the upload of the order it
+		// leads to), which is most of what a good order wins on a 150 us launch: measure the first launches of a geometry
+		// (under the guessed order, then under the first measured one), after that only every 256th (camera and scene
+		// move on; a stale order is still a valid one).
+		const int cslot = cs.cost_cursor % kSlots;
+		bool in_flight = false;
+		for (bool b : cs.cost_pending) in_flight = in_flight || b;
+		const bool measure = !in_flight && (cs.orders_made < 2 || cs.launches_since_measured >= 256);
+		cs.launches_since_measured++;
+		if (measure && !cs.cost_pending[cslot])
+		{
+			cs.launches_since_measured = 0;
+			RT_CUDA(ctx, cudaMemsetAsync(cs.d_cost + (size_t)cslot * kMaxCells, 0, sizeof(unsigned int) * (size_t)n_cells, stream));
+			p.cell_cost = cs.d_cost + (size_t)cslot * kMaxCells;
+			*cost_slot = cslot;
+		}
+		return RT_OK;
+	}
+
+	int finish_cell_order(rt_context* ctx, DeviceState& d, const rt::FrameParams& p, cudaStream_t stream, int cost_slot)
+	{
+		DeviceState::CellSchedule& cs = d.cells;
+		if (!p.cell_cost && !p.cell_order) return RT_OK;
+		RT_CUDA(ctx, cudaEventRecord(cs.ev_last, stream));
+		if (cost_slot < 0) return RT_OK;
+		constexpr int kMaxCells = DeviceState::CellSchedule::kMaxCells;
+		RT_CUDA(ctx, cudaMemcpyAsync(cs.h_cost + (size_t)cost_slot * kMaxCells, cs.d_cost + (size_t)cost_slot * kMaxCells,
+		                             sizeof(unsigned int) * (size_t)cs.n_cells, cudaMemcpyDeviceToHost, stream));
+		RT_CUDA(ctx, cudaEventRecord(cs.ev_cost[cost_slot], stream));
+		cs.cost_pending[cost_slot] = true; cs.cost_cursor++;
+		return RT_OK;
+	}
+
 	int launch(rt_context* ctx, DeviceState& d, rt::FrameParams p, cudaStream_t stream, int n_strips)
 	{
 		if (n_strips <= 0) return RT_OK;
@@ -652,9 +796,15 @@ namespace
 			// overlap - other streams - are far fewer than the ring is long)
 			const KernelFn fn = persistent;
 			tiles_to_render_first(ctx, p, n_strips, wave * (rt::kPersistentThreads / 32));
+			int cost_slot = -1;
+			const int prc = prepare_cell_order(ctx, d, p, stream, n_strips, wave * (rt::kPersistentThreads / 32), &cost_slot);
+			if (prc != RT_OK) return prc;
 			p.queue = d.d_queues + 2 * (d.queue_cursor++ % kQueueRing);
 			const long long ctas_of_work = (tiles * rt::kSignalsPerTile + rt::kPersistentThreads / 32 - 1) / (rt::kPersistentThreads / 32);
 			fn<<<(unsigned)std::min<long long>(wave, ctas_of_work), rt::kPersistentThreads, 0, stream>>>(d.view, p);
+			RT_CUDA(ctx, cudaGetLastError());
+			const int frc = finish_cell_order(ctx, d, p, stream, cost_slot);
+			if (frc != RT_OK) return frc;
 		}
 		RT_CUDA(ctx, cudaGetLastError());
 		ctx->timing.kernel_launches++;
@@ -1242,6 +1392,10 @@ int rt_destroy(rt_context* ctx)
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
+		cudaFree(d.cells.d_cost); cudaFree(d.cells.d_order); cudaFreeHost(d.cells.h_cost); cudaFreeHost(d.cells.h_order);
+		for (cudaEvent_t e : d.cells.ev_cost) if (e) cudaEventDestroy(e);
+		for (cudaEvent_t e : d.cells.ev_order) if (e) cudaEventDestroy(e);
+		if (d.cells.ev_last) cudaEventDestroy(d.cells.ev_last);
 		for (auto& sd : d.sources) { cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices); cudaFree(sd.normals_alt); cudaFree(sd.indices_alt); cudaFree(sd.build_block); }
 		if (d.ev_begin) cudaEventDestroy(d.ev_begin);
 		if (d.ev_kernel) cudaEventDestroy(d.ev_kernel);

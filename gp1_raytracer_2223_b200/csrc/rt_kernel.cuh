@@ -87,6 +87,14 @@ namespace rt
 		int32_t first_tiles;             // (first_x1 - first_x0) * (first_k1 - first_k0)
 		uint32_t first_w_magic;          // floor(2^32 / (first_x1 - first_x0)) + 1
 		uint32_t rest_w_magic;           // floor(2^32 / (grid_x - (first_x1 - first_x0))) + 1 (unused when the rectangle spans the width)
+		// ... or cell by cell: the tile grid is cut into cells of 8 columns x (1 << cell_h_log2) strips, and the queue
+		// walks them in the order of cell_order (most expensive cell of the previous launch first).  Cells on the right
+		// and bottom edge are padded: queue positions that fall outside the grid render nothing.
+		const uint8_t* cell_order;       // cell_order[r] = r-th cell to render (NULL = off)
+		unsigned int* cell_cost;         // += SM clocks / 16 of every warp tile, per cell (NULL = off)
+		int32_t cells_x, cell_h_log2;
+		uint32_t cells_x_magic;          // floor(2^32 / cells_x) + 1
+		int32_t total_items;             // queue positions of the launch when cells pad it (0 = grid_x * n_strips * kSignalsPerTile)
 	};
 
 	struct Ray
@@ -945,13 +953,24 @@ namespace rt
 		return (int)__shfl_sync(0xffffffffu, id, 0);
 	}
 
-	struct TileCoords { int k, px, py, local_y; bool valid; };
+	struct TileCoords { int k, px, py, local_y, cell; bool valid; };
+	constexpr int kCellWLog2 = 3;        // cells are 8 tile columns wide
 	__device__ __forceinline__ TileCoords decode_work_item(const FrameParams& p, int item, int lane)
 	{
 		TileCoords c;
 		const unsigned int tile = (unsigned int)item / kSignalsPerTile, warp = (unsigned int)item % kSignalsPerTile;
 		int bx;
-		if (p.first_tiles == 0)
+		if (p.cell_order)
+		{
+			const int shift = kCellWLog2 + p.cell_h_log2;
+			const unsigned int rank = tile >> shift, within = tile & ((1u << shift) - 1u);
+			const unsigned int cell = __ldg(p.cell_order + rank);
+			const int cy = (int)__umulhi(cell, p.cells_x_magic), cx = (int)cell - cy * p.cells_x;
+			c.k = (cy << p.cell_h_log2) + (int)(within >> kCellWLog2);
+			bx = (cx << kCellWLog2) + (int)(within & ((1u << kCellWLog2) - 1u));
+			if (bx >= p.grid_x || c.k >= p.n_strips) { bx = p.grid_x; c.k = p.n_strips; }      // padding: lands outside the frame below
+		}
+		else if (p.first_tiles == 0)
 		{
 			c.k = (int)__umulhi(tile, p.grid_x_magic);
 			bx = (int)tile - c.k * p.grid_x;
@@ -996,7 +1015,8 @@ namespace rt
 		c.px = bx * kBlockW + wx * kTileW + (lane & (kTileW - 1));
 		c.local_y = wy * kTileH + (lane >> 3);
 		c.py = p.row_begin + (c.k * p.strip_step + p.strip_first) * kBlockH + c.local_y;
-		c.valid = (c.px < p.width) && (c.py < p.row_end);
+		c.valid = (c.px < p.width) && (c.py < p.row_end) && (bx < p.grid_x) && (c.k < p.n_strips);
+		c.cell = (c.k >> p.cell_h_log2) * p.cells_x + (bx >> kCellWLog2);
 		return c;
 	}
 
@@ -1014,11 +1034,12 @@ namespace rt
 	render_kernel_persistent(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
 		__shared__ SharedScene sc;
+		__shared__ unsigned int tile_clock[kPersistentThreads / 32];
 		stage_scene<kPersistentThreads>(sc, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
 
 		const int lane = threadIdx.x & 31;
-		const int total = p.grid_x * p.n_strips * kSignalsPerTile;
+		const int total = p.total_items ? p.total_items : p.grid_x * p.n_strips * kSignalsPerTile;
 		Counters<false> cnt;
 
 #ifdef RT_DRAIN_PROBE
@@ -1034,6 +1055,7 @@ namespace rt
 			const int upcoming = next_work_item(p.queue, lane);
 #endif
 			uint32_t pixel = 0;
+			if (p.cell_cost && lane == 0) tile_clock[threadIdx.x >> 5] = (unsigned int)clock();      // parked in shared memory: no register across the traversals
 			{
 				const TileCoords c = decode_work_item(p, item, lane);
 				if (c.valid) pixel = render_pixel<MODE, SHADOWS, BVH, false>(sc, dev, p, c.px, c.py, cnt);
@@ -1060,6 +1082,7 @@ namespace rt
 				__syncwarp();
 				if (lane == 0) signal_band_done(p, c.k, 1u);
 			}
+			if (p.cell_cost && lane == 0 && c.k < p.n_strips) atomicAdd(p.cell_cost + c.cell, ((unsigned int)clock() - tile_clock[threadIdx.x >> 5]) >> 4);
 #ifdef RT_PERSIST_PREFETCH
 			item = upcoming;
 #else

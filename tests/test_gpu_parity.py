@@ -179,6 +179,18 @@ def test_mesh_rectangle_first_order_of_the_persistent_kernel(gpu, name, world, o
         torch.cuda.synchronize()
         frames[variant] = bands.unstripe_numpy(packed.cpu().numpy().view(np.uint32), W, H, world)
     assert np.array_equal(frames[1], frames[3])
+    # the same share again and again: from the second launch on the cells are walked in the order of their measured
+    # cost (prepare_cell_order), and the order keeps changing with the measurements
+    for rank in range(world):
+        for repeat in range(4):
+            packed[rank].fill_(-1)
+            r.render_strips_device(rank, world, packed[rank].data_ptr())
+            torch.cuda.synchronize()
+            got = bands.unstripe_numpy(packed.cpu().numpy().view(np.uint32), W, H, world)
+            mine = np.zeros(H, dtype=bool)
+            for s0 in range(rank * 8, H, world * 8):
+                mine[s0:s0 + 8] = True
+            assert np.array_equal(got[mine], frames[1][mine]), (rank, repeat)
     if origin is None:
         identical, max_err, n_diff = compare_frames(frames[3], load_golden_frame(name))
         if name.startswith("bunny"):
