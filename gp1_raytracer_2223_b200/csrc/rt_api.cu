@@ -99,20 +99,20 @@ namespace
 		// Cost feedback for the persistent kernel's tile order on small shares (see prepare_cell_order)
 		struct CellSchedule
 		{
-			static constexpr int kSlots = 4, kMaxCells = 256;
+			static constexpr int kSlots = 4, kMaxCells = 2048;
 			// the launch geometry the costs belong to; anything else starts over
 			int n_strips = 0, grid_x = 0, strip_first = -1, strip_step = -1, row_begin = -1, row_end = -1, cells_x = 0, cell_h_log2 = 0, n_cells = 0;
 			cudaStream_t stream = nullptr;
 			unsigned int* d_cost = nullptr;                 // kSlots x kMaxCells, one slice per launch in flight
 			unsigned int* h_cost = nullptr;                 // pinned read-back, same shape
-			uint8_t* d_order = nullptr;                     // kSlots x kMaxCells order tables
-			uint8_t* h_order = nullptr;                     // pinned sources of their uploads
+			uint16_t* d_order = nullptr;                    // kSlots x kMaxCells order tables
+			uint16_t* h_order = nullptr;                    // pinned sources of their uploads
 			cudaEvent_t ev_cost[kSlots] = {}, ev_order[kSlots] = {};
 			cudaEvent_t ev_last = nullptr;                  // after the newest launch that read a table / wrote costs
 			bool cost_pending[kSlots] = {}, order_used[kSlots] = {};
 			int cost_cursor = 0, order_cursor = 0;
 			int orders_made = 0, launches_since_measured = 0;
-			const uint8_t* current = nullptr;               // the table the next launch walks (NULL: none learned yet)
+			const uint16_t* current = nullptr;              // the table the next launch walks (NULL: none learned yet)
 		} cells;
 		int sm_count = 0;
 		rt::SceneDevice view{};
@@ -635,7 +635,7 @@ namespace
 	// ---- ... and, from the second launch of the same geometry on, the cells that WERE expensive first -----------------
 	// The rectangle above is a guess made before anything is known; it misses, for instance, the floor in front of the
 	// bunny, whose shadow rays climb through the mesh's box.  The kernel therefore also measures: every warp tile adds
-	// its SM clocks to the counter of its cell (8 tile columns x 2^h strips, at most 256 cells per launch), the
+	// its SM clocks to the counter of its cell (4 or 8 tile columns x 2^h strips, at most 2048 cells per launch), the
 	// counters are read back asynchronously, and the next launch of the same geometry on the same stream walks the
 	// cells in descending cost (longest processing time first).  Nothing here waits: a read-back that has not
 	// finished is simply not used yet.  Same conditions as the rectangle (small shares, no progressive present).
@@ -645,9 +645,9 @@ namespace
 		if (cs.d_cost) return RT_OK;
 		constexpr size_t n = (size_t)DeviceState::CellSchedule::kSlots * DeviceState::CellSchedule::kMaxCells;
 		RT_CUDA(ctx, cudaMalloc(&cs.d_cost, n * sizeof(unsigned int)));
-		RT_CUDA(ctx, cudaMalloc(&cs.d_order, n));
+		RT_CUDA(ctx, cudaMalloc(&cs.d_order, n * sizeof(uint16_t)));
 		RT_CUDA(ctx, cudaHostAlloc(&cs.h_cost, n * sizeof(unsigned int), cudaHostAllocPortable));
-		RT_CUDA(ctx, cudaHostAlloc(&cs.h_order, n, cudaHostAllocPortable));
+		RT_CUDA(ctx, cudaHostAlloc(&cs.h_order, n * sizeof(uint16_t), cudaHostAllocPortable));
 		for (int i = 0; i < DeviceState::CellSchedule::kSlots; ++i)
 		{
 			RT_CUDA(ctx, cudaEventCreateWithFlags(&cs.ev_cost[i], cudaEventDisableTiming));
@@ -663,14 +663,17 @@ namespace
 	{
 		static const bool off = getenv("RT_B200_PLAIN_ORDER") != nullptr || getenv("RT_B200_NO_COST_FEEDBACK") != nullptr;
 		*cost_slot = -1;
-		p.cell_order = nullptr; p.cell_cost = nullptr; p.total_items = 0; p.cells_x = 1; p.cell_h_log2 = 0; p.cells_x_magic = 0;
+		p.cell_order = nullptr; p.cell_cost = nullptr; p.total_items = 0; p.cells_x = 1; p.cell_w_log2 = 3; p.cell_h_log2 = 0; p.cells_x_magic = 0;
 		if (off || p.band_done || p.grid_x < 2 || n_strips < 2) return RT_OK;
 		// measured on the 4K bunny frame against the plain order: whole frame -1.6 %, a half -4 %, a quarter -5 %, an
 		// eighth -12 % (RT_B200_ORDER_GATE = n: only launches with fewer than n warp tiles per resident warp)
 		static const long long gate = [] { const char* e = getenv("RT_B200_ORDER_GATE"); const int v = e ? atoi(e) : 0; return (long long)(v > 0 ? v : (1 << 20)); }();
 		if ((long long)p.grid_x * n_strips * rt::kSignalsPerTile >= gate * resident_warps) return RT_OK;
 		constexpr int kSlots = DeviceState::CellSchedule::kSlots, kMaxCells = DeviceState::CellSchedule::kMaxCells;
-		const int cells_x = (p.grid_x + (1 << rt::kCellWLog2) - 1) >> rt::kCellWLog2;
+		// small shares want fine cells (4 tile columns: an eighth of the 4K frame 0.148 -> 0.142 ms, a quarter 0.238 -> 0.229),
+		// large ones lose a little locality to them (a half 0.419 -> 0.430): 8 columns from 16 warp tiles per warp on
+		const int w_log2 = ((long long)p.grid_x * n_strips * rt::kSignalsPerTile < 16ll * resident_warps) ? 2 : 3;
+		const int cells_x = (p.grid_x + (1 << w_log2) - 1) >> w_log2;
 		if (cells_x < 2 || cells_x > kMaxCells / 2) return RT_OK;
 		int h = 0;
 		while ((((n_strips + (1 << h) - 1) >> h) * cells_x) > kMaxCells) ++h;
@@ -690,7 +693,7 @@ namespace
 			cs.row_begin = p.row_begin; cs.row_end = p.row_end; cs.stream = stream;
 			cs.cells_x = cells_x; cs.cell_h_log2 = h; cs.n_cells = n_cells;
 		}
-		p.cells_x = cells_x; p.cell_h_log2 = h; p.cells_x_magic = (uint32_t)((1ull << 32) / (unsigned)cells_x) + 1u;
+		p.cells_x = cells_x; p.cell_w_log2 = w_log2; p.cell_h_log2 = h; p.cells_x_magic = (uint32_t)((1ull << 32) / (unsigned)cells_x) + 1u;
 		// newest finished read-back -> a new order table
 		int fresh = -1;
 		for (int i = 0; i < kSlots; ++i)
@@ -707,12 +710,12 @@ namespace
 			if (!cs.order_used[oslot] || cudaEventQuery(cs.ev_order[oslot]) == cudaSuccess)
 			{
 				const unsigned int* cost = cs.h_cost + (size_t)fresh * kMaxCells;
-				uint8_t* order = cs.h_order + (size_t)oslot * kMaxCells;
-				int idx[kMaxCells];
+				uint16_t* order = cs.h_order + (size_t)oslot * kMaxCells;
+				static thread_local int idx[kMaxCells];
 				for (int c = 0; c < n_cells; ++c) idx[c] = c;
 				std::stable_sort(idx, idx + n_cells, [&](int a, int b) { return cost[a] > cost[b]; });
-				for (int c = 0; c < n_cells; ++c) order[c] = (uint8_t)idx[c];
-				RT_CUDA(ctx, cudaMemcpyAsync(cs.d_order + (size_t)oslot * kMaxCells, order, (size_t)n_cells, cudaMemcpyHostToDevice, stream));
+				for (int c = 0; c < n_cells; ++c) order[c] = (uint16_t)idx[c];
+				RT_CUDA(ctx, cudaMemcpyAsync(cs.d_order + (size_t)oslot * kMaxCells, order, sizeof(uint16_t) * (size_t)n_cells, cudaMemcpyHostToDevice, stream));
 				RT_CUDA(ctx, cudaEventRecord(cs.ev_order[oslot], stream));
 				cs.order_used[oslot] = true; cs.order_cursor++; cs.orders_made++;
 				cs.current = cs.d_order + (size_t)oslot * kMaxCells;
@@ -722,7 +725,7 @@ namespace
 		if (cs.current)
 		{
 			p.cell_order = cs.current;
-			p.total_items = (n_cells << (rt::kCellWLog2 + h)) * rt::kSignalsPerTile;
+			p.total_items = (n_cells << (w_log2 + h)) * rt::kSignalsPerTile;
 			p.first_tiles = 0;                                // the measured order replaces the guessed rectangle
 		}
 		// Measuring costs three stream operations around the kernel (clear, read back, and the upload of the order it

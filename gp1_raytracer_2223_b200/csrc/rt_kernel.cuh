@@ -87,12 +87,12 @@ namespace rt
 		int32_t first_tiles;             // (first_x1 - first_x0) * (first_k1 - first_k0)
 		uint32_t first_w_magic;          // floor(2^32 / (first_x1 - first_x0)) + 1
 		uint32_t rest_w_magic;           // floor(2^32 / (grid_x - (first_x1 - first_x0))) + 1 (unused when the rectangle spans the width)
-		// ... or cell by cell: the tile grid is cut into cells of 8 columns x (1 << cell_h_log2) strips, and the queue
+		// ... or cell by cell: the tile grid is cut into cells of (1 << cell_w_log2) columns x (1 << cell_h_log2) strips, and the queue
 		// walks them in the order of cell_order (most expensive cell of the previous launch first).  Cells on the right
 		// and bottom edge are padded: queue positions that fall outside the grid render nothing.
-		const uint8_t* cell_order;       // cell_order[r] = r-th cell to render (NULL = off)
+		const uint16_t* cell_order;      // cell_order[r] = r-th cell to render (NULL = off)
 		unsigned int* cell_cost;         // += SM clocks / 16 of every warp tile, per cell (NULL = off)
-		int32_t cells_x, cell_h_log2;
+		int32_t cells_x, cell_w_log2, cell_h_log2;
 		uint32_t cells_x_magic;          // floor(2^32 / cells_x) + 1
 		int32_t total_items;             // queue positions of the launch when cells pad it (0 = grid_x * n_strips * kSignalsPerTile)
 	};
@@ -954,7 +954,6 @@ namespace rt
 	}
 
 	struct TileCoords { int k, px, py, local_y, cell; bool valid; };
-	constexpr int kCellWLog2 = 3;        // cells are 8 tile columns wide
 	__device__ __forceinline__ TileCoords decode_work_item(const FrameParams& p, int item, int lane)
 	{
 		TileCoords c;
@@ -962,12 +961,12 @@ namespace rt
 		int bx;
 		if (p.cell_order)
 		{
-			const int shift = kCellWLog2 + p.cell_h_log2;
+			const int shift = p.cell_w_log2 + p.cell_h_log2;
 			const unsigned int rank = tile >> shift, within = tile & ((1u << shift) - 1u);
 			const unsigned int cell = __ldg(p.cell_order + rank);
 			const int cy = (int)__umulhi(cell, p.cells_x_magic), cx = (int)cell - cy * p.cells_x;
-			c.k = (cy << p.cell_h_log2) + (int)(within >> kCellWLog2);
-			bx = (cx << kCellWLog2) + (int)(within & ((1u << kCellWLog2) - 1u));
+			c.k = (cy << p.cell_h_log2) + (int)(within >> p.cell_w_log2);
+			bx = (cx << p.cell_w_log2) + (int)(within & ((1u << p.cell_w_log2) - 1u));
 			if (bx >= p.grid_x || c.k >= p.n_strips) { bx = p.grid_x; c.k = p.n_strips; }      // padding: lands outside the frame below
 		}
 		else if (p.first_tiles == 0)
@@ -1016,7 +1015,7 @@ namespace rt
 		c.local_y = wy * kTileH + (lane >> 3);
 		c.py = p.row_begin + (c.k * p.strip_step + p.strip_first) * kBlockH + c.local_y;
 		c.valid = (c.px < p.width) && (c.py < p.row_end) && (bx < p.grid_x) && (c.k < p.n_strips);
-		c.cell = (c.k >> p.cell_h_log2) * p.cells_x + (bx >> kCellWLog2);
+		c.cell = (c.k >> p.cell_h_log2) * p.cells_x + (bx >> p.cell_w_log2);
 		return c;
 	}
 
