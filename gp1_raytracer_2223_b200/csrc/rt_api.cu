@@ -102,6 +102,8 @@ namespace
 			static constexpr int kSlots = 4, kMaxCells = 2048;
 			// the launch geometry the costs belong to; anything else starts over
 			int n_strips = 0, grid_x = 0, strip_first = -1, strip_step = -1, row_begin = -1, row_end = -1, cells_x = 0, cell_h_log2 = 0, n_cells = 0;
+			int mesh_path = -1, lighting_mode = -1, shadows = -1;
+			unsigned long long measured_scene = 0;          // rt_context::scene_version at the last measurement
 			cudaStream_t stream = nullptr;
 			unsigned int* d_cost = nullptr;                 // kSlots x kMaxCells, one slice per launch in flight
 			unsigned int* h_cost = nullptr;                 // pinned read-back, same shape
@@ -143,6 +145,7 @@ struct rt_context
 	rt_timing timing{};
 	int32_t last_width = 0, last_height = 0;
 
+	unsigned long long scene_version = 1; // bumped by every scene copy / device-side transform: what the measured tile costs belong to
 	int32_t* h_build_status = nullptr;  // pinned, one word per mesh: status of the last device-side BVH build (device 0)
 
 	void* registered_host = nullptr;    // host surface we pinned ourselves
@@ -546,9 +549,10 @@ namespace
 	int flush_uploads(rt_context* ctx)
 	{
 		int rc = RT_OK;
-		if (ctx->static_dirty) { if ((rc = push_static(ctx)) != RT_OK) return rc; ctx->static_dirty = false; }
+		if (ctx->static_dirty) { if ((rc = push_static(ctx)) != RT_OK) return rc; ctx->static_dirty = false; ctx->scene_version++; }
 		bool pushed = false;
-		if (ctx->mesh_dirty) { if ((rc = push_meshes(ctx)) != RT_OK) return rc; ctx->mesh_dirty = false; pushed = true; }
+		if (ctx->mesh_dirty) { if ((rc = push_meshes(ctx)) != RT_OK) return rc; ctx->mesh_dirty = false; pushed = true; ctx->scene_version++; }
+		for (const HostMesh& hm : ctx->meshes) if (hm.transform_dirty || !hm.pending_builds.empty()) { ctx->scene_version++; break; }
 		return run_device_transforms(ctx, pushed);
 	}
 
@@ -659,7 +663,7 @@ namespace
 
 	// Before a persistent launch.  Sets p.cell_* (order and / or cost slice); *cost_slot = the slice to read back after
 	// the launch, or -1.
-	int prepare_cell_order(rt_context* ctx, DeviceState& d, rt::FrameParams& p, cudaStream_t stream, int n_strips, int resident_warps, int* cost_slot)
+	int prepare_cell_order(rt_context* ctx, DeviceState& d, rt::FrameParams& p, cudaStream_t stream, int n_strips, int resident_warps, int mesh_path, int* cost_slot)
 	{
 		static const bool off = getenv("RT_B200_PLAIN_ORDER") != nullptr || getenv("RT_B200_NO_COST_FEEDBACK") != nullptr;
 		*cost_slot = -1;
@@ -683,7 +687,8 @@ namespace
 		if (rc != RT_OK) return rc;
 		DeviceState::CellSchedule& cs = d.cells;
 		if (cs.n_strips != n_strips || cs.grid_x != p.grid_x || cs.strip_first != p.strip_first || cs.strip_step != p.strip_step ||
-		    cs.row_begin != p.row_begin || cs.row_end != p.row_end || cs.stream != stream)
+		    cs.row_begin != p.row_begin || cs.row_end != p.row_end || cs.stream != stream ||
+		    cs.mesh_path != mesh_path || cs.lighting_mode != p.lighting_mode || cs.shadows != p.shadows)
 		{
 			// tables and counters of the old stream may still be in use there: the new stream queues up behind it
 			if (cs.stream && cs.stream != stream) RT_CUDA(ctx, cudaStreamWaitEvent(stream, cs.ev_last, 0));
@@ -691,6 +696,7 @@ namespace
 			for (bool& b : cs.cost_pending) b = false;           // late read-backs of the old geometry are ignored
 			cs.n_strips = n_strips; cs.grid_x = p.grid_x; cs.strip_first = p.strip_first; cs.strip_step = p.strip_step;
 			cs.row_begin = p.row_begin; cs.row_end = p.row_end; cs.stream = stream;
+			cs.mesh_path = mesh_path; cs.lighting_mode = p.lighting_mode; cs.shadows = p.shadows;
 			cs.cells_x = cells_x; cs.cell_h_log2 = h; cs.n_cells = n_cells;
 		}
 		p.cells_x = cells_x; p.cell_w_log2 = w_log2; p.cell_h_log2 = h; p.cells_x_magic = (uint32_t)((1ull << 32) / (unsigned)cells_x) + 1u;
@@ -735,11 +741,13 @@ namespace
 		const int cslot = cs.cost_cursor % kSlots;
 		bool in_flight = false;
 		for (bool b : cs.cost_pending) in_flight = in_flight || b;
-		const bool measure = !in_flight && (cs.orders_made < 2 || cs.launches_since_measured >= 256);
+		// ... or every 16th while the scene keeps changing (uploads, new poses)
+		const bool measure = !in_flight && (cs.orders_made < 2 || cs.launches_since_measured >= 256 ||
+		                                    (cs.measured_scene != ctx->scene_version && cs.launches_since_measured >= 16));
 		cs.launches_since_measured++;
 		if (measure && !cs.cost_pending[cslot])
 		{
-			cs.launches_since_measured = 0;
+			cs.launches_since_measured = 0; cs.measured_scene = ctx->scene_version;
 			RT_CUDA(ctx, cudaMemsetAsync(cs.d_cost + (size_t)cslot * kMaxCells, 0, sizeof(unsigned int) * (size_t)n_cells, stream));
 			p.cell_cost = cs.d_cost + (size_t)cslot * kMaxCells;
 			*cost_slot = cslot;
@@ -802,7 +810,7 @@ namespace
 			const KernelFn fn = persistent;
 			tiles_to_render_first(ctx, p, n_strips, wave * (rt::kPersistentThreads / 32));
 			int cost_slot = -1;
-			const int prc = prepare_cell_order(ctx, d, p, stream, n_strips, wave * (rt::kPersistentThreads / 32), &cost_slot);
+			const int prc = prepare_cell_order(ctx, d, p, stream, n_strips, wave * (rt::kPersistentThreads / 32), path, &cost_slot);
 			if (prc != RT_OK) return prc;
 			p.queue = d.d_queues + 2 * (d.queue_cursor++ % kQueueRing);
 			const long long ctas_of_work = (tiles * rt::kSignalsPerTile + rt::kPersistentThreads / 32 - 1) / (rt::kPersistentThreads / 32);
