@@ -10,7 +10,7 @@ r.ctx.set_kernel_variant(3)
 frame = torch.empty((2160, 3840), dtype=torch.int32, device="cuda")
 stream = torch.cuda.current_stream().cuda_stream
 for world in (1, 8):
-    for rep in range(3):
+    for rep in range(6):
         r.render_strips_device(0, world, frame.data_ptr(), stream)
     torch.cuda.synchronize()
 r.close()
