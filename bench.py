@@ -48,6 +48,7 @@ WIDTH, HEIGHT = 3840, 2160
 RAYS_PER_FRAME = WIDTH * HEIGHT * 4          # 1 primary + 3 shadow rays per pixel (every pixel hits; re-checked below)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_render")
 L2_FLUSH_BYTES = 256 << 20
+KERNEL_NOTE = "persistent warps (one pixel per thread, 8x4 warp tiles pulled off a device queue; 128-thread CTAs, 9 per SM); rt_render overlaps the present copy with rendering (progressive present)"
 
 
 def parse_args():
@@ -169,19 +170,45 @@ def bounded_reference_run(steps: int, warmup: int, budget_s: float):
     return res, frames, kind
 
 
+def run_reference_scene(scene: str, width: int, height: int, frames: int, warmup: int, extra=()):
+    """Any reference scene through the compiled reference (oracle/_ref/ref_render), all host cores."""
+    args = [REF_BIN, "--scene", scene, "--width", str(width), "--height", str(height), "--mode", "3", "--shadows", "1",
+            "--frames", str(frames), "--warmup", str(warmup), "--threads", str(host_cores())] + list(extra)
+    env = {k: v for k, v in os.environ.items() if k != "OMP_NUM_THREADS"}
+    out = subprocess.run(args, check=True, capture_output=True, text=True, env=env).stdout
+    return json.loads(out.strip().splitlines()[-1])
+
+
+DATA = "reference scene fixture tests/golden/bunny_4k.rtsc (dumped from the reference's Scene_W4_BunnyScene::Initialize; deterministic, no RNG)"
+
+
+def bench_config():
+    """The workload both arms run, word for word the same dict in both lines (the driver compares them)."""
+    return {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "rays_per_frame": RAYS_PER_FRAME, "triangles": 292, "lights": 3,
+            "lighting_mode": "Combined", "shadows": True, "mesh_path": "BVH (what the reference ships, source/Utils.h:296-297)",
+            "l2": f"GPU arm: {L2_FLUSH_BYTES >> 20} MiB memset between timed steps (outside the event pairs); the CPU arm has no device cache to flush"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    res, frames, kind = bounded_reference_run(args.steps, args.warmup, budget_s=150.0)
+    warmup = max(args.warmup, 3)              # same warm-up rule as the GPU arm
+    runner = run_reference if reference_available() else run_port
+    kind = "reference" if reference_available() else "port"
+    est_ms = runner(1, 1)["ms_median"]      # 1 warm-up + 1 timed frame: how long is a frame on this box?
+    frames = max(1, min(args.steps, int(150e3 / max(est_ms, 1e-3)) - warmup))
+    res = runner(frames, warmup)
     ms = statistics.mean(res["ms"])
     value = RAYS_PER_FRAME / (ms * 1e-3) / 1e6
     sample = f"{frames} full {WIDTH}x{HEIGHT} frames of Renderer::Render" + ("" if frames == args.steps else f" (of {args.steps} requested steps; bounded to ~150 s)")
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": frames, "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32", "data": "reference scene (Scene_W4_BunnyScene, deterministic)",
-        "config": {"workload": WORKLOAD, "rays_per_frame": RAYS_PER_FRAME, "path": res.get("path")},
+        "steps": frames, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": DATA,
+        "config": bench_config(),
+        "step_ms": {"min": min(res["ms"]), "median": statistics.median(res["ms"]), "max": max(res["ms"])},
+        "reference_path": res.get("path"),
         "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": res["threads"], "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,12 +246,16 @@ def main():
             sys.exit(f"--gpus {args.gpus} needs a torchrun launch with {args.gpus} ranks (one process per GPU)")
         sys.exit(f"--gpus {args.gpus} does not match WORLD_SIZE {world}")
     torch.cuda.set_device(local_rank)
+    host_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # host-side barriers (no kernel spinning on anybody's GPU) for the legs rank 0 runs alone on ALL devices
+        host_group = dist.new_group(backend="gloo")
 
     from gp1_raytracer_2223_b200 import Renderer, bands, build, load_rtsc
     from gp1_raytracer_2223_b200.flops import algorithmic_flops, rays
-    build.ensure()
+    build.ensure()                              # rebuilds when the library is not what the sources in the tree compile to
+    library = build.provenance()
 
     scene = load_rtsc(FIXTURE)
     mesh = scene.meshes[0]
@@ -293,6 +324,8 @@ def main():
             surface.unlink()                        # the mappings keep it alive; nothing is left behind
         if everybody_opened:
             shared_surface = surface.frame
+            # every rank pins ITS mapping of the surface for direct copies; the mapping outlives the context (rt_b200.h)
+            r.register_surface(surface.ptr, surface.surface_bytes)
         else:
             present_mode, surface = "gather", None
     band = frame_dev = gathered = None
@@ -329,6 +362,40 @@ def main():
         if rank == 0:
             frame_dev = torch.empty((HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
             gathered = torch.empty((world,) + tuple(band.shape), dtype=torch.int32, device="cuda")
+
+    import lzma
+    golden = None
+    if rank == 0:
+        with open(os.path.join(ROOT, "tests", "golden", "bunny_4k.frame.xz"), "rb") as f:
+            planar = np.frombuffer(lzma.decompress(f.read()), dtype=np.uint8).reshape(3, HEIGHT, WIDTH).astype(np.uint32)
+        golden = (planar[0] << 16) | (planar[1] << 8) | planar[2]
+    POISON = 0xDEADBEEF
+
+    def frame_check_of(produced):
+        return {"differing_pixels_vs_reference_frame": int((produced != golden).sum()), "pixels": WIDTH * HEIGHT,
+                "poisoned_pixels_left": int((produced == POISON).sum())}
+
+    def poison_device_frame():
+        """Before a device-timed leg: the frame buffer that leg fills holds a poison pattern, so the check after the leg
+        cannot pass on what an earlier leg left there."""
+        barrier()
+        if rank == 0:
+            if frame_dev is not None:
+                frame_dev.fill_(POISON - (1 << 32))
+            else:
+                r.clear_frame(POISON)
+        barrier()
+
+    def device_frame_check():
+        """After a device-timed leg: the frame that leg left in rank 0's HBM, against the frame the reference rendered."""
+        barrier()
+        if rank != 0:
+            return None
+        if frame_dev is not None:
+            produced = frame_dev.cpu().numpy().view(np.uint32)
+        else:
+            produced = r.download()               # rank 0's exported frame (rt_download_frame)
+        return frame_check_of(produced)
 
     def render_step():
         """This rank's kernel launch of one frame."""
@@ -401,6 +468,7 @@ def main():
 
     # ---- device-timed region ---------------------------------------------------------------------
     def timed_device_region(sampler):
+        poison_device_frame()
         for _ in range(max(args.warmup, 3)):
             device_step()
         barrier()
@@ -424,42 +492,87 @@ def main():
         if world > 1:
             dist.all_reduce(step_ms, op=dist.ReduceOp.MAX)     # per step, the slowest rank
             dist.all_reduce(kern_ms, op=dist.ReduceOp.MAX)
-        return float(step_ms.sum()), float(kern_ms.mean())
+        steps_sorted = sorted(float(x) for x in step_ms)
+        stats = {"min": steps_sorted[0], "median": steps_sorted[len(steps_sorted) // 2], "max": steps_sorted[-1]}
+        return float(step_ms.sum()), float(kern_ms.mean()), stats, device_frame_check()
 
     sampler = ClockSampler(local_rank)
     r.ctx.set_mesh_path(PATHS["slab_linear"])
-    slab_total_ms, slab_kernel_ms = timed_device_region(ClockSampler(local_rank))
+    slab_total_ms, slab_kernel_ms, slab_stats, slab_check = timed_device_region(ClockSampler(local_rank))
     r.ctx.set_mesh_path(0)                                     # default: BVH, the fixture carries the reference's nodes
-    total_ms, kernel_ms = timed_device_region(sampler)
+    total_ms, kernel_ms, step_stats, device_check = timed_device_region(sampler)
 
     # ---- end-to-end region -----------------------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        for _ in range(3):
+        if rank == 0:                             # the host surface starts poisoned, like the device frames
+            (shared_surface if shared_surface is not None else host_frame.numpy().view(np.uint32))[...] = POISON
+        barrier()
+        for _ in range(max(args.warmup, 3)):
             e2e_step()
         e2e_parts[:] = [0.0] * 6                  # the first call pins the surface: not part of the per-step picture
         barrier()
         sampler2 = ClockSampler(local_rank)
+        per_step = []
         with sampler2:
             t0 = time.perf_counter()
             for _ in range(args.steps):
+                ta = time.perf_counter()
                 e2e_step()
+                per_step.append((time.perf_counter() - ta) * 1e3)
             barrier()
             t1 = time.perf_counter()
         sampler.merge(sampler2)
         e2e_s = torch.tensor([t1 - t0], dtype=torch.float64, device="cuda")
+        per_step_t = torch.tensor(per_step, dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+            dist.all_reduce(per_step_t, op=dist.ReduceOp.MAX)
         e2e_ms = float(e2e_s) * 1e3 / args.steps
+        per_step = sorted(float(x) for x in per_step_t)
         h2d = int(mesh.positions.nbytes + mesh.indices.nbytes + mesh.normals.nbytes) * world
         e2e = {"value": RAYS_PER_FRAME / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": WIDTH * HEIGHT * 4}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
+               "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
+               "timing": "host wall clock around the blocking C-ABI calls of every step (upload + render into host memory), max over ranks"}
         if present_mode == "direct" and e2e_parts[5] > 0:
             # where a step's time goes, slowest rank per component, averaged over the timed steps
             parts = torch.tensor([x / e2e_parts[5] * 1e3 for x in e2e_parts[:5]], dtype=torch.float64, device="cuda")
             dist.all_reduce(parts, op=dist.ReduceOp.MAX)
             e2e["breakdown_ms_max_over_ranks"] = dict(zip(["host_upload_mesh", "host_render_strips_to_host_call", "host_wait_for_all_ranks",
                                                            "device_kernel", "device_kernel_and_copies"], [float(x) for x in parts]))
+
+    # ---- in-process leg (N > 1): ONE context over all N devices on rank 0's process - the path under the reference's
+    # `pRenderer->Render(pScene)` (source/main.cpp:91) when the drop-in is given RT_B200_DEVICES.  The other ranks wait
+    # in a host-side (gloo) barrier with idle GPUs.
+    in_process = None
+    if world > 1 and not args.no_e2e:
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                rr = Renderer(WIDTH, HEIGHT, device_ids=list(range(world)))
+                rr.SetScene(scene)
+                surface_ip = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
+                surface_ip.numpy().view(np.uint32)[...] = POISON
+                for _ in range(max(args.warmup, 3)):
+                    rr.ctx.upload_mesh(0, mesh)
+                    rr.render_host_ptr(surface_ip.data_ptr(), WIDTH * 4)
+                ms_ip, k_ip = [], []
+                for _ in range(args.steps):
+                    ta = time.perf_counter()
+                    rr.ctx.upload_mesh(0, mesh)
+                    tm = rr.render_host_ptr(surface_ip.data_ptr(), WIDTH * 4)
+                    ms_ip.append((time.perf_counter() - ta) * 1e3)
+                    k_ip.append(tm["kernel_ms"])
+                in_process = {"what": f"rt_create over devices 0..{world - 1} in one process, rt_upload_mesh + rt_render into pinned host memory per step (direct present: every device copies its own strips)",
+                              "ms_per_step": statistics.mean(ms_ip), "step_ms": {"min": min(ms_ip), "median": statistics.median(ms_ip), "max": max(ms_ip)},
+                              "Mrays_per_s": RAYS_PER_FRAME / (statistics.mean(ms_ip) * 1e-3) / 1e6, "kernel_ms_max_over_devices": statistics.mean(k_ip),
+                              "devices": rr.ctx.device_count, "frame_check": frame_check_of(surface_ip.numpy().view(np.uint32))}
+                rr.close()
+            except Exception as exc:                   # noqa: BLE001  (reported; the headline legs are already measured)
+                in_process = {"error": str(exc)}
+        dist.barrier(group=host_group)
 
     if rank != 0:
         if world > 1:
@@ -469,16 +582,9 @@ def main():
             dist.destroy_process_group()
         return 0
 
-    # ---- the frame the timed path produced, against the frame the reference rendered ----------------
-    import lzma
-    with open(os.path.join(ROOT, "tests", "golden", "bunny_4k.frame.xz"), "rb") as f:
-        planar = np.frombuffer(lzma.decompress(f.read()), dtype=np.uint8).reshape(3, HEIGHT, WIDTH).astype(np.uint32)
-    golden = (planar[0] << 16) | (planar[1] << 8) | planar[2]
+    # ---- the frame the end-to-end leg produced, against the frame the reference rendered ------------
     produced = (shared_surface if shared_surface is not None else host_frame.numpy().view(np.uint32)) if e2e is not None else None
-    frame_check = None
-    if produced is not None:
-        differing = int((produced != golden).sum())
-        frame_check = {"differing_pixels_vs_reference_frame": differing, "pixels": WIDTH * HEIGHT}
+    frame_check = frame_check_of(produced) if produced is not None else None
 
     # ---- roofline (rank 0's GPU) -----------------------------------------------------------------
     peak_nofma = r.ctx.measure_fp32_peak(False)
@@ -498,6 +604,8 @@ def main():
         return {
             "bound": "fp32", "achieved": achieved, "peak": peak_nofma["tflops"], "unit": "TFLOP/s",
             "frac": achieved / peak_nofma["tflops"], "traffic": traffic if pname == "bvh" else None,
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel, read from profiles/roofline_traffic.json (NOT measured in this run)" if pname == "bvh" else None,
+            "frac_definition": "EXECUTED work: SURVEY.md 8(d) FLOP weights x the events THIS mesh body executes (counters build of the same kernel) / kernel time / peak",
             "peak_source": "measured live on this GPU (rt_measure_fp32_peak): FMUL+FADD issue peak; the reference's arithmetic is unfused, so FFMA is not available to this path",
             "peak_fma": peak_fma["tflops"], "frac_of_fma_peak": achieved / peak_fma["tflops"],
             "algorithmic_gflop_per_frame": flop_per_frame[pname] / 1e9,
@@ -511,8 +619,13 @@ def main():
     # the same kernel time against the north-star algorithm's FLOP count (what a brute-force kernel would have to do)
     roofline["survey_algorithmic_gflop_per_frame"] = flop_per_frame["slab_linear"] / 1e9
     roofline["survey_algorithmic_tflops_equivalent"] = flop_per_frame["slab_linear"] / world / (kernel_ms * 1e-3) / 1e12
+    # SURVEY.md 8(d) read literally: the brute-force (slab + every triangle) FLOP count over THIS kernel's time.  The BVH
+    # body skips most of that work, so this can exceed 1; `frac` above counts only what the kernel executes, and
+    # north_star_slab_linear.roofline.frac is the kernel that really runs 8(d)'s algorithm.
+    roofline["frac_survey_8d"] = roofline["survey_algorithmic_tflops_equivalent"] / peak_nofma["tflops"]
     slab_ms_per_step = slab_total_ms / args.steps
     north_star = {"value": RAYS_PER_FRAME / (slab_ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": slab_ms_per_step,
+                  "step_ms": slab_stats, "frame_check_device_leg": slab_check,
                   "roofline": roofline_of("slab_linear", slab_kernel_ms, "rt::render_kernel_persistent<Combined, shadows, slab + linear>")}
 
     # ---- CPU baseline (rank 0, N = 1 only) -------------------------------------------------------
@@ -531,7 +644,11 @@ def main():
         other = {}
         for label, fixture, mode_shadows in (("Scene_W1 640x480 no shadows", "w1_640", (3, False)), ("Scene_W3 640x480", "w3_640", (3, True)),
                                              ("Scene_W4_ReferenceScene 640x480", "w4ref_640", (3, True)), ("Scene_W4_BunnyScene 640x480", "bunny_640", (3, True)),
-                                             ("Scene_W4_OptionalScene 320x240 (3082 triangles)", "optional_320", (3, True))):
+                                             ("Scene_W4_OptionalScene 320x240 (3082 triangles)", "optional_320", (3, True)),
+                                             ("Scene_W4_OptionalScene 640x480 (3082 triangles)", "optional_640", (3, True)),
+                                             ("Scene_W4_OptionalScene 3840x2160 (3082 triangles)", "optional_4k", (3, True)),
+                                             ("Scene_W2 3840x2160", "w2_4k", (3, True)), ("Scene_W3 3840x2160", "w3_4k", (3, True)),
+                                             ("Scene_W4_ReferenceScene 3840x2160", "w4ref_4k", (3, True))):
             sc = load_rtsc(os.path.join(ROOT, "tests", "golden", fixture + ".rtsc"))
             rr = Renderer(sc.width, sc.height, device_ids=[local_rank])
             if not mode_shadows[1]:
@@ -552,6 +669,18 @@ def main():
             other[label] = {"kernel_ms": float(np.mean(k_ms)), "e2e_ms": e_ms, "rays_per_frame": n_rays,
                             "Mrays_per_s_kernel": n_rays / (float(np.mean(k_ms)) * 1e-3) / 1e6,
                             "differing_pixels_vs_reference_frame": int((host.numpy().view(np.uint32) != want).sum())}
+            if fixture in ("optional_640", "optional_4k"):
+                # N3 at the BASELINE sizes: roofline of the executed work and the reference's own CPU loop beside it
+                flop = algorithmic_flops(rr.count_frame(mesh_path=2), 3)
+                ach = flop / (float(np.mean(k_ms)) * 1e-3) / 1e12
+                other[label]["roofline"] = {"bound": "fp32", "achieved": ach, "peak": peak_nofma["tflops"], "unit": "TFLOP/s", "frac": ach / peak_nofma["tflops"],
+                                            "algorithmic_gflop_per_frame": flop / 1e9, "frac_definition": "executed work of the BVH body, as for the headline"}
+                if not args.no_cpu_baseline and reference_available():
+                    n_frames = 3 if fixture == "optional_640" else 1
+                    ref = run_reference_scene("W4_Optional", sc.width, sc.height, n_frames, 0)
+                    ref_ms = statistics.mean(ref["ms"])
+                    other[label]["cpu_baseline"] = {"value": n_rays / (ref_ms * 1e-3) / 1e6, "unit": "Mrays/s", "cores": ref["threads"], "kind": "reference",
+                                                    "ms_per_frame": ref_ms, "sample": f"{n_frames} full {sc.width}x{sc.height} frame(s) of Renderer::Render, no warm-up"}
             rr.close()
 
         # N1: untransformed mesh uploaded once, 64 bytes of transform per frame, vertices / normals
@@ -617,24 +746,46 @@ def main():
         except Exception as exc:                       # noqa: BLE001
             other["device-side UpdateTransforms + BuildBVH"] = {"error": str(exc)}
 
+        # ... and the reference's own animated loop on this box's host cores: Scene::Update (RotateY + UpdateTransforms +
+        # BuildBVH on the main thread, source/Scene.cpp:431-437, source/DataTypes.h:210-236) + Renderer::Render per frame
+        if not args.no_cpu_baseline and reference_available():
+            try:
+                ref = run_reference_scene("W4_Bunny", WIDTH, HEIGHT, 10, 1, extra=["--animate", "0.016"])
+                upd, ren = statistics.mean(ref["update_ms"]), statistics.mean(ref["ms"])
+                other["reference animated loop, bunny 3840x2160: Scene::Update + Render per frame"] = {
+                    "update_ms": upd, "render_ms": ren, "frame_ms": upd + ren, "cores": ref["threads"], "kind": "reference",
+                    "sample": "10 frames, timer advanced by 16 ms per frame (a new mesh yaw every frame), 1 warm-up"}
+                key = "device-side UpdateTransforms + BuildBVH, bunny 3840x2160, new pose every frame, BVH body"
+                if key in other and "e2e_ms" in other[key]:
+                    other[key]["vs_reference_animated_loop"] = (upd + ren) / other[key]["e2e_ms"]
+            except Exception as exc:                   # noqa: BLE001
+                other["reference animated loop"] = {"error": str(exc)}
+
     ms_per_step = total_ms / args.steps
+    exchange = ("single GPU" if world == 1 else ("peer stores into rank 0's frame over NVLink (fused gather), completion by peer signal word + stream wait" if signals else
+                ("peer stores into rank 0's frame over NVLink (fused gather) + NCCL barrier" if fused else "NCCL gather to rank 0 + unstripe")))
     line = {
         "metric": "Mrays/s", "value": RAYS_PER_FRAME / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "reference scene fixture tests/golden/bunny_4k.rtsc (dumped from the reference's Scene_W4_BunnyScene::Initialize; deterministic, no RNG)",
-        "config": {"workload": WORKLOAD, "width": WIDTH, "height": HEIGHT, "rays_per_frame": RAYS_PER_FRAME,
-                   "triangles": int(mesh.triangle_count), "lights": 3, "partition": f"{bands.STRIP_ROWS}-row strips round-robin over {world} rank(s); " + ("single GPU" if world == 1 else ("peer stores into rank 0's frame over NVLink (fused gather), completion by peer signal word + stream wait" if signals else ("peer stores into rank 0's frame over NVLink (fused gather) + NCCL barrier" if fused else "NCCL gather to rank 0 + unstripe"))),
-                   "l2": f"{L2_FLUSH_BYTES >> 20} MiB memset between timed steps (outside the event pairs)"},
+        "data": DATA,
+        "config": bench_config(),
+        "step_ms": step_stats,
+        "partition": f"{bands.STRIP_ROWS}-row strips round-robin over {world} rank(s); " + exchange,
+        "value_definition": "sum over the timed steps of (max over ranks of that step's CUDA-event time: kernel launch .. frame complete in rank 0's HBM)" +
+                            ("" if world == 1 else "; ranks are NOT re-synchronised between steps (non-root ranks only signal, rank 0 waits for all signals of step k), so this is the frame-throughput of the free-running pipeline; the frame latency with back-pressure on every rank is the e2e leg"),
         "clocks": sampler.summary(),
         "e2e": e2e,
         "e2e_present": {"single": "one GPU: progressive present (copy follows the kernel band by band)",
                         "direct": "every rank copies its own strips into the shared host surface over its own PCIe link (rt_render_strips_to_host), band by band behind its kernel; completion by one flag word per rank in the same mapping; no peer traffic and no collective on this leg",
                         "gather": "strips stored into GPU 0's frame over NVLink, GPU 0 presents band by band (one PCIe link)"}[present_mode],
         "frame_check": frame_check,
+        "frame_check_device_leg": device_check,
+        "in_process_multi_device": in_process,
         "gpu_launches": args.steps * (world + ((world - 1) if signals else (0 if fused or world == 1 else 1))),
+        "library": library,
         "mesh_path": "bvh (reference's shipped IntersectionTest_BVH over the reference's own nodes)",
-        "kernel_variant": "persistent warps (one pixel per thread, 8x4 warp tiles pulled off a device queue; 128-thread CTAs, 9 per SM); rt_render overlaps the present copy with rendering (progressive present)",
+        "kernel_variant": KERNEL_NOTE,
         "roofline": roofline,
         "north_star_slab_linear": north_star,
         "other_configs": other,

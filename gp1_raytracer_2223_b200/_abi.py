@@ -8,7 +8,7 @@ import numpy as np
 from .scene_file import BVH_NODE_DTYPE, Camera, FlatScene, Mesh
 
 RT_COUNTER_SLOTS = 40
-RT_B200_ABI_VERSION = 2
+RT_B200_ABI_VERSION = 3
 MESH_PATH_AUTO, MESH_PATH_SLAB_LINEAR, MESH_PATH_BVH = 0, 1, 2
 
 c_float_p = C.POINTER(C.c_float)

@@ -37,6 +37,9 @@ SYMBOLS = {
     "rt_render": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_void_p, C.c_int32]),
     "rt_render_device": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc)]),
     "rt_download_frame": (C.c_int, [_ctx, C.c_void_p, C.c_int32]),
+    "rt_clear_frame": (C.c_int, [_ctx, C.c_uint32]),
+    "rt_register_surface": (C.c_int, [_ctx, C.c_void_p, C.c_size_t]),
+    "rt_unregister_surface": (C.c_int, [_ctx, C.c_void_p]),
     "rt_render_rows_device": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p]),
     "rt_render_strips_device": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32, C.c_int32,

@@ -4,7 +4,8 @@
 // surface.  There is deliberately no host fallback: every entry point fails loudly when
 // CUDA is not there.
 #include "rt_kernel.cuh"
-#include "rt_kernel_x2.cuh"
+#include "rt_aux_kernels.cuh"
+#include "rt_pick.h"
 #include "rt_bvh_build.cuh"
 
 #include <cuda.h>
@@ -76,6 +77,8 @@ namespace
 		size_t mesh_capacity = 0;          // in float4
 		size_t triangle_offset = 0, node_offset = 0;   // in float4, inside d_mesh
 		cudaEvent_t ev_upload = nullptr;   // last scene copy on this device (pinned source may be reused after it)
+		cudaEvent_t ev_foreign = nullptr;  // last pixel-kernel launch on a caller-supplied stream: scene writes on `stream` wait for it
+		bool foreign_pending = false;
 		struct MeshSourceDevice
 		{
 			float* positions = nullptr; float* normals = nullptr; int32_t* indices = nullptr;
@@ -148,9 +151,10 @@ struct rt_context
 	unsigned long long scene_version = 1; // bumped by every scene copy / device-side transform: what the measured tile costs belong to
 	int32_t* h_build_status = nullptr;  // pinned, one word per mesh: status of the last device-side BVH build (device 0)
 
-	void* registered_host = nullptr;    // host surface we pinned ourselves
-	size_t registered_bytes = 0;
-	void* staging = nullptr;            // pinned bounce buffer when the surface cannot be pinned
+	// host surfaces the CALLER asked us to pin (rt_register_surface): the registration lives until
+	// rt_unregister_surface / rt_destroy, and the caller must keep the memory mapped that long
+	std::vector<std::pair<void*, size_t>> registered;
+	void* staging = nullptr;            // pinned bounce buffer for surfaces CUDA does not know as pinned
 	size_t staging_bytes = 0;
 };
 
@@ -176,37 +180,15 @@ namespace
 
 	inline float bits_as_float(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
 
-	using KernelFn = void (*)(const rt::SceneDevice, const rt::FrameParams);
+	// Bitwise comparison of an uploaded array with its slice of the pinned mirror: an upload that changes nothing (the
+	// drop-in re-sends the whole scene every frame) must not dirty the block, wait for copies or bump the scene version.
+	template <typename T>
+	inline bool same_bits(const T* mirror, const T* src, int n) { return n <= 0 || memcmp(mirror, src, sizeof(T) * (size_t)n) == 0; }
 
-	KernelFn pick_kernel(int mode, int shadows, bool bvh)
-	{
-#define RT_ROW(M) { { rt::render_kernel<M, 0, false, false>, rt::render_kernel<M, 1, false, false> }, { rt::render_kernel<M, 0, true, false>, rt::render_kernel<M, 1, true, false> } }
-		static const KernelFn table[4][2][2] = {
-			RT_ROW(RT_LIGHTING_OBSERVED_AREA), RT_ROW(RT_LIGHTING_RADIANCE), RT_ROW(RT_LIGHTING_BRDF), RT_ROW(RT_LIGHTING_COMBINED),
-		};
-#undef RT_ROW
-		return table[mode][bvh ? 1 : 0][shadows ? 1 : 0];
-	}
-
-	KernelFn pick_kernel_x2(int mode, int shadows, bool bvh)
-	{
-#define RT_ROW(M) { { rt::x2::render_kernel_x2<M, 0, false>, rt::x2::render_kernel_x2<M, 1, false> }, { rt::x2::render_kernel_x2<M, 0, true>, rt::x2::render_kernel_x2<M, 1, true> } }
-		static const KernelFn table[4][2][2] = {
-			RT_ROW(RT_LIGHTING_OBSERVED_AREA), RT_ROW(RT_LIGHTING_RADIANCE), RT_ROW(RT_LIGHTING_BRDF), RT_ROW(RT_LIGHTING_COMBINED),
-		};
-#undef RT_ROW
-		return table[mode][bvh ? 1 : 0][shadows ? 1 : 0];
-	}
-
-	KernelFn pick_kernel_persistent(int mode, int shadows, bool bvh)
-	{
-#define RT_ROW(M) { { rt::render_kernel_persistent<M, 0, false>, rt::render_kernel_persistent<M, 1, false> }, { rt::render_kernel_persistent<M, 0, true>, rt::render_kernel_persistent<M, 1, true> } }
-		static const KernelFn table[4][2][2] = {
-			RT_ROW(RT_LIGHTING_OBSERVED_AREA), RT_ROW(RT_LIGHTING_RADIANCE), RT_ROW(RT_LIGHTING_BRDF), RT_ROW(RT_LIGHTING_COMBINED),
-		};
-#undef RT_ROW
-		return table[mode][bvh ? 1 : 0][shadows ? 1 : 0];
-	}
+	using rt::KernelFn;
+	using rt::pick_kernel;
+	using rt::pick_kernel_x2;
+	using rt::pick_kernel_persistent;
 
 	// One wave of the persistent kernel: SMs x CTAs resident per SM (asked of the runtime once per kernel).
 	int persistent_ctas_per_sm(KernelFn fn)
@@ -267,6 +249,14 @@ namespace
 		p.lighting_mode = f->lighting_mode; p.shadows = f->shadows_enabled ? 1 : 0;
 		p.r_shift = f->r_shift; p.g_shift = f->g_shift; p.b_shift = f->b_shift; p.alpha_mask = f->alpha_mask;
 		return p;
+	}
+
+	// 32-bit pattern fill (driver memset through the runtime: cudaMemset2D would need a pitch; D32 is exact)
+	inline cudaError_t cuda_fill32(uint32_t* dst, uint32_t value, size_t count, cudaStream_t stream)
+	{
+		if ((value & 0xffu) * 0x01010101u == value) return cudaMemsetAsync(dst, (int)(value & 0xffu), count * sizeof(uint32_t), stream);
+		rt::fill32_kernel<<<(unsigned)std::min<size_t>((count + 255) / 256, 148 * 8), 256, 0, stream>>>(dst, value, count);
+		return cudaGetLastError();
 	}
 
 	// Byte offset of the signal word behind a frame of `pixels` pixels (same formula on every rank).
@@ -549,6 +539,20 @@ namespace
 	int flush_uploads(rt_context* ctx)
 	{
 		int rc = RT_OK;
+		bool writes = ctx->static_dirty || ctx->mesh_dirty;
+		for (const HostMesh& hm : ctx->meshes) writes = writes || hm.transform_dirty || hm.source_dirty || !hm.pending_builds.empty();
+		if (writes)
+		{
+			// A pixel kernel launched on a caller-supplied stream may still be reading d_static / d_mesh: every scene
+			// write below rides d.stream, so d.stream queues up behind that launch first (launch() recorded ev_foreign).
+			for (DeviceState& d : ctx->devs)
+			{
+				if (!d.foreign_pending) continue;
+				RT_CUDA(ctx, cudaSetDevice(d.device));
+				RT_CUDA(ctx, cudaStreamWaitEvent(d.stream, d.ev_foreign, 0));
+				d.foreign_pending = false;
+			}
+		}
 		if (ctx->static_dirty) { if ((rc = push_static(ctx)) != RT_OK) return rc; ctx->static_dirty = false; ctx->scene_version++; }
 		bool pushed = false;
 		if (ctx->mesh_dirty) { if ((rc = push_meshes(ctx)) != RT_OK) return rc; ctx->mesh_dirty = false; pushed = true; ctx->scene_version++; }
@@ -778,9 +782,6 @@ namespace
 		const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)n_strips, 1);
 		if (grid.y > 65535u) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "frame too tall for one launch");
 		if (stream != d.stream) RT_CUDA(ctx, cudaStreamWaitEvent(stream, d.ev_upload, 0));   // scene copies ride d.stream
-#ifndef RT_EXPERIMENT_BLOCK
-		static_assert(rt::x2::kBlockW == rt::kBlockW, "both kernels must cut the frame into the same CTA grid");
-#endif
 		p.grid_x = (int32_t)grid.x; p.n_strips = n_strips;
 		p.grid_x_magic = (uint32_t)((1ull << 32) / grid.x) + 1u;
 		// the persistent kernel decodes tile -> (strip, column) with one multiply; exact while tile * grid_x < 2^32
@@ -800,7 +801,7 @@ namespace
 				variant = (tiles * rt::kSignalsPerTile >= (p.band_done ? 8ll : 4ll) * wave * (rt::kPersistentThreads / 32)) ? RT_KERNEL_PERSISTENT : RT_KERNEL_SCALAR;
 			if (!decodable) variant = RT_KERNEL_SCALAR;
 		}
-		if (variant == RT_KERNEL_PACKED) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::x2::kThreads, 0, stream>>>(d.view, p);
+		if (variant == RT_KERNEL_PACKED) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::pick_threads_x2(), 0, stream>>>(d.view, p);
 		else if (variant == RT_KERNEL_SCALAR) pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
 		else
 		{
@@ -820,6 +821,11 @@ namespace
 			if (frc != RT_OK) return frc;
 		}
 		RT_CUDA(ctx, cudaGetLastError());
+		if (stream != d.stream)
+		{
+			RT_CUDA(ctx, cudaEventRecord(d.ev_foreign, stream));
+			d.foreign_pending = true;
+		}
 		ctx->timing.kernel_launches++;
 		return RT_OK;
 	}
@@ -930,22 +936,24 @@ namespace
 		return RT_OK;
 	}
 
-	// Make `host` a legal target for an asynchronous device-to-host copy.  Returns the pointer
-	// to copy into (host itself, or the pinned bounce buffer) through `target`.
+	// Make `host` a legal target for an asynchronous device-to-host copy.  Returns the pointer to copy into through
+	// `target`: host itself when CUDA already knows the range as pinned (cudaHostAlloc / cudaHostRegister by the caller,
+	// rt_register_surface, managed memory), else the library's own pinned bounce buffer.  The library never pins caller
+	// memory behind the caller's back: a registration outliving the buffer (free + a new mapping at the same address)
+	// would send later copies through stale pages.
 	int prepare_host(rt_context* ctx, void* host, size_t bytes, void** target)
 	{
 		static const bool force_bounce = getenv("RT_B200_FORCE_STAGING") != nullptr;     // tests: take the bounce-buffer path
-		cudaPointerAttributes attr{};
-		const cudaError_t e = cudaPointerGetAttributes(&attr, host);
-		if (!force_bounce && e == cudaSuccess && (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged)) { *target = host; return RT_OK; }
-		cudaGetLastError();
-		if (!force_bounce && ctx->registered_host == host && ctx->registered_bytes >= bytes) { *target = host; return RT_OK; }
-		if (ctx->registered_host) { cudaHostUnregister(ctx->registered_host); ctx->registered_host = nullptr; ctx->registered_bytes = 0; }
-		if (!force_bounce && cudaHostRegister(host, bytes, cudaHostRegisterPortable) == cudaSuccess)
+		if (!force_bounce)
 		{
-			ctx->registered_host = host; ctx->registered_bytes = bytes; *target = host; return RT_OK;
+			// both ends of the span must be pinned (a surface larger than its registration falls back to the bounce buffer)
+			cudaPointerAttributes first{}, last{};
+			const cudaError_t e0 = cudaPointerGetAttributes(&first, host);
+			const cudaError_t e1 = cudaPointerGetAttributes(&last, (char*)host + (bytes ? bytes - 1 : 0));
+			cudaGetLastError();
+			auto pinned = [](cudaError_t e, const cudaPointerAttributes& a) { return e == cudaSuccess && (a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged); };
+			if (pinned(e0, first) && pinned(e1, last)) { *target = host; return RT_OK; }
 		}
-		cudaGetLastError();
 		if (ctx->staging_bytes < bytes)
 		{
 			if (ctx->staging) cudaFreeHost(ctx->staging);
@@ -1350,6 +1358,7 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		RT_CREATE(cudaMalloc(&d.d_static, StaticBlock::total));
 		RT_CREATE(cudaEventCreateWithFlags(&d.ev_upload, cudaEventDisableTiming));
 		RT_CREATE(cudaEventRecord(d.ev_upload, d.stream));
+		RT_CREATE(cudaEventCreateWithFlags(&d.ev_foreign, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS));
 		RT_CREATE(cudaEventCreate(&d.ev_begin));
 		RT_CREATE(cudaEventCreate(&d.ev_kernel));
@@ -1405,6 +1414,7 @@ int rt_destroy(rt_context* ctx)
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
+		if (d.ev_foreign) cudaEventDestroy(d.ev_foreign);
 		cudaFree(d.cells.d_cost); cudaFree(d.cells.d_order); cudaFreeHost(d.cells.h_cost); cudaFreeHost(d.cells.h_order);
 		for (cudaEvent_t e : d.cells.ev_cost) if (e) cudaEventDestroy(e);
 		for (cudaEvent_t e : d.cells.ev_order) if (e) cudaEventDestroy(e);
@@ -1419,7 +1429,7 @@ int rt_destroy(rt_context* ctx)
 	}
 	if (ctx->ev_gather) cudaEventDestroy(ctx->ev_gather);
 	if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
-	if (ctx->registered_host) cudaHostUnregister(ctx->registered_host);
+	for (auto& r : ctx->registered) cudaHostUnregister(r.first);
 	if (ctx->staging) cudaFreeHost(ctx->staging);
 	if (ctx->h_static) cudaFreeHost(ctx->h_static);
 	if (ctx->h_mesh) cudaFreeHost(ctx->h_mesh);
@@ -1436,8 +1446,11 @@ int rt_upload_spheres(rt_context* ctx, const rt_spheres_soa* s)
 	if (s->count > rt::kMaxSpheres) return fail(ctx, RT_ERR_CAPACITY, "%d spheres exceed the capacity of %d", s->count, rt::kMaxSpheres);
 	if (s->count > 0 && (!s->origin_x || !s->origin_y || !s->origin_z || !s->radius || !s->material_index))
 		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "sphere SoA has a NULL array");
-	if (int w = wait_uploads(ctx)) return w;
 	float* a = ctx->arena + ArenaLayout::sphere;
+	if (s->count == ctx->n_spheres && same_bits(a, s->origin_x, s->count) && same_bits(a + rt::kMaxSpheres, s->origin_y, s->count) &&
+	    same_bits(a + 2 * rt::kMaxSpheres, s->origin_z, s->count) && same_bits(a + 3 * rt::kMaxSpheres, s->radius, s->count) &&
+	    same_bits(ctx->bytes, s->material_index, s->count)) return RT_OK;
+	if (int w = wait_uploads(ctx)) return w;
 	for (int i = 0; i < s->count; ++i)
 	{
 		a[i] = s->origin_x[i]; a[rt::kMaxSpheres + i] = s->origin_y[i]; a[2 * rt::kMaxSpheres + i] = s->origin_z[i];
@@ -1456,9 +1469,12 @@ int rt_upload_planes(rt_context* ctx, const rt_planes_soa* p)
 	if (p->count > rt::kMaxPlanes) return fail(ctx, RT_ERR_CAPACITY, "%d planes exceed the capacity of %d", p->count, rt::kMaxPlanes);
 	if (p->count > 0 && (!p->origin_x || !p->origin_y || !p->origin_z || !p->normal_x || !p->normal_y || !p->normal_z || !p->material_index))
 		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "plane SoA has a NULL array");
-	if (int w = wait_uploads(ctx)) return w;
 	float* a = ctx->arena + ArenaLayout::plane;
 	const int M = rt::kMaxPlanes;
+	if (p->count == ctx->n_planes && same_bits(a, p->origin_x, p->count) && same_bits(a + M, p->origin_y, p->count) && same_bits(a + 2 * M, p->origin_z, p->count) &&
+	    same_bits(a + 3 * M, p->normal_x, p->count) && same_bits(a + 4 * M, p->normal_y, p->count) && same_bits(a + 5 * M, p->normal_z, p->count) &&
+	    same_bits(ctx->bytes + rt::kMaxSpheres, p->material_index, p->count)) return RT_OK;
+	if (int w = wait_uploads(ctx)) return w;
 	for (int i = 0; i < p->count; ++i)
 	{
 		a[i] = p->origin_x[i]; a[M + i] = p->origin_y[i]; a[2 * M + i] = p->origin_z[i];
@@ -1477,9 +1493,12 @@ int rt_upload_lights(rt_context* ctx, const rt_lights_soa* l)
 	if (l->count > rt::kMaxLights) return fail(ctx, RT_ERR_CAPACITY, "%d lights exceed the capacity of %d", l->count, rt::kMaxLights);
 	if (l->count > 0 && (!l->origin_x || !l->origin_y || !l->origin_z || !l->color_r || !l->color_g || !l->color_b || !l->intensity || !l->type))
 		return fail(ctx, RT_ERR_INVALID_ARGUMENT, "light SoA has a NULL array");
-	if (int w = wait_uploads(ctx)) return w;
 	float* a = ctx->arena + ArenaLayout::light;
 	const int M = rt::kMaxLights;
+	if (l->count == ctx->n_lights && same_bits(a, l->origin_x, l->count) && same_bits(a + M, l->origin_y, l->count) && same_bits(a + 2 * M, l->origin_z, l->count) &&
+	    same_bits(a + 3 * M, l->color_r, l->count) && same_bits(a + 4 * M, l->color_g, l->count) && same_bits(a + 5 * M, l->color_b, l->count) &&
+	    same_bits(a + 6 * M, l->intensity, l->count) && same_bits(ctx->light_type, l->type, l->count)) return RT_OK;
+	if (int w = wait_uploads(ctx)) return w;
 	for (int i = 0; i < l->count; ++i)
 	{
 		a[i] = l->origin_x[i]; a[M + i] = l->origin_y[i]; a[2 * M + i] = l->origin_z[i];
@@ -1499,6 +1518,14 @@ int rt_upload_materials(rt_context* ctx, const rt_material_desc* materials, int3
 	if (count > rt::kMaxMaterials) return fail(ctx, RT_ERR_CAPACITY, "%d materials exceed the capacity of %d", count, rt::kMaxMaterials);
 	for (int i = 0; i < count; ++i)
 		if (materials[i].tag < RT_MATERIAL_SOLID_COLOR || materials[i].tag > RT_MATERIAL_COOK_TORRENCE) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "material %d has unknown tag %d", i, materials[i].tag);
+	bool unchanged = count == ctx->n_materials;
+	for (int i = 0; unchanged && i < count; ++i)
+	{
+		const rt_material_desc& m = materials[i];
+		const float4 m0 = make_float4(bits_as_float(m.tag), m.color[0], m.color[1], m.color[2]), m1 = make_float4(m.p0, m.p1, m.p2, 0.f);
+		unchanged = memcmp(&ctx->materials[2 * i], &m0, sizeof m0) == 0 && memcmp(&ctx->materials[2 * i + 1], &m1, sizeof m1) == 0;
+	}
+	if (unchanged) return RT_OK;
 	if (int w = wait_uploads(ctx)) return w;
 	for (int i = 0; i < count; ++i)
 	{
@@ -1516,6 +1543,7 @@ int rt_set_mesh_count(rt_context* ctx, int32_t mesh_count)
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
 	if (mesh_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "negative mesh count");
 	if (mesh_count > rt::kMaxMeshes) return fail(ctx, RT_ERR_CAPACITY, "%d meshes exceed the capacity of %d", mesh_count, rt::kMaxMeshes);
+	if ((size_t)mesh_count == ctx->meshes.size()) return RT_OK;      // called every frame by the drop-in: nothing changed
 	ctx->meshes.resize((size_t)mesh_count);
 	ctx->mesh_dirty = true;
 	return RT_OK;
@@ -1610,6 +1638,21 @@ int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
 		if (mesh->indices[i] < 0 || mesh->indices[i] >= mesh->vertex_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "index %d of mesh %d is out of range", i, mesh_id);
 
 	HostMesh& hm = ctx->meshes[(size_t)mesh_id];
+	if (hm.has_source)
+	{
+		// the id held a device-transformed mesh: forget its build state and give its device buffers back
+		hm.device_bvh = false; hm.pending_builds.clear(); hm.transform_dirty = false; hm.source_dirty = false;
+		hm.src_positions.clear(); hm.src_normals.clear(); hm.src_indices.clear();
+		for (DeviceState& d : ctx->devs)
+		{
+			if ((size_t)mesh_id >= d.sources.size()) continue;
+			RT_CUDA(ctx, cudaSetDevice(d.device));
+			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+			DeviceState::MeshSourceDevice& sd = d.sources[(size_t)mesh_id];
+			cudaFree(sd.positions); cudaFree(sd.normals); cudaFree(sd.indices); cudaFree(sd.normals_alt); cudaFree(sd.indices_alt); cudaFree(sd.build_block);
+			sd = DeviceState::MeshSourceDevice{};
+		}
+	}
 	hm.has_source = false; hm.has_transform = false;
 	hm.triangles.resize(3 * (size_t)mesh->triangle_count);
 	// Bounds of the indexed vertices, started like a BVH root box (reference
@@ -1938,6 +1981,45 @@ int rt_frame_wait(rt_context* ctx, uint32_t expected, void* cuda_stream)
 	return RT_OK;
 }
 
+int rt_register_surface(rt_context* ctx, void* host_ptr, size_t bytes)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	if (!host_ptr || bytes == 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "bad surface");
+	for (auto& r : ctx->registered) if (r.first == host_ptr) return fail(ctx, RT_ERR_BAD_STATE, "surface %p is already registered", host_ptr);
+	RT_CUDA(ctx, cudaSetDevice(ctx->devs[0].device));
+	RT_CUDA(ctx, cudaHostRegister(host_ptr, bytes, cudaHostRegisterPortable));
+	ctx->registered.emplace_back(host_ptr, bytes);
+	return RT_OK;
+}
+
+int rt_unregister_surface(rt_context* ctx, void* host_ptr)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	for (size_t i = 0; i < ctx->registered.size(); ++i)
+	{
+		if (ctx->registered[i].first != host_ptr) continue;
+		// no copy of ours may still target it: every rt_render* that writes host memory is blocking, so only a sync for safety
+		for (DeviceState& d : ctx->devs) { cudaSetDevice(d.device); cudaStreamSynchronize(d.copy_stream); cudaStreamSynchronize(d.stream); }
+		cudaSetDevice(ctx->devs[0].device);
+		RT_CUDA(ctx, cudaHostUnregister(host_ptr));
+		ctx->registered.erase(ctx->registered.begin() + (long)i);
+		return RT_OK;
+	}
+	return fail(ctx, RT_ERR_BAD_STATE, "surface %p was not registered with rt_register_surface", host_ptr);
+}
+
+int rt_clear_frame(rt_context* ctx, uint32_t pixel)
+{
+	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
+	DeviceState& d = ctx->devs[0];
+	if (!d.d_frame || ctx->last_width <= 0 || ctx->last_height <= 0) return fail(ctx, RT_ERR_BAD_STATE, "no frame buffer yet (render or export a frame first)");
+	RT_CUDA(ctx, cudaSetDevice(d.device));
+	const size_t pixels = (size_t)ctx->last_width * (size_t)ctx->last_height;
+	RT_CUDA(ctx, cuda_fill32(d.d_frame, pixel, pixels, d.stream));
+	RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+	return RT_OK;
+}
+
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing)
 {
 	if (!ctx || !out_timing) return RT_ERR_INVALID_ARGUMENT;
@@ -2004,8 +2086,7 @@ int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc
 	p.dst_full_frame = 1; p.dst = d.d_frame; p.counters = d.d_counters;
 	p.vector_store = (p.width % 4 == 0);
 	const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)((p.height + rt::kBlockH - 1) / rt::kBlockH), 1);
-	if (path == RT_MESH_PATH_BVH) rt::render_kernel<-1, -1, true, true><<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
-	else rt::render_kernel<-1, -1, false, true><<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
+	rt::pick_kernel_count(path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
 	RT_CUDA(ctx, cudaGetLastError());
 	RT_CUDA(ctx, cudaMemcpyAsync(out_counters->slot, d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS, cudaMemcpyDeviceToHost, d.stream));
 	RT_CUDA(ctx, cudaStreamSynchronize(d.stream));

@@ -52,7 +52,10 @@ namespace
 	std::mutex g_mutex;
 	std::unordered_map<const Renderer*, std::unique_ptr<DeviceSide>> g_devices;
 
-	DeviceSide* DeviceFor(const Renderer* renderer)
+	// `surface` / `surface_bytes`: the window surface's pixels (source/Renderer.cpp:27-29).  They live as long as the
+	// window, i.e. longer than this context, so they are pinned once for direct device-to-host copies
+	// (rt_register_surface's lifetime rule); if that fails rt_render goes through its bounce buffer.
+	DeviceSide* DeviceFor(const Renderer* renderer, void* surface, size_t surface_bytes)
 	{
 		std::lock_guard<std::mutex> lock(g_mutex);
 		auto it = g_devices.find(renderer);
@@ -78,6 +81,8 @@ namespace
 			std::fprintf(stderr, "rt_b200: rt_create failed (%d): %s\n", rc, rt_last_error(nullptr));
 			side->ctx = nullptr;
 		}
+		else if (surface && surface_bytes && rt_register_surface(side->ctx, surface, surface_bytes) != RT_OK)
+			std::fprintf(stderr, "rt_b200: the window surface could not be pinned (%s); frames go through a bounce buffer\n", rt_last_error(side->ctx));
 		if (const char* env = std::getenv("RT_B200_DEVICE_TRANSFORM")) side->scratch.device_transform = std::max(0, std::min(2, std::atoi(env)));
 		DeviceSide* raw = side.get();
 		g_devices.emplace(renderer, std::move(side));
@@ -109,7 +114,7 @@ Renderer::Renderer(SDL_Window* pWindow) :
 
 void Renderer::Render(Scene* pScene) const
 {
-	DeviceSide* side = DeviceFor(this);
+	DeviceSide* side = DeviceFor(this, m_pBufferPixels, (size_t)m_pBuffer->pitch * (size_t)m_Height);
 	if (!side->ctx) return;
 
 	std::string why;
@@ -141,7 +146,7 @@ void Renderer::Render(Scene* pScene) const
 // the row that holds it is rendered on the GPU and the pixel copied into the surface.
 void Renderer::RenderPixel(Scene* pScene, uint32_t pixelIndex, float, const Camera&, const std::vector<Light>&, const std::vector<Material*>&) const
 {
-	DeviceSide* side = DeviceFor(this);
+	DeviceSide* side = DeviceFor(this, m_pBufferPixels, (size_t)m_pBuffer->pitch * (size_t)m_Height);
 	if (!side->ctx) return;
 	std::string why;
 	if (rt_host::UploadScene(side->ctx, pScene, side->scratch, why) != RT_OK) return;

@@ -255,6 +255,17 @@ class Renderer:
     def frame_present(self, host_ptr: int, pitch_bytes: int, bands: int, frame_number: int) -> None:
         self.ctx.check(self.ctx.lib.rt_frame_present(self.ctx.handle, host_ptr, pitch_bytes, bands, frame_number & 0xFFFFFFFF), "rt_frame_present")
 
+    def clear_frame(self, pixel: int = 0xDEADBEEF) -> None:
+        """Poison device 0's frame buffer (a later frame check cannot pass on a stale frame)."""
+        self.ctx.check(self.ctx.lib.rt_clear_frame(self.ctx.handle, pixel & 0xFFFFFFFF), "rt_clear_frame")
+
+    def register_surface(self, host_ptr: int, nbytes: int) -> None:
+        """Pin a caller-owned surface for direct device-to-host copies; it must outlive the registration (rt_b200.h)."""
+        self.ctx.check(self.ctx.lib.rt_register_surface(self.ctx.handle, host_ptr, nbytes), "rt_register_surface")
+
+    def unregister_surface(self, host_ptr: int) -> None:
+        self.ctx.check(self.ctx.lib.rt_unregister_surface(self.ctx.handle, host_ptr), "rt_unregister_surface")
+
     def download_to(self, host_ptr: int, pitch_bytes: int) -> None:
         self.ctx.check(self.ctx.lib.rt_download_frame(self.ctx.handle, host_ptr, pitch_bytes), "rt_download_frame")
 

@@ -18,13 +18,14 @@
 #ifndef RT_B200_H
 #define RT_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 typedef struct rt_context rt_context;
 
@@ -361,16 +362,41 @@ int rt_set_kernel_variant(rt_context* ctx, int32_t variant);
 
 /* Replaces Renderer::Render (source/Renderer.cpp:34-98): blocking; on return host_dst holds
  * height rows of width uint32 pixels, row stride pitch_bytes (>= 4*width), exactly what the
- * reference leaves in m_pBufferPixels.  Row bands are split over the context's devices and
- * gathered on device 0 before the copy out. */
+ * reference leaves in m_pBufferPixels.
+ *   One device: one kernel launch; the copy to host_dst follows the kernel band by band (progressive present).
+ *   Several devices (default, "direct present"): device k renders the 8-row strips k, k + n, ... into its OWN
+ *     full-frame buffer (width * height * 4 bytes are allocated on every device) and copies exactly those strips
+ *     to host_dst over its own PCIe link; nothing is gathered on device 0.  RT_B200_PRESENT=gather in the
+ *     environment selects the older flow (peer stores into device 0's frame, device 0 presents).
+ * host_dst and pinning: when CUDA knows [host_dst, host_dst + pitch_bytes * (height - 1) + 4 * width) as pinned
+ * memory (cudaHostAlloc / cudaHostRegister by the caller, or rt_register_surface below) the copies land in it
+ * directly; otherwise they go through a pinned bounce buffer owned by the context and are memcpy'd out before
+ * the call returns.  The library never registers caller memory on its own. */
 int rt_render(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame,
               uint32_t* host_dst, int32_t pitch_bytes);
+
+/* Pin the surface rt_render* writes (the SDL surface's pixels, source/Renderer.cpp:27-29: they live as long as
+ * the window) so that device-to-host copies target it directly.  LIFETIME RULE: the range must stay mapped, at
+ * this address, until rt_unregister_surface(ctx, host_ptr) or rt_destroy(ctx) - freeing or re-mapping registered
+ * memory is undefined behaviour in CUDA.  RT_ERR_CUDA when the range cannot be registered (the bounce buffer is
+ * used then), RT_ERR_BAD_STATE for a pointer registered twice / never registered. */
+int rt_register_surface(rt_context* ctx, void* host_ptr, size_t bytes);
+int rt_unregister_surface(rt_context* ctx, void* host_ptr);
 
 /* Same frame, left in device 0's frame buffer (no host copy): kernel-only measurement. */
 int rt_render_device(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame);
 
 /* Copy the frame of the last rt_render_device out of device 0. */
 int rt_download_frame(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes);
+
+/* Fill device 0's frame buffer (the one rt_render_device / rt_frame_export / rt_render_strips_to_frame(NULL) use)
+ * with one pixel value; blocking.  Measurement and tests: a frame check must not pass on a stale frame. */
+int rt_clear_frame(rt_context* ctx, uint32_t pixel);
+
+/* Stream ordering of the *_device / *_to_frame calls that take a cuda_stream: the kernel is ordered after every
+ * earlier scene upload (the caller's stream waits on the context's upload event), and every LATER scene upload /
+ * rt_transform_mesh is ordered after that kernel (the context's stream waits on an event recorded behind it), so
+ * a caller may enqueue frame k + 1's uploads without synchronising frame k's stream. */
 
 /* One rank's share of a frame, for one-process-per-GPU launches: renders rows
  * [row_begin, row_begin + row_count) of the frame on the context's first device into

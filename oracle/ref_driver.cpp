@@ -69,6 +69,8 @@ namespace
 		bool stepsOnDevice = false; // --steps-on-device (drop-in build only): RotateY(a); Render(); RotateY(b); Render(); ... -
 		                            // the host never runs UpdateTransforms for the steps, the drop-in's device side does
 		std::string resources; // directory that CONTAINS "Resources/"
+		float animateDt = 0.f; // --animate DT: every timed frame is Scene::Update(timer advanced by DT) + Render, as in
+		                       // the reference's main loop (source/main.cpp:88-91); the two are timed separately
 	};
 
 	[[noreturn]] void Usage(const char* why)
@@ -80,7 +82,7 @@ namespace
 			"  [--threads T] [--time SECONDS] [--mesh-yaw RAD] [--cam-origin X Y Z]\n"
 			"  [--cam-rot PITCH YAW] [--fov DEGREES] [--out FILE] [--dump-scene FILE] [--dump-mesh-source FILE]\n"
 			"  [--yaw-steps A,B,... [--dump-mesh-steps FILE] [--steps-on-device]]\n"
-			"  [--resources DIR]\n", why);
+			"  [--resources DIR] [--animate DT_SECONDS]\n", why);
 		std::exit(2);
 	}
 
@@ -124,6 +126,7 @@ namespace
 			}
 			else if (a == "--resources") { need(i, 1); o.resources = argv[++i]; }
 			else if (a == "--steps-on-device") o.stepsOnDevice = true;
+			else if (a == "--animate") { need(i, 1); o.animateDt = std::strtof(argv[++i], nullptr); }
 			else Usage(("unknown argument " + a).c_str());
 		}
 		if (o.width <= 0 || o.height <= 0 || o.frames < 0 || o.mode < 0 || o.mode > 3) Usage("bad value");
@@ -364,10 +367,23 @@ int main(int argc, char** argv)
 		cam.CalculateForwardVector();    // source/Camera.h:61-66
 	}
 
-	std::vector<double> ms;
-	for (int i = 0; i < o.warmup; ++i) pRenderer->Render(pScene);
+	std::vector<double> ms, updateMs;
+	auto update = [&]()
+	{
+		// source/main.cpp:88: pScene->Update(pTimer) with the timer one frame further (mesh yaw = PI/2 * total time on the
+		// W4 scenes, source/Scene.cpp:391-400, 431-437, 468-474: RotateY + UpdateTransforms incl. BuildBVH)
+		if (o.animateDt <= 0.f) return;
+		const auto u0 = std::chrono::steady_clock::now();
+		pTimer->m_TotalTime += o.animateDt;
+		pTimer->m_ElapsedTime = o.animateDt;
+		pScene->Update(pTimer);
+		updateMs.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - u0).count());
+	};
+	for (int i = 0; i < o.warmup; ++i) { update(); pRenderer->Render(pScene); }
+	updateMs.clear();
 	for (int i = 0; i < o.frames; ++i)
 	{
+		update();
 		const auto t0 = std::chrono::steady_clock::now();
 		pRenderer->Render(pScene);
 		const auto t1 = std::chrono::steady_clock::now();
@@ -394,6 +410,11 @@ int main(int argc, char** argv)
 		o.scene.c_str(), o.width, o.height, o.mode, o.shadows, omp_get_max_threads(), o.frames, o.warmup,
 		median, sorted.empty() ? 0.0 : sorted.front());
 	for (size_t i = 0; i < ms.size(); ++i) std::printf("%s%.6f", i ? ", " : "", ms[i]);
+	if (!updateMs.empty())
+	{
+		std::printf("], \"update_ms\": [");
+		for (size_t i = 0; i < updateMs.size(); ++i) std::printf("%s%.6f", i ? ", " : "", updateMs[i]);
+	}
 #ifdef GP1_DROPIN
 	const char* path = "drop-in Renderer -> librt_b200.so (B200)";
 #else

@@ -70,6 +70,14 @@ CASES = {
     "optional_320_steps2": ("W4_Optional", SMALL, 3, 1, ["--yaw-steps", "0.3,0.9"]),
     # BASELINE.json configs[4]: the headline frame
     "bunny_4k": ("W4_Bunny", L, 3, 1, []),
+    # the frames SURVEY.md 0.4 / 8(c) found most sensitive to a single contracted operation (shadow-terminator pixels,
+    # Renderer.cpp:137-141) at the headline size, plus the spheres + planes + SolidColor check of config 0
+    "w2_4k": ("W2", L, 3, 1, []),
+    "w3_4k": ("W3", L, 3, 1, []),
+    "w4ref_4k": ("W4_Reference", L, 3, 1, []),
+    # N3 at the BASELINE sizes
+    "optional_640": ("W4_Optional", S, 3, 1, []),
+    "optional_4k": ("W4_Optional", L, 3, 1, []),
 }
 
 

@@ -63,3 +63,11 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "rt_oracle" not in src and "oracle/" not in src.replace("oracle/ref_driver", ""), f
+
+
+def test_library_is_built_from_the_sources_in_the_tree(lib):
+    """build.ensure() stores a hash of csrc/* + flags beside the library and rebuilds on a mismatch."""
+    assert not build.needs_build()
+    assert build.built_hash() == build.source_hash()
+    info = build.provenance()
+    assert info["fresh"] and info["source_sha256_16"] == build.source_hash()[:16]

@@ -425,3 +425,61 @@ print("ok")
 ''' % (ROOT, os.path.join(ROOT, "tests"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, RT_B200_FORCE_STAGING="1"), timeout=300)
     assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_registered_surface_lifetime_and_unpinned_surfaces(gpu):
+    """rt_register_surface / rt_unregister_surface (rt_b200.h): a caller-pinned surface is written directly, a pageable
+    one goes through the context's bounce buffer - and the library never keeps a registration of memory the caller may
+    free (round-1 advisor finding: a fresh 33 MB numpy array per frame is unmapped and mapped again at the same address)."""
+    want = load_golden_frame("bunny_4k")
+    r = make_renderer("bunny_4k")
+    for _ in range(3):
+        out = np.empty((2160, 3840), dtype=np.uint32)          # above glibc's mmap threshold: a new mapping every time
+        out[...] = 0xDEADBEEF
+        assert np.array_equal(r.Render(out), want)
+        del out
+    surface = np.full((2160, 3840), 0xDEADBEEF, dtype=np.uint32)
+    r.register_surface(surface.ctypes.data, surface.nbytes)
+    with pytest.raises(Exception):
+        r.register_surface(surface.ctypes.data, surface.nbytes)   # twice
+    assert np.array_equal(r.Render(surface), want)
+    r.unregister_surface(surface.ctypes.data)
+    with pytest.raises(Exception):
+        r.unregister_surface(surface.ctypes.data)                 # not registered any more
+    surface[...] = 0
+    assert np.array_equal(r.Render(surface), want)                # pageable again: bounce buffer
+    r.close()
+
+
+def test_clear_frame_poisons_device_frame(gpu):
+    r = make_renderer("bunny_333x77")
+    r.render_device()
+    r.clear_frame(0xDEADBEEF)
+    assert (r.download() == 0xDEADBEEF).all()
+    r.clear_frame(0x01010101)
+    assert (r.download() == 0x01010101).all()
+    r.render_device()
+    assert np.array_equal(r.download(), load_golden_frame("bunny_333x77"))
+    r.close()
+
+
+def test_uploads_after_a_launch_on_a_foreign_stream_wait_for_it(gpu):
+    """A frame launched on a caller-supplied stream, then - without synchronising - a new mesh and the next frame: the
+    upload must queue up behind the first kernel (it still reads the old geometry) and the second kernel behind the
+    upload (round-1 advisor finding).  Both frames must be what their own geometry renders to."""
+    torch = gpu
+    a, b = load_golden_scene("bunny_320_yaw05"), load_golden_scene("bunny_320_yaw25")
+    want_a, want_b = load_golden_frame("bunny_320_yaw05"), load_golden_frame("bunny_320_yaw25")
+    r = make_renderer("bunny_320_yaw05")
+    stream = torch.cuda.Stream()
+    out_a = torch.zeros((240, 320), dtype=torch.int32, device="cuda")
+    out_b = torch.zeros((240, 320), dtype=torch.int32, device="cuda")
+    for _ in range(20):
+        r.ctx.upload_mesh(0, a.meshes[0])
+        r.render_strips_device(0, 1, out_a.data_ptr(), stream.cuda_stream)
+        r.ctx.upload_mesh(0, b.meshes[0])                          # no synchronisation in between
+        r.render_strips_device(0, 1, out_b.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        assert np.array_equal(out_a.cpu().numpy().view(np.uint32), want_a)
+        assert np.array_equal(out_b.cpu().numpy().view(np.uint32), want_b)
+    r.close()

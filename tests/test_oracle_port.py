@@ -20,6 +20,10 @@ def test_port_matches_reference_frame(name):
     paths = [rt_oracle.MESH_SLAB_LINEAR]
     if scene.meshes and all(m.bvh_nodes is not None for m in scene.meshes):
         paths.append(rt_oracle.MESH_BVH)
+        # the every-triangle loop over a 3 082-triangle mesh at 4K is minutes of CPU: the BVH body pins that frame here
+        # (the slab + linear body of the same scene is pinned at 320x240 and 640x480)
+        if sum(m.triangle_count for m in scene.meshes) * info["width"] * info["height"] > 3e9:
+            paths.remove(rt_oracle.MESH_SLAB_LINEAR)
     for path in paths:
         got = rt_oracle.render(scene, info["width"], info["height"], info["mode"], bool(info["shadows"]), mesh_path=path)
         assert np.array_equal(got, want), f"{name}: path {path} differs in {(got != want).sum()} pixels"
