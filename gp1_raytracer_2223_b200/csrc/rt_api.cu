@@ -1001,7 +1001,8 @@ namespace
 		out.clear();
 		const int32_t n = mesh->bvh_node_count;
 		if (!mesh->bvh_nodes || n <= 0 || mesh->triangle_count == 0) return RT_OK;
-		if (n > rt::BvhLink::kEscapeMask - 1) return fail(ctx, RT_ERR_CAPACITY, "%d BVH nodes exceed the capacity of %d", n, rt::BvhLink::kEscapeMask - 1);
+		if (n > rt::BvhLink::kMaxNodes) return fail(ctx, RT_ERR_CAPACITY, "%d BVH nodes exceed the capacity of %d", n, rt::BvhLink::kMaxNodes);
+		if (mesh->triangle_count > rt::BvhLink::kFirstMask) return fail(ctx, RT_ERR_CAPACITY, "%d triangles exceed what a leaf link can address (%d)", mesh->triangle_count, rt::BvhLink::kFirstMask);
 		out.assign(2 * (size_t)n, make_float4(0.f, 0.f, 0.f, 0.f));
 		std::vector<char> seen((size_t)n, 0);
 		struct Item { int32_t node, escape; };
@@ -1034,8 +1035,9 @@ namespace
 				stack.push_back({ first, first + 1 });
 			}
 			out[2 * (size_t)it.node + 0] = make_float4(nd.min_aabb[0], nd.max_aabb[0], nd.min_aabb[1], nd.max_aabb[1]);
-			out[2 * (size_t)it.node + 1] = make_float4(nd.min_aabb[2], nd.max_aabb[2], bits_as_float(first),
-			                                            bits_as_float((it.escape + 1) | (leaf_tris << rt::BvhLink::kEscapeBits)));
+			out[2 * (size_t)it.node + 1] = make_float4(nd.min_aabb[2], nd.max_aabb[2],
+			                                            bits_as_float(leaf_tris > 0 ? rt::BvhLink::leaf(first, leaf_tris) : rt::BvhLink::inner(first)),
+			                                            bits_as_float(rt::BvhLink::miss(it.escape)));
 		}
 		if (covered != mesh->triangle_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH leaves cover %lld of %d triangles", (long long)covered, mesh->triangle_count);
 		return RT_OK;
@@ -1610,7 +1612,7 @@ int rt_set_mesh_device_bvh(rt_context* ctx, int32_t mesh_id, int32_t enable)
 	if (!hm.has_source) return fail(ctx, RT_ERR_BAD_STATE, "mesh %d was not uploaded with rt_upload_mesh_source", mesh_id);
 	if (hm.has_transform) return fail(ctx, RT_ERR_BAD_STATE, "rt_set_mesh_device_bvh must be called before the first rt_transform_mesh of mesh %d", mesh_id);
 	const size_t T = hm.src_indices.size() / 3;
-	if (enable && 2 * T > (size_t)rt::BvhLink::kEscapeMask) return fail(ctx, RT_ERR_CAPACITY, "%zu triangles exceed what the BVH node links can address", T);
+	if (enable && T > (size_t)rt::BvhLink::kFirstMask) return fail(ctx, RT_ERR_CAPACITY, "%zu triangles exceed what the BVH node links can address", T);
 	hm.device_bvh = enable != 0;
 	// node slice: 2T - 1 nodes at most, written by emit_mesh_kernel
 	if (hm.device_bvh && T > 0) hm.nodes.assign(2 * (2 * T - 1), make_float4(0.f, 0.f, 0.f, 0.f)); else hm.nodes.clear();
@@ -2055,13 +2057,13 @@ int rt_read_mesh_build(rt_context* ctx, int32_t mesh_id, int32_t* indices, float
 		for (int32_t n = 0; n < info[0]; ++n)
 		{
 			const float4 a = records[2 * (size_t)n], b = records[2 * (size_t)n + 1];
-			int32_t first, link;
-			memcpy(&first, &b.z, sizeof first); memcpy(&link, &b.w, sizeof link);
+			int32_t hit, miss;
+			memcpy(&hit, &b.z, sizeof hit); memcpy(&miss, &b.w, sizeof miss);
 			rt_built_node& out = nodes[n];
 			out.min_aabb[0] = a.x; out.max_aabb[0] = a.y; out.min_aabb[1] = a.z; out.max_aabb[1] = a.w; out.min_aabb[2] = b.x; out.max_aabb[2] = b.y;
-			out.first = first;
-			out.triangle_count = link >> rt::BvhLink::kEscapeBits;
-			out.escape = (link & rt::BvhLink::kEscapeMask) - 1;
+			out.first = rt::BvhLink::is_leaf(hit) ? rt::BvhLink::leaf_first(hit) : hit / rt::BvhLink::kNodeBytes;
+			out.triangle_count = rt::BvhLink::is_leaf(hit) ? rt::BvhLink::leaf_count(hit) : 0;
+			out.escape = miss < 0 ? -1 : miss / rt::BvhLink::kNodeBytes;
 		}
 	}
 	return RT_OK;

@@ -155,9 +155,9 @@ namespace rt
 	{
 		const float* b = p.node_box + 6 * node;
 		if (leaf && leaf_triangles > BvhLink::kMaxLeafTriangles) atomicExch(p.result_info + 1, 1);
-		const int link = (p.node_escape[node] + 1) | ((leaf ? leaf_triangles : 0) << BvhLink::kEscapeBits);
+		const int hit = leaf ? BvhLink::leaf(first_or_child, leaf_triangles) : BvhLink::inner(first_or_child);
 		p.result_nodes[2 * node] = make_float4(b[0], b[3], b[1], b[4]);
-		p.result_nodes[2 * node + 1] = make_float4(b[2], b[5], __int_as_float(first_or_child), __int_as_float(link));
+		p.result_nodes[2 * node + 1] = make_float4(b[2], b[5], __int_as_float(hit), __int_as_float(BvhLink::miss(p.node_escape[node])));
 	}
 
 	// The in-place partition of Subdivide (DataTypes.h:344-363) over positions [first, first + count):

@@ -52,7 +52,7 @@ namespace rt
 		const float4* materials;       // 2 float4 per material: {tag bits, r, g, b} {p0, p1, p2, -}
 		const float4* mesh_table;      // 3 float4 per mesh: {min.x, max.x, min.y, max.y}, {min.z, max.z, first triangle, triangle count}, {cull, material, first BVH node, BVH node count}
 		const float4* triangles;       // 3 float4 per triangle: {v0 xyz, n.x} {e1 xyz, n.y} {e2 xyz, n.z}
-		const float4* bvh_nodes;       // 2 float4 per node: {min.x, max.x, min.y, max.y}, {min.z, max.z, first, link}; see BvhLink
+		const float4* bvh_nodes;       // 2 float4 per node: {min.x, max.x, min.y, max.y}, {min.z, max.z, hit, miss}; see BvhLink
 		int32_t n_spheres, n_planes, n_lights, n_materials, n_meshes;
 		// (-0,-0), (1,1), (-1,-1): third operands of the packed FFMA2 arithmetic (struct Pk).  They are
 		// kernel parameters on purpose - see rt_kernel_x2.cuh on why literals would break exactness.
@@ -122,14 +122,46 @@ namespace rt
 		float4 mesh[3 * kMaxMeshes];
 		float4 material[2 * kMaxMaterials];
 		float4 sphere_view[kMaxSpheres];     // {c - camera origin, |c - camera origin|^2}: HitTest_Sphere's ray-independent part for view rays
+		// the planes once more, two per record, laid out for the packed plane loops (plane_pair_*): planes 2j and 2j + 1 as
+		// {ox0, ox1, oy0, oy1} {oz0, oz1, nx0, nx1} {ny0, ny1, nz0, nz1}; an odd count is padded with a copy of the last
+		// plane (same test, same result: an any-hit cannot change, and a closest hit keeps the first of two equal t)
+		float4 plane_pair[3 * (kMaxPlanes / 2)];
+		float2 plane_pair_view[kMaxPlanes / 2];   // {num0, num1} of HitTest_Plane for view rays, as plane_n[].w
 		uint8_t sphere_mat[kMaxSpheres];
 	};
+
+	// The staged scene seen from the pixel code: ONE 32-bit shared-memory address plus compile-time field offsets, read
+	// with explicit ld.shared.  (Passing `SharedScene&` around makes nvcc rebuild the block's shared-window base - S2R
+	// SR_CgaCtaId, MOV, LEA - in every iteration of every loop that touches the scene.)  The handle is created after the
+	// staging barrier and made opaque there, so no load can be scheduled above the barrier.
+	struct Staged
+	{
+		unsigned int base;
+		static __device__ __forceinline__ float4 ld4(unsigned int a) { float4 v; asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v; }
+		static __device__ __forceinline__ float2 ld2(unsigned int a) { float2 v; asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+		static __device__ __forceinline__ int ld8(unsigned int a) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+#define RT_STAGED_F4(name, field) __device__ __forceinline__ float4 name(int i) const { return ld4(base + (unsigned int)offsetof(SharedScene, field) + 16u * (unsigned int)i); }
+		RT_STAGED_F4(sphere, sphere) RT_STAGED_F4(sphere_view, sphere_view) RT_STAGED_F4(plane_o, plane_o) RT_STAGED_F4(plane_n, plane_n)
+		RT_STAGED_F4(light_a, light_a) RT_STAGED_F4(light_b, light_b) RT_STAGED_F4(mesh, mesh) RT_STAGED_F4(material, material) RT_STAGED_F4(plane_pair, plane_pair)
+#undef RT_STAGED_F4
+		__device__ __forceinline__ float2 plane_pair_view(int j) const { return ld2(base + (unsigned int)offsetof(SharedScene, plane_pair_view) + 8u * (unsigned int)j); }
+		__device__ __forceinline__ int sphere_mat(int i) const { return ld8(base + (unsigned int)offsetof(SharedScene, sphere_mat) + (unsigned int)i); }
+	};
+	// call after the __syncthreads() that ends stage_scene
+	__device__ __forceinline__ Staged staged_handle(const SharedScene& sc)
+	{
+		Staged s;
+		s.base = (unsigned int)__cvta_generic_to_shared(&sc);
+		asm volatile("" : "+r"(s.base) :: "memory");
+		return s;
+	}
 
 	template <bool COUNT>
 	struct Counters
 	{
 		__device__ __forceinline__ void hit(int) {}
 		__device__ __forceinline__ void flush(unsigned long long*) {}
+		__device__ __forceinline__ void flush_partial(unsigned long long*) {}
 	};
 	template <>
 	struct Counters<true>
@@ -137,6 +169,11 @@ namespace rt
 		unsigned int c[RT_COUNTER_SLOTS];
 		__device__ Counters() { for (int i = 0; i < RT_COUNTER_SLOTS; ++i) c[i] = 0; }
 		__device__ __forceinline__ void hit(int slot) { c[slot]++; }
+		// one thread's counts (the out-of-line literal walk: divergent, so no warp reduction)
+		__device__ void flush_partial(unsigned long long* out)
+		{
+			for (int i = 0; i < RT_COUNTER_SLOTS; ++i) if (c[i]) atomicAdd(&out[i], (unsigned long long)c[i]);
+		}
 		__device__ void flush(unsigned long long* out)
 		{
 			for (int i = 0; i < RT_COUNTER_SLOTS; ++i)
@@ -146,6 +183,19 @@ namespace rt
 			}
 		}
 	};
+
+	// Packed FP32 arithmetic (Blackwell FFMA2): two independent IEEE multiplies / adds / subtracts per issue
+	// slot, each individually rounded:  a*b = fma(a, b, -0),  a+b = fma(a, 1, b),  a-b = fma(b, -1, a).
+	// The constants are run-time values (SceneDevice::k_*), never literals (rt_kernel_x2.cuh explains why).
+	struct Pk
+	{
+		float2 neg0, one, mone;
+		__device__ __forceinline__ float2 mul(float2 a, float2 b) const { return __ffma2_rn(a, b, neg0); }
+		__device__ __forceinline__ float2 add(float2 a, float2 b) const { return __ffma2_rn(a, one, b); }
+		__device__ __forceinline__ float2 sub(float2 a, float2 b) const { return __ffma2_rn(b, mone, a); }
+	};
+	__device__ __forceinline__ Pk make_pk(const SceneDevice& dev) { Pk k; k.neg0 = dev.k_neg0; k.one = dev.k_one; k.mone = dev.k_mone; return k; }
+	__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
 
 	__device__ __forceinline__ Ray make_ray(V3 o, V3 d, float tmin, float tmax)
 	{
@@ -180,17 +230,19 @@ namespace rt
 		return hit_sphere_from<SHADOW>(ov, dot(ov, ov), s.w, ray, t_out, cnt);
 	}
 
-	// Can t = RN(num / den) satisfy tmin <= t < tmax (tmin = 1e-4)?  Returns false only when that is
-	// impossible, so the IEEE division is skipped for the planes a ray cannot reach:
-	//   num or den zero          -> t is +-0, +-inf or NaN
-	//   opposite signs           -> t <= -0
-	//   |num| > |den|*tmax*(1+1e-6) (computed without underflow) -> num/den > tmax, and rounding is monotonic
-	// NaN operands fall through to the exact test.
-	__device__ __forceinline__ bool plane_may_hit(float num, float den, float tmax)
+	// Can t = RN(num / den) satisfy tmin <= t < limit (tmin = 1e-4 > 0)?  Returns false only when that is impossible,
+	// so the IEEE division is skipped for the planes a ray cannot reach:
+	//   opposite signs                              -> t <= -0 < tmin
+	//   |num| > |den| * limit * (1 + 1e-6)          -> |num / den| > limit * (1 + 7e-7) in exact arithmetic (the two
+	//                                                  roundings of the bound cost < 2.4e-7), and rounding is monotonic:
+	//                                                  t >= limit.  Not used when the bound is so small that it may
+	//                                                  have lost precision to underflow.
+	// Zero and NaN operands fall through to the exact test (0 / x, x / 0 and NaN all fail its range check there).
+	// `limit_up` = limit * 1.000001f, computed once per ray by the caller.
+	__device__ __forceinline__ bool plane_may_hit(float num, float den, float limit_up)
 	{
-		if (num == 0.f || den == 0.f) return false;
+		const float bound = mul(fabsf(den), limit_up);
 		if ((__float_as_int(num) ^ __float_as_int(den)) < 0) return false;
-		const float bound = mul(mul(fabsf(den), tmax), 1.000001f);
 		if (bound > 1e-30f && fabsf(num) > bound) return false;
 		return true;
 	}
@@ -201,7 +253,7 @@ namespace rt
 	{
 		const float den = dot(ray.d, v3(pn));
 		cnt.hit(SHADOW ? RT_CNT_PLANE_S_TEST : RT_CNT_PLANE_P_TEST);
-		if (!plane_may_hit(num, den, ray.tmax)) return false;
+		if (!plane_may_hit(num, den, mul(ray.tmax, 1.000001f))) return false;
 		const float t = quo(num, den);
 		if (t >= ray.tmin && t < ray.tmax) { t_out = t; return true; }
 		return false;
@@ -213,18 +265,71 @@ namespace rt
 		return hit_plane_from<SHADOW>(dot(v3(po) - ray.o, v3(pn)), pn, ray, t_out, cnt);
 	}
 
-	// Packed FP32 arithmetic (Blackwell FFMA2): two independent IEEE multiplies / adds / subtracts per issue
-	// slot, each individually rounded:  a*b = fma(a, b, -0),  a+b = fma(a, 1, b),  a-b = fma(b, -1, a).
-	// The constants are run-time values (SceneDevice::k_*), never literals (rt_kernel_x2.cuh explains why).
-	struct Pk
+	// HitTest_Plane for two planes at once (Utils.h:82-98): the numerators (plane origin - ray origin) . n and the
+	// denominators d . n of planes 2j and 2j + 1 in the lanes of packed FFMA2s, every operation individually rounded
+	// in the reference's order (Pk) - 13 instructions per pair of shadow-ray tests instead of 26, 5 instead of 10 for
+	// view rays, whose numerators are staged per CTA.
+	__device__ __forceinline__ float2 plane_pair_den(const Pk& K, const float4 b, const float4 c, const V3 d)
 	{
-		float2 neg0, one, mone;
-		__device__ __forceinline__ float2 mul(float2 a, float2 b) const { return __ffma2_rn(a, b, neg0); }
-		__device__ __forceinline__ float2 add(float2 a, float2 b) const { return __ffma2_rn(a, one, b); }
-		__device__ __forceinline__ float2 sub(float2 a, float2 b) const { return __ffma2_rn(b, mone, a); }
-	};
-	__device__ __forceinline__ Pk make_pk(const SceneDevice& dev) { Pk k; k.neg0 = dev.k_neg0; k.one = dev.k_one; k.mone = dev.k_mone; return k; }
-	__device__ __forceinline__ float2 splat(float s) { return make_float2(s, s); }
+		const float2 nx = make_float2(b.z, b.w), ny = make_float2(c.x, c.y), nz = make_float2(c.z, c.w);
+		return K.add(K.add(K.mul(splat(d.x), nx), K.mul(splat(d.y), ny)), K.mul(splat(d.z), nz));
+	}
+	__device__ __forceinline__ float2 plane_pair_num(const Pk& K, const float4 a, const float4 b, const float4 c, const V3 o)
+	{
+		const float2 nx = make_float2(b.z, b.w), ny = make_float2(c.x, c.y), nz = make_float2(c.z, c.w);
+		const float2 dx = K.sub(make_float2(a.x, a.y), splat(o.x)), dy = K.sub(make_float2(a.z, a.w), splat(o.y)), dz = K.sub(make_float2(b.x, b.y), splat(o.z));
+		return K.add(K.add(K.mul(dx, nx), K.mul(dy, ny)), K.mul(dz, nz));
+	}
+
+	// Any plane between a shadow ray's origin and its light?  (Scene::DoesHit's plane loop, Scene.cpp:79-85)
+	template <bool COUNT>
+	__device__ __forceinline__ bool planes_any(const Pk& K, const Staged sc, int n_planes, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		const float limit_up = mul(ray.tmax, 1.000001f);
+#pragma unroll 1
+		for (int j = 0; 2 * j < n_planes; ++j)
+		{
+			const float4 a = sc.plane_pair(3 * j), b = sc.plane_pair(3 * j + 1), c = sc.plane_pair(3 * j + 2);
+			const float2 num = plane_pair_num(K, a, b, c, ray.o), den = plane_pair_den(K, b, c, ray.d);
+			cnt.hit(RT_CNT_PLANE_S_TEST);
+			if (2 * j + 1 < n_planes) cnt.hit(RT_CNT_PLANE_S_TEST);
+			if (plane_may_hit(num.x, den.x, limit_up) || plane_may_hit(num.y, den.y, limit_up))
+			{
+				// rare: the exact test for both planes of the pair (the filter only ever skips planes whose exact test fails)
+				const float t0 = quo(num.x, den.x), t1 = quo(num.y, den.y);
+				if ((t0 >= ray.tmin && t0 < ray.tmax) || (t1 >= ray.tmin && t1 < ray.tmax)) return true;
+			}
+		}
+		return false;
+	}
+
+	// Closest plane in front of a view ray (Scene::GetClosestHit's plane loop, Scene.cpp:45-53): planes in order, strict
+	// '<' so the first one wins ties.  `best_t` comes in as the closest sphere's t.  Only planes that can still beat
+	// best_t reach the division (the counters build keeps the reference's own range so that its counts are the reference's).
+	template <bool COUNT>
+	__device__ __forceinline__ void planes_closest(const Pk& K, const Staged sc, int n_planes, const Ray& ray, float& best_t, int& best_plane, Counters<COUNT>& cnt)
+	{
+#pragma unroll 1
+		for (int j = 0; 2 * j < n_planes; ++j)
+		{
+			const float4 b = sc.plane_pair(3 * j + 1), c = sc.plane_pair(3 * j + 2);
+			const float2 num = sc.plane_pair_view(j), den = plane_pair_den(K, b, c, ray.d);
+			cnt.hit(RT_CNT_PLANE_P_TEST);
+			if (2 * j + 1 < n_planes) cnt.hit(RT_CNT_PLANE_P_TEST);
+			const float limit_up = mul(COUNT ? ray.tmax : best_t, 1.000001f);
+			if (plane_may_hit(num.x, den.x, limit_up))
+			{
+				const float t = quo(num.x, den.x);
+				if (t >= ray.tmin && t < ray.tmax) { cnt.hit(RT_CNT_PLANE_P_HIT); if (t < best_t) { best_t = t; best_plane = 2 * j; } }
+			}
+			// (the second plane is filtered against the limit of before the first one: still a valid limit, only looser)
+			if ((!COUNT || 2 * j + 1 < n_planes) && plane_may_hit(num.y, den.y, limit_up))
+			{
+				const float t = quo(num.y, den.y);
+				if (t >= ray.tmin && t < ray.tmax) { cnt.hit(RT_CNT_PLANE_P_HIT); if (t < best_t) { best_t = t; best_plane = 2 * j + 1; } }
+			}
+		}
+	}
 
 	// SlabTest_TriangleMesh / SlabTest_BVH, Utils.h:194-216, 221-243, on a box stored as
 	// b0 = {min.x, max.x, min.y, max.y}, b1 = {min.z, max.z, -, -}: the (tx1, tx2), (ty1, ty2), (tz1, tz2)
@@ -236,15 +341,16 @@ namespace rt
 	// whose inverse direction is finite (Ray::nan_safe, all but axis-parallel rays) take the fast
 	// form with the same boolean result; the others take the literal one.
 	template <bool FAST>
-	__device__ __forceinline__ bool slab_test(const Pk& K, const float4 b0, const float4 b1, const Ray& ray)
+	__device__ __forceinline__ bool slab_test(const Pk&, const float4 b0, const float4 b1, const Ray& ray)
 	{
-		// The products are a * b + (+0) here, not a * b + (-0): the two differ only in the sign of a zero
-		// product, and the t values only meet comparisons and min / max below, which cannot see it.  +0 is the
-		// zero register, so the loop carries one constant pair less.
-		const float2 zero = make_float2(0.f, 0.f);
-		const float2 tx = __ffma2_rn(K.sub(make_float2(b0.x, b0.y), splat(ray.o.x)), splat(ray.inv.x), zero);
-		const float2 ty = __ffma2_rn(K.sub(make_float2(b0.z, b0.w), splat(ray.o.y)), splat(ray.inv.y), zero);
-		const float2 tz = __ffma2_rn(K.sub(make_float2(b1.x, b1.y), splat(ray.o.z)), splat(ray.inv.z), zero);
+		// (b - o) * inv per pair: b - o = fma(o, -1, b) and x * inv = fma(x, inv, +0), each rounded once like the FSUB / FMUL
+		// they replace.  The constants are literals here (unlike Pk's): ptxas can only contract a multiply INTO a
+		// following add, and these products feed nothing but min / max and comparisons.  The products are a * b + (+0),
+		// not a * b + (-0): the two differ only in the sign of a zero product, which those cannot see either.
+		const float2 zero = make_float2(0.f, 0.f), mone = make_float2(-1.f, -1.f);
+		const float2 tx = __ffma2_rn(__ffma2_rn(splat(ray.o.x), mone, make_float2(b0.x, b0.y)), splat(ray.inv.x), zero);
+		const float2 ty = __ffma2_rn(__ffma2_rn(splat(ray.o.y), mone, make_float2(b0.z, b0.w)), splat(ray.inv.y), zero);
+		const float2 tz = __ffma2_rn(__ffma2_rn(splat(ray.o.z), mone, make_float2(b1.x, b1.y)), splat(ray.inv.z), zero);
 		if (FAST)
 		{
 			const float t_min = fmaxf(fmaxf(fminf(tx.x, tx.y), fminf(ty.x, ty.y)), fminf(tz.x, tz.y));
@@ -384,69 +490,101 @@ namespace rt
 	// order, exactly as the recursion meets them (strict '<' tie-breaking is preserved).
 	struct BvhLink
 	{
-		// node.w words: first = left child (inner) or first triangle (leaf), relative to the mesh;
-		// link  = (escape + 1) | (leaf triangle count << kEscapeBits); escape + 1 == 0 ends the walk
-		static constexpr int kEscapeBits = 20;
-		static constexpr int kEscapeMask = (1 << kEscapeBits) - 1;
-		static constexpr int kMaxLeafTriangles = (1 << (31 - kEscapeBits)) - 1;
+		// The two link words of a node record {min.x, max.x, min.y, max.y} {min.z, max.z, hit, miss}:
+		//   hit   where the walk goes when the ray meets the box: an inner node's left child as a BYTE offset from the
+		//         mesh's first node record (>= 0, ready to be added to the base address), or, with the sign bit set, a
+		//         leaf's triangles: kLeafBit | count << kFirstBits | first triangle (relative to the mesh)
+		//   miss  the escape link as a byte offset: the node that follows this subtree in the reference's depth-first
+		//         order; -1 ends the walk
+		// A walk step is therefore: test the box, take `hit` or `miss`, add it to the base - no index arithmetic, no
+		// decode except on leaves.
+		static constexpr int kNodeBytes = 32;
+		static constexpr int kFirstBits = 20;
+		static constexpr int kFirstMask = (1 << kFirstBits) - 1;
+		static constexpr int kMaxLeafTriangles = (1 << (31 - kFirstBits)) - 1;
+		static constexpr int kMaxNodes = (1 << 25) - 1;                     // byte offsets stay positive ints
+		static constexpr int kEnd = -1;
+		static constexpr unsigned int kLeafBit = 0x80000000u;
+		__host__ __device__ static int inner(int left_child) { return left_child * kNodeBytes; }
+		__host__ __device__ static int leaf(int first_triangle, int count) { return (int)(kLeafBit | ((unsigned int)count << kFirstBits) | (unsigned int)first_triangle); }
+		__host__ __device__ static int miss(int escape_node) { return escape_node < 0 ? kEnd : escape_node * kNodeBytes; }
+		__host__ __device__ static bool is_leaf(int hit) { return hit < 0; }
+		__host__ __device__ static int leaf_first(int hit) { return hit & kFirstMask; }
+		__host__ __device__ static int leaf_count(int hit) { return (int)(((unsigned int)hit & ~kLeafBit) >> kFirstBits); }
 	};
-
-	template <int CULL, bool FAST, bool COUNT>
-	__device__ __forceinline__ void bvh_closest(const Pk& K, const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	__device__ __forceinline__ const float4* node_at(const float4* nodes, int offset)
 	{
-		int node = 0;
-		while (node >= 0)
-		{
-			const float4 n0 = __ldg(nodes + 2 * node), n1 = __ldg(nodes + 2 * node + 1);
-			const int link = __float_as_int(n1.w);
-			const int escape = (link & BvhLink::kEscapeMask) - 1;
-			cnt.hit(RT_CNT_BVH_P_NODE);
-			if (!slab_test<FAST>(K, n0, n1, ray)) { node = escape; continue; }
-			const int count = link >> BvhLink::kEscapeBits;
-			const int first = __float_as_int(n1.z);
-			if (count == 0) { node = first; continue; }
-			for (int k = 0; k < count; ++k)
-				closest_one<CULL>(load_tri(tri + 3 * (first + k)), first + k, ray, best_t, best_tri, cnt);
-			node = escape;
-		}
+		return reinterpret_cast<const float4*>(reinterpret_cast<const char*>(nodes) + (unsigned int)offset);
 	}
 
-	template <int CULL, bool FAST, bool COUNT>
-	__device__ __forceinline__ bool bvh_any(const Pk& K, const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
+	// One leaf of the walk: its triangles in ascending order (the order the recursion meets them).  The cull mode is a
+	// warp-uniform switch here, not a template parameter of the whole walk: the node loop does not depend on it.
+	template <bool COUNT>
+	__device__ __forceinline__ void leaf_closest(int cull, const float4* tri, int first, int count, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
 	{
-		int node = 0;
-		while (node >= 0)
-		{
-			const float4 n0 = __ldg(nodes + 2 * node), n1 = __ldg(nodes + 2 * node + 1);
-			const int link = __float_as_int(n1.w);
-			const int escape = (link & BvhLink::kEscapeMask) - 1;
-			cnt.hit(RT_CNT_BVH_S_NODE);
-			if (!slab_test<FAST>(K, n0, n1, ray)) { node = escape; continue; }
-			const int count = link >> BvhLink::kEscapeBits;
-			const int first = __float_as_int(n1.z);
-			if (count == 0) { node = first; continue; }
-			for (int k = 0; k < count; ++k)
-				if (shadow_one<CULL>(load_tri(tri + 3 * (first + k)), ray, cnt)) return true;
-			node = escape;
-		}
+		if (cull == RT_CULL_BACK_FACE) { for (int k = 0; k < count; ++k) closest_one<RT_CULL_BACK_FACE>(load_tri(tri + 3 * (first + k)), first + k, ray, best_t, best_tri, cnt); }
+		else if (cull == RT_CULL_FRONT_FACE) { for (int k = 0; k < count; ++k) closest_one<RT_CULL_FRONT_FACE>(load_tri(tri + 3 * (first + k)), first + k, ray, best_t, best_tri, cnt); }
+		else { for (int k = 0; k < count; ++k) closest_one<RT_CULL_NONE>(load_tri(tri + 3 * (first + k)), first + k, ray, best_t, best_tri, cnt); }
+	}
+
+	// `cull` is the mode that applies to shadow rays (already inverted, Utils.h:114-127)
+	template <bool COUNT>
+	__device__ __forceinline__ bool leaf_any(int cull, const float4* tri, int first, int count, const Ray& ray, Counters<COUNT>& cnt)
+	{
+		if (cull == RT_CULL_BACK_FACE) { for (int k = 0; k < count; ++k) if (shadow_one<RT_CULL_BACK_FACE>(load_tri(tri + 3 * (first + k)), ray, cnt)) return true; }
+		else if (cull == RT_CULL_FRONT_FACE) { for (int k = 0; k < count; ++k) if (shadow_one<RT_CULL_FRONT_FACE>(load_tri(tri + 3 * (first + k)), ray, cnt)) return true; }
+		else { for (int k = 0; k < count; ++k) if (shadow_one<RT_CULL_NONE>(load_tri(tri + 3 * (first + k)), ray, cnt)) return true; }
 		return false;
 	}
 
-	template <bool FAST, bool COUNT>
+	// The walk.  ANY = DoesHit's form (stop at the first triangle hit: the reference only leaves the leaf and keeps
+	// walking, which cannot change the boolean), else GetClosestHit's (strict '<': the first triangle in walk order
+	// wins ties).  FAST: see slab_test.
+	template <bool ANY, bool FAST, bool COUNT>
+	__device__ __forceinline__ bool bvh_walk(const Pk& K, int cull, const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
+	{
+		// the 64-bit base stays in a register pair (made opaque: ptxas would otherwise rebuild it from the constant bank
+		// and the mesh table in every iteration - five instructions instead of one)
+		unsigned long long base = reinterpret_cast<unsigned long long>(nodes);
+		asm volatile("" : "+l"(base));
+		int at = 0;
+		do
+		{
+			const float4* rec = reinterpret_cast<const float4*>(base + (unsigned int)at);
+			const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1);
+			cnt.hit(ANY ? RT_CNT_BVH_S_NODE : RT_CNT_BVH_P_NODE);
+			const bool inside = slab_test<FAST>(K, n0, n1, ray);
+			const int hit = __float_as_int(n1.z), miss = __float_as_int(n1.w);
+			at = inside ? hit : miss;
+			if (inside && BvhLink::is_leaf(hit))
+			{
+				const int first = BvhLink::leaf_first(hit), count = BvhLink::leaf_count(hit);
+				if (ANY) { if (leaf_any(cull, tri, first, count, ray, cnt)) return true; }
+				else leaf_closest(cull, tri, first, count, ray, best_t, best_tri, cnt);
+				at = miss;
+			}
+		} while (at >= 0);
+		return false;
+	}
+
+	// Rays with an infinite 1 / dir component (axis-parallel: a handful per frame at most) take the literal
+	// std::min / std::max form of the slab test: a second inline copy of the walk that is practically never executed
+	// (it costs code size, not registers or instruction-cache footprint).
+	template <bool COUNT>
 	__device__ __forceinline__ void bvh_closest_any_cull(const Pk& K, int cull, const float4* nodes, const float4* tri, const Ray& ray, float& best_t, int& best_tri, Counters<COUNT>& cnt)
 	{
-		if (cull == RT_CULL_BACK_FACE) bvh_closest<RT_CULL_BACK_FACE, FAST>(K, nodes, tri, ray, best_t, best_tri, cnt);
-		else if (cull == RT_CULL_FRONT_FACE) bvh_closest<RT_CULL_FRONT_FACE, FAST>(K, nodes, tri, ray, best_t, best_tri, cnt);
-		else bvh_closest<RT_CULL_NONE, FAST>(K, nodes, tri, ray, best_t, best_tri, cnt);
+		if (ray.nan_safe) bvh_walk<false, true>(K, cull, nodes, tri, ray, best_t, best_tri, cnt);
+		else bvh_walk<false, false>(K, cull, nodes, tri, ray, best_t, best_tri, cnt);
 	}
 
 	// Utils.h:114-127: shadow rays see the opposite cull mode
-	template <bool FAST, bool COUNT>
+	template <bool COUNT>
 	__device__ __forceinline__ bool bvh_any_any_cull(const Pk& K, int cull, const float4* nodes, const float4* tri, const Ray& ray, Counters<COUNT>& cnt)
 	{
-		if (cull == RT_CULL_BACK_FACE) return bvh_any<RT_CULL_FRONT_FACE, FAST>(K, nodes, tri, ray, cnt);
-		if (cull == RT_CULL_FRONT_FACE) return bvh_any<RT_CULL_BACK_FACE, FAST>(K, nodes, tri, ray, cnt);
-		return bvh_any<RT_CULL_NONE, FAST>(K, nodes, tri, ray, cnt);
+		const int shadow_cull = cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : (cull == RT_CULL_FRONT_FACE ? RT_CULL_BACK_FACE : RT_CULL_NONE);
+		float t = FLT_MAX; int tri_id = -1;
+		if (ray.nan_safe) return bvh_walk<true, true>(K, shadow_cull, nodes, tri, ray, t, tri_id, cnt);
+		return bvh_walk<true, false>(K, shadow_cull, nodes, tri, ray, t, tri_id, cnt);
 	}
 
 	// Scene::GetClosestHit, Scene.cpp:29-66: spheres, planes, meshes in order; strict '<' keeps
@@ -454,7 +592,7 @@ namespace rt
 	// outcome (its stale t is always >= the running closest t), so a plain running minimum is
 	// the same function.
 	template <bool BVH, bool COUNT>
-	__device__ __forceinline__ Hit closest_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
+	__device__ __forceinline__ Hit closest_hit(const Staged sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt, unsigned long long* dev_counters)
 	{
 		const Pk K = make_pk(dev);
 		Hit best;
@@ -466,44 +604,36 @@ namespace rt
 		for (int i = 0; i < dev.n_spheres; ++i)
 		{
 			float t;
-			const float4 sv = sc.sphere_view[i];
-			if (hit_sphere_from<false>(v3(sv), sv.w, sc.sphere[i].w, ray, t, cnt))
+			const float4 sv = sc.sphere_view(i);
+			if (hit_sphere_from<false>(v3(sv), sv.w, sc.sphere(i).w, ray, t, cnt))
 			{
 				if (t < best.t) { best.t = t; best_sphere = i; cnt.hit(RT_CNT_SPHERE_P_CLOSEST); }
 			}
 		}
 		if (best_sphere >= 0)
 		{
-			const float4 s = sc.sphere[best_sphere];
+			const float4 s = sc.sphere(best_sphere);
 			best.did = true;
-			best.material = sc.sphere_mat[best_sphere];
+			best.material = sc.sphere_mat(best_sphere);
 			best.origin = ray.o + ray.d * best.t;          // Utils.h:67
 			best.normal = best.origin - v3(s);             // Utils.h:68
 			normalize(best.normal);                        // Scene.cpp:40
 		}
 
-#pragma unroll 1
-		for (int i = 0; i < dev.n_planes; ++i)
+		int best_plane = -1;
+		planes_closest(K, sc, dev.n_planes, ray, best.t, best_plane, cnt);
+		if (best_plane >= 0)
 		{
-			float t;
-			const float4 po = sc.plane_o[i], pn = sc.plane_n[i];
-			if (hit_plane_from<false>(pn.w, pn, ray, t, cnt))
-			{
-				cnt.hit(RT_CNT_PLANE_P_HIT);
-				if (t < best.t)
-				{
-					best.t = t; best.did = true;
-					best.material = __float_as_int(po.w);
-					best.normal = v3(pn);                      // Utils.h:91
-					best.origin = ray.o + ray.d * t;           // Utils.h:92
-				}
-			}
+			best.did = true;
+			best.material = __float_as_int(sc.plane_o(best_plane).w);
+			best.normal = v3(sc.plane_n(best_plane));          // Utils.h:91
+			best.origin = ray.o + ray.d * best.t;              // Utils.h:92
 		}
 
 #pragma unroll 1
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
-			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			const float4 b0 = sc.mesh(3 * m), b1 = sc.mesh(3 * m + 1), info = sc.mesh(3 * m + 2);
 			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
@@ -512,8 +642,7 @@ namespace rt
 			{
 				if (count == 0) continue;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				if (!ray.nan_safe) bvh_closest_any_cull<false>(K, cull, nodes, tri, ray, best.t, best_tri, cnt);
-				else bvh_closest_any_cull<true>(K, cull, nodes, tri, ray, best.t, best_tri, cnt);
+				bvh_closest_any_cull(K, cull, nodes, tri, ray, best.t, best_tri, cnt);
 			}
 			else
 			{
@@ -538,20 +667,18 @@ namespace rt
 
 	// Scene::DoesHit, Scene.cpp:68-96: any-hit in the same order.
 	template <bool BVH, bool COUNT>
-	__device__ __forceinline__ bool does_hit(const SharedScene& sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt)
+	__device__ __forceinline__ bool does_hit(const Staged sc, const SceneDevice& dev, const Ray& ray, Counters<COUNT>& cnt, unsigned long long* dev_counters)
 	{
 		const Pk K = make_pk(dev);
 		float t;
 #pragma unroll 1
 		for (int i = 0; i < dev.n_spheres; ++i)
-			if (hit_sphere<true>(sc.sphere[i], ray, t, cnt)) return true;
-#pragma unroll 1
-		for (int i = 0; i < dev.n_planes; ++i)
-			if (hit_plane<true>(sc.plane_o[i], sc.plane_n[i], ray, t, cnt)) return true;
+			if (hit_sphere<true>(sc.sphere(i), ray, t, cnt)) return true;
+		if (planes_any(K, sc, dev.n_planes, ray, cnt)) return true;
 #pragma unroll 1
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
-			const float4 b0 = sc.mesh[3 * m], b1 = sc.mesh[3 * m + 1], info = sc.mesh[3 * m + 2];
+			const float4 b0 = sc.mesh(3 * m), b1 = sc.mesh(3 * m + 1), info = sc.mesh(3 * m + 2);
 			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
 			const int cull = __float_as_int(info.x);
 			const float4* tri = dev.triangles + 3 * (size_t)first;
@@ -561,8 +688,7 @@ namespace rt
 			{
 				if (count == 0) continue;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				if (!ray.nan_safe) hit = bvh_any_any_cull<false>(K, cull, nodes, tri, ray, cnt);
-				else hit = bvh_any_any_cull<true>(K, cull, nodes, tri, ray, cnt);
+				hit = bvh_any_any_cull(K, cull, nodes, tri, ray, cnt);
 			}
 			else
 			{
@@ -592,9 +718,8 @@ namespace rt
 
 	// Material::Shade as a tagged-union switch (Material.h:41-44, 60-63, 83-87, 107-123).
 	template <bool COUNT>
-	__device__ __forceinline__ V3 shade(const SharedScene& sc, int material, V3 n, V3 l, V3 v, Counters<COUNT>& cnt)
+	__device__ __forceinline__ V3 shade(const float4 m0, const float4 m1, V3 n, V3 l, V3 v, Counters<COUNT>& cnt)
 	{
-		const float4 m0 = sc.material[2 * material], m1 = sc.material[2 * material + 1];
 		const int tag = __float_as_int(m0.x);
 		const V3 color = v3(m0.y, m0.z, m0.w);
 		if (tag == RT_MATERIAL_SOLID_COLOR)
@@ -658,7 +783,7 @@ namespace rt
 	}
 
 	template <int MODE, int SHADOWS, bool BVH, bool COUNT>
-	__device__ __forceinline__ uint32_t render_pixel(const SharedScene& sc, const SceneDevice& dev, const FrameParams& p,
+	__device__ __forceinline__ uint32_t render_pixel(const Staged sc, const SceneDevice& dev, const FrameParams& p,
 	                                                  int px, int py, Counters<COUNT>& cnt)
 	{
 		const int mode = (MODE >= 0) ? MODE : p.lighting_mode;
@@ -676,7 +801,7 @@ namespace rt
 		normalize(d);
 		const Ray view = make_ray(v3(p.cam_ox, p.cam_oy, p.cam_oz), d, 0.0001f, FLT_MAX);
 
-		const Hit hit = closest_hit<BVH>(sc, dev, view, cnt);
+		const Hit hit = closest_hit<BVH>(sc, dev, view, cnt, p.counters);
 
 		float shadow_factor = 1.f;
 		V3 color = v3(0.f, 0.f, 0.f);
@@ -693,13 +818,13 @@ namespace rt
 #pragma unroll 1
 				for (int li = 0; li < dev.n_lights; ++li)
 				{
-					const float4 la = sc.light_a[li];
-					const int ltype = __float_as_int(sc.light_b[li].w);
+					const float4 la = sc.light_a(li);
+					const int ltype = __float_as_int(sc.light_b(li).w);
 					V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
 					const float mag = normalize(l);
 					cnt.hit(RT_CNT_SHADOW_RAYS);
 					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);   // Renderer.cpp:136
-					if (does_hit<BVH>(sc, dev, shadow_ray, cnt)) { occluded |= 1u << li; cnt.hit(RT_CNT_OCCLUDED); }
+					if (does_hit<BVH>(sc, dev, shadow_ray, cnt, p.counters)) { occluded |= 1u << li; cnt.hit(RT_CNT_OCCLUDED); }
 				}
 			}
 			// Pass 2: the lights that are not occluded, in light order (same accumulation order as the
@@ -712,7 +837,7 @@ namespace rt
 				cnt.hit(RT_CNT_LIGHT_ITERATIONS);
 				if ((occluded >> li) & 1u) { shadow_factor = mul(shadow_factor, 0.95f); continue; }
 				cnt.hit(RT_CNT_LIT);
-				const float4 la = sc.light_a[li], lb = sc.light_b[li];
+				const float4 la = sc.light_a(li), lb = sc.light_b(li);
 				const int ltype = __float_as_int(lb.w);
 				V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
 				normalize(l);
@@ -720,7 +845,7 @@ namespace rt
 				{
 					const float oa = std_max(dot(hit.normal, l), 0.f);
 					const V3 e = radiance(la, lb, hit.origin);
-					const V3 brdf = shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+					const V3 brdf = shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
 					// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
 					color = color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
 				}
@@ -735,7 +860,7 @@ namespace rt
 				}
 				else if (mode == RT_LIGHTING_BRDF)
 				{
-					color = color + shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+					color = color + shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
 				}
 			}
 			color = color * shadow_factor;                                  // Renderer.cpp:173
@@ -753,7 +878,7 @@ namespace rt
 			for (int li = 0; li < dev.n_lights; ++li)
 			{
 				cnt.hit(RT_CNT_LIGHT_ITERATIONS);
-				const float4 la = sc.light_a[li], lb = sc.light_b[li];
+				const float4 la = sc.light_a(li), lb = sc.light_b(li);
 				const int ltype = __float_as_int(lb.w);
 				// GetDirectionToLight, Utils.h:341-353: light.origin - p for both light types
 				V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
@@ -763,7 +888,7 @@ namespace rt
 				{
 					cnt.hit(RT_CNT_SHADOW_RAYS);
 					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);   // Renderer.cpp:136
-					if (does_hit<BVH>(sc, dev, shadow_ray, cnt))
+					if (does_hit<BVH>(sc, dev, shadow_ray, cnt, p.counters))
 					{
 						cnt.hit(RT_CNT_OCCLUDED);
 						shadow_factor = mul(shadow_factor, 0.95f);     // Renderer.cpp:139-140
@@ -776,7 +901,7 @@ namespace rt
 				{
 					const float oa = std_max(dot(hit.normal, l), 0.f);
 					const V3 e = radiance(la, lb, hit.origin);
-					const V3 brdf = shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+					const V3 brdf = shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
 					// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
 					color = color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
 				}
@@ -791,7 +916,7 @@ namespace rt
 				}
 				else if (mode == RT_LIGHTING_BRDF)
 				{
-					color = color + shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+					color = color + shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
 				}
 			}
 			color = color * shadow_factor;                                  // Renderer.cpp:173
@@ -832,6 +957,21 @@ namespace rt
 			const V3 n = v3(dev.plane_nx[i], dev.plane_ny[i], dev.plane_nz[i]);
 			sc.plane_o[i] = po;
 			sc.plane_n[i] = make_float4(n.x, n.y, n.z, dot(v3(po) - cam, n));
+		}
+		for (int j = tid; j < (dev.n_planes + 1) / 2; j += THREADS)
+		{
+			float o[2][3], n[2][3], num[2];
+			for (int h = 0; h < 2; ++h)
+			{
+				const int i = min(2 * j + h, dev.n_planes - 1);
+				o[h][0] = dev.plane_ox[i]; o[h][1] = dev.plane_oy[i]; o[h][2] = dev.plane_oz[i];
+				n[h][0] = dev.plane_nx[i]; n[h][1] = dev.plane_ny[i]; n[h][2] = dev.plane_nz[i];
+				num[h] = dot(v3(o[h][0], o[h][1], o[h][2]) - cam, v3(n[h][0], n[h][1], n[h][2]));
+			}
+			sc.plane_pair[3 * j + 0] = make_float4(o[0][0], o[1][0], o[0][1], o[1][1]);
+			sc.plane_pair[3 * j + 1] = make_float4(o[0][2], o[1][2], n[0][0], n[1][0]);
+			sc.plane_pair[3 * j + 2] = make_float4(n[0][1], n[1][1], n[0][2], n[1][2]);
+			sc.plane_pair_view[j] = make_float2(num[0], num[1]);
 		}
 		for (int i = tid; i < dev.n_lights; i += THREADS)
 		{
@@ -903,9 +1043,10 @@ namespace rt
 	__global__ void __launch_bounds__(kThreads)
 	render_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
-		__shared__ SharedScene sc;
-		stage_scene<kThreads>(sc, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
+		__shared__ SharedScene storage;
+		stage_scene<kThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
+		const Staged sc = staged_handle(storage);
 
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 		const int tx = lane & (kTileW - 1), ty = lane >> 3;
@@ -1019,10 +1160,10 @@ namespace rt
 		return c;
 	}
 
-	// 128-thread CTAs, 9 per SM: 56 registers, 36 warps per SM (measured best on the 4K bunny frame: 64
-	// registers / 32 warps +1.4 %, 48 registers / 40 warps +6 %, 80 registers / 24 warps +13 %)
+	// 128-thread CTAs, 8 per SM: 64 registers, 32 warps per SM.  (Round 1 ran 9 CTAs at 56 registers; with the round-2
+	// loops the 56-register build spills into the per-light code and is 7 % slower on the 4K bunny frame: 0.761 vs 0.708 ms.)
 #ifndef RT_PERSISTENT_MIN_CTAS
-#define RT_PERSISTENT_MIN_CTAS 9
+#define RT_PERSISTENT_MIN_CTAS 8
 #endif
 #ifndef RT_PERSISTENT_THREADS
 #define RT_PERSISTENT_THREADS 128
@@ -1032,10 +1173,11 @@ namespace rt
 	__global__ void __launch_bounds__(kPersistentThreads, RT_PERSISTENT_MIN_CTAS)
 	render_kernel_persistent(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
-		__shared__ SharedScene sc;
+		__shared__ SharedScene storage;
 		__shared__ unsigned int tile_clock[kPersistentThreads / 32];
-		stage_scene<kPersistentThreads>(sc, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
+		stage_scene<kPersistentThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
+		const Staged sc = staged_handle(storage);
 
 		const int lane = threadIdx.x & 31;
 		const int total = p.total_items ? p.total_items : p.grid_x * p.n_strips * kSignalsPerTile;

@@ -115,8 +115,8 @@ namespace x2
 		const V3x2 n = splat3(pn.x, pn.y, pn.z);
 		const float2 num = K.dot(K.sub(splat3(po.x, po.y, po.z), r.o), n);
 		const float2 den = K.dot(r.d, n);
-		h0 = on0 && plane_may_hit(num.x, den.x, r.tmax.x);
-		h1 = on1 && plane_may_hit(num.y, den.y, r.tmax.y);
+		h0 = on0 && plane_may_hit(num.x, den.x, rt::mul(r.tmax.x, 1.000001f));
+		h1 = on1 && plane_may_hit(num.y, den.y, rt::mul(r.tmax.y, 1.000001f));
 		t = make_float2(0.f, 0.f);
 		if (h0) { t.x = quo(num.x, den.x); h0 = (t.x >= kTMin && t.x < r.tmax.x); }
 		if (h1) { t.y = quo(num.y, den.y); h1 = (t.y >= kTMin && t.y < r.tmax.y); }
@@ -244,9 +244,11 @@ namespace x2
 		{
 			if (res0 == node) res0 = kAwake;
 			if (res1 == node) res1 = kAwake;
-			const float4 n0 = __ldg(nodes + 2 * node), n1 = __ldg(nodes + 2 * node + 1);
-			const int link = __float_as_int(n1.w);
-			const int escape = (link & BvhLink::kEscapeMask) - 1;
+			// `node` is the record's byte offset (rt::BvhLink): offsets name nodes as well as indices do
+			const float4* rec = node_at(nodes, node);
+			const float4 n0 = __ldg(rec), n1 = __ldg(rec + 1);
+			const int hit_link = __float_as_int(n1.z);
+			const int escape = __float_as_int(n1.w);
 			bool h0, h1;
 			slab2<FAST>(K, n0.x, n0.z, n1.x, n0.y, n0.w, n1.y, r, h0, h1);
 			h0 = h0 && (res0 == kAwake);
@@ -254,9 +256,8 @@ namespace x2
 			if (!h0 && res0 == kAwake) res0 = escape;     // this ray skips the subtree, like the early return of Utils.h:251-254
 			if (!h1 && res1 == kAwake) res1 = escape;
 			if (!(h0 | h1)) { node = escape; continue; }
-			const int count = link >> BvhLink::kEscapeBits;
-			const int first = __float_as_int(n1.z);
-			if (count == 0) { node = first; continue; }
+			if (!BvhLink::is_leaf(hit_link)) { node = hit_link; continue; }
+			const int count = BvhLink::leaf_count(hit_link), first = BvhLink::leaf_first(hit_link);
 			for (int k = 0; k < count && (h0 | h1); ++k)
 			{
 				const Tri T = load_tri(tri + 3 * (first + k));
@@ -466,7 +467,7 @@ namespace x2
 		{
 			const float oa = std_max(dot(hit.normal, l), 0.f);
 			const V3 e = radiance(la, lb, hit.origin);
-			const V3 brdf = shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+			const V3 brdf = shade(sc.material[2 * hit.material], sc.material[2 * hit.material + 1], hit.normal, l, view_neg, cnt);
 			return v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));   // Renderer.cpp:152
 		}
 		if (MODE == RT_LIGHTING_OBSERVED_AREA)
@@ -475,7 +476,7 @@ namespace x2
 			return v3(oa, oa, oa);
 		}
 		if (MODE == RT_LIGHTING_RADIANCE) return radiance(la, lb, hit.origin);
-		return shade(sc, hit.material, hit.normal, l, view_neg, cnt);
+		return shade(sc.material[2 * hit.material], sc.material[2 * hit.material + 1], hit.normal, l, view_neg, cnt);
 	}
 
 	template <int MODE, int SHADOWS, bool BVH>
