@@ -717,8 +717,14 @@ namespace rt
 	}
 
 	// Material::Shade as a tagged-union switch (Material.h:41-44, 60-63, 83-87, 107-123).
-	template <bool COUNT>
-	__device__ __forceinline__ V3 shade(const float4 m0, const float4 m1, V3 n, V3 l, V3 v, Counters<COUNT>& cnt)
+	// `view`: anything with load(2) = {-viewDir, -}: only the Phong and Cook-Torrance branches fetch it
+	struct ViewInRegisters
+	{
+		V3 v;
+		__device__ __forceinline__ float4 load(int) const { return make_float4(v.x, v.y, v.z, 0.f); }
+	};
+	template <bool COUNT, class View>
+	__device__ __forceinline__ V3 shade(const float4 m0, const float4 m1, V3 n, V3 l, const View& view, Counters<COUNT>& cnt)
 	{
 		const int tag = __float_as_int(m0.x);
 		const V3 color = v3(m0.y, m0.z, m0.w);
@@ -733,6 +739,7 @@ namespace rt
 			V3 out = color;
 			if (tag == RT_MATERIAL_LAMBERT) { cnt.hit(RT_CNT_SHADE_LAMBERT); return out; }
 			cnt.hit(RT_CNT_SHADE_PHONG);
+			const V3 v = v3(view.load(2));
 			// BRDF::Phong, BRDFs.h:33-40
 			const float nl = std_max(dot(n, l), 0.f);
 			const V3 reflect = l - n * mul(2.f, nl);
@@ -743,6 +750,7 @@ namespace rt
 		if (tag == RT_MATERIAL_COOK_TORRENCE)
 		{
 			cnt.hit(RT_CNT_SHADE_COOK_TORRENCE);
+			const V3 v = v3(view.load(2));
 			const float metal = m1.x, rough = m1.y;
 			V3 h = v + l;
 			normalize(h);
@@ -782,8 +790,41 @@ namespace rt
 		return v3(0.f, 0.f, 0.f);
 	}
 
+	// What only the shading of a pixel needs - hit point, normal, material, view direction - waits in shared memory
+	// while the shadow rays are traced, instead of occupying ten registers (or, as ptxas would have it, local memory
+	// inside the light loop).  One slot of three float4 per thread, [record][thread] so that a warp's 128-bit
+	// accesses are conflict-free.  Volatile: the loads stay where they are written, after the traversal.
+	template <int THREADS>
+	struct Parked
+	{
+		float4 slot[3][THREADS];
+	};
+	struct ParkedRef
+	{
+		unsigned int at;         // shared address of this thread's first record
+		unsigned int stride;     // bytes between records
+		__device__ __forceinline__ void store(int k, float4 v) const
+		{
+			asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(at + (unsigned int)k * stride), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+		}
+		__device__ __forceinline__ float4 load(int k) const
+		{
+			float4 v;
+			asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(at + (unsigned int)k * stride) : "memory");
+			return v;
+		}
+	};
+	template <int THREADS>
+	__device__ __forceinline__ ParkedRef parked_ref(const Parked<THREADS>& storage)
+	{
+		ParkedRef r;
+		r.at = (unsigned int)__cvta_generic_to_shared(&storage.slot[0][threadIdx.x]);
+		r.stride = (unsigned int)(sizeof(float4) * THREADS);
+		return r;
+	}
+
 	template <int MODE, int SHADOWS, bool BVH, bool COUNT>
-	__device__ __forceinline__ uint32_t render_pixel(const Staged sc, const SceneDevice& dev, const FrameParams& p,
+	__device__ __forceinline__ uint32_t render_pixel(const Staged sc, const ParkedRef park, const SceneDevice& dev, const FrameParams& p,
 	                                                  int px, int py, Counters<COUNT>& cnt)
 	{
 		const int mode = (MODE >= 0) ? MODE : p.lighting_mode;
@@ -795,99 +836,45 @@ namespace rt
 		const float cy = mul(sub(1.f, quo(mul(2.f, add((float)py, 0.5f)), (float)p.height)), p.fov);
 
 		// Matrix::TransformVector(cx, cy, 1), Matrix.cpp:35-42; x * 1.f is exact
-		V3 d = v3(add(add(mul(p.right_x, cx), mul(p.up_x, cy)), p.fwd_x),
-		          add(add(mul(p.right_y, cx), mul(p.up_y, cy)), p.fwd_y),
-		          add(add(mul(p.right_z, cx), mul(p.up_z, cy)), p.fwd_z));
-		normalize(d);
-		const Ray view = make_ray(v3(p.cam_ox, p.cam_oy, p.cam_oz), d, 0.0001f, FLT_MAX);
-
-		const Hit hit = closest_hit<BVH>(sc, dev, view, cnt, p.counters);
+		Ray view;
+		view.o = v3(p.cam_ox, p.cam_oy, p.cam_oz);
+		view.d = v3(add(add(mul(p.right_x, cx), mul(p.up_x, cy)), p.fwd_x),
+		            add(add(mul(p.right_y, cx), mul(p.up_y, cy)), p.fwd_y),
+		            add(add(mul(p.right_z, cx), mul(p.up_z, cy)), p.fwd_z));
+		normalize_and_invert(view.d, view.inv, view.nan_safe);        // Renderer.cpp:111-113, DataTypes.h:550-563
+		view.tmin = 0.0001f; view.tmax = FLT_MAX;
 
 		float shadow_factor = 1.f;
 		V3 color = v3(0.f, 0.f, 0.f);
-#ifdef RT_MASK_FIRST
-		if (hit.did)
+		V3 origin_offset;
+		bool did;
 		{
-			cnt.hit(RT_CNT_HIT_PIXELS);
-			const V3 origin_offset = hit.origin + hit.normal * 0.0001f;   // Renderer.cpp:126
-			// Pass 1: the shadow rays of every light (Renderer.cpp:131-141).  Only the occlusion bit of each
-			// light leaves this loop, so the colour state is not live across the traversals.
-			unsigned int occluded = 0u;
-			if (shadows)
-			{
-#pragma unroll 1
-				for (int li = 0; li < dev.n_lights; ++li)
-				{
-					const float4 la = sc.light_a(li);
-					const int ltype = __float_as_int(sc.light_b(li).w);
-					V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
-					const float mag = normalize(l);
-					cnt.hit(RT_CNT_SHADOW_RAYS);
-					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);   // Renderer.cpp:136
-					if (does_hit<BVH>(sc, dev, shadow_ray, cnt, p.counters)) { occluded |= 1u << li; cnt.hit(RT_CNT_OCCLUDED); }
-				}
-			}
-			// Pass 2: the lights that are not occluded, in light order (same accumulation order as the
-			// reference's single loop); every occluded light scales shadowFactor by 0.95f (Renderer.cpp:139-140;
-			// the factor is the same for each of them, so their position in the order does not matter).
-			const V3 view_neg = neg(d);
-#pragma unroll 1
-			for (int li = 0; li < dev.n_lights; ++li)
-			{
-				cnt.hit(RT_CNT_LIGHT_ITERATIONS);
-				if ((occluded >> li) & 1u) { shadow_factor = mul(shadow_factor, 0.95f); continue; }
-				cnt.hit(RT_CNT_LIT);
-				const float4 la = sc.light_a(li), lb = sc.light_b(li);
-				const int ltype = __float_as_int(lb.w);
-				V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
-				normalize(l);
-				if (mode == RT_LIGHTING_COMBINED)
-				{
-					const float oa = std_max(dot(hit.normal, l), 0.f);
-					const V3 e = radiance(la, lb, hit.origin);
-					const V3 brdf = shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
-					// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
-					color = color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
-				}
-				else if (mode == RT_LIGHTING_OBSERVED_AREA)
-				{
-					const float oa = std_max(dot(hit.normal, l), 0.f);
-					color = color + v3(oa, oa, oa);
-				}
-				else if (mode == RT_LIGHTING_RADIANCE)
-				{
-					color = color + radiance(la, lb, hit.origin);
-				}
-				else if (mode == RT_LIGHTING_BRDF)
-				{
-					color = color + shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
-				}
-			}
-			color = color * shadow_factor;                                  // Renderer.cpp:173
+			const Hit hit = closest_hit<BVH>(sc, dev, view, cnt, p.counters);
+			did = hit.did;
+			origin_offset = hit.origin + hit.normal * 0.0001f;          // Renderer.cpp:126
+			park.store(0, make_float4(hit.origin.x, hit.origin.y, hit.origin.z, __int_as_float(hit.material)));
+			park.store(1, make_float4(hit.normal.x, hit.normal.y, hit.normal.z, 0.f));
+			park.store(2, make_float4(-view.d.x, -view.d.y, -view.d.z, 0.f));      // Renderer.cpp:150: Shade(hit, l, -viewDir)
 		}
-#else
-		if (hit.did)
+		if (did)
 		{
 			cnt.hit(RT_CNT_HIT_PIXELS);
-			V3 origin_offset = hit.origin + hit.normal * 0.0001f;   // Renderer.cpp:126
-			// keep it in registers: under register pressure ptxas would otherwise re-evaluate the three
-			// multiply-adds inside the shadow traversal loops (once per BVH node)
-			asm volatile("" : "+f"(origin_offset.x), "+f"(origin_offset.y), "+f"(origin_offset.z));
-			const V3 view_neg = neg(d);
 #pragma unroll 1
 			for (int li = 0; li < dev.n_lights; ++li)
 			{
 				cnt.hit(RT_CNT_LIGHT_ITERATIONS);
-				const float4 la = sc.light_a(li), lb = sc.light_b(li);
-				const int ltype = __float_as_int(lb.w);
+				const float4 la = sc.light_a(li);
+				const int ltype = __float_as_int(sc.light_b(li).w);
 				// GetDirectionToLight, Utils.h:341-353: light.origin - p for both light types
-				V3 l = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
-				const float mag = normalize(l);
+				Ray shadow_ray;
+				shadow_ray.o = origin_offset;
+				shadow_ray.d = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
+				shadow_ray.tmax = normalize_and_invert(shadow_ray.d, shadow_ray.inv, shadow_ray.nan_safe);   // Renderer.cpp:131-136
+				shadow_ray.tmin = 0.0001f;
 
 				if (shadows)
 				{
 					cnt.hit(RT_CNT_SHADOW_RAYS);
-					const Ray shadow_ray = make_ray(origin_offset, l, 0.0001f, mag);   // Renderer.cpp:136
 					if (does_hit<BVH>(sc, dev, shadow_ray, cnt, p.counters))
 					{
 						cnt.hit(RT_CNT_OCCLUDED);
@@ -897,32 +884,35 @@ namespace rt
 				}
 				cnt.hit(RT_CNT_LIT);
 
+				const V3 l = shadow_ray.d;
+				const float4 h0 = park.load(0), h1 = park.load(1);
+				const V3 hit_origin = v3(h0), hit_normal = v3(h1);
+				const int material = __float_as_int(h0.w);
+				const float4 lb = sc.light_b(li);
 				if (mode == RT_LIGHTING_COMBINED)
 				{
-					const float oa = std_max(dot(hit.normal, l), 0.f);
-					const V3 e = radiance(la, lb, hit.origin);
-					const V3 brdf = shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
+					const float oa = std_max(dot(hit_normal, l), 0.f);
+					const V3 e = radiance(la, lb, hit_origin);
+					const V3 brdf = shade(sc.material(2 * material), sc.material(2 * material + 1), hit_normal, l, park, cnt);
 					// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
 					color = color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
 				}
 				else if (mode == RT_LIGHTING_OBSERVED_AREA)
 				{
-					const float oa = std_max(dot(hit.normal, l), 0.f);
+					const float oa = std_max(dot(hit_normal, l), 0.f);
 					color = color + v3(oa, oa, oa);
 				}
 				else if (mode == RT_LIGHTING_RADIANCE)
 				{
-					color = color + radiance(la, lb, hit.origin);
+					color = color + radiance(la, lb, hit_origin);
 				}
 				else if (mode == RT_LIGHTING_BRDF)
 				{
-					color = color + shade(sc.material(2 * hit.material), sc.material(2 * hit.material + 1), hit.normal, l, view_neg, cnt);
+					color = color + shade(sc.material(2 * material), sc.material(2 * material + 1), hit_normal, l, park, cnt);
 				}
 			}
 			color = color * shadow_factor;                                  // Renderer.cpp:173
 		}
-
-#endif
 
 		// ColorRGB::MaxToOne, ColorRGB.h:12-17
 		const float max_value = std_max(color.x, std_max(color.y, color.z));
@@ -1047,6 +1037,8 @@ namespace rt
 		stage_scene<kThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
 		const Staged sc = staged_handle(storage);
+		__shared__ Parked<kThreads> parked;
+		const ParkedRef park = parked_ref(parked);
 
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 		const int tx = lane & (kTileW - 1), ty = lane >> 3;
@@ -1058,7 +1050,7 @@ namespace rt
 
 		Counters<COUNT> cnt;
 		uint32_t pixel = 0;
-		if (valid) pixel = render_pixel<MODE, SHADOWS, BVH, COUNT>(sc, dev, p, px, py, cnt);
+		if (valid) pixel = render_pixel<MODE, SHADOWS, BVH, COUNT>(sc, park, dev, p, px, py, cnt);
 		if (COUNT) cnt.flush(p.counters);
 
 		const int dst_row = p.dst_full_frame ? py : ((int)blockIdx.y * kBlockH + local_y);
@@ -1178,6 +1170,8 @@ namespace rt
 		stage_scene<kPersistentThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
 		const Staged sc = staged_handle(storage);
+		__shared__ Parked<kPersistentThreads> parked;
+		const ParkedRef park = parked_ref(parked);
 
 		const int lane = threadIdx.x & 31;
 		const int total = p.total_items ? p.total_items : p.grid_x * p.n_strips * kSignalsPerTile;
@@ -1199,7 +1193,7 @@ namespace rt
 			if (p.cell_cost && lane == 0) tile_clock[threadIdx.x >> 5] = (unsigned int)clock();      // parked in shared memory: no register across the traversals
 			{
 				const TileCoords c = decode_work_item(p, item, lane);
-				if (c.valid) pixel = render_pixel<MODE, SHADOWS, BVH, false>(sc, dev, p, c.px, c.py, cnt);
+				if (c.valid) pixel = render_pixel<MODE, SHADOWS, BVH, false>(sc, park, dev, p, c.px, c.py, cnt);
 			}
 			// Only `item` is carried across the pixel: its coordinates are decoded again (a handful of integer
 			// instructions) instead of occupying registers during the traversals.

@@ -467,7 +467,7 @@ namespace x2
 		{
 			const float oa = std_max(dot(hit.normal, l), 0.f);
 			const V3 e = radiance(la, lb, hit.origin);
-			const V3 brdf = shade(sc.material[2 * hit.material], sc.material[2 * hit.material + 1], hit.normal, l, view_neg, cnt);
+			const V3 brdf = shade(sc.material[2 * hit.material], sc.material[2 * hit.material + 1], hit.normal, l, ViewInRegisters{ view_neg }, cnt);
 			return v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));   // Renderer.cpp:152
 		}
 		if (MODE == RT_LIGHTING_OBSERVED_AREA)
@@ -476,7 +476,7 @@ namespace x2
 			return v3(oa, oa, oa);
 		}
 		if (MODE == RT_LIGHTING_RADIANCE) return radiance(la, lb, hit.origin);
-		return shade(sc.material[2 * hit.material], sc.material[2 * hit.material + 1], hit.normal, l, view_neg, cnt);
+		return shade(sc.material[2 * hit.material], sc.material[2 * hit.material + 1], hit.normal, l, ViewInRegisters{ view_neg }, cnt);
 	}
 
 	template <int MODE, int SHADOWS, bool BVH>
