@@ -191,16 +191,17 @@ namespace
 	using rt::pick_kernel_persistent;
 
 	// One wave of the persistent kernel: SMs x CTAs resident per SM (asked of the runtime once per kernel).
-	int persistent_ctas_per_sm(KernelFn fn)
+	int persistent_ctas_per_sm(KernelFn fn, size_t dynamic_smem)
 	{
-		static std::map<KernelFn, int> cache;
+		static std::map<std::pair<KernelFn, size_t>, int> cache;
 		static std::mutex lock;
 		std::lock_guard<std::mutex> guard(lock);
-		auto it = cache.find(fn);
+		const auto key = std::make_pair(fn, dynamic_smem);
+		auto it = cache.find(key);
 		if (it != cache.end()) return it->second;
 		int n = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, rt::kPersistentThreads, 0) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
-		cache[fn] = n;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, rt::kPersistentThreads, dynamic_smem) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+		cache[key] = n;
 		return n;
 	}
 
@@ -793,7 +794,7 @@ namespace
 		if (variant == RT_KERNEL_AUTO || variant == RT_KERNEL_PERSISTENT)
 		{
 			persistent = pick_kernel_persistent(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH);
-			wave = d.sm_count * persistent_ctas_per_sm(persistent);
+			wave = d.sm_count * persistent_ctas_per_sm(persistent, rt::dynamic_smem_bytes(rt::kPersistentThreads, ctx->n_materials));
 			// AUTO: persistent warps pay off once the frame is many waves deep; small frames keep one CTA per tile.
 			// Device-only launches can walk their tiles in measured-cost order (prepare_cell_order), which already pays at
 			// 6 warp tiles per resident warp (an eighth of the 4K bunny frame: 0.148 ms against 0.162 ms tiled)
@@ -802,7 +803,7 @@ namespace
 			if (!decodable) variant = RT_KERNEL_SCALAR;
 		}
 		if (variant == RT_KERNEL_PACKED) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::pick_threads_x2(), 0, stream>>>(d.view, p);
-		else if (variant == RT_KERNEL_SCALAR) pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, stream>>>(d.view, p);
+		else if (variant == RT_KERNEL_SCALAR) pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, rt::dynamic_smem_bytes(rt::kThreads, ctx->n_materials), stream>>>(d.view, p);
 		else
 		{
 			// persistent warps: one wave of CTAs, never more than the launch has tiles; every launch takes the
@@ -815,7 +816,7 @@ namespace
 			if (prc != RT_OK) return prc;
 			p.queue = d.d_queues + 2 * (d.queue_cursor++ % kQueueRing);
 			const long long ctas_of_work = (tiles * rt::kSignalsPerTile + rt::kPersistentThreads / 32 - 1) / (rt::kPersistentThreads / 32);
-			fn<<<(unsigned)std::min<long long>(wave, ctas_of_work), rt::kPersistentThreads, 0, stream>>>(d.view, p);
+			fn<<<(unsigned)std::min<long long>(wave, ctas_of_work), rt::kPersistentThreads, rt::dynamic_smem_bytes(rt::kPersistentThreads, ctx->n_materials), stream>>>(d.view, p);
 			RT_CUDA(ctx, cudaGetLastError());
 			const int frc = finish_cell_order(ctx, d, p, stream, cost_slot);
 			if (frc != RT_OK) return frc;
@@ -2088,7 +2089,7 @@ int rt_count_frame(rt_context* ctx, const rt_camera* camera, const rt_frame_desc
 	p.dst_full_frame = 1; p.dst = d.d_frame; p.counters = d.d_counters;
 	p.vector_store = (p.width % 4 == 0);
 	const dim3 grid((unsigned)((p.width + rt::kBlockW - 1) / rt::kBlockW), (unsigned)((p.height + rt::kBlockH - 1) / rt::kBlockH), 1);
-	rt::pick_kernel_count(path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, 0, d.stream>>>(d.view, p);
+	rt::pick_kernel_count(path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, rt::dynamic_smem_bytes(rt::kThreads, ctx->n_materials), d.stream>>>(d.view, p);
 	RT_CUDA(ctx, cudaGetLastError());
 	RT_CUDA(ctx, cudaMemcpyAsync(out_counters->slot, d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS, cudaMemcpyDeviceToHost, d.stream));
 	RT_CUDA(ctx, cudaStreamSynchronize(d.stream));

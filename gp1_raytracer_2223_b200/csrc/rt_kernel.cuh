@@ -120,15 +120,22 @@ namespace rt
 		float4 light_a[kMaxLights];          // {ox, oy, oz, intensity}
 		float4 light_b[kMaxLights];          // {r, g, b, type bits}
 		float4 mesh[3 * kMaxMeshes];
-		float4 material[2 * kMaxMaterials];
 		float4 sphere_view[kMaxSpheres];     // {c - camera origin, |c - camera origin|^2}: HitTest_Sphere's ray-independent part for view rays
 		// the planes once more, two per record, laid out for the packed plane loops (plane_pair_*): planes 2j and 2j + 1 as
 		// {ox0, ox1, oy0, oy1} {oz0, oz1, nx0, nx1} {ny0, ny1, nz0, nz1}; an odd count is padded with a copy of the last
 		// plane (same test, same result: an any-hit cannot change, and a closest hit keeps the first of two equal t)
 		float4 plane_pair[3 * (kMaxPlanes / 2)];
 		float2 plane_pair_view[kMaxPlanes / 2];   // {num0, num1} of HitTest_Plane for view rays, as plane_n[].w
+		// per mesh: the addresses of its first triangle record and its first node record (two 64-bit pointers as bits),
+		// so that a ray entering a mesh does no pointer arithmetic
+		float4 mesh_ptr[kMaxMeshes];
 		uint8_t sphere_mat[kMaxSpheres];
+		// LAST, and only its first 2 * n_materials records exist in the scalar kernels' dynamic shared memory
+		// (staged_scene_bytes): a full table is 8 KB per CTA for scenes that use a handful of materials
+		float4 material[2 * kMaxMaterials];
 	};
+	inline __host__ __device__ size_t staged_scene_bytes(int n_materials) { return offsetof(SharedScene, material) + sizeof(float4) * 2 * (size_t)n_materials; }
+
 
 	// The staged scene seen from the pixel code: ONE 32-bit shared-memory address plus compile-time field offsets, read
 	// with explicit ld.shared.  (Passing `SharedScene&` around makes nvcc rebuild the block's shared-window base - S2R
@@ -142,7 +149,7 @@ namespace rt
 		static __device__ __forceinline__ int ld8(unsigned int a) { int v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 #define RT_STAGED_F4(name, field) __device__ __forceinline__ float4 name(int i) const { return ld4(base + (unsigned int)offsetof(SharedScene, field) + 16u * (unsigned int)i); }
 		RT_STAGED_F4(sphere, sphere) RT_STAGED_F4(sphere_view, sphere_view) RT_STAGED_F4(plane_o, plane_o) RT_STAGED_F4(plane_n, plane_n)
-		RT_STAGED_F4(light_a, light_a) RT_STAGED_F4(light_b, light_b) RT_STAGED_F4(mesh, mesh) RT_STAGED_F4(material, material) RT_STAGED_F4(plane_pair, plane_pair)
+		RT_STAGED_F4(light_a, light_a) RT_STAGED_F4(light_b, light_b) RT_STAGED_F4(mesh, mesh) RT_STAGED_F4(material, material) RT_STAGED_F4(plane_pair, plane_pair) RT_STAGED_F4(mesh_ptr, mesh_ptr)
 #undef RT_STAGED_F4
 		__device__ __forceinline__ float2 plane_pair_view(int j) const { return ld2(base + (unsigned int)offsetof(SharedScene, plane_pair_view) + 8u * (unsigned int)j); }
 		__device__ __forceinline__ int sphere_mat(int i) const { return ld8(base + (unsigned int)offsetof(SharedScene, sphere_mat) + (unsigned int)i); }
@@ -286,7 +293,7 @@ namespace rt
 	__device__ __forceinline__ bool planes_any(const Pk& K, const Staged sc, int n_planes, const Ray& ray, Counters<COUNT>& cnt)
 	{
 		const float limit_up = mul(ray.tmax, 1.000001f);
-#pragma unroll 1
+#pragma unroll 2      // two pairs per trip: measured best on the 4K frames (1: +3 %, 3: +1 %)
 		for (int j = 0; 2 * j < n_planes; ++j)
 		{
 			const float4 a = sc.plane_pair(3 * j), b = sc.plane_pair(3 * j + 1), c = sc.plane_pair(3 * j + 2);
@@ -587,6 +594,11 @@ namespace rt
 		return bvh_walk<true, false>(K, shadow_cull, nodes, tri, ray, t, tri_id, cnt);
 	}
 
+	__device__ __forceinline__ const float4* pointer_from_bits(float lo, float hi)
+	{
+		return reinterpret_cast<const float4*>(((unsigned long long)(unsigned int)__float_as_int(hi) << 32) | (unsigned long long)(unsigned int)__float_as_int(lo));
+	}
+
 	// Scene::GetClosestHit, Scene.cpp:29-66: spheres, planes, meshes in order; strict '<' keeps
 	// the first primitive on ties.  The reference's shared scratch HitRecord never changes the
 	// outcome (its stale t is always >= the running closest t), so a plain running minimum is
@@ -633,19 +645,19 @@ namespace rt
 #pragma unroll 1
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
-			const float4 b0 = sc.mesh(3 * m), b1 = sc.mesh(3 * m + 1), info = sc.mesh(3 * m + 2);
-			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
+			const float4 info = sc.mesh(3 * m + 2), ptrs = sc.mesh_ptr(m);
 			const int cull = __float_as_int(info.x);
-			const float4* tri = dev.triangles + 3 * (size_t)first;
+			const float4* tri = pointer_from_bits(ptrs.x, ptrs.y);
 			int best_tri = -1;
 			if (BVH)
 			{
-				if (count == 0) continue;
-				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				bvh_closest_any_cull(K, cull, nodes, tri, ray, best.t, best_tri, cnt);
+				if (__float_as_int(info.w) == 0) continue;           // no nodes: an empty mesh
+				bvh_closest_any_cull(K, cull, pointer_from_bits(ptrs.z, ptrs.w), tri, ray, best.t, best_tri, cnt);
 			}
 			else
 			{
+				const float4 b0 = sc.mesh(3 * m), b1 = sc.mesh(3 * m + 1);
+				const int count = __float_as_int(b1.w);
 				cnt.hit(RT_CNT_SLAB_P_TEST);
 				if (!(ray.nan_safe ? slab_test<true>(K, b0, b1, ray) : slab_test<false>(K, b0, b1, ray))) continue;
 				cnt.hit(RT_CNT_SLAB_P_PASS);
@@ -678,20 +690,20 @@ namespace rt
 #pragma unroll 1
 		for (int m = 0; m < dev.n_meshes; ++m)
 		{
-			const float4 b0 = sc.mesh(3 * m), b1 = sc.mesh(3 * m + 1), info = sc.mesh(3 * m + 2);
-			const int first = __float_as_int(b1.z), count = __float_as_int(b1.w);
+			const float4 info = sc.mesh(3 * m + 2), ptrs = sc.mesh_ptr(m);
 			const int cull = __float_as_int(info.x);
-			const float4* tri = dev.triangles + 3 * (size_t)first;
+			const float4* tri = pointer_from_bits(ptrs.x, ptrs.y);
 			// Utils.h:114-127: shadow rays see the opposite cull mode
 			bool hit;
 			if (BVH)
 			{
-				if (count == 0) continue;
-				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				hit = bvh_any_any_cull(K, cull, nodes, tri, ray, cnt);
+				if (__float_as_int(info.w) == 0) continue;
+				hit = bvh_any_any_cull(K, cull, pointer_from_bits(ptrs.z, ptrs.w), tri, ray, cnt);
 			}
 			else
 			{
+				const float4 b0 = sc.mesh(3 * m), b1 = sc.mesh(3 * m + 1);
+				const int count = __float_as_int(b1.w);
 				cnt.hit(RT_CNT_SLAB_S_TEST);
 				if (!(ray.nan_safe ? slab_test<true>(K, b0, b1, ray) : slab_test<false>(K, b0, b1, ray))) continue;
 				cnt.hit(RT_CNT_SLAB_S_PASS);
@@ -797,12 +809,14 @@ namespace rt
 	template <int THREADS>
 	struct Parked
 	{
-		float4 slot[3][THREADS];
+		float4 slot[4][THREADS];           // record 3 = the persistent kernel's tile coordinates (two words)
 	};
 	struct ParkedRef
 	{
 		unsigned int at;         // shared address of this thread's first record
 		unsigned int stride;     // bytes between records
+		__device__ __forceinline__ void store_words(unsigned int a, unsigned int b) const { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(at + 3u * stride), "r"(a), "r"(b) : "memory"); }
+		__device__ __forceinline__ uint2 load_words() const { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(at + 3u * stride) : "memory"); return v; }
 		__device__ __forceinline__ void store(int k, float4 v) const
 		{
 			asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(at + (unsigned int)k * stride), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -969,6 +983,14 @@ namespace rt
 			sc.light_b[i] = make_float4(dev.light_r[i], dev.light_g[i], dev.light_b[i], __int_as_float(dev.light_type[i]));
 		}
 		for (int i = tid; i < 3 * dev.n_meshes; i += THREADS) sc.mesh[i] = dev.mesh_table[i];
+		for (int m = tid; m < dev.n_meshes; m += THREADS)
+		{
+			const float4 b1 = dev.mesh_table[3 * m + 1], info = dev.mesh_table[3 * m + 2];
+			const unsigned long long tri = reinterpret_cast<unsigned long long>(dev.triangles + 3 * (size_t)__float_as_int(b1.z));
+			const unsigned long long nodes = reinterpret_cast<unsigned long long>(dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z));
+			sc.mesh_ptr[m] = make_float4(__int_as_float((int)(unsigned int)tri), __int_as_float((int)(unsigned int)(tri >> 32)),
+			                             __int_as_float((int)(unsigned int)nodes), __int_as_float((int)(unsigned int)(nodes >> 32)));
+		}
 		for (int i = tid; i < dev.n_materials; i += THREADS)
 		{
 			float4 m0 = dev.materials[2 * i];
@@ -1033,11 +1055,13 @@ namespace rt
 	__global__ void __launch_bounds__(kThreads)
 	render_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
-		__shared__ SharedScene storage;
+		// dynamic shared memory: Parked<kThreads> | SharedScene cut after its last material (dynamic_smem_bytes)
+		extern __shared__ __align__(16) unsigned char dynamic_smem[];
+		Parked<kThreads>& parked = *reinterpret_cast<Parked<kThreads>*>(dynamic_smem);
+		SharedScene& storage = *reinterpret_cast<SharedScene*>(dynamic_smem + sizeof(Parked<kThreads>));
 		stage_scene<kThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
 		const Staged sc = staged_handle(storage);
-		__shared__ Parked<kThreads> parked;
 		const ParkedRef park = parked_ref(parked);
 
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1161,16 +1185,19 @@ namespace rt
 #define RT_PERSISTENT_THREADS 128
 #endif
 	constexpr int kPersistentThreads = RT_PERSISTENT_THREADS;   // CTA size is free here: warps are the workers
+	// dynamic shared memory of a launch of the tiled (kThreads) / persistent (kPersistentThreads) kernel
+	inline size_t dynamic_smem_bytes(int threads, int n_materials) { return sizeof(float4) * 4 * (size_t)threads + staged_scene_bytes(n_materials); }
 	template <int MODE, int SHADOWS, bool BVH>
 	__global__ void __launch_bounds__(kPersistentThreads, RT_PERSISTENT_MIN_CTAS)
 	render_kernel_persistent(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
-		__shared__ SharedScene storage;
+		extern __shared__ __align__(16) unsigned char dynamic_smem[];
+		Parked<kPersistentThreads>& parked = *reinterpret_cast<Parked<kPersistentThreads>*>(dynamic_smem);
+		SharedScene& storage = *reinterpret_cast<SharedScene*>(dynamic_smem + sizeof(Parked<kPersistentThreads>));
 		__shared__ unsigned int tile_clock[kPersistentThreads / 32];
 		stage_scene<kPersistentThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
 		const Staged sc = staged_handle(storage);
-		__shared__ Parked<kPersistentThreads> parked;
 		const ParkedRef park = parked_ref(parked);
 
 		const int lane = threadIdx.x & 31;
@@ -1191,14 +1218,21 @@ namespace rt
 #endif
 			uint32_t pixel = 0;
 			if (p.cell_cost && lane == 0) tile_clock[threadIdx.x >> 5] = (unsigned int)clock();      // parked in shared memory: no register across the traversals
+			// The tile's coordinates wait in shared memory while the pixel is rendered, as two packed words ({py, px} and
+			// {valid, strip, row in strip}): cheaper than decoding the work item a second time, and no registers across the
+			// traversals either.
 			{
 				const TileCoords c = decode_work_item(p, item, lane);
+				park.store_words(((unsigned int)c.py << 16) | ((unsigned int)c.px & 0xffffu), (c.valid ? 0x80000000u : 0u) | ((unsigned int)c.k << 3) | (unsigned int)c.local_y);
 				if (c.valid) pixel = render_pixel<MODE, SHADOWS, BVH, false>(sc, park, dev, p, c.px, c.py, cnt);
 			}
-			// Only `item` is carried across the pixel: its coordinates are decoded again (a handful of integer
-			// instructions) instead of occupying registers during the traversals.
-			asm volatile("" : "+r"(item));
-			const TileCoords c = decode_work_item(p, item, lane);
+			TileCoords c;
+			{
+				const uint2 words = park.load_words();
+				const unsigned int where = words.x, strip_row = words.y;
+				c.px = (int)(where & 0xffffu); c.py = (int)(where >> 16);
+				c.k = (int)((strip_row & 0x7fffffffu) >> 3); c.local_y = (int)(strip_row & 7u); c.valid = (strip_row >> 31) != 0u;
+			}
 			const int dst_row = p.dst_full_frame ? c.py : (c.k * kBlockH + c.local_y);
 			uint32_t* row = p.dst + (size_t)dst_row * (size_t)p.width;
 			if (p.vector_store)
@@ -1217,7 +1251,7 @@ namespace rt
 				__syncwarp();
 				if (lane == 0) signal_band_done(p, c.k, 1u);
 			}
-			if (p.cell_cost && lane == 0 && c.k < p.n_strips) atomicAdd(p.cell_cost + c.cell, ((unsigned int)clock() - tile_clock[threadIdx.x >> 5]) >> 4);
+			if (p.cell_cost && lane == 0 && c.k < p.n_strips) atomicAdd(p.cell_cost + decode_work_item(p, item, lane).cell, ((unsigned int)clock() - tile_clock[threadIdx.x >> 5]) >> 4);
 #ifdef RT_PERSIST_PREFETCH
 			item = upcoming;
 #else
