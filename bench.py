@@ -432,20 +432,23 @@ def main():
         exchange_step()
 
     e2e_parts = [0.0] * 6      # host seconds in upload / render call / handshake, device seconds kernel / kernel + copies, steps
+    mesh_desc = r.ctx.mesh_descriptor(mesh)       # the same host arrays every step, like the drop-in's TriangleMesh vectors
 
     def e2e_step():
         """Host buffers in, host buffer out, through the C ABI."""
         t_a = time.perf_counter()
-        r.ctx.upload_mesh(0, mesh)                                  # H2D: what UpdateTransforms produced this frame
+        r.ctx.upload_mesh_descriptor(0, mesh_desc)                  # H2D: what UpdateTransforms produced this frame
         t_b = time.perf_counter()
         e2e_parts[0] += t_b - t_a
         if world == 1:
-            r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + progressive D2H, blocking
+            tm = r.render_host_ptr(host_frame.data_ptr(), WIDTH * 4)     # kernel + progressive D2H, blocking
+            e2e_parts[1] += time.perf_counter() - t_b
+            e2e_parts[3] += tm["kernel_ms"] * 1e-3; e2e_parts[4] += tm["total_ms"] * 1e-3; e2e_parts[5] += 1
             return
         if present_mode == "direct":
             tm = r.render_strips_to_host(rank, world, surface.ptr, surface.pitch_bytes)   # blocking: this rank's strips are in host memory
             t_c = time.perf_counter()
-            surface.arrive_and_wait()             # surface complete; nobody starts the next frame earlier
+            surface.arrive_and_wait(lib=r.ctx.lib)  # surface complete; nobody starts the next frame earlier
             e2e_parts[1] += t_c - t_b; e2e_parts[2] += time.perf_counter() - t_c
             e2e_parts[3] += tm["kernel_ms"] * 1e-3; e2e_parts[4] += tm["total_ms"] * 1e-3; e2e_parts[5] += 1
             return
@@ -535,10 +538,11 @@ def main():
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": WIDTH * HEIGHT * 4,
                "step_ms": {"min": per_step[0], "median": per_step[len(per_step) // 2], "max": per_step[-1]},
                "timing": "host wall clock around the blocking C-ABI calls of every step (upload + render into host memory), max over ranks"}
-        if present_mode == "direct" and e2e_parts[5] > 0:
+        if e2e_parts[5] > 0:
             # where a step's time goes, slowest rank per component, averaged over the timed steps
             parts = torch.tensor([x / e2e_parts[5] * 1e3 for x in e2e_parts[:5]], dtype=torch.float64, device="cuda")
-            dist.all_reduce(parts, op=dist.ReduceOp.MAX)
+            if world > 1:
+                dist.all_reduce(parts, op=dist.ReduceOp.MAX)
             e2e["breakdown_ms_max_over_ranks"] = dict(zip(["host_upload_mesh", "host_render_strips_to_host_call", "host_wait_for_all_ranks",
                                                            "device_kernel", "device_kernel_and_copies"], [float(x) for x in parts]))
 

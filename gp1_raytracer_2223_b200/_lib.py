@@ -58,6 +58,7 @@ SYMBOLS = {
     "rt_render_strips_to_frame_banded": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32, C.c_int32,
                                                    C.c_void_p, C.c_int32, C.c_void_p]),
     "rt_frame_present": (C.c_int, [_ctx, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32]),
+    "rt_host_arrive_and_wait": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_double]),
     "rt_get_timing": (C.c_int, [_ctx, C.POINTER(rt_timing)]),
     "rt_measure_fp32_peak": (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "rt_count_frame": (C.c_int, [_ctx, C.POINTER(rt_camera), C.POINTER(rt_frame_desc), C.c_int32,

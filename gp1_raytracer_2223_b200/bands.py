@@ -107,10 +107,16 @@ class SharedSurface:
         import os
         os.unlink(self.path)
 
-    def arrive_and_wait(self, timeout_s: float = 60.0) -> int:
-        """This rank's strips of the next frame are in the surface; returns when everybody's are."""
+    def arrive_and_wait(self, timeout_s: float = 60.0, lib=None) -> int:
+        """This rank's strips of the next frame are in the surface; returns when everybody's are.  With `lib` (the
+        loaded C ABI) the spin runs in rt_host_arrive_and_wait instead of the interpreter."""
         import time
         self.presented += 1
+        if lib is not None:
+            rc = lib.rt_host_arrive_and_wait(self.arrived.ctypes.data, 8, self.rank, self.world, self.presented, timeout_s)
+            if rc != 0:
+                raise TimeoutError(f"rank {self.rank}: frame {self.presented} incomplete, arrivals {self.arrived.tolist()}")
+            return self.presented
         self.arrived[self.rank] = self.presented
         deadline = time.monotonic() + timeout_s
         spins = 0

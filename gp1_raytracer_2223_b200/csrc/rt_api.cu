@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -2021,6 +2022,24 @@ int rt_clear_frame(rt_context* ctx, uint32_t pixel)
 	RT_CUDA(ctx, cuda_fill32(d.d_frame, pixel, pixels, d.stream));
 	RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
 	return RT_OK;
+}
+
+int rt_host_arrive_and_wait(volatile int64_t* words, int32_t stride_words, int32_t rank, int32_t world, int64_t frame, double timeout_seconds)
+{
+	if (!words || stride_words <= 0 || world <= 0 || rank < 0 || rank >= world) return RT_ERR_INVALID_ARGUMENT;
+	__atomic_store_n(const_cast<int64_t*>(words) + (size_t)rank * stride_words, frame, __ATOMIC_RELEASE);
+	const auto t0 = std::chrono::steady_clock::now();
+	for (unsigned long long spins = 0;; ++spins)
+	{
+		bool all = true;
+		for (int r = 0; r < world && all; ++r)
+			all = __atomic_load_n(const_cast<int64_t*>(words) + (size_t)r * stride_words, __ATOMIC_ACQUIRE) >= frame;
+		if (all) return RT_OK;
+#if defined(__x86_64__)
+		__builtin_ia32_pause();
+#endif
+		if ((spins & 0xffffu) == 0xffffu && std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_seconds) return RT_ERR_BAD_STATE;
+	}
 }
 
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing)

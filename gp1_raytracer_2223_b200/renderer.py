@@ -115,9 +115,18 @@ class Context:
 
     def upload_mesh(self, mesh_id: int, mesh) -> None:
         """Re-upload one mesh after TriangleMesh::UpdateTransforms (reference source/DataTypes.h:210-236)."""
+        self.upload_mesh_descriptor(mesh_id, self.mesh_descriptor(mesh))
+
+    def mesh_descriptor(self, mesh):
+        """The rt_mesh_desc of a mesh, built once: a caller that re-uploads the same host arrays every frame (what the
+        C++ drop-in does with the TriangleMesh's vectors) pays for the ctypes marshalling only here."""
         v = SceneViews.__new__(SceneViews)
         v._keep = []
         desc = SceneViews.mesh_desc(v, mesh)
+        desc._keepalive = v
+        return desc
+
+    def upload_mesh_descriptor(self, mesh_id: int, desc) -> None:
         self.check(self.lib.rt_upload_mesh(self.handle, mesh_id, C.byref(desc)), "rt_upload_mesh")
 
     def measure_fp32_peak(self, use_fma: bool) -> dict:
@@ -279,8 +288,12 @@ class Renderer:
         return np.array(list(cnt.slot), dtype=np.uint64)
 
     def _frame(self):
-        return frame_struct(self.width, self.height, self.lighting_mode, self.shadows_enabled, self.aspect_ratio,
-                            self.shifts, self.alpha_mask)
+        key = (self.width, self.height, self.lighting_mode, self.shadows_enabled, self.aspect_ratio, self.shifts, self.alpha_mask)
+        if getattr(self, "_frame_key", None) != key:
+            self._frame_key = key
+            self._frame_struct = frame_struct(self.width, self.height, self.lighting_mode, self.shadows_enabled, self.aspect_ratio,
+                                              self.shifts, self.alpha_mask)
+        return self._frame_struct
 
     def close(self):
         self.ctx.close()

@@ -463,6 +463,13 @@ int rt_render_strips_to_frame_banded(rt_context* ctx, const rt_camera* camera, c
                                      int32_t bands, void* cuda_stream);
 int rt_frame_present(rt_context* ctx, uint32_t* host_dst, int32_t pitch_bytes, int32_t bands, uint32_t frame_number);
 
+/* Host-side completion handshake of the direct present across processes: `words` points at one 64-bit arrival word per
+ * rank in memory every rank maps (stride_words 64-bit words apart, e.g. 8 = one cache line each).  Stores `frame` into
+ * this rank's word (release) and returns once every rank's word has reached `frame` (acquire): all strips of that frame
+ * are in the shared surface.  No device work, no context: it only spares the caller an interpreted spin loop.
+ * RT_ERR_BAD_STATE after timeout_seconds. */
+int rt_host_arrive_and_wait(volatile int64_t* words, int32_t stride_words, int32_t rank, int32_t world, int64_t frame, double timeout_seconds);
+
 int rt_get_timing(const rt_context* ctx, rt_timing* out_timing);
 
 /* Counters build of the same kernel: fills the test histogram for one frame (slow path,

@@ -7,8 +7,10 @@ import numpy as np
 import pytest
 
 from conftest import load_golden_frame, load_golden_scene
-from gp1_raytracer_2223_b200 import bands
+from gp1_raytracer_2223_b200 import _lib, bands, build
 from oracle import rt_oracle
+
+build.ensure()          # rt_host_arrive_and_wait lives in the C-ABI library (it needs no GPU)
 
 
 @pytest.mark.parametrize("height", [1, 7, 8, 9, 77, 480, 2160])
@@ -101,7 +103,8 @@ def _surface_worker(rank, world, port, path, frames, q):
                 y0 = strip * bands.STRIP_ROWS
                 n = min(bands.STRIP_ROWS, 203 - y0)
                 surface.frame[y0:y0 + n] = rt_oracle.render(scene, 101, 203, row_begin=y0, row_count=n)
-            assert surface.arrive_and_wait() == k + 1
+            # odd frames through the interpreted spin, even ones through the C ABI's rt_host_arrive_and_wait
+            assert surface.arrive_and_wait(lib=_lib.load() if k % 2 == 0 else None) == k + 1
             if rank == 0:
                 q.put(surface.frame.copy())
             dist.barrier()                              # the test's own pacing: rank 0 has copied before anyone overwrites
@@ -137,3 +140,5 @@ def test_shared_surface_handshake_times_out_instead_of_hanging(tmp_path):
     s = bands.SharedSurface(16, 16, 2, 0, path, create=True)
     with pytest.raises(TimeoutError):
         s.arrive_and_wait(timeout_s=0.05)            # rank 1 never arrives
+    with pytest.raises(TimeoutError):
+        s.arrive_and_wait(timeout_s=0.05, lib=_lib.load())
