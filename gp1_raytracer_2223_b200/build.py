@@ -20,8 +20,8 @@ LIB = os.path.join(HERE, "librt_b200.so")
 # One translation unit per family of kernel instantiations: ptxas is the long pole (dozens of template instantiations
 # of a 6 000-instruction kernel), so the units are compiled in parallel and linked once.  No relocatable device code:
 # every kernel is complete inside its unit; the units only exchange host function pointers (rt_pick.h).
-SOURCES = ["rt_api.cu", "rt_pick_tiled.cu", "rt_pick_persistent.cu", "rt_pick_x2.cu"]
-HEADERS = ["rt_kernel.cuh", "rt_kernel_x2.cuh", "rt_device.cuh", "rt_bvh_build.cuh", "rt_aux_kernels.cuh", "rt_pick.h",
+SOURCES = ["rt_api.cu", "rt_pick_tiled.cu", "rt_pick_persistent.cu", "rt_pick_x2.cu", "rt_pick_wave.cu"]
+HEADERS = ["rt_kernel.cuh", "rt_kernel_x2.cuh", "rt_device.cuh", "rt_bvh_build.cuh", "rt_aux_kernels.cuh", "rt_kernel_wave.cuh", "rt_wave_params.h", "rt_pick.h",
            os.path.join("..", "..", "include", "rt_b200.h")]
 
 NVCC_FLAGS = [

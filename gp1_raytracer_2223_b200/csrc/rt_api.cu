@@ -6,6 +6,7 @@
 #include "rt_kernel.cuh"
 #include "rt_aux_kernels.cuh"
 #include "rt_pick.h"
+#include "rt_wave_params.h"
 #include "rt_bvh_build.cuh"
 
 #include <cuda.h>
@@ -32,6 +33,8 @@ namespace
 	{
 		std::vector<float4> triangles;   // 3 per triangle
 		std::vector<float4> nodes;       // 2 per BVH node, threaded (rt::BvhLink); empty when the mesh came without nodes
+		std::vector<int32_t> split;      // rt::wave::kSplitStride words: the tree cut into subtrees (RT_KERNEL_WAVEFRONT); empty: none
+		std::vector<uint8_t> root_map;   // per node: subtree number + 1 for the subtrees' roots, else 0
 		float aabb_min[3] = { 0, 0, 0 };
 		float aabb_max[3] = { 0, 0, 0 };
 		int32_t cull_mode = RT_CULL_BACK_FACE;
@@ -120,6 +123,13 @@ namespace
 			int orders_made = 0, launches_since_measured = 0;
 			const uint16_t* current = nullptr;              // the table the next launch walks (NULL: none learned yet)
 		} cells;
+		// RT_KERNEL_WAVEFRONT: the split tables of all meshes and the per-pixel scratch of the five launches
+		int32_t* d_split = nullptr;
+		uint8_t* d_root_map = nullptr;
+		size_t root_map_capacity = 0;
+		void* d_wave = nullptr;
+		size_t wave_pixels = 0, wave_view_tasks = 0, wave_shadow_tasks = 0;
+		rt::wave::WaveParams wave{};
 		int sm_count = 0;
 		rt::SceneDevice view{};
 	};
@@ -134,6 +144,9 @@ struct rt_context
 	int32_t kernel_variant = RT_KERNEL_AUTO;
 
 	// pinned host mirror of the static block (SoA, as uploaded) and of the mesh block
+	int32_t* h_split = nullptr;         // pinned mirror of the split tables (kMaxMeshes * kSplitStride words)
+	uint8_t* h_root_map = nullptr;      // pinned mirror of the node -> subtree maps of all meshes, back to back
+	size_t h_root_map_capacity = 0;
 	uint8_t* h_static = nullptr;
 	float* arena = nullptr;             // views into h_static
 	float4* materials = nullptr;
@@ -355,9 +368,43 @@ namespace
 			first += count; first_node += node_count;
 		}
 		for (int k = 0; k < 6; ++k) tris[n_tris + k] = make_float4(0.f, 0.f, 0.f, 0.f);
+		constexpr size_t split_words = (size_t)rt::kMaxMeshes * rt::wave::kSplitStride;
+		memset(ctx->h_split, 0, split_words * sizeof(int32_t));
+		size_t map_bytes = 16;
+		for (const HostMesh& hm : ctx->meshes) map_bytes += hm.root_map.size();
+		if (map_bytes > ctx->h_root_map_capacity)
+		{
+			if (ctx->h_root_map) cudaFreeHost(ctx->h_root_map);
+			ctx->h_root_map = nullptr; ctx->h_root_map_capacity = 0;
+			RT_CUDA(ctx, cudaHostAlloc(&ctx->h_root_map, map_bytes * 2, cudaHostAllocPortable));
+			ctx->h_root_map_capacity = map_bytes * 2;
+		}
+		{
+			size_t at = 0;
+			for (size_t m = 0; m < ctx->meshes.size(); ++m)
+			{
+				const HostMesh& hm = ctx->meshes[m];
+				if (hm.split.empty()) continue;
+				int32_t* block = ctx->h_split + m * rt::wave::kSplitStride;
+				memcpy(block, hm.split.data(), sizeof(int32_t) * rt::wave::kSplitStride);
+				block[1] = (int32_t)at;
+				memcpy(ctx->h_root_map + at, hm.root_map.data(), hm.root_map.size());
+				at += hm.root_map.size();
+			}
+		}
 		for (DeviceState& d : ctx->devs)
 		{
 			RT_CUDA(ctx, cudaSetDevice(d.device));
+			if (map_bytes > d.root_map_capacity)
+			{
+				RT_CUDA(ctx, cudaDeviceSynchronize());
+				if (d.d_root_map) RT_CUDA(ctx, cudaFree(d.d_root_map));
+				d.d_root_map = nullptr;
+				RT_CUDA(ctx, cudaMalloc(&d.d_root_map, map_bytes * 2));
+				d.root_map_capacity = map_bytes * 2;
+			}
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_root_map, ctx->h_root_map, map_bytes, cudaMemcpyHostToDevice, d.stream));
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_split, ctx->h_split, split_words * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
 			if (total > d.mesh_capacity)
 			{
 				RT_CUDA(ctx, cudaDeviceSynchronize());
@@ -790,6 +837,25 @@ namespace
 		const bool decodable = grid.x > 1u && (unsigned long long)grid.x * grid.y * grid.x < (1ull << 32);
 		int variant = ctx->kernel_variant;
 		const long long tiles = (long long)grid.x * (long long)grid.y;
+		// RT_KERNEL_WAVEFRONT needs the BVH body, host-uploaded trees (their split tables) and few enough lights for one mask word
+		bool wave_possible = path == RT_MESH_PATH_BVH && ctx->n_lights <= 16 && tiles * rt::kSignalsPerTile < (1ll << 23);
+		long long mesh_nodes = 0, wave_subtrees = 0;
+		for (const HostMesh& hm : ctx->meshes)
+		{
+			if (hm.triangles.empty()) continue;
+			if (hm.split.empty()) wave_possible = false; else wave_subtrees += hm.split[0];
+			mesh_nodes += (long long)(hm.nodes.size() / 2);
+		}
+		// the job lists are sized for the worst case (every tile reaches every subtree for every light): keep them below 64 MB
+		if (tiles * rt::kSignalsPerTile * std::max(wave_subtrees, 1ll) * std::max(ctx->n_lights, 1) > (8ll << 20)) wave_possible = false;
+		if (variant == RT_KERNEL_WAVEFRONT && !wave_possible) variant = RT_KERNEL_AUTO;
+		// AUTO: rays as the unit of work pay when the frame alone cannot fill the machine (fewer than ~4 warp tiles per
+		// resident warp) while its pixels are expensive (deep trees walked without pruning): measured on
+		// Scene_W4_OptionalScene, see DESIGN.md
+		static const long long wave_min_nodes = [] { const char* e = getenv("RT_B200_WAVE_MIN_NODES"); return e ? atoll(e) : 1024ll; }();
+		static const long long wave_max_tiles_per_sm = [] { const char* e = getenv("RT_B200_WAVE_MAX_TILES_PER_SM"); return e ? atoll(e) : 256ll; }();
+		if (variant == RT_KERNEL_AUTO && wave_possible && mesh_nodes >= wave_min_nodes && tiles * rt::kSignalsPerTile <= wave_max_tiles_per_sm * d.sm_count)
+			variant = RT_KERNEL_WAVEFRONT;
 		KernelFn persistent = nullptr;
 		int wave = 0;
 		if (variant == RT_KERNEL_AUTO || variant == RT_KERNEL_PERSISTENT)
@@ -803,7 +869,35 @@ namespace
 				variant = (tiles * rt::kSignalsPerTile >= (p.band_done ? 8ll : 4ll) * wave * (rt::kPersistentThreads / 32)) ? RT_KERNEL_PERSISTENT : RT_KERNEL_SCALAR;
 			if (!decodable) variant = RT_KERNEL_SCALAR;
 		}
-		if (variant == RT_KERNEL_PACKED) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::pick_threads_x2(), 0, stream>>>(d.view, p);
+		if (variant == RT_KERNEL_WAVEFRONT)
+		{
+			const size_t pixels = (size_t)tiles * rt::kThreads;
+			// a job per (warp tile, subtree) and, for shadow rays, per light: sized for the worst case, so the lists cannot overflow
+			const size_t view_jobs = (size_t)tiles * rt::kSignalsPerTile * (size_t)wave_subtrees;
+			const size_t shadow_jobs = view_jobs * (size_t)std::max(ctx->n_lights, 1);
+			if (pixels > d.wave_pixels || view_jobs > d.wave_view_tasks || shadow_jobs > d.wave_shadow_tasks)
+			{
+				RT_CUDA(ctx, cudaDeviceSynchronize());
+				if (d.d_wave) RT_CUDA(ctx, cudaFree(d.d_wave));
+				d.d_wave = nullptr;
+				const size_t bytes = pixels * (8 + 16 + 4) + (view_jobs + shadow_jobs) * 8 + 256;
+				RT_CUDA(ctx, cudaMalloc(&d.d_wave, bytes));
+				char* base = (char*)d.d_wave;
+				d.wave.shadow_origin = (float4*)base; base += pixels * 16;
+				d.wave.hit_key = (unsigned long long*)base; base += pixels * 8;
+				d.wave.view_jobs = (uint2*)base; base += view_jobs * 8;
+				d.wave.shadow_jobs = (uint2*)base; base += shadow_jobs * 8;
+				d.wave.occluded = (unsigned int*)base; base += pixels * 4;
+				d.wave.counters = (unsigned int*)(((uintptr_t)base + 15) & ~(uintptr_t)15);
+				d.wave_pixels = pixels; d.wave_view_tasks = view_jobs; d.wave_shadow_tasks = shadow_jobs;
+			}
+			d.wave.view_capacity = (unsigned int)d.wave_view_tasks; d.wave.shadow_capacity = (unsigned int)d.wave_shadow_tasks;
+			d.wave.split = d.d_split;
+			d.wave.root_map = d.d_root_map;
+			RT_CUDA(ctx, rt::wave_launch(d.view, p, d.wave, grid, d.sm_count, stream));
+			ctx->timing.kernel_launches += rt::wave_launch_count(p.shadows) - 1;
+		}
+		else if (variant == RT_KERNEL_PACKED) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::pick_threads_x2(), 0, stream>>>(d.view, p);
 		else if (variant == RT_KERNEL_SCALAR) pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, rt::dynamic_smem_bytes(rt::kThreads, ctx->n_materials), stream>>>(d.view, p);
 		else
 		{
@@ -998,9 +1092,11 @@ namespace
 {
 	// Turns the reference's BVHNode array into the threaded layout of rt::BvhLink.  Every index is
 	// validated: a malformed tree is an error, never a hang or an out-of-bounds read on the GPU.
-	int thread_bvh(rt_context* ctx, const rt_mesh_desc* mesh, std::vector<float4>& out)
+	int thread_bvh(rt_context* ctx, const rt_mesh_desc* mesh, std::vector<float4>& out, std::vector<int32_t>& split, std::vector<uint8_t>& root_map)
 	{
 		out.clear();
+		split.clear();
+		root_map.clear();
 		const int32_t n = mesh->bvh_node_count;
 		if (!mesh->bvh_nodes || n <= 0 || mesh->triangle_count == 0) return RT_OK;
 		if (n > rt::BvhLink::kMaxNodes) return fail(ctx, RT_ERR_CAPACITY, "%d BVH nodes exceed the capacity of %d", n, rt::BvhLink::kMaxNodes);
@@ -1042,6 +1138,65 @@ namespace
 			                                            bits_as_float(rt::BvhLink::miss(it.escape)));
 		}
 		if (covered != mesh->triangle_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH leaves cover %lld of %d triangles", (long long)covered, mesh->triangle_count);
+
+		// RT_KERNEL_WAVEFRONT: cut the tree into at most kMaxSubtrees subtrees of comparable size.  Start from the root and
+		// keep replacing the largest inner subtree by its two children (each inherits the parent's ancestor list + the
+		// parent); a subtree is walked from its root until the walk leaves through the root's escape link.
+		{
+			using namespace rt::wave;
+			std::vector<int32_t> size((size_t)n, 1), escape((size_t)n, -1);
+			std::vector<int32_t> order;           // pre-order, to accumulate sizes bottom-up
+			{
+				std::vector<Item> st;
+				st.push_back({ 0, -1 });
+				while (!st.empty())
+				{
+					const Item it = st.back(); st.pop_back();
+					order.push_back(it.node); escape[(size_t)it.node] = it.escape;
+					const rt_bvh_node& nd = mesh->bvh_nodes[it.node];
+					if (nd.idx_count == 0) { st.push_back({ (int32_t)nd.left_node + 1, it.escape }); st.push_back({ (int32_t)nd.left_node, (int32_t)nd.left_node + 1 }); }
+				}
+				for (size_t i = order.size(); i-- > 0;)
+				{
+					const rt_bvh_node& nd = mesh->bvh_nodes[order[i]];
+					if (nd.idx_count == 0) size[(size_t)order[i]] = 1 + size[nd.left_node] + size[nd.left_node + 1];
+				}
+			}
+			struct Entry { int32_t node; std::vector<int32_t> ancestors; };
+			std::vector<Entry> entries;
+			entries.push_back({ 0, {} });
+			static const int cap = [] { const char* e = getenv("RT_B200_WAVE_SUBTREES"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxSubtrees) ? v : kMaxSubtrees; }();
+			const int wanted = n >= 64 ? cap : 1;        // a shallow tree is one job
+			while ((int)entries.size() < wanted)
+			{
+				int pick = -1;
+				for (size_t e = 0; e < entries.size(); ++e)
+				{
+					const rt_bvh_node& nd = mesh->bvh_nodes[entries[e].node];
+					if (nd.idx_count != 0 || (int)entries[e].ancestors.size() >= kMaxAncestors) continue;
+					if (pick < 0 || size[(size_t)entries[e].node] > size[(size_t)entries[(size_t)pick].node]) pick = (int)e;
+				}
+				if (pick < 0) break;
+				const Entry parent = entries[(size_t)pick];
+				const int32_t left = (int32_t)mesh->bvh_nodes[parent.node].left_node;
+				std::vector<int32_t> anc = parent.ancestors;
+				anc.push_back(parent.node);
+				entries[(size_t)pick] = { left, anc };
+				entries.insert(entries.begin() + pick + 1, Entry{ left + 1, anc });
+			}
+			split.assign((size_t)kSplitStride, 0);
+			split[0] = (int32_t)entries.size();
+			root_map.assign((size_t)n, 0);
+			for (size_t e = 0; e < entries.size(); ++e) root_map[(size_t)entries[e].node] = (uint8_t)(e + 1);
+			for (size_t e = 0; e < entries.size(); ++e)
+			{
+				int32_t* rec = split.data() + kSplitHeader + e * kSplitWords;
+				rec[0] = entries[e].node * rt::BvhLink::kNodeBytes;
+				rec[1] = rt::BvhLink::miss(escape[(size_t)entries[e].node]);
+				rec[2] = (int32_t)entries[e].ancestors.size();
+				for (size_t k = 0; k < entries[e].ancestors.size(); ++k) rec[3 + k] = entries[e].ancestors[k] * rt::BvhLink::kNodeBytes;
+			}
+		}
 		return RT_OK;
 	}
 }
@@ -1371,6 +1526,8 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 128));
 		RT_CREATE(cudaMemset(d.d_band_done, 0, sizeof(unsigned int) * 128));
+		RT_CREATE(cudaMalloc(&d.d_split, sizeof(int32_t) * rt::kMaxMeshes * rt::wave::kSplitStride));
+		RT_CREATE(cudaMemset(d.d_split, 0, sizeof(int32_t) * rt::kMaxMeshes * rt::wave::kSplitStride));
 		RT_CREATE(cudaMalloc(&d.d_queues, sizeof(unsigned int) * 2 * kQueueRing));
 		RT_CREATE(cudaMemset(d.d_queues, 0, sizeof(unsigned int) * 2 * kQueueRing));
 		d.sm_count = prop.multiProcessorCount;
@@ -1379,6 +1536,7 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 	RT_CREATE(cudaSetDevice(ids[0]));
 	RT_CREATE(cudaHostAlloc(&ctx->h_build_status, sizeof(int32_t) * rt::kMaxMeshes, cudaHostAllocPortable));
 	memset(ctx->h_build_status, 0, sizeof(int32_t) * rt::kMaxMeshes);
+	RT_CREATE(cudaHostAlloc(&ctx->h_split, sizeof(int32_t) * rt::kMaxMeshes * rt::wave::kSplitStride, cudaHostAllocPortable));
 	RT_CREATE(cudaHostAlloc(&ctx->h_static, StaticBlock::total, cudaHostAllocPortable));
 	memset(ctx->h_static, 0, StaticBlock::total);
 	ctx->arena = reinterpret_cast<float*>(ctx->h_static + StaticBlock::arena);
@@ -1417,6 +1575,7 @@ int rt_destroy(rt_context* ctx)
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
+		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
 		if (d.ev_foreign) cudaEventDestroy(d.ev_foreign);
 		cudaFree(d.cells.d_cost); cudaFree(d.cells.d_order); cudaFreeHost(d.cells.h_cost); cudaFreeHost(d.cells.h_order);
@@ -1435,6 +1594,8 @@ int rt_destroy(rt_context* ctx)
 	if (ctx->ev_d2h) cudaEventDestroy(ctx->ev_d2h);
 	for (auto& r : ctx->registered) cudaHostUnregister(r.first);
 	if (ctx->staging) cudaFreeHost(ctx->staging);
+	if (ctx->h_split) cudaFreeHost(ctx->h_split);
+	if (ctx->h_root_map) cudaFreeHost(ctx->h_root_map);
 	if (ctx->h_static) cudaFreeHost(ctx->h_static);
 	if (ctx->h_mesh) cudaFreeHost(ctx->h_mesh);
 	if (ctx->h_build_status) cudaFreeHost(ctx->h_build_status);
@@ -1578,6 +1739,7 @@ int rt_upload_mesh_source(rt_context* ctx, int32_t mesh_id, const rt_mesh_source
 	// (rt_set_mesh_device_bvh reserves the node slice and switches to update_transforms_bvh_kernel)
 	hm.triangles.assign(3 * (size_t)src->triangle_count, make_float4(0.f, 0.f, 0.f, 0.f));
 	hm.nodes.clear();
+	hm.split.clear(); hm.root_map.clear();
 	hm.device_bvh = false; hm.pending_builds.clear();
 	for (int k = 0; k < 3; ++k) { hm.aabb_min[k] = 0.f; hm.aabb_max[k] = 0.f; }
 	hm.cull_mode = src->cull_mode;
@@ -1626,7 +1788,7 @@ int rt_set_mesh_device_bvh(rt_context* ctx, int32_t mesh_id, int32_t enable)
 int rt_set_kernel_variant(rt_context* ctx, int32_t variant)
 {
 	if (!ctx) return RT_ERR_INVALID_ARGUMENT;
-	if (variant < RT_KERNEL_AUTO || variant > RT_KERNEL_PERSISTENT) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", variant);
+	if (variant < RT_KERNEL_AUTO || variant > RT_KERNEL_WAVEFRONT) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", variant);
 	ctx->kernel_variant = variant;
 	return RT_OK;
 }
@@ -1684,7 +1846,7 @@ int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
 	hm.cull_mode = mesh->cull_mode;
 	hm.material = mesh->material_index;
 	if (mesh->bvh_node_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "negative BVH node count");
-	const int brc = thread_bvh(ctx, mesh, hm.nodes);
+	const int brc = thread_bvh(ctx, mesh, hm.nodes, hm.split, hm.root_map);
 	if (brc != RT_OK) { hm.uploaded = false; return brc; }
 	hm.uploaded = true;
 	ctx->mesh_dirty = true;

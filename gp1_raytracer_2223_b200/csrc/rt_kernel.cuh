@@ -802,6 +802,71 @@ namespace rt
 		return v3(0.f, 0.f, 0.f);
 	}
 
+	// Ray generation, Renderer.cpp:104-114
+	__device__ __forceinline__ Ray view_ray(const FrameParams& p, int px, int py)
+	{
+		// Renderer.cpp:107-108 (the two expressions really do associate differently)
+		const float cx = mul(mul(sub(mul(2.f, quo(add((float)px, 0.5f), (float)p.width)), 1.f), p.aspect), p.fov);
+		const float cy = mul(sub(1.f, quo(mul(2.f, add((float)py, 0.5f)), (float)p.height)), p.fov);
+
+		// Matrix::TransformVector(cx, cy, 1), Matrix.cpp:35-42; x * 1.f is exact
+		Ray view;
+		view.o = v3(p.cam_ox, p.cam_oy, p.cam_oz);
+		view.d = v3(add(add(mul(p.right_x, cx), mul(p.up_x, cy)), p.fwd_x),
+		            add(add(mul(p.right_y, cx), mul(p.up_y, cy)), p.fwd_y),
+		            add(add(mul(p.right_z, cx), mul(p.up_z, cy)), p.fwd_z));
+		normalize_and_invert(view.d, view.inv, view.nan_safe);        // Renderer.cpp:111-113, DataTypes.h:550-563
+		view.tmin = 0.0001f; view.tmax = FLT_MAX;
+		return view;
+	}
+
+	// The shadow ray of one light, Renderer.cpp:128-136; its direction is also the `l` of the shading
+	// (GetDirectionToLight, Utils.h:341-353: light.origin - p for both light types)
+	__device__ __forceinline__ Ray shadow_ray_to(const float4 la, int ltype, const V3 origin_offset)
+	{
+		Ray r;
+		r.o = origin_offset;
+		r.d = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
+		r.tmax = normalize_and_invert(r.d, r.inv, r.nan_safe);
+		r.tmin = 0.0001f;
+		return r;
+	}
+
+	// One unshadowed light's contribution by lighting mode, Renderer.cpp:143-171
+	template <bool COUNT, class View>
+	__device__ __forceinline__ V3 add_light(int mode, V3 color, const Staged sc, const float4 la, const float4 lb, const V3 l, const V3 hit_origin, const V3 hit_normal,
+	                                        int material, const View& view, Counters<COUNT>& cnt)
+	{
+		if (mode == RT_LIGHTING_COMBINED)
+		{
+			const float oa = std_max(dot(hit_normal, l), 0.f);
+			const V3 e = radiance(la, lb, hit_origin);
+			const V3 brdf = shade(sc.material(2 * material), sc.material(2 * material + 1), hit_normal, l, view, cnt);
+			// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
+			return color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
+		}
+		if (mode == RT_LIGHTING_OBSERVED_AREA)
+		{
+			const float oa = std_max(dot(hit_normal, l), 0.f);
+			return color + v3(oa, oa, oa);
+		}
+		if (mode == RT_LIGHTING_RADIANCE) return color + radiance(la, lb, hit_origin);
+		if (mode == RT_LIGHTING_BRDF) return color + shade(sc.material(2 * material), sc.material(2 * material + 1), hit_normal, l, view, cnt);
+		return color;
+	}
+
+	// ColorRGB::MaxToOne (ColorRGB.h:12-17), static_cast<uint8_t>(c * 255) (truncation; the x86 reference goes through
+	// cvttss2si and keeps the low byte) and SDL_MapRGB, Renderer.cpp:176-181
+	__device__ __forceinline__ uint32_t pack_pixel(const FrameParams& p, V3 color)
+	{
+		const float max_value = std_max(color.x, std_max(color.y, color.z));
+		if (max_value > 1.f) { color.x = quo(color.x, max_value); color.y = quo(color.y, max_value); color.z = quo(color.z, max_value); }
+		const uint32_t R = (uint32_t)__float2int_rz(mul(color.x, 255.f)) & 0xffu;
+		const uint32_t G = (uint32_t)__float2int_rz(mul(color.y, 255.f)) & 0xffu;
+		const uint32_t B = (uint32_t)__float2int_rz(mul(color.z, 255.f)) & 0xffu;
+		return (R << p.r_shift) | (G << p.g_shift) | (B << p.b_shift) | p.alpha_mask;
+	}
+
 	// What only the shading of a pixel needs - hit point, normal, material, view direction - waits in shared memory
 	// while the shadow rays are traced, instead of occupying ten registers (or, as ptxas would have it, local memory
 	// inside the light loop).  One slot of three float4 per thread, [record][thread] so that a warp's 128-bit
@@ -845,18 +910,7 @@ namespace rt
 		const bool shadows = (SHADOWS >= 0) ? (SHADOWS != 0) : (p.shadows != 0);
 		cnt.hit(RT_CNT_PIXELS);
 
-		// Renderer.cpp:107-108 (the two expressions really do associate differently)
-		const float cx = mul(mul(sub(mul(2.f, quo(add((float)px, 0.5f), (float)p.width)), 1.f), p.aspect), p.fov);
-		const float cy = mul(sub(1.f, quo(mul(2.f, add((float)py, 0.5f)), (float)p.height)), p.fov);
-
-		// Matrix::TransformVector(cx, cy, 1), Matrix.cpp:35-42; x * 1.f is exact
-		Ray view;
-		view.o = v3(p.cam_ox, p.cam_oy, p.cam_oz);
-		view.d = v3(add(add(mul(p.right_x, cx), mul(p.up_x, cy)), p.fwd_x),
-		            add(add(mul(p.right_y, cx), mul(p.up_y, cy)), p.fwd_y),
-		            add(add(mul(p.right_z, cx), mul(p.up_z, cy)), p.fwd_z));
-		normalize_and_invert(view.d, view.inv, view.nan_safe);        // Renderer.cpp:111-113, DataTypes.h:550-563
-		view.tmin = 0.0001f; view.tmax = FLT_MAX;
+		const Ray view = view_ray(p, px, py);
 
 		float shadow_factor = 1.f;
 		V3 color = v3(0.f, 0.f, 0.f);
@@ -880,11 +934,7 @@ namespace rt
 				const float4 la = sc.light_a(li);
 				const int ltype = __float_as_int(sc.light_b(li).w);
 				// GetDirectionToLight, Utils.h:341-353: light.origin - p for both light types
-				Ray shadow_ray;
-				shadow_ray.o = origin_offset;
-				shadow_ray.d = (ltype == RT_LIGHT_POINT || ltype == RT_LIGHT_DIRECTIONAL) ? (v3(la) - origin_offset) : v3(0.f, 0.f, 0.f);
-				shadow_ray.tmax = normalize_and_invert(shadow_ray.d, shadow_ray.inv, shadow_ray.nan_safe);   // Renderer.cpp:131-136
-				shadow_ray.tmin = 0.0001f;
+				const Ray shadow_ray = shadow_ray_to(la, ltype, origin_offset);
 
 				if (shadows)
 				{
@@ -903,41 +953,12 @@ namespace rt
 				const V3 hit_origin = v3(h0), hit_normal = v3(h1);
 				const int material = __float_as_int(h0.w);
 				const float4 lb = sc.light_b(li);
-				if (mode == RT_LIGHTING_COMBINED)
-				{
-					const float oa = std_max(dot(hit_normal, l), 0.f);
-					const V3 e = radiance(la, lb, hit_origin);
-					const V3 brdf = shade(sc.material(2 * material), sc.material(2 * material + 1), hit_normal, l, park, cnt);
-					// observedArea * radiance * brdf == (radiance * oa) * brdf, Renderer.cpp:152
-					color = color + v3(mul(mul(e.x, oa), brdf.x), mul(mul(e.y, oa), brdf.y), mul(mul(e.z, oa), brdf.z));
-				}
-				else if (mode == RT_LIGHTING_OBSERVED_AREA)
-				{
-					const float oa = std_max(dot(hit_normal, l), 0.f);
-					color = color + v3(oa, oa, oa);
-				}
-				else if (mode == RT_LIGHTING_RADIANCE)
-				{
-					color = color + radiance(la, lb, hit_origin);
-				}
-				else if (mode == RT_LIGHTING_BRDF)
-				{
-					color = color + shade(sc.material(2 * material), sc.material(2 * material + 1), hit_normal, l, park, cnt);
-				}
+				color = add_light(mode, color, sc, la, lb, l, hit_origin, hit_normal, material, park, cnt);
 			}
 			color = color * shadow_factor;                                  // Renderer.cpp:173
 		}
 
-		// ColorRGB::MaxToOne, ColorRGB.h:12-17
-		const float max_value = std_max(color.x, std_max(color.y, color.z));
-		if (max_value > 1.f) { color.x = quo(color.x, max_value); color.y = quo(color.y, max_value); color.z = quo(color.z, max_value); }
-
-		// static_cast<uint8_t>(c * 255) (truncation; the x86 reference goes through cvttss2si
-		// and keeps the low byte) + SDL_MapRGB, Renderer.cpp:178-181
-		const uint32_t R = (uint32_t)__float2int_rz(mul(color.x, 255.f)) & 0xffu;
-		const uint32_t G = (uint32_t)__float2int_rz(mul(color.y, 255.f)) & 0xffu;
-		const uint32_t B = (uint32_t)__float2int_rz(mul(color.z, 255.f)) & 0xffu;
-		return (R << p.r_shift) | (G << p.g_shift) | (B << p.b_shift) | p.alpha_mask;
+		return pack_pixel(p, color);
 	}
 
 	// `cam` is the origin every view ray of the frame starts from: the parts of HitTest_Sphere / HitTest_Plane

@@ -4,6 +4,7 @@
 #pragma once
 
 #include "rt_kernel.cuh"
+#include "rt_wave_params.h"
 
 namespace rt
 {
@@ -15,4 +16,8 @@ namespace rt
 	int pick_threads_x2();
 	int pick_block_w_x2();
 	KernelFn pick_kernel_persistent(int mode, int shadows, bool bvh);    // render_kernel_persistent, kPersistentThreads per CTA
+
+	// RT_KERNEL_WAVEFRONT (rt_kernel_wave.cuh): all five launches of one frame share, BVH body only
+	cudaError_t wave_launch(const SceneDevice& dev, const FrameParams& p, const wave::WaveParams& w, dim3 grid, int sm_count, cudaStream_t stream);
+	int wave_launch_count(int shadows);
 }

@@ -348,13 +348,19 @@ int rt_read_mesh_build(rt_context* ctx, int32_t mesh_id, int32_t* indices, float
  *   RT_KERNEL_SCALAR      one pixel per thread, one CTA per 32x8 pixel tile (also what rt_count_frame instruments)
  *   RT_KERNEL_PACKED      two pixels per thread on Blackwell's packed FP32 (FFMA2), one CTA per tile
  *   RT_KERNEL_PERSISTENT  one pixel per thread, persistent warps pulling 8x4 warp tiles off a device queue
- *                         (default: what RT_KERNEL_AUTO selects) */
+ *                         (what RT_KERNEL_AUTO selects for large frames)
+ *   RT_KERNEL_WAVEFRONT   rays, not pixels: five launches, one warp per (warp tile, mesh subtree) for the view rays and per
+ *                         (warp tile, light, mesh subtree) for the shadow rays (source/Utils.h:246-288 walked subtree by
+ *                         subtree, results merged with atomics); needs the BVH body over trees uploaded with rt_upload_mesh.
+ *                         RT_KERNEL_AUTO selects it for small frames over deep trees; requested where it cannot run, AUTO's
+ *                         choice is used */
 enum rt_kernel_variant
 {
 	RT_KERNEL_AUTO = 0,
 	RT_KERNEL_SCALAR = 1,
 	RT_KERNEL_PACKED = 2,
-	RT_KERNEL_PERSISTENT = 3
+	RT_KERNEL_PERSISTENT = 3,
+	RT_KERNEL_WAVEFRONT = 4
 };
 int rt_set_kernel_variant(rt_context* ctx, int32_t variant);
 

@@ -72,6 +72,8 @@ def test_packed_kernel_matches_reference(gpu, name, mesh_path):
     assert np.array_equal(got, r.Render()), "packed and scalar kernels disagree"
     r.ctx.set_kernel_variant(3)
     assert np.array_equal(got, r.Render()), "persistent and tiled kernels disagree"
+    r.ctx.set_kernel_variant(4)          # rays as the unit of work (five launches); runs AUTO's choice where it cannot (slab body, no meshes)
+    assert np.array_equal(got, r.Render()), "wavefront and tiled kernels disagree"
     identical, max_err, n_diff = compare_frames(got, load_golden_frame(name))
     if name in EXACT:
         assert n_diff == 0
@@ -482,4 +484,31 @@ def test_uploads_after_a_launch_on_a_foreign_stream_wait_for_it(gpu):
         stream.synchronize()
         assert np.array_equal(out_a.cpu().numpy().view(np.uint32), want_a)
         assert np.array_equal(out_b.cpu().numpy().view(np.uint32), want_b)
+    r.close()
+
+
+def test_wavefront_kernel_in_every_mode_and_on_strips(gpu):
+    """RT_KERNEL_WAVEFRONT (rt_kernel_wave.cuh): closest hit merged over subtrees with atomicMin on (t, primitive), any hit
+    with atomicOr - bit-identical to the reference frames in all four lighting modes, with shadows off, on an odd-sized
+    frame, on a rank's strips and through the progressive present."""
+    for name in ("bunny_640_observed", "bunny_640_radiance", "bunny_640_brdf", "bunny_640_noshadow", "bunny_333x77", "w4ref_101x203",
+                 "optional_320", "optional_320_steps2", "w4ref_320_cam"):
+        r = make_renderer(name)
+        r.ctx.set_mesh_path(2)
+        r.ctx.set_kernel_variant(4)
+        identical, max_err, n_diff = compare_frames(r.Render(), load_golden_frame(name))
+        assert (n_diff == 0) if name in EXACT else (identical >= MIN_IDENTICAL and max_err <= MAX_LSB), (name, n_diff, max_err)
+        r.render_device()
+        identical, max_err, n_diff = compare_frames(r.download(), load_golden_frame(name))
+        assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (name, n_diff, max_err)
+        r.close()
+    # strips of three "ranks" into one host surface
+    r = make_renderer("optional_320")
+    r.ctx.set_kernel_variant(4)
+    want = load_golden_frame("optional_320")
+    surface = np.zeros((240, 320), dtype=np.uint32)
+    for rank in range(3):
+        r.render_strips_to_host(rank, 3, surface.ctypes.data, 320 * 4)
+    identical, max_err, n_diff = compare_frames(surface, want)
+    assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (n_diff, max_err)
     r.close()
