@@ -128,7 +128,7 @@ namespace
 		uint8_t* d_root_map = nullptr;
 		size_t root_map_capacity = 0;
 		void* d_wave = nullptr;
-		size_t wave_pixels = 0, wave_view_tasks = 0, wave_shadow_tasks = 0;
+		size_t wave_pixels = 0, wave_view_tasks = 0, wave_shadow_tasks = 0, wave_meshes = 0, wave_lights = 0;
 		rt::wave::WaveParams wave{};
 		int sm_count = 0;
 		rt::SceneDevice view{};
@@ -848,12 +848,13 @@ namespace
 		}
 		// the job lists are sized for the worst case (every tile reaches every subtree for every light): keep them below 64 MB
 		if (tiles * rt::kSignalsPerTile * std::max(wave_subtrees, 1ll) * std::max(ctx->n_lights, 1) > (8ll << 20)) wave_possible = false;
+		if (tiles * rt::kThreads * (long long)std::max<size_t>(ctx->meshes.size(), 1) * std::max(ctx->n_lights, 1) > (16ll << 20)) wave_possible = false;     // the per-ray subtree masks: <= 128 MB
 		if (variant == RT_KERNEL_WAVEFRONT && !wave_possible) variant = RT_KERNEL_AUTO;
 		// AUTO: rays as the unit of work pay when the frame alone cannot fill the machine (fewer than ~4 warp tiles per
 		// resident warp) while its pixels are expensive (deep trees walked without pruning): measured on
 		// Scene_W4_OptionalScene, see DESIGN.md
 		static const long long wave_min_nodes = [] { const char* e = getenv("RT_B200_WAVE_MIN_NODES"); return e ? atoll(e) : 1024ll; }();
-		static const long long wave_max_tiles_per_sm = [] { const char* e = getenv("RT_B200_WAVE_MAX_TILES_PER_SM"); return e ? atoll(e) : 256ll; }();
+		static const long long wave_max_tiles_per_sm = [] { const char* e = getenv("RT_B200_WAVE_MAX_TILES_PER_SM"); return e ? atoll(e) : 320ll; }();
 		if (variant == RT_KERNEL_AUTO && wave_possible && mesh_nodes >= wave_min_nodes && tiles * rt::kSignalsPerTile <= wave_max_tiles_per_sm * d.sm_count)
 			variant = RT_KERNEL_WAVEFRONT;
 		KernelFn persistent = nullptr;
@@ -875,21 +876,24 @@ namespace
 			// a job per (warp tile, subtree) and, for shadow rays, per light: sized for the worst case, so the lists cannot overflow
 			const size_t view_jobs = (size_t)tiles * rt::kSignalsPerTile * (size_t)wave_subtrees;
 			const size_t shadow_jobs = view_jobs * (size_t)std::max(ctx->n_lights, 1);
-			if (pixels > d.wave_pixels || view_jobs > d.wave_view_tasks || shadow_jobs > d.wave_shadow_tasks)
+			if (pixels > d.wave_pixels || view_jobs > d.wave_view_tasks || shadow_jobs > d.wave_shadow_tasks || ctx->meshes.size() != d.wave_meshes || (size_t)ctx->n_lights != d.wave_lights)
 			{
 				RT_CUDA(ctx, cudaDeviceSynchronize());
 				if (d.d_wave) RT_CUDA(ctx, cudaFree(d.d_wave));
 				d.d_wave = nullptr;
-				const size_t bytes = pixels * (8 + 16 + 4) + (view_jobs + shadow_jobs) * 8 + 256;
+				const size_t n_m = std::max<size_t>(ctx->meshes.size(), 1), n_l = (size_t)std::max(ctx->n_lights, 1);
+				const size_t bytes = pixels * (8 + 16 + 4 + 8 * n_m + 8 * n_m * n_l) + (view_jobs + shadow_jobs) * 8 + 256;
 				RT_CUDA(ctx, cudaMalloc(&d.d_wave, bytes));
 				char* base = (char*)d.d_wave;
 				d.wave.shadow_origin = (float4*)base; base += pixels * 16;
 				d.wave.hit_key = (unsigned long long*)base; base += pixels * 8;
 				d.wave.view_jobs = (uint2*)base; base += view_jobs * 8;
 				d.wave.shadow_jobs = (uint2*)base; base += shadow_jobs * 8;
+				d.wave.view_alive = (unsigned long long*)base; base += pixels * 8 * n_m;
+				d.wave.shadow_alive = (unsigned long long*)base; base += pixels * 8 * n_m * n_l;
 				d.wave.occluded = (unsigned int*)base; base += pixels * 4;
 				d.wave.counters = (unsigned int*)(((uintptr_t)base + 15) & ~(uintptr_t)15);
-				d.wave_pixels = pixels; d.wave_view_tasks = view_jobs; d.wave_shadow_tasks = shadow_jobs;
+				d.wave_pixels = pixels; d.wave_view_tasks = view_jobs; d.wave_shadow_tasks = shadow_jobs; d.wave_meshes = ctx->meshes.size(); d.wave_lights = (size_t)ctx->n_lights;
 			}
 			d.wave.view_capacity = (unsigned int)d.wave_view_tasks; d.wave.shadow_capacity = (unsigned int)d.wave_shadow_tasks;
 			d.wave.split = d.d_split;

@@ -97,19 +97,13 @@ namespace wave
 		}
 	}
 
-	// The walk of ONE subtree: from its root until the walk leaves it through the root's escape link `end`, after the
-	// boxes of the root's ancestors.
+	// The walk of ONE subtree: from its root until the walk leaves it through the root's escape link `end`.  Only rays
+	// that reached the root in walk_top (the recursion tested the boxes of the root's ancestors there) call this.
 	template <bool ANY, bool FAST>
 	__device__ __forceinline__ bool walk_subtree(int cull, const float4* nodes, const float4* tri, const int32_t* entry, const Ray& ray, float& best_t, int& best_tri)
 	{
 		Counters<false> cnt;
 		Pk K{};
-		const int n_ancestors = __ldg(entry + 2);
-		for (int a = 0; a < n_ancestors; ++a)
-		{
-			const float4* rec = node_at(nodes, __ldg(entry + 3 + a));
-			if (!slab_test<FAST>(K, __ldg(rec), __ldg(rec + 1), ray)) return false;      // the recursion never gets here (Utils.h:251-254)
-		}
 		int at = __ldg(entry);
 		const int end = __ldg(entry + 1);
 		while (at != end)
@@ -177,6 +171,7 @@ namespace wave
 			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
 			unsigned long long alive = 0ull;
 			if (me.valid) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
+			w.view_alive[(size_t)pixel * dev.n_meshes + m] = alive;
 			emit_jobs(alive, tile, (unsigned int)m << 8, w.view_jobs, w.counters, w.view_capacity, w.counters + 4);
 		}
 	}
@@ -200,14 +195,14 @@ namespace wave
 			const unsigned int cta = tile / kSignalsPerTile;
 			const int tid = (int)((tile % kSignalsPerTile) * 32u + lane);
 			const Where me = where_am_i(p, (int)(cta % (unsigned int)p.grid_x), (int)(cta / (unsigned int)p.grid_x), tid);
-			if (!me.valid) continue;
+			const unsigned int pixel = cta * kThreads + (unsigned int)tid;
+			if (!me.valid || !((w.view_alive[(size_t)pixel * dev.n_meshes + m] >> s) & 1ull)) continue;      // this ray never reaches the subtree
 			const Ray ray = view_ray(p, me.px, me.py);
 			const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
 			const int first_tri = __float_as_int(b1.z);
 			const float4* tri = dev.triangles + 3 * (size_t)first_tri;
 			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
 			const int cull = __float_as_int(info.x);
-			const unsigned int pixel = cta * kThreads + (unsigned int)tid;
 			float best_t = __uint_as_float((unsigned int)(w.hit_key[pixel] >> 32));       // a stale read only makes the bound looser
 			int best_tri = -1;
 			// (the bound only decides which candidates are worth an atomic: the triangle tests never see it)
@@ -315,6 +310,7 @@ namespace wave
 					const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
 					unsigned long long alive = 0ull;
 					if (open) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
+					w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] = alive;
 					emit_jobs(alive, tile, ((unsigned int)li << 16) | ((unsigned int)m << 8), w.shadow_jobs, w.counters + 1, w.shadow_capacity, w.counters + 4);
 				}
 			}
@@ -341,7 +337,8 @@ namespace wave
 			const unsigned int pixel = cta * kThreads + (tile % kSignalsPerTile) * 32u + lane;
 			const float4 so = w.shadow_origin[pixel];
 			const unsigned int bit = 1u << li;
-			if (so.w == 0.f || (w.occluded[pixel] & bit)) continue;       // no hit pixel / already known to be in shadow (racy read: an optimisation only)
+			if (!((w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] >> s) & 1ull)) continue;      // this ray never reaches the subtree
+			if (w.occluded[pixel] & bit) continue;                        // already known to be in shadow (racy read: an optimisation only)
 			const float4 la = make_float4(__ldg(dev.light_ox + li), __ldg(dev.light_oy + li), __ldg(dev.light_oz + li), 0.f);
 			const Ray ray = shadow_ray_to(la, __ldg(dev.light_type + li), v3(so));
 			const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);

@@ -24,6 +24,8 @@ namespace wave
 		unsigned long long* hit_key;       // per pixel of the launch (CTA-major: cta * kThreads + thread)
 		float4* shadow_origin;             // per pixel: {origin + normal * 1e-4, 1 if the view ray hit anything}
 		unsigned int* occluded;            // per pixel: bit li = light li's shadow ray is blocked
+		unsigned long long* view_alive;    // per (pixel, mesh): the subtrees the view ray reaches (walk_top)
+		unsigned long long* shadow_alive;  // per (pixel, light, mesh): the same for the shadow rays
 		uint2* view_jobs;                  // {warp tile, mesh << 8 | subtree}: some ray of the tile reaches that subtree's root
 		uint2* shadow_jobs;                // {warp tile, light << 16 | mesh << 8 | subtree}
 		unsigned int* counters;            // [0] view jobs, [1] shadow jobs, [2] / [3] next job of the view / shadow walk, [4] overflow flag
