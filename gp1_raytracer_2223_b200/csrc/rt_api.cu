@@ -101,6 +101,9 @@ namespace
 		cudaStream_t copy_stream = nullptr;                 // device-to-host copies that overlap the next band's kernel
 		cudaEvent_t ev_band[16] = {};
 		unsigned int* d_band_done = nullptr;                // kMaxBands counters for the single-launch progressive present
+		uint8_t* d_band_table = nullptr;                    // strip -> band of the current schedule (make_band_schedule)
+		uint8_t* h_band_table = nullptr;                    // its pinned source
+		int band_table_strips = 0, band_table_bands = 0;
 		unsigned int* d_queues = nullptr;                   // kQueueRing work queues {next, finished} of the persistent kernel (self re-arming)
 		unsigned int queue_cursor = 0;
 		// Cost feedback for the persistent kernel's tile order on small shares (see prepare_cell_order)
@@ -1222,6 +1225,65 @@ namespace
 		return fn;
 	}
 
+	// ---- the bands of a progressive present -------------------------------------------------------------------------
+	// The copy stream runs  wait(band b complete) -> copy(band b)  band after band.  Measured on one B200 (4K frame,
+	// tools/share_e2e.py with RT_B200_PIPELINE_BANDS): with equal bands the frame is in host memory 0.149 / 0.103 / 0.086 /
+	// 0.16 ms after the kernel for 4 / 8 / 16 / 32 bands - the last band's bytes against ~9 us of fixed cost per band.
+	// Bands of unequal size (small at both ends, RT_B200_BAND_PROFILE=1) were tried and lost at N = 1 (0.826 vs 0.792 ms
+	// kernel + copies with 12 vs 16 bands) and won little on an eighth of the frame (0.172 vs 0.182 ms): equal bands stay
+	// the default, the table-driven form stays for experiments.
+	struct BandSchedule
+	{
+		int bands = 0;
+		int first[65] = {};      // band b = strips [first[b], first[b + 1])
+	};
+	BandSchedule make_band_schedule(int total_strips, int wanted)
+	{
+		BandSchedule s;
+		const int n = std::max(1, std::min(std::min(wanted, 64), total_strips));
+		static const bool equal = getenv("RT_B200_BAND_PROFILE") == nullptr;          // default: equal bands
+		double weight[64], sum = 0.0;
+		for (int b = 0; b < n; ++b)
+		{
+			// a raised sine over the band index: ends ~1/8 of the middle
+			const double x = std::sin(3.14159265358979323846 * (b + 0.5) / n);
+			weight[b] = equal ? 1.0 : 0.12 + x * x;
+			sum += weight[b];
+		}
+		double acc = 0.0;
+		s.first[0] = 0;
+		int made = 0;
+		for (int b = 0; b < n; ++b)
+		{
+			acc += weight[b];
+			int end = (b == n - 1) ? total_strips : (int)std::lround(acc / sum * total_strips);
+			end = std::max(end, s.first[made] + 1);
+			end = std::min(end, total_strips);
+			if (end <= s.first[made]) continue;
+			s.first[++made] = end;
+			if (end == total_strips) break;
+		}
+		if (s.first[made] != total_strips) s.first[made] = total_strips;
+		s.bands = made;
+		return s;
+	}
+
+	// Makes the device's strip -> band table the one of `s` (a copy on the device's stream, ordered before the kernel).
+	int use_band_schedule(rt_context* ctx, DeviceState& d, const BandSchedule& s, int total_strips, rt::FrameParams& p)
+	{
+		if (total_strips > 8192 || s.bands > 64) { p.band_table = nullptr; return RT_OK; }      // callers then fall back to equal bands
+		if (d.band_table_strips != total_strips || d.band_table_bands != s.bands)
+		{
+			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));                // the pinned source may still be in flight
+			for (int b = 0; b < s.bands; ++b)
+				for (int k = s.first[b]; k < s.first[b + 1]; ++k) d.h_band_table[k] = (uint8_t)b;
+			RT_CUDA(ctx, cudaMemcpyAsync(d.d_band_table, d.h_band_table, (size_t)total_strips, cudaMemcpyHostToDevice, d.stream));
+			d.band_table_strips = total_strips; d.band_table_bands = s.bands;
+		}
+		p.band_table = d.d_band_table;
+		return RT_OK;
+	}
+
 	// One device: rt_render overlaps the present copy with the rendering.  The frame is cut into bands
 	// of strips.  Preferred form ("progressive present"): ONE kernel launch; every CTA bumps its band's
 	// counter when its pixels are in memory, and the copy stream waits on each counter with
@@ -1251,9 +1313,14 @@ namespace
 		const int wanted = requested ? requested : (wait ? 16 : 4);
 		const int bands = std::min(std::min(std::min(wanted, wait ? 64 : 16), max_bands), total_strips);
 		const int strips_per_band = (total_strips + bands - 1) / bands;
+		// one device: bands of unequal size (make_band_schedule); the multi-device gather flow keeps equal bands
+		// (its per-GPU share arithmetic in signal_band_done assumes them)
+		const BandSchedule schedule = make_band_schedule(total_strips, bands);
 
 		RT_CUDA(ctx, cudaSetDevice(d.device));
 		rt::FrameParams base = make_params(camera, frame);
+		if (wait && n_dev == 1 && (rc = use_band_schedule(ctx, d, schedule, total_strips, base)) != RT_OK) return rc;
+		const bool scheduled = base.band_table != nullptr;
 		auto copy_band = [&](int r0, int r1) -> int
 		{
 			char* dst = (char*)target + (size_t)r0 * (size_t)pitch_bytes;
@@ -1287,9 +1354,9 @@ namespace
 			}
 			RT_CUDA(ctx, cudaSetDevice(d.device));
 			for (int k = 1; k < n_dev; ++k) RT_CUDA(ctx, cudaStreamWaitEvent(d.stream, ctx->devs[k].ev_kernel, 0));
-			for (int b = 0; b < bands; ++b)
+			for (int b = 0; b < (scheduled ? schedule.bands : bands); ++b)
 			{
-				const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
+				const int s0 = scheduled ? schedule.first[b] : b * strips_per_band, s1 = scheduled ? schedule.first[b + 1] : std::min(total_strips, (b + 1) * strips_per_band);
 				if (s1 <= s0) break;
 				const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)((s1 - s0) * grid_x * rt::kSignalsPerTile), CU_STREAM_WAIT_VALUE_GEQ);
 				if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
@@ -1380,10 +1447,13 @@ namespace
 		const int max_bands = std::max(1, (int)(((long long)my_strips * grid_x) / 512));
 		const int bands = std::max(1, std::min(std::min(requested ? requested : 16, max_bands), total_strips));
 		const int strips_per_band = (total_strips + bands - 1) / bands;
+		const BandSchedule schedule = make_band_schedule(total_strips, bands);
 
 		RT_CUDA(ctx, cudaSetDevice(d.device));
 		rt::FrameParams p = base;
 		p.row_begin = 0; p.row_end = H; p.strip_first = strip_first; p.strip_step = strip_step; p.dst_full_frame = 1; p.dst = d.d_frame;
+		if (wait && my_strips > 0 && (rc = use_band_schedule(ctx, d, schedule, total_strips, p)) != RT_OK) return rc;
+		const bool scheduled = p.band_table != nullptr;
 		if (wait && my_strips > 0)
 		{
 			RT_CUDA(ctx, cudaMemsetAsync(d.d_band_done, 0, sizeof(unsigned int) * 64, d.stream));
@@ -1393,9 +1463,9 @@ namespace
 			p.band_done = d.d_band_done; p.strips_per_band = strips_per_band; p.band_local = nullptr;
 			if ((rc = launch(ctx, d, p, d.stream, my_strips)) != RT_OK) return rc;
 			RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
-			for (int b = 0; b < bands; ++b)
+			for (int b = 0; b < (scheduled ? schedule.bands : bands); ++b)
 			{
-				const int s0 = b * strips_per_band, s1 = std::min(total_strips, (b + 1) * strips_per_band);
+				const int s0 = scheduled ? schedule.first[b] : b * strips_per_band, s1 = scheduled ? schedule.first[b + 1] : std::min(total_strips, (b + 1) * strips_per_band);
 				if (s1 <= s0) break;
 				// this device's strips of the band: those congruent to strip_first modulo strip_step (as signal_band_done counts them)
 				const int first_mine = s0 + ((strip_first - s0) % strip_step + strip_step) % strip_step;
@@ -1529,6 +1599,8 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		RT_CREATE(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
 		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 128));
+		RT_CREATE(cudaMalloc(&d.d_band_table, 8192));
+		RT_CREATE(cudaHostAlloc(&d.h_band_table, 8192, cudaHostAllocPortable));
 		RT_CREATE(cudaMemset(d.d_band_done, 0, sizeof(unsigned int) * 128));
 		RT_CREATE(cudaMalloc(&d.d_split, sizeof(int32_t) * rt::kMaxMeshes * rt::wave::kSplitStride));
 		RT_CREATE(cudaMemset(d.d_split, 0, sizeof(int32_t) * rt::kMaxMeshes * rt::wave::kSplitStride));
@@ -1579,7 +1651,7 @@ int rt_destroy(rt_context* ctx)
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
-		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map);
+		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map); cudaFree(d.d_band_table); cudaFreeHost(d.h_band_table);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
 		if (d.ev_foreign) cudaEventDestroy(d.ev_foreign);
 		cudaFree(d.cells.d_cost); cudaFree(d.cells.d_order); cudaFreeHost(d.cells.h_cost); cudaFreeHost(d.cells.h_order);

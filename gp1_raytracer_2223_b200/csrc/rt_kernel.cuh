@@ -76,7 +76,8 @@ namespace rt
 		uint32_t* dst;
 		unsigned long long* counters;    // counters build only
 		unsigned int* band_done;         // progressive present: band_done[b] counts the finished CTAs of band b (NULL = off)
-		int32_t strips_per_band;         // a band = this many consecutive 8-row strips of the frame
+		int32_t strips_per_band;         // a band = this many consecutive 8-row strips of the frame ...
+		const uint8_t* band_table;       // ... or, when set, band_table[strip]: bands of unequal size (single-GPU counters only)
 		unsigned int* band_local;        // multi-GPU: this GPU's own per-band counters (see signal_band_done)
 		int32_t grid_x, n_strips;        // the launch's tile grid: 32-pixel columns x 8-row strips (set by launch())
 		unsigned int* queue;             // persistent kernel: {next work item, finished warps}, both zero between launches
@@ -1044,7 +1045,7 @@ namespace rt
 	__device__ __forceinline__ void signal_band_done(const FrameParams& p, int k, unsigned int units)
 	{
 		const int strip = k * p.strip_step + p.strip_first;      // position in the frame, whoever renders it
-		const int band = strip / p.strips_per_band;
+		const int band = p.band_table ? (int)__ldg(p.band_table + strip) : strip / p.strips_per_band;
 		if (!p.band_local)
 		{
 			asm volatile("red.release.gpu.global.add.u32 [%0], %1;" :: "l"(p.band_done + band), "r"(units) : "memory");
