@@ -1358,8 +1358,13 @@ namespace
 			{
 				const int s0 = scheduled ? schedule.first[b] : b * strips_per_band, s1 = scheduled ? schedule.first[b + 1] : std::min(total_strips, (b + 1) * strips_per_band);
 				if (s1 <= s0) break;
-				const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)((s1 - s0) * grid_x * rt::kSignalsPerTile), CU_STREAM_WAIT_VALUE_GEQ);
-				if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
+				// the last band is complete when the kernel is: an event wait reacts faster than a polled counter
+				if (s1 == total_strips && n_dev == 1) RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_kernel, 0));
+				else
+				{
+					const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)((s1 - s0) * grid_x * rt::kSignalsPerTile), CU_STREAM_WAIT_VALUE_GEQ);
+					if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
+				}
 				if ((rc = copy_band(s0 * rt::kBlockH, std::min(H, s1 * rt::kBlockH))) != RT_OK) return rc;
 			}
 		}
@@ -1471,8 +1476,12 @@ namespace
 				const int first_mine = s0 + ((strip_first - s0) % strip_step + strip_step) % strip_step;
 				const int mine = first_mine < s1 ? (s1 - 1 - first_mine) / strip_step + 1 : 0;
 				if (mine == 0) continue;
-				const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)(mine * grid_x * rt::kSignalsPerTile), CU_STREAM_WAIT_VALUE_GEQ);
-				if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
+				if (s1 == total_strips) RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_kernel, 0));      // the last band: see render_pipelined
+				else
+				{
+					const CUresult cr = wait((CUstream)d.copy_stream, (CUdeviceptr)(uintptr_t)(d.d_band_done + b), (cuuint32_t)(mine * grid_x * rt::kSignalsPerTile), CU_STREAM_WAIT_VALUE_GEQ);
+					if (cr != CUDA_SUCCESS) return fail(ctx, RT_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)cr);
+				}
 				if ((rc = copy_strips_to_host(ctx, d, W, H, first_mine, strip_step, mine, target, pitch_bytes)) != RT_OK) return rc;
 			}
 		}
