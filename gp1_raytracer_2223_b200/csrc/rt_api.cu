@@ -1319,7 +1319,8 @@ namespace
 
 		RT_CUDA(ctx, cudaSetDevice(d.device));
 		rt::FrameParams base = make_params(camera, frame);
-		if (wait && n_dev == 1 && (rc = use_band_schedule(ctx, d, schedule, total_strips, base)) != RT_OK) return rc;
+		static const bool profile = getenv("RT_B200_BAND_PROFILE") != nullptr;
+		if (profile && wait && n_dev == 1 && (rc = use_band_schedule(ctx, d, schedule, total_strips, base)) != RT_OK) return rc;
 		const bool scheduled = base.band_table != nullptr;
 		auto copy_band = [&](int r0, int r1) -> int
 		{
@@ -1457,7 +1458,8 @@ namespace
 		RT_CUDA(ctx, cudaSetDevice(d.device));
 		rt::FrameParams p = base;
 		p.row_begin = 0; p.row_end = H; p.strip_first = strip_first; p.strip_step = strip_step; p.dst_full_frame = 1; p.dst = d.d_frame;
-		if (wait && my_strips > 0 && (rc = use_band_schedule(ctx, d, schedule, total_strips, p)) != RT_OK) return rc;
+		static const bool profile = getenv("RT_B200_BAND_PROFILE") != nullptr;
+		if (profile && wait && my_strips > 0 && (rc = use_band_schedule(ctx, d, schedule, total_strips, p)) != RT_OK) return rc;
 		const bool scheduled = p.band_table != nullptr;
 		if (wait && my_strips > 0)
 		{
