@@ -101,6 +101,16 @@ namespace
 		cudaStream_t copy_stream = nullptr;                 // device-to-host copies that overlap the next band's kernel
 		cudaEvent_t ev_band[16] = {};
 		unsigned int* d_band_done = nullptr;                // kMaxBands counters for the single-launch progressive present
+		unsigned int* h_flags = nullptr;                    // 64 words of mapped pinned memory: the band watcher's messages to the host
+		unsigned int* d_flags = nullptr;                    // the same words as the device sees them
+		uint32_t watch_tag = 0;                             // value the watcher stores for the current frame
+		struct PendingPresent                               // a watched frame whose band copies the host still has to issue
+		{
+			bool active = false;
+			int bands = 0, next = 0, strips_per_band = 0, strip_first = 0, strip_step = 1, total_strips = 0, W = 0, H = 0;
+			void* target = nullptr; int32_t pitch_bytes = 0;
+			unsigned long long spins = 0;
+		} pending;
 		uint8_t* d_band_table = nullptr;                    // strip -> band of the current schedule (make_band_schedule)
 		uint8_t* h_band_table = nullptr;                    // its pinned source
 		int band_table_strips = 0, band_table_bands = 0;
@@ -825,8 +835,11 @@ namespace
 		return RT_OK;
 	}
 
-	int launch(rt_context* ctx, DeviceState& d, rt::FrameParams p, cudaStream_t stream, int n_strips)
+	// `watched` (optional): p.host_flags asks for the band watcher (rt_kernel.cuh, watch_bands); set to true when the launch
+	// has one - only the persistent kernel can - else the caller orders its copies with stream waits.
+	int launch(rt_context* ctx, DeviceState& d, rt::FrameParams p, cudaStream_t stream, int n_strips, bool* watched = nullptr)
 	{
+		if (watched) *watched = false;
 		if (n_strips <= 0) return RT_OK;
 		const int path = resolve_mesh_path(ctx, ctx->mesh_path);
 		if (path < 0) return RT_ERR_BAD_STATE;
@@ -873,6 +886,7 @@ namespace
 				variant = (tiles * rt::kSignalsPerTile >= (p.band_done ? 8ll : 4ll) * wave * (rt::kPersistentThreads / 32)) ? RT_KERNEL_PERSISTENT : RT_KERNEL_SCALAR;
 			if (!decodable) variant = RT_KERNEL_SCALAR;
 		}
+		if (variant != RT_KERNEL_PERSISTENT) p.host_flags = nullptr;
 		if (variant == RT_KERNEL_WAVEFRONT)
 		{
 			const size_t pixels = (size_t)tiles * rt::kThreads;
@@ -918,7 +932,12 @@ namespace
 			if (prc != RT_OK) return prc;
 			p.queue = d.d_queues + 2 * (d.queue_cursor++ % kQueueRing);
 			const long long ctas_of_work = (tiles * rt::kSignalsPerTile + rt::kPersistentThreads / 32 - 1) / (rt::kPersistentThreads / 32);
-			fn<<<(unsigned)std::min<long long>(wave, ctas_of_work), rt::kPersistentThreads, rt::dynamic_smem_bytes(rt::kPersistentThreads, ctx->n_materials), stream>>>(d.view, p);
+			// band watcher: CTA 0 of the wave tells the host when a band is complete instead of rendering
+			static const bool no_watcher = getenv("RT_B200_NO_BAND_WATCHER") != nullptr;
+			const bool watcher = watched && p.host_flags && p.band_done && !p.band_local && !p.band_table && !no_watcher && wave > 8;
+			if (!watcher) p.host_flags = nullptr;
+			if (watched) *watched = watcher;
+			fn<<<(unsigned)std::min<long long>(wave, ctas_of_work + (watcher ? 1 : 0)), rt::kPersistentThreads, rt::dynamic_smem_bytes(rt::kPersistentThreads, ctx->n_materials), stream>>>(d.view, p);
 			RT_CUDA(ctx, cudaGetLastError());
 			const int frc = finish_cell_order(ctx, d, p, stream, cost_slot);
 			if (frc != RT_OK) return frc;
@@ -1438,7 +1457,56 @@ namespace
 		return RT_OK;
 	}
 
+	// The host side of the band watcher: issue the copies of a device's pending frame for every band whose flag has
+	// arrived.  Returns through `done` whether all of the device's bands have been issued.  `block` = spin until the next
+	// band is ready (single device) instead of returning when it is not.
+	int service_present(rt_context* ctx, DeviceState& d, bool block, bool* done)
+	{
+		DeviceState::PendingPresent& pp = d.pending;
+		*done = !pp.active;
+		if (!pp.active) return RT_OK;
+		RT_CUDA(ctx, cudaSetDevice(d.device));
+		while (pp.next < pp.bands)
+		{
+			const int b = pp.next;
+			const int s0 = b * pp.strips_per_band, s1 = std::min(pp.total_strips, (b + 1) * pp.strips_per_band);
+			if (s1 <= s0) { pp.next = pp.bands; break; }
+			if (__atomic_load_n(d.h_flags + b, __ATOMIC_ACQUIRE) != d.watch_tag)
+			{
+				// a kernel that ended without the flag (launch failure, fault) must not hang the caller
+				if ((++pp.spins & 0xfffu) == 0)
+				{
+					const cudaError_t q = cudaStreamQuery(d.stream);
+					if (q != cudaErrorNotReady)
+					{
+						if (q != cudaSuccess) return fail(ctx, RT_ERR_CUDA, "the pixel kernel failed: %s", cudaGetErrorString(q));
+						if (__atomic_load_n(d.h_flags + b, __ATOMIC_ACQUIRE) != d.watch_tag) return fail(ctx, RT_ERR_CUDA, "the pixel kernel ended without reporting band %d", b);
+					}
+				}
+				if (!block) return RT_OK;
+#if defined(__x86_64__)
+				__builtin_ia32_pause();
+#endif
+				continue;
+			}
+			const int first_mine = s0 + ((pp.strip_first - s0) % pp.strip_step + pp.strip_step) % pp.strip_step;
+			const int mine = first_mine < s1 ? (s1 - 1 - first_mine) / pp.strip_step + 1 : 0;
+			if (mine > 0)
+			{
+				const int rc = copy_strips_to_host(ctx, d, pp.W, pp.H, first_mine, pp.strip_step, mine, pp.target, pp.pitch_bytes);
+				if (rc != RT_OK) return rc;
+			}
+			++pp.next;
+		}
+		pp.active = false;
+		*done = true;
+		RT_CUDA(ctx, cudaEventRecord(d.ev_done, d.copy_stream));
+		return RT_OK;
+	}
+
 	// Enqueues kernel + copies of one device's share; the caller synchronises d.copy_stream (ev_done is its last event).
+	// With a band watcher in the launch the copies are NOT enqueued here: d.pending says what the host has to issue as the
+	// bands arrive (service_present).
 	int enqueue_direct_present(rt_context* ctx, DeviceState& d, const rt::FrameParams& base, int strip_first, int strip_step, void* target, int32_t pitch_bytes)
 	{
 		const int W = base.width, H = base.height;
@@ -1468,8 +1536,17 @@ namespace
 			RT_CUDA(ctx, cudaStreamWaitEvent(d.copy_stream, d.ev_band[0], 0));      // counters are zero before anyone polls them
 			RT_CUDA(ctx, cudaEventRecord(d.ev_begin, d.stream));
 			p.band_done = d.d_band_done; p.strips_per_band = strips_per_band; p.band_local = nullptr;
-			if ((rc = launch(ctx, d, p, d.stream, my_strips)) != RT_OK) return rc;
+			p.host_flags = d.d_flags; p.watch_tag = ++d.watch_tag; p.watch_bands = bands;
+			bool watched = false;
+			if ((rc = launch(ctx, d, p, d.stream, my_strips, &watched)) != RT_OK) return rc;
 			RT_CUDA(ctx, cudaEventRecord(d.ev_kernel, d.stream));
+			if (watched)
+			{
+				DeviceState::PendingPresent& pp = d.pending;
+				pp.active = true; pp.spins = 0; pp.bands = bands; pp.next = 0; pp.strips_per_band = strips_per_band; pp.strip_first = strip_first; pp.strip_step = strip_step;
+				pp.total_strips = total_strips; pp.W = W; pp.H = H; pp.target = target; pp.pitch_bytes = pitch_bytes;
+				return RT_OK;
+			}
 			for (int b = 0; b < (scheduled ? schedule.bands : bands); ++b)
 			{
 				const int s0 = scheduled ? schedule.first[b] : b * strips_per_band, s1 = scheduled ? schedule.first[b + 1] : std::min(total_strips, (b + 1) * strips_per_band);
@@ -1525,6 +1602,17 @@ namespace
 		const rt::FrameParams base = make_params(camera, frame);
 		for (int k = 0; k < n_present; ++k)
 			if ((rc = enqueue_direct_present(ctx, ctx->devs[k], base, strip_first + k, strip_step, target, pitch_bytes)) != RT_OK) return rc;
+		// watched launches: this thread issues every device's band copies as the bands arrive
+		for (bool all_done = false; !all_done;)
+		{
+			all_done = true;
+			for (int k = 0; k < n_present; ++k)
+			{
+				bool done = true;
+				if ((rc = service_present(ctx, ctx->devs[k], n_present == 1, &done)) != RT_OK) return rc;
+				all_done = all_done && done;
+			}
+		}
 		float kernel_ms = 0.f, total_ms = 0.f;
 		for (int k = 0; k < n_present; ++k)
 		{
@@ -1610,6 +1698,9 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		RT_CREATE(cudaStreamCreateWithFlags(&d.copy_stream, cudaStreamNonBlocking));
 		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 128));
+		RT_CREATE(cudaHostAlloc(&d.h_flags, sizeof(unsigned int) * 64, cudaHostAllocMapped | cudaHostAllocPortable));
+		memset(d.h_flags, 0, sizeof(unsigned int) * 64);
+		RT_CREATE(cudaHostGetDevicePointer((void**)&d.d_flags, d.h_flags, 0));
 		RT_CREATE(cudaMalloc(&d.d_band_table, 8192));
 		RT_CREATE(cudaHostAlloc(&d.h_band_table, 8192, cudaHostAllocPortable));
 		RT_CREATE(cudaMemset(d.d_band_done, 0, sizeof(unsigned int) * 128));
@@ -1662,7 +1753,7 @@ int rt_destroy(rt_context* ctx)
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
-		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map); cudaFree(d.d_band_table); cudaFreeHost(d.h_band_table);
+		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map); cudaFree(d.d_band_table); cudaFreeHost(d.h_band_table); cudaFreeHost(d.h_flags);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
 		if (d.ev_foreign) cudaEventDestroy(d.ev_foreign);
 		cudaFree(d.cells.d_cost); cudaFree(d.cells.d_order); cudaFreeHost(d.cells.h_cost); cudaFreeHost(d.cells.h_order);
@@ -1958,6 +2049,10 @@ int rt_render(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* fra
 	// (RT_B200_PRESENT=gather keeps the flow through device 0's frame buffer, e.g. to compare)
 	static const bool gather_first = [] { const char* e = getenv("RT_B200_PRESENT"); return e && strcmp(e, "gather") == 0; }();
 	if (ctx->devs.size() > 1 && !gather_first) return render_direct(ctx, camera, frame, host_dst, pitch_bytes, (int)ctx->devs.size(), 0, (int)ctx->devs.size());
+	// one device: the same flow with a single share - kernel with band counters, band copies issued by this thread as the
+	// kernel's band watcher reports them (RT_B200_SINGLE_PRESENT=stream keeps round 1's copy stream with polled waits)
+	static const bool stream_present = [] { const char* e = getenv("RT_B200_SINGLE_PRESENT"); return e && strcmp(e, "stream") == 0; }();
+	if (ctx->devs.size() == 1 && !stream_present) return render_direct(ctx, camera, frame, host_dst, pitch_bytes, 1, 0, 1);
 	if (ctx->devs.size() == 1 || (ctx->peer_stores && wait_value32())) return render_pipelined(ctx, camera, frame, host_dst, pitch_bytes);
 	int rc = render_to_device0(ctx, camera, frame);
 	if (rc != RT_OK) return rc;

@@ -78,6 +78,12 @@ namespace rt
 		unsigned int* band_done;         // progressive present: band_done[b] counts the finished CTAs of band b (NULL = off)
 		int32_t strips_per_band;         // a band = this many consecutive 8-row strips of the frame ...
 		const uint8_t* band_table;       // ... or, when set, band_table[strip]: bands of unequal size (single-GPU counters only)
+		// Band watcher (persistent kernel): CTA 0 does not render; one of its threads waits for each band's counter and then
+		// stores watch_tag into host_flags[band] (mapped pinned memory) - the host thread blocked in rt_render polls those
+		// words and issues the band's copy itself (no stream memory operations, see watch_bands)
+		unsigned int* host_flags;        // NULL = off
+		uint32_t watch_tag;
+		int32_t watch_bands;
 		unsigned int* band_local;        // multi-GPU: this GPU's own per-band counters (see signal_band_done)
 		int32_t grid_x, n_strips;        // the launch's tile grid: 32-pixel columns x 8-row strips (set by launch())
 		unsigned int* queue;             // persistent kernel: {next work item, finished warps}, both zero between launches
@@ -1198,6 +1204,41 @@ namespace rt
 		return c;
 	}
 
+	// ---- band watcher ------------------------------------------------------------------------------------------------
+	// A copy stream that waits on every band's counter with cuStreamWaitValue32 reacts late when it reaches the wait
+	// before the band is complete (the wait is polled by the front end: tens of microseconds), which is the normal
+	// case whenever rendering a band and copying it take about equally long.  Instead ONE thread of the persistent grid
+	// watches the counters (an acquire load every ~100 ns, from L2) and tells the host, which is blocked in rt_render
+	// anyway, through a word of mapped pinned memory; the host issues that band's copy immediately.
+	__device__ __forceinline__ unsigned int load_acquire_gpu(const unsigned int* p)
+	{
+		unsigned int v;
+		asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+		return v;
+	}
+
+	__device__ __forceinline__ void watch_bands(const FrameParams& p)
+	{
+		if (threadIdx.x != 0) return;
+		const int total_strips = (p.row_end - p.row_begin + kBlockH - 1) / kBlockH;
+		for (int b = 0; b < p.watch_bands; ++b)
+		{
+			const int s0 = b * p.strips_per_band, s1 = min(total_strips, s0 + p.strips_per_band);
+			if (s1 <= s0) break;
+			// this launch's strips of the band: those congruent to strip_first modulo strip_step (as signal_band_done counts them)
+			const int first_mine = s0 + ((p.strip_first - s0) % p.strip_step + p.strip_step) % p.strip_step;
+			const int mine = first_mine < s1 ? (s1 - 1 - first_mine) / p.strip_step + 1 : 0;
+			if (mine > 0)
+			{
+				const unsigned int expected = (unsigned int)mine * (unsigned int)p.grid_x * (unsigned int)kSignalsPerTile;
+				while (load_acquire_gpu(p.band_done + b) < expected) __nanosleep(100);
+			}
+			// the band's pixels are in device memory (the acquire above pairs with the tiles' releases); the host only
+			// needs to learn that: a system-scope release store into its mapped word
+			asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p.host_flags + b), "r"(p.watch_tag) : "memory");
+		}
+	}
+
 	// 128-thread CTAs, 8 per SM: 64 registers, 32 warps per SM.  (Round 1 ran 9 CTAs at 56 registers; with the round-2
 	// loops the 56-register build spills into the per-light code and is 7 % slower on the 4K bunny frame: 0.761 vs 0.708 ms.)
 #ifndef RT_PERSISTENT_MIN_CTAS
@@ -1213,6 +1254,11 @@ namespace rt
 	__global__ void __launch_bounds__(kPersistentThreads, RT_PERSISTENT_MIN_CTAS)
 	render_kernel_persistent(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p)
 	{
+		if (p.host_flags && blockIdx.x == 0)       // this CTA is the frame's band watcher
+		{
+			watch_bands(p);
+			return;
+		}
 		extern __shared__ __align__(16) unsigned char dynamic_smem[];
 		Parked<kPersistentThreads>& parked = *reinterpret_cast<Parked<kPersistentThreads>*>(dynamic_smem);
 		SharedScene& storage = *reinterpret_cast<SharedScene*>(dynamic_smem + sizeof(Parked<kPersistentThreads>));
@@ -1288,7 +1334,7 @@ namespace rt
 		// every warp of the grid arrives here exactly once, after its last fetch
 		if (lane == 0)
 		{
-			const unsigned int warps = gridDim.x * (unsigned int)(kPersistentThreads / 32);
+			const unsigned int warps = (gridDim.x - (p.host_flags ? 1u : 0u)) * (unsigned int)(kPersistentThreads / 32);
 			if (atomicAdd(p.queue + 1, 1u) + 1u == warps)
 			{
 				p.queue[0] = 0u;
