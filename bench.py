@@ -48,7 +48,7 @@ WIDTH, HEIGHT = 3840, 2160
 RAYS_PER_FRAME = WIDTH * HEIGHT * 4          # 1 primary + 3 shadow rays per pixel (every pixel hits; re-checked below)
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "ref_render")
 L2_FLUSH_BYTES = 256 << 20
-KERNEL_NOTE = "persistent warps (one pixel per thread, 8x4 warp tiles pulled off a device queue; 128-thread CTAs, 9 per SM); rt_render overlaps the present copy with rendering (progressive present)"
+KERNEL_NOTE = "persistent warps (one pixel per thread, 8x4 warp tiles pulled off a device queue; 128-thread CTAs, 8 per SM, 64 registers); rt_render overlaps the present copies with rendering (band watcher in the kernel, copies issued by the host thread as bands complete)"
 
 
 def parse_args():
