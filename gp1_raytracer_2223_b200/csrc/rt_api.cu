@@ -1465,7 +1465,7 @@ namespace
 		DeviceState::PendingPresent& pp = d.pending;
 		*done = !pp.active;
 		if (!pp.active) return RT_OK;
-		RT_CUDA(ctx, cudaSetDevice(d.device));
+		bool current = false;            // cudaSetDevice only when there is something to issue: polling the flags needs no device
 		while (pp.next < pp.bands)
 		{
 			const int b = pp.next;
@@ -1476,6 +1476,7 @@ namespace
 				// a kernel that ended without the flag (launch failure, fault) must not hang the caller
 				if ((++pp.spins & 0xfffu) == 0)
 				{
+					if (!current) { RT_CUDA(ctx, cudaSetDevice(d.device)); current = true; }
 					const cudaError_t q = cudaStreamQuery(d.stream);
 					if (q != cudaErrorNotReady)
 					{
@@ -1493,6 +1494,7 @@ namespace
 			const int mine = first_mine < s1 ? (s1 - 1 - first_mine) / pp.strip_step + 1 : 0;
 			if (mine > 0)
 			{
+				if (!current) { RT_CUDA(ctx, cudaSetDevice(d.device)); current = true; }
 				const int rc = copy_strips_to_host(ctx, d, pp.W, pp.H, first_mine, pp.strip_step, mine, pp.target, pp.pitch_bytes);
 				if (rc != RT_OK) return rc;
 			}
@@ -1500,6 +1502,7 @@ namespace
 		}
 		pp.active = false;
 		*done = true;
+		if (!current) RT_CUDA(ctx, cudaSetDevice(d.device));
 		RT_CUDA(ctx, cudaEventRecord(d.ev_done, d.copy_stream));
 		return RT_OK;
 	}

@@ -369,11 +369,13 @@ int rt_set_kernel_variant(rt_context* ctx, int32_t variant);
 /* Replaces Renderer::Render (source/Renderer.cpp:34-98): blocking; on return host_dst holds
  * height rows of width uint32 pixels, row stride pitch_bytes (>= 4*width), exactly what the
  * reference leaves in m_pBufferPixels.
- *   One device: one kernel launch; the copy to host_dst follows the kernel band by band (progressive present).
- *   Several devices (default, "direct present"): device k renders the 8-row strips k, k + n, ... into its OWN
- *     full-frame buffer (width * height * 4 bytes are allocated on every device) and copies exactly those strips
- *     to host_dst over its own PCIe link; nothing is gathered on device 0.  RT_B200_PRESENT=gather in the
- *     environment selects the older flow (peer stores into device 0's frame, device 0 presents).
+ *   Every device renders the 8-row strips k, k + n, ... of the frame (k = its position in the context, n = the number of
+ *   devices; one device: all of them) into its OWN full-frame buffer (width * height * 4 bytes per device) and copies
+ *   exactly those strips to host_dst over its own PCIe link while later strips are still rendering: the kernel counts
+ *   finished tiles per band of the frame, one of its CTAs reports complete bands through mapped pinned memory, and the
+ *   calling thread issues each band's copy as it is reported ("direct present"; nothing is gathered on device 0).
+ *   RT_B200_PRESENT=gather in the environment selects the older multi-device flow (peer stores into device 0's frame,
+ *   device 0 presents), RT_B200_SINGLE_PRESENT=stream the older single-device one (copy stream with polled waits).
  * host_dst and pinning: when CUDA knows [host_dst, host_dst + pitch_bytes * (height - 1) + 4 * width) as pinned
  * memory (cudaHostAlloc / cudaHostRegister by the caller, or rt_register_surface below) the copies land in it
  * directly; otherwise they go through a pinned bounce buffer owned by the context and are memcpy'd out before
