@@ -890,8 +890,13 @@ namespace
 		if (variant == RT_KERNEL_WAVEFRONT)
 		{
 			const size_t pixels = (size_t)tiles * rt::kThreads;
+			// small frames wait for their longest jobs: those kernels take the subtrees in parts (rt_wave_params.h); measured
+			// crossover (tools/wave_sweep.sh): ~110 jobs per SM
+			static const long long parts_below_per_sm = [] { const char* e = getenv("RT_B200_WAVE_PARTS_BELOW"); return e ? atoll(e) : 110ll; }();
+			d.wave.parts_below = (unsigned int)std::min<long long>(parts_below_per_sm * d.sm_count, 0x7fffffffll);
+			const long long warp_tiles = tiles * rt::kSignalsPerTile;
 			// a job per (warp tile, subtree) and, for shadow rays, per light: sized for the worst case, so the lists cannot overflow
-			const size_t view_jobs = (size_t)tiles * rt::kSignalsPerTile * (size_t)wave_subtrees;
+			const size_t view_jobs = (size_t)warp_tiles * (size_t)wave_subtrees;
 			const size_t shadow_jobs = view_jobs * (size_t)std::max(ctx->n_lights, 1);
 			if (pixels > d.wave_pixels || view_jobs > d.wave_view_tasks || shadow_jobs > d.wave_shadow_tasks || ctx->meshes.size() != d.wave_meshes || (size_t)ctx->n_lights != d.wave_lights)
 			{
@@ -916,7 +921,7 @@ namespace
 			d.wave.split = d.d_split;
 			d.wave.root_map = d.d_root_map;
 			RT_CUDA(ctx, rt::wave_launch(d.view, p, d.wave, grid, d.sm_count, stream));
-			ctx->timing.kernel_launches += rt::wave_launch_count(p.shadows) - 1;
+			ctx->timing.kernel_launches += rt::wave_launch_count(p.shadows && ctx->n_lights > 0) - 1;
 		}
 		else if (variant == RT_KERNEL_PACKED) pick_kernel_x2(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::pick_threads_x2(), 0, stream>>>(d.view, p);
 		else if (variant == RT_KERNEL_SCALAR) pick_kernel(p.lighting_mode, p.shadows, path == RT_MESH_PATH_BVH)<<<grid, rt::kThreads, rt::dynamic_smem_bytes(rt::kThreads, ctx->n_materials), stream>>>(d.view, p);
@@ -1165,9 +1170,9 @@ namespace
 		}
 		if (covered != mesh->triangle_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH leaves cover %lld of %d triangles", (long long)covered, mesh->triangle_count);
 
-		// RT_KERNEL_WAVEFRONT: cut the tree into at most kMaxSubtrees subtrees of comparable size.  Start from the root and
-		// keep replacing the largest inner subtree by its two children (each inherits the parent's ancestor list + the
-		// parent); a subtree is walked from its root until the walk leaves through the root's escape link.
+		// RT_KERNEL_WAVEFRONT: cut the tree into at most kMaxSubtrees subtrees of comparable size and every subtree into at
+		// most kFine parts (rt_wave_params.h); a part is walked from its root until the walk leaves through the root's
+		// escape link.
 		{
 			using namespace rt::wave;
 			std::vector<int32_t> size((size_t)n, 1), escape((size_t)n, -1);
@@ -1188,39 +1193,82 @@ namespace
 					if (nd.idx_count == 0) size[(size_t)order[i]] = 1 + size[nd.left_node] + size[nd.left_node + 1];
 				}
 			}
-			struct Entry { int32_t node; std::vector<int32_t> ancestors; };
-			std::vector<Entry> entries;
-			entries.push_back({ 0, {} });
-			static const int cap = [] { const char* e = getenv("RT_B200_WAVE_SUBTREES"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxSubtrees) ? v : kMaxSubtrees; }();
-			const int wanted = n >= 64 ? cap : 1;        // a shallow tree is one job
-			while ((int)entries.size() < wanted)
+			// what a subtree spans: node records and triangles (lowest / highest index below the root, triangles of its leaves)
+			std::vector<int32_t> node_lo((size_t)n, INT32_MAX), node_hi((size_t)n, -1), tri_lo((size_t)n, INT32_MAX), tri_hi((size_t)n, -1), tri_sum((size_t)n, 0);
+			for (size_t i = order.size(); i-- > 0;)
 			{
-				int pick = -1;
-				for (size_t e = 0; e < entries.size(); ++e)
+				const int32_t node = order[i];
+				const rt_bvh_node& nd = mesh->bvh_nodes[node];
+				if (nd.idx_count > 0)
 				{
-					const rt_bvh_node& nd = mesh->bvh_nodes[entries[e].node];
-					if (nd.idx_count != 0 || (int)entries[e].ancestors.size() >= kMaxAncestors) continue;
-					if (pick < 0 || size[(size_t)entries[e].node] > size[(size_t)entries[(size_t)pick].node]) pick = (int)e;
+					tri_lo[(size_t)node] = (int32_t)(nd.first_idx / 3);
+					tri_hi[(size_t)node] = (int32_t)((nd.first_idx + nd.idx_count) / 3) - 1;
+					tri_sum[(size_t)node] = (int32_t)(nd.idx_count / 3);
+					continue;
 				}
-				if (pick < 0) break;
-				const Entry parent = entries[(size_t)pick];
-				const int32_t left = (int32_t)mesh->bvh_nodes[parent.node].left_node;
-				std::vector<int32_t> anc = parent.ancestors;
-				anc.push_back(parent.node);
-				entries[(size_t)pick] = { left, anc };
-				entries.insert(entries.begin() + pick + 1, Entry{ left + 1, anc });
+				for (int32_t child = (int32_t)nd.left_node; child <= (int32_t)nd.left_node + 1; ++child)
+				{
+					node_lo[(size_t)node] = std::min(node_lo[(size_t)node], std::min(child, node_lo[(size_t)child]));
+					node_hi[(size_t)node] = std::max(node_hi[(size_t)node], std::max(child, node_hi[(size_t)child]));
+					tri_lo[(size_t)node] = std::min(tri_lo[(size_t)node], tri_lo[(size_t)child]);
+					tri_hi[(size_t)node] = std::max(tri_hi[(size_t)node], tri_hi[(size_t)child]);
+					tri_sum[(size_t)node] += tri_sum[(size_t)child];
+				}
 			}
-			split.assign((size_t)kSplitStride, 0);
-			split[0] = (int32_t)entries.size();
-			root_map.assign((size_t)n, 0);
-			for (size_t e = 0; e < entries.size(); ++e) root_map[(size_t)entries[e].node] = (uint8_t)(e + 1);
-			for (size_t e = 0; e < entries.size(); ++e)
+			// cut(root, pieces, depth): start from `root` and keep replacing the largest inner piece by its two children
+			// (each remembers the nodes between `root` and itself) until there are `pieces` or nothing is left to cut
+			struct Piece { int32_t node; std::vector<int32_t> above; };
+			auto cut = [&](int32_t root, int pieces, int depth)
 			{
-				int32_t* rec = split.data() + kSplitHeader + e * kSplitWords;
-				rec[0] = entries[e].node * rt::BvhLink::kNodeBytes;
-				rec[1] = rt::BvhLink::miss(escape[(size_t)entries[e].node]);
-				rec[2] = (int32_t)entries[e].ancestors.size();
-				for (size_t k = 0; k < entries[e].ancestors.size(); ++k) rec[3 + k] = entries[e].ancestors[k] * rt::BvhLink::kNodeBytes;
+				std::vector<Piece> out_pieces;
+				out_pieces.push_back({ root, {} });
+				while ((int)out_pieces.size() < pieces)
+				{
+					int pick = -1;
+					for (size_t e = 0; e < out_pieces.size(); ++e)
+					{
+						if (mesh->bvh_nodes[out_pieces[e].node].idx_count != 0 || (int)out_pieces[e].above.size() >= depth) continue;
+						if (pick < 0 || size[(size_t)out_pieces[e].node] > size[(size_t)out_pieces[(size_t)pick].node]) pick = (int)e;
+					}
+					if (pick < 0) break;
+					const Piece parent = out_pieces[(size_t)pick];
+					const int32_t left = (int32_t)mesh->bvh_nodes[parent.node].left_node;
+					std::vector<int32_t> above = parent.above;
+					above.push_back(parent.node);
+					out_pieces[(size_t)pick] = { left, above };
+					out_pieces.insert(out_pieces.begin() + pick + 1, Piece{ left + 1, above });
+				}
+				return out_pieces;
+			};
+			static const int cap = [] { const char* e = getenv("RT_B200_WAVE_SUBTREES"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxSubtrees) ? v : kMaxSubtrees; }();
+			static const int fine_cap = [] { const char* e = getenv("RT_B200_WAVE_PARTS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kFine) ? v : kFine; }();
+			const std::vector<Piece> subtrees = cut(0, n >= 64 ? cap : 1, n);        // a shallow tree is one job
+			split.assign((size_t)kSplitStride, 0);
+			split[0] = (int32_t)subtrees.size();
+			root_map.assign((size_t)n, 0);
+			for (size_t e = 0; e < subtrees.size(); ++e) root_map[(size_t)subtrees[e].node] = (uint8_t)(e + 1);
+			for (size_t e = 0; e < subtrees.size(); ++e)
+			{
+				std::vector<Piece> parts = cut(subtrees[e].node, fine_cap, kFineAncestors);
+				for (size_t f = 0; f <= (size_t)kFine; ++f)
+				{
+					if (f < (size_t)kFine && f >= parts.size()) continue;
+					const Piece piece = f < (size_t)kFine ? parts[f] : Piece{ subtrees[e].node, {} };
+					const int32_t node = piece.node;
+					int32_t* rec = split.data() + kSplitHeader + (e * (kFine + 1) + f) * kSplitWords;
+					rec[0] = node * rt::BvhLink::kNodeBytes;
+					rec[1] = rt::BvhLink::miss(escape[(size_t)node]);
+					const int32_t below = size[(size_t)node] - 1, tris = tri_sum[(size_t)node];
+					const bool nodes_contiguous = below == 0 || (node_lo[(size_t)node] == (int32_t)mesh->bvh_nodes[node].left_node && node_hi[(size_t)node] - node_lo[(size_t)node] + 1 == below);
+					const bool tris_contiguous = tri_hi[(size_t)node] - tri_lo[(size_t)node] + 1 == tris;
+					rec[2] = below ? node_lo[(size_t)node] * rt::BvhLink::kNodeBytes : 0;
+					rec[3] = below;
+					rec[4] = tri_lo[(size_t)node];
+					rec[5] = tris;
+					rec[6] = kPartPresent | ((nodes_contiguous && tris_contiguous && (size_t)(1 + below) * 32 + (size_t)tris * 48 <= (size_t)kStageBytes) ? kPartStageable : 0);
+					rec[7] = (int32_t)piece.above.size();
+					for (size_t k = 0; k < piece.above.size(); ++k) rec[8 + k] = piece.above[k] * rt::BvhLink::kNodeBytes;
+				}
 			}
 		}
 		return RT_OK;

@@ -124,6 +124,124 @@ namespace wave
 		return false;
 	}
 
+	// ---- the same walk out of shared memory ----------------------------------------------------------------------------
+	// A job's time is a chain of dependent fetches - node, node, leaf, triangle, ... - and a frame's walk kernels take as
+	// long as their longest job (measured, tools/wave_jobs.py: the jobs of Scene_W4_OptionalScene at 320x240 add up to
+	// 2 us of the machine, the longest one alone takes 57 us, nearly all of it waiting for L2).  So the warp first copies
+	// the subtree - some tens of node records and triangles, contiguous in memory (rt_wave_params.h) - into its own piece of
+	// shared memory with independent, coalesced loads, rewriting the links as offsets into the copy; the walk then waits
+	// for shared memory instead.  Same boxes, same triangles, same order, same arithmetic.
+	// (cp.async: global -> shared without a register in between, so the copy is in flight while the warp sets its rays up)
+	__device__ __forceinline__ void copy16_async(float4* dst_shared, const float4* src)
+	{
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"((unsigned int)__cvta_generic_to_shared(dst_shared)), "l"(src) : "memory");
+	}
+	// layout of a warp's piece of shared memory: kFineAncestors node records (the boxes above the part), the part's root,
+	// its descendants, its triangles
+	constexpr int kStagedAncestorWords = 2 * kFineAncestors;
+	__device__ __forceinline__ int stage_begin(float4* region, const float4* nodes, const float4* tri, const int32_t* entry, unsigned int lane)
+	{
+		const int root = __ldg(entry), below = __ldg(entry + 2), n_below = __ldg(entry + 3), tri_first = __ldg(entry + 4), n_tri = __ldg(entry + 5), n_above = __ldg(entry + 7);
+		if ((int)lane < 2 * n_above) copy16_async(region + lane, node_at(nodes, __ldg(entry + 8 + (lane >> 1))) + (lane & 1));
+		float4* staged_nodes = region + kStagedAncestorWords;
+		const float4* root_rec = node_at(nodes, root);
+		const float4* below_rec = node_at(nodes, below);
+		const int node_words = 2 * (1 + n_below);
+		for (int j = (int)lane; j < node_words; j += 32) copy16_async(staged_nodes + j, j < 2 ? root_rec + j : below_rec + (j - 2));
+		float4* staged_tri = staged_nodes + node_words;
+		const float4* src = tri + 3 * (size_t)tri_first;
+		for (int j = (int)lane; j < 3 * n_tri; j += 32) copy16_async(staged_tri + j, src + j);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		return node_words;
+	}
+	// waits for the copy and rewrites the links as offsets into it: the root is record 0, its descendants follow; a
+	// leaf's first triangle counts from the part's first triangle
+	__device__ __forceinline__ void stage_finish(float4* region, int node_words, const int32_t* entry, unsigned int lane)
+	{
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncwarp();                       // a thread only waits for its own copies
+		const int end = __ldg(entry + 1), below = __ldg(entry + 2), tri_first = __ldg(entry + 4);
+		float4* staged_nodes = region + kStagedAncestorWords;
+		for (int j = 2 * (int)lane + 1; j < node_words; j += 64)             // every lane fixes what it copied or what a neighbour copied: hence the barrier below
+		{
+			int2* links = reinterpret_cast<int2*>(&staged_nodes[j].z);
+			int2 l = *links;
+			l.x = BvhLink::is_leaf(l.x) ? l.x - tri_first : l.x - below + BvhLink::kNodeBytes;
+			l.y = l.y == end ? BvhLink::kEnd : l.y - below + BvhLink::kNodeBytes;
+			*links = l;
+		}
+		__syncwarp();
+	}
+
+	// the boxes between the subtree's root and the part, out of the copy
+	template <bool FAST>
+	__device__ __forceinline__ bool enters_staged(const float4* region, int n_above, const Ray& ray)
+	{
+		Pk K{};
+		bool in = true;
+		for (int k = 0; k < n_above && in; ++k) in = slab_test<FAST>(K, region[2 * k], region[2 * k + 1], ray);
+		return in;
+	}
+
+	__device__ __forceinline__ Tri staged_tri_at(const float4* tri, int i)
+	{
+		Tri t;
+		t.a0 = tri[3 * i]; t.a1 = tri[3 * i + 1]; t.a2 = tri[3 * i + 2];
+		return t;
+	}
+
+	// walk_subtree over the copy; best_tri counts from the subtree's first triangle
+	template <bool ANY, bool FAST>
+	__device__ __forceinline__ bool walk_staged(int cull, const float4* region, int node_words, const Ray& ray, float& best_t, int& best_tri)
+	{
+		Counters<false> cnt;
+		Pk K{};
+		const float4* staged_nodes = region + kStagedAncestorWords;
+		const float4* tri = staged_nodes + node_words;
+		int at = 0;
+		do
+		{
+			const float4* rec = node_at(staged_nodes, at);
+			const float4 n0 = rec[0], n1 = rec[1];
+			const bool inside = slab_test<FAST>(K, n0, n1, ray);
+			const int hit = __float_as_int(n1.z), miss = __float_as_int(n1.w);
+			at = inside ? hit : miss;
+			if (inside && BvhLink::is_leaf(hit))
+			{
+				const int first = BvhLink::leaf_first(hit), count = BvhLink::leaf_count(hit);
+				if (ANY)
+				{
+					if (cull == RT_CULL_BACK_FACE) { for (int k = 0; k < count; ++k) if (shadow_one<RT_CULL_BACK_FACE>(staged_tri_at(tri, first + k), ray, cnt)) return true; }
+					else if (cull == RT_CULL_FRONT_FACE) { for (int k = 0; k < count; ++k) if (shadow_one<RT_CULL_FRONT_FACE>(staged_tri_at(tri, first + k), ray, cnt)) return true; }
+					else { for (int k = 0; k < count; ++k) if (shadow_one<RT_CULL_NONE>(staged_tri_at(tri, first + k), ray, cnt)) return true; }
+				}
+				else
+				{
+					if (cull == RT_CULL_BACK_FACE) { for (int k = 0; k < count; ++k) closest_one<RT_CULL_BACK_FACE>(staged_tri_at(tri, first + k), first + k, ray, best_t, best_tri, cnt); }
+					else if (cull == RT_CULL_FRONT_FACE) { for (int k = 0; k < count; ++k) closest_one<RT_CULL_FRONT_FACE>(staged_tri_at(tri, first + k), first + k, ray, best_t, best_tri, cnt); }
+					else { for (int k = 0; k < count; ++k) closest_one<RT_CULL_NONE>(staged_tri_at(tri, first + k), first + k, ray, best_t, best_tri, cnt); }
+				}
+				at = miss;
+			}
+		} while (at >= 0);
+		return false;
+	}
+
+	// The boxes between a subtree's root and one of its parts: all must be met for the recursion to arrive at the part
+	template <bool FAST>
+	__device__ __forceinline__ bool enters_part(const float4* nodes, const int32_t* entry, const Ray& ray)
+	{
+		Pk K{};
+		const int n = __ldg(entry + 7);
+		bool in = true;
+		for (int k = 0; k < n && in; ++k)
+		{
+			const float4* rec = node_at(nodes, __ldg(entry + 8 + k));
+			in = slab_test<FAST>(K, __ldg(rec), __ldg(rec + 1), ray);
+		}
+		return in;
+	}
+
 	// ---- K1 ----------------------------------------------------------------------------------------------------------
 	__global__ void __launch_bounds__(kThreads)
 	primary_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
@@ -159,6 +277,7 @@ namespace wave
 			else if (best_sphere >= 0) key = make_key(best_t, (unsigned int)best_sphere);
 		}
 		w.hit_key[pixel] = key;
+		w.occluded[pixel] = 0u;            // K3 and K4 only ever set bits
 
 		// view jobs: (warp tile, mesh, subtree) for every subtree some ray of the tile reaches
 		const unsigned int tile = cta * kSignalsPerTile + (threadIdx.x >> 5);
@@ -177,41 +296,76 @@ namespace wave
 	}
 
 	// ---- K2 ----------------------------------------------------------------------------------------------------------
-	__global__ void __launch_bounds__(256)
+	__global__ void __launch_bounds__(kWalkWarps * 32, 8)
 	view_walk_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
+		extern __shared__ __align__(16) unsigned char dynamic_smem[];
+		float4* region = reinterpret_cast<float4*>(dynamic_smem + (threadIdx.x >> 5) * kRegionBytes);
 		// jobs are handed out by a counter: their costs differ by orders of magnitude
 		const unsigned int lane = threadIdx.x & 31;
 		const unsigned int n_jobs = min(w.counters[0], w.view_capacity);
+		// whole subtrees or their parts (rt_wave_params.h): parts while the kernel would otherwise wait for its longest job
+		const unsigned int shift = n_jobs < w.parts_below ? kFineShift : 0, n_units = n_jobs << shift;
+		// units are handed out by a counter, one at a time: their costs differ by orders of magnitude, and a warp that
+		// reserved units ahead would sit on them while it works through a long one
 		for (;;)
 		{
-			unsigned int job = 0;
-			if (lane == 0) job = atomicAdd(w.counters + 2, 1u);
-			job = __shfl_sync(0xffffffffu, job, 0);
-			if (job >= n_jobs) break;
-			const uint2 word = w.view_jobs[job];
+			unsigned int unit = 0;
+			if (lane == 0) unit = atomicAdd(w.counters + 2, 1u);
+			unit = __shfl_sync(0xffffffffu, unit, 0);
+			if (unit >= n_units) break;
+			const long long unit_began = w.job_cycles ? clock64() : 0ll;
+			const uint2 word = w.view_jobs[unit >> shift];
 			const unsigned int tile = word.x, m = (word.y >> 8) & 0xffu, s = word.y & 0xffu;
-			const int32_t* split = w.split + (size_t)m * kSplitStride;
-			const unsigned int cta = tile / kSignalsPerTile;
-			const int tid = (int)((tile % kSignalsPerTile) * 32u + lane);
-			const Where me = where_am_i(p, (int)(cta % (unsigned int)p.grid_x), (int)(cta / (unsigned int)p.grid_x), tid);
-			const unsigned int pixel = cta * kThreads + (unsigned int)tid;
-			if (!me.valid || !((w.view_alive[(size_t)pixel * dev.n_meshes + m] >> s) & 1ull)) continue;      // this ray never reaches the subtree
-			const Ray ray = view_ray(p, me.px, me.py);
-			const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
-			const int first_tri = __float_as_int(b1.z);
-			const float4* tri = dev.triangles + 3 * (size_t)first_tri;
-			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-			const int cull = __float_as_int(info.x);
-			float best_t = __uint_as_float((unsigned int)(w.hit_key[pixel] >> 32));       // a stale read only makes the bound looser
-			int best_tri = -1;
-			// (the bound only decides which candidates are worth an atomic: the triangle tests never see it)
-			float t = FLT_MAX;
-			const int32_t* entry = split + kSplitHeader + s * kSplitWords;
-			if (ray.nan_safe) walk_subtree<false, true>(cull, nodes, tri, entry, ray, t, best_tri);
-			else walk_subtree<false, false>(cull, nodes, tri, entry, ray, t, best_tri);
-			if (best_tri >= 0 && t <= best_t && t < FLT_MAX)
-				atomicMin(w.hit_key + pixel, make_key(t, kTriangleBase + (unsigned int)(first_tri + best_tri)));
+			const int32_t* entry = w.split + (size_t)m * kSplitStride + kSplitHeader + (s * (kFine + 1) + (shift ? unit % kFine : kFine)) * kSplitWords;
+			const int flags = __ldg(entry + 6);
+			if (flags & kPartPresent)
+			{
+				const unsigned int cta = tile / kSignalsPerTile;
+				const int tid = (int)((tile % kSignalsPerTile) * 32u + lane);
+				const Where me = where_am_i(p, (int)(cta % (unsigned int)p.grid_x), (int)(cta / (unsigned int)p.grid_x), tid);
+				const unsigned int pixel = cta * kThreads + (unsigned int)tid;
+				const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
+				const int first_tri = __float_as_int(b1.z);
+				const float4* tri = dev.triangles + 3 * (size_t)first_tri;
+				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+				const int cull = __float_as_int(info.x);
+				// rays that never reach the subtree, or do not get from its root to this part, sit the unit out
+				bool reaches = me.valid && ((w.view_alive[(size_t)pixel * dev.n_meshes + m] >> s) & 1ull);
+				if (__ballot_sync(0xffffffffu, reaches) != 0u)
+				{
+					const bool staged = (flags & kPartStageable) != 0;
+					int node_words = 0;
+					if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
+					Ray ray{};
+					if (reaches) ray = view_ray(p, me.px, me.py);
+					if (staged)
+					{
+						stage_finish(region, node_words, entry, lane);
+						if (reaches) reaches = ray.nan_safe ? enters_staged<true>(region, __ldg(entry + 7), ray) : enters_staged<false>(region, __ldg(entry + 7), ray);
+					}
+					else if (reaches) reaches = ray.nan_safe ? enters_part<true>(nodes, entry, ray) : enters_part<false>(nodes, entry, ray);
+					if (reaches)
+					{
+						const float best_t = __uint_as_float((unsigned int)(w.hit_key[pixel] >> 32));       // a stale read only makes the bound looser
+						// (the bound only decides which candidates are worth an atomic: the triangle tests never see it)
+						float t = FLT_MAX;
+						int best_tri = -1;
+						if (staged)
+						{
+							if (ray.nan_safe) walk_staged<false, true>(cull, region, node_words, ray, t, best_tri);
+							else walk_staged<false, false>(cull, region, node_words, ray, t, best_tri);
+							best_tri += __ldg(entry + 4);
+						}
+						else if (ray.nan_safe) walk_subtree<false, true>(cull, nodes, tri, entry, ray, t, best_tri);
+						else walk_subtree<false, false>(cull, nodes, tri, entry, ray, t, best_tri);
+						if (t < FLT_MAX && t <= best_t)
+							atomicMin(w.hit_key + pixel, make_key(t, kTriangleBase + (unsigned int)(first_tri + best_tri)));
+					}
+					__syncwarp();                // the next unit overwrites the copy
+				}
+			}
+			if (w.job_cycles) { __syncwarp(); if (lane == 0) w.job_cycles[unit] = (unsigned int)(clock64() - unit_began); }
 		}
 	}
 
@@ -256,7 +410,8 @@ namespace wave
 	}
 
 	// ---- K3 ----------------------------------------------------------------------------------------------------------
-	template <int SHADOWS>
+	// gridDim.z = lights: a pixel's shadow rays are set up by one thread each (the top of the tree is a chain of dependent
+	// steps, and a small frame has too few pixels to hide three of them back to back)
 	__global__ void __launch_bounds__(kThreads)
 	shadow_setup_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
@@ -270,88 +425,113 @@ namespace wave
 		const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
 		const unsigned int pixel = cta * kThreads + threadIdx.x;
 		const unsigned int tile = cta * kSignalsPerTile + (threadIdx.x >> 5);
+		const int li = (int)blockIdx.z;
 		Counters<false> cnt;
 		const Pk K = make_pk(dev);
 
-		bool did = false;
+		bool open = false;
 		V3 origin_offset = v3(0.f, 0.f, 0.f);
 		if (me.valid)
 		{
 			const Ray view = view_ray(p, me.px, me.py);
 			const Hit hit = hit_of_key(sc, dev, view, w.hit_key[pixel]);
-			did = hit.did;
+			open = hit.did;
 			origin_offset = hit.origin + hit.normal * 0.0001f;          // Renderer.cpp:126
 		}
-		w.shadow_origin[pixel] = make_float4(origin_offset.x, origin_offset.y, origin_offset.z, did ? 1.f : 0.f);
-		unsigned int occluded = 0u;
-		if (SHADOWS)
+		if (li == 0) w.shadow_origin[pixel] = make_float4(origin_offset.x, origin_offset.y, origin_offset.z, open ? 1.f : 0.f);
+
+		Ray ray{};
+		if (open)
 		{
+			ray = shadow_ray_to(sc.light_a(li), __float_as_int(sc.light_b(li).w), origin_offset);
+			float t;
 #pragma unroll 1
-			for (int li = 0; li < dev.n_lights; ++li)
-			{
-				Ray ray{};
-				bool open = did;
-				if (did)
-				{
-					ray = shadow_ray_to(sc.light_a(li), __float_as_int(sc.light_b(li).w), origin_offset);
-					float t;
-#pragma unroll 1
-					for (int i = 0; i < dev.n_spheres && open; ++i)
-						if (hit_sphere<true>(sc.sphere(i), ray, t, cnt)) open = false;
-					if (open && planes_any(K, sc, dev.n_planes, ray, cnt)) open = false;
-					if (!open) occluded |= 1u << li;
-				}
-#pragma unroll 1
-				for (int m = 0; m < dev.n_meshes; ++m)
-				{
-					const float4 info = sc.mesh(3 * m + 2);
-					if (__float_as_int(info.w) == 0) continue;
-					const int32_t* split = w.split + (size_t)m * kSplitStride;
-					const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-					unsigned long long alive = 0ull;
-					if (open) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
-					w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] = alive;
-					emit_jobs(alive, tile, ((unsigned int)li << 16) | ((unsigned int)m << 8), w.shadow_jobs, w.counters + 1, w.shadow_capacity, w.counters + 4);
-				}
-			}
+			for (int i = 0; i < dev.n_spheres && open; ++i)
+				if (hit_sphere<true>(sc.sphere(i), ray, t, cnt)) open = false;
+			if (open && planes_any(K, sc, dev.n_planes, ray, cnt)) open = false;
+			if (!open) atomicOr(w.occluded + pixel, 1u << li);
 		}
-		w.occluded[pixel] = occluded;
+#pragma unroll 1
+		for (int m = 0; m < dev.n_meshes; ++m)
+		{
+			const float4 info = sc.mesh(3 * m + 2);
+			if (__float_as_int(info.w) == 0) continue;
+			const int32_t* split = w.split + (size_t)m * kSplitStride;
+			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+			unsigned long long alive = 0ull;
+			if (open) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
+			w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] = alive;
+			emit_jobs(alive, tile, ((unsigned int)li << 16) | ((unsigned int)m << 8), w.shadow_jobs, w.counters + 1, w.shadow_capacity, w.counters + 4);
+		}
 	}
 
 	// ---- K4 ----------------------------------------------------------------------------------------------------------
-	__global__ void __launch_bounds__(256)
+	__global__ void __launch_bounds__(kWalkWarps * 32, 8)
 	shadow_walk_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
+		extern __shared__ __align__(16) unsigned char dynamic_smem[];
+		float4* region = reinterpret_cast<float4*>(dynamic_smem + (threadIdx.x >> 5) * kRegionBytes);
 		const unsigned int lane = threadIdx.x & 31;
 		const unsigned int n_jobs = min(w.counters[1], w.shadow_capacity);
+		// whole subtrees or their parts (rt_wave_params.h): parts while the kernel would otherwise wait for its longest job
+		const unsigned int shift = n_jobs < w.parts_below ? kFineShift : 0, n_units = n_jobs << shift;
+		// units are handed out by a counter, one at a time: their costs differ by orders of magnitude, and a warp that
+		// reserved units ahead would sit on them while it works through a long one
 		for (;;)
 		{
-			unsigned int job = 0;
-			if (lane == 0) job = atomicAdd(w.counters + 3, 1u);
-			job = __shfl_sync(0xffffffffu, job, 0);
-			if (job >= n_jobs) break;
-			const uint2 word = w.shadow_jobs[job];
+			unsigned int unit = 0;
+			if (lane == 0) unit = atomicAdd(w.counters + 3, 1u);
+			unit = __shfl_sync(0xffffffffu, unit, 0);
+			if (unit >= n_units) break;
+			const long long unit_began = w.job_cycles ? clock64() : 0ll;
+			const uint2 word = w.shadow_jobs[unit >> shift];
 			const unsigned int tile = word.x, li = (word.y >> 16) & 0xffu, m = (word.y >> 8) & 0xffu, s = word.y & 0xffu;
-			const int32_t* split = w.split + (size_t)m * kSplitStride;
-			const unsigned int cta = tile / kSignalsPerTile;
-			const unsigned int pixel = cta * kThreads + (tile % kSignalsPerTile) * 32u + lane;
-			const float4 so = w.shadow_origin[pixel];
-			const unsigned int bit = 1u << li;
-			if (!((w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] >> s) & 1ull)) continue;      // this ray never reaches the subtree
-			if (w.occluded[pixel] & bit) continue;                        // already known to be in shadow (racy read: an optimisation only)
-			const float4 la = make_float4(__ldg(dev.light_ox + li), __ldg(dev.light_oy + li), __ldg(dev.light_oz + li), 0.f);
-			const Ray ray = shadow_ray_to(la, __ldg(dev.light_type + li), v3(so));
-			const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
-			const float4* tri = dev.triangles + 3 * (size_t)__float_as_int(b1.z);
-			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-			const int cull = __float_as_int(info.x);
-			// Utils.h:114-127: shadow rays see the opposite cull mode
-			const int shadow_cull = cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : (cull == RT_CULL_FRONT_FACE ? RT_CULL_BACK_FACE : RT_CULL_NONE);
-			float t = FLT_MAX; int tri_id = -1;
-			const int32_t* entry = split + kSplitHeader + s * kSplitWords;
-			const bool blocked = ray.nan_safe ? walk_subtree<true, true>(shadow_cull, nodes, tri, entry, ray, t, tri_id)
-			                                  : walk_subtree<true, false>(shadow_cull, nodes, tri, entry, ray, t, tri_id);
-			if (blocked) atomicOr(w.occluded + pixel, bit);
+			const int32_t* entry = w.split + (size_t)m * kSplitStride + kSplitHeader + (s * (kFine + 1) + (shift ? unit % kFine : kFine)) * kSplitWords;
+			const int flags = __ldg(entry + 6);
+			if (flags & kPartPresent)
+			{
+				const unsigned int cta = tile / kSignalsPerTile;
+				const unsigned int pixel = cta * kThreads + (tile % kSignalsPerTile) * 32u + lane;
+				const unsigned int bit = 1u << li;
+				const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
+				const float4* tri = dev.triangles + 3 * (size_t)__float_as_int(b1.z);
+				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+				const int cull = __float_as_int(info.x);
+				// Utils.h:114-127: shadow rays see the opposite cull mode
+				const int shadow_cull = cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : (cull == RT_CULL_FRONT_FACE ? RT_CULL_BACK_FACE : RT_CULL_NONE);
+				// rays that never reach the subtree, do not get from its root to this part, or are already known to be in shadow
+				// (racy read: an optimisation only) sit the unit out
+				const float4 so = w.shadow_origin[pixel];                  // (with the two loads below: one round trip)
+				bool reaches = ((w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] >> s) & 1ull) && !(w.occluded[pixel] & bit);
+				if (__ballot_sync(0xffffffffu, reaches) != 0u)
+				{
+					const bool staged = (flags & kPartStageable) != 0;
+					int node_words = 0;
+					if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
+					Ray ray{};
+					if (reaches)
+					{
+						const float4 la = make_float4(__ldg(dev.light_ox + li), __ldg(dev.light_oy + li), __ldg(dev.light_oz + li), 0.f);
+						ray = shadow_ray_to(la, __ldg(dev.light_type + li), v3(so));
+					}
+					if (staged)
+					{
+						stage_finish(region, node_words, entry, lane);
+						if (reaches) reaches = ray.nan_safe ? enters_staged<true>(region, __ldg(entry + 7), ray) : enters_staged<false>(region, __ldg(entry + 7), ray);
+					}
+					else if (reaches) reaches = ray.nan_safe ? enters_part<true>(nodes, entry, ray) : enters_part<false>(nodes, entry, ray);
+					if (reaches)
+					{
+						float t = FLT_MAX; int tri_id = -1;
+						bool blocked;
+						if (staged) blocked = ray.nan_safe ? walk_staged<true, true>(shadow_cull, region, node_words, ray, t, tri_id) : walk_staged<true, false>(shadow_cull, region, node_words, ray, t, tri_id);
+						else blocked = ray.nan_safe ? walk_subtree<true, true>(shadow_cull, nodes, tri, entry, ray, t, tri_id) : walk_subtree<true, false>(shadow_cull, nodes, tri, entry, ray, t, tri_id);
+						if (blocked) atomicOr(w.occluded + pixel, bit);
+					}
+					__syncwarp();                // the next unit overwrites the copy
+				}
+			}
+			if (w.job_cycles) { __syncwarp(); if (lane == 0) w.job_cycles[(size_t)w.view_capacity * kFine + unit] = (unsigned int)(clock64() - unit_began); }
 		}
 	}
 

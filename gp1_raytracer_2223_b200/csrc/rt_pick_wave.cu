@@ -4,11 +4,22 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <vector>
 
 namespace rt
 {
-	cudaError_t wave_launch(const SceneDevice& dev, const FrameParams& p, const wave::WaveParams& w, dim3 grid, int sm_count, cudaStream_t stream)
+	cudaError_t wave_launch(const SceneDevice& dev, const FrameParams& p, const wave::WaveParams& w_in, dim3 grid, int sm_count, cudaStream_t stream)
 	{
+		wave::WaveParams w = w_in;
+		w.job_cycles = nullptr;
+		// RT_B200_WAVE_JOB_CLOCKS=1 (measurement only, with RT_B200_WAVE_TIMING): the clocks every job took
+		static const bool job_clocks = getenv("RT_B200_WAVE_JOB_CLOCKS") != nullptr && getenv("RT_B200_WAVE_TIMING") != nullptr;
+		if (job_clocks)
+		{
+			cudaMalloc(&w.job_cycles, sizeof(unsigned int) * wave::kFine * ((size_t)w.view_capacity + w.shadow_capacity));
+			cudaMemsetAsync(w.job_cycles, 0, sizeof(unsigned int) * wave::kFine * ((size_t)w.view_capacity + w.shadow_capacity), stream);
+		}
 		const size_t smem = staged_scene_bytes(dev.n_materials);
 		cudaError_t e = cudaMemsetAsync(w.counters, 0, 8 * sizeof(unsigned int), stream);
 		if (e != cudaSuccess) return e;
@@ -18,15 +29,25 @@ namespace rt
 		int n_ev = 0;
 		auto mark = [&]() { if (timing) { cudaEventCreate(&ev[n_ev]); cudaEventRecord(ev[n_ev], stream); ++n_ev; } };
 		mark();
-		const unsigned int walkers = (unsigned int)sm_count * 8u;         // 8 CTAs of 8 warps per SM: one wave of walkers, grid-stride over the jobs
+		// the walkers: one wave of CTAs of kWalkWarps warps, each warp with room for its job's subtree; jobs come from a counter
+		constexpr size_t walk_smem = (size_t)wave::kWalkWarps * wave::kRegionBytes;
+		static const unsigned int walkers_per_sm = [&]
+		{
+			int a = 0, b = 0;
+			cudaFuncSetAttribute(wave::view_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem);
+			cudaFuncSetAttribute(wave::shadow_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, wave::view_walk_kernel, wave::kWalkWarps * 32, walk_smem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, wave::shadow_walk_kernel, wave::kWalkWarps * 32, walk_smem);
+			return (unsigned int)std::max(1, std::min(a, b));
+		}();
+		const unsigned int walkers = (unsigned int)sm_count * walkers_per_sm;
 		wave::primary_kernel<<<grid, kThreads, smem, stream>>>(dev, p, w);
 		mark();
-		wave::view_walk_kernel<<<walkers, 256, 0, stream>>>(dev, p, w);
+		wave::view_walk_kernel<<<walkers, wave::kWalkWarps * 32, walk_smem, stream>>>(dev, p, w);
 		mark();
-		if (p.shadows) wave::shadow_setup_kernel<1><<<grid, kThreads, smem, stream>>>(dev, p, w);
-		else wave::shadow_setup_kernel<0><<<grid, kThreads, smem, stream>>>(dev, p, w);
+		if (p.shadows && dev.n_lights > 0) wave::shadow_setup_kernel<<<dim3(grid.x, grid.y, (unsigned int)dev.n_lights), kThreads, smem, stream>>>(dev, p, w);
 		mark();
-		if (p.shadows) wave::shadow_walk_kernel<<<walkers, 256, 0, stream>>>(dev, p, w);
+		if (p.shadows && dev.n_lights > 0) wave::shadow_walk_kernel<<<walkers, wave::kWalkWarps * 32, walk_smem, stream>>>(dev, p, w);
 		mark();
 		switch (p.lighting_mode)
 		{
@@ -46,8 +67,27 @@ namespace rt
 			fprintf(stderr, "wave: primary %.1f us, view walk %.1f us (%u jobs), shadow setup %.1f us, shadow walk %.1f us (%u jobs), shade %.1f us\n",
 			        ms[0] * 1e3f, ms[1] * 1e3f, counters[0], ms[2] * 1e3f, ms[3] * 1e3f, counters[1], ms[4] * 1e3f);
 			for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
+			if (w.job_cycles)
+			{
+				auto report = [&](const char* name, size_t first, size_t n)
+				{
+					if (n == 0) return;
+					std::vector<unsigned int> c(n);
+					cudaMemcpy(c.data(), w.job_cycles + first, n * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+					c.erase(std::remove(c.begin(), c.end(), 0u), c.end());       // units that never ran (whole-subtree units use the first n)
+					n = c.size();
+					if (n == 0) return;
+					std::sort(c.begin(), c.end());
+					double sum = 0; for (unsigned int v : c) sum += v;
+					fprintf(stderr, "wave: %s units: clocks mean %.0f, p50 %u, p90 %u, p99 %u, max %u; sum / (%d SMs x 64 warps) = %.0f clocks\n",
+					        name, sum / (double)n, c[n / 2], c[n * 9 / 10], c[n * 99 / 100], c[n - 1], sm_count, sum / (sm_count * 64.0));
+				};
+				report("view", 0, (size_t)wave::kFine * std::min(counters[0], w.view_capacity));
+				report("shadow", (size_t)wave::kFine * w.view_capacity, (size_t)wave::kFine * std::min(counters[1], w.shadow_capacity));
+			}
 		}
+		if (w.job_cycles) cudaFree(w.job_cycles);
 		return cudaGetLastError();
 	}
-	int wave_launch_count(int shadows) { return shadows ? 5 : 4; }
+	int wave_launch_count(int shadows) { return shadows ? 5 : 3; }
 }
