@@ -101,6 +101,8 @@ namespace
 		cudaStream_t copy_stream = nullptr;                 // device-to-host copies that overlap the next band's kernel
 		cudaEvent_t ev_band[16] = {};
 		unsigned int* d_band_done = nullptr;                // kMaxBands counters for the single-launch progressive present
+		unsigned int* h_wave_jobs = nullptr;                // mapped pinned: {view jobs, shadow jobs} of the last wavefront frame (a hint for the next one)
+		unsigned int* d_wave_jobs = nullptr;                // ... as the device sees it
 		unsigned int* h_flags = nullptr;                    // 64 words of mapped pinned memory: the band watcher's messages to the host
 		unsigned int* d_flags = nullptr;                    // the same words as the device sees them
 		uint32_t watch_tag = 0;                             // value the watcher stores for the current frame
@@ -893,8 +895,15 @@ namespace
 			// small frames wait for their longest jobs: those kernels take the subtrees in parts (rt_wave_params.h); measured
 			// crossover (tools/wave_sweep.sh): ~110 jobs per SM
 			static const long long parts_below_per_sm = [] { const char* e = getenv("RT_B200_WAVE_PARTS_BELOW"); return e ? atoll(e) : 110ll; }();
-			d.wave.parts_below = (unsigned int)std::min<long long>(parts_below_per_sm * d.sm_count, 0x7fffffffll);
+			const long long parts_below = parts_below_per_sm * d.sm_count;
 			const long long warp_tiles = tiles * rt::kSignalsPerTile;
+			// the job counts of the wavefront frame before this one (whatever has arrived: a hint, the frame is the same
+			// either way); before the first frame: a guess from the number of tiles
+			const long long view_jobs_hint = d.h_wave_jobs[0] ? (long long)d.h_wave_jobs[0] : 2 * warp_tiles;
+			const long long shadow_jobs_hint = d.h_wave_jobs[1] ? (long long)d.h_wave_jobs[1] : 4 * warp_tiles * std::max(ctx->n_lights, 1);
+			d.wave.view_parts = view_jobs_hint < parts_below ? 1u : 0u;
+			d.wave.shadow_parts = shadow_jobs_hint < parts_below ? 1u : 0u;
+			d.wave.setup_per_light = warp_tiles <= parts_below ? 1u : 0u;
 			// a job per (warp tile, subtree) and, for shadow rays, per light: sized for the worst case, so the lists cannot overflow
 			const size_t view_jobs = (size_t)warp_tiles * (size_t)wave_subtrees;
 			const size_t shadow_jobs = view_jobs * (size_t)std::max(ctx->n_lights, 1);
@@ -918,6 +927,7 @@ namespace
 				d.wave_pixels = pixels; d.wave_view_tasks = view_jobs; d.wave_shadow_tasks = shadow_jobs; d.wave_meshes = ctx->meshes.size(); d.wave_lights = (size_t)ctx->n_lights;
 			}
 			d.wave.view_capacity = (unsigned int)d.wave_view_tasks; d.wave.shadow_capacity = (unsigned int)d.wave_shadow_tasks;
+			d.wave.jobs_report = d.d_wave_jobs;
 			d.wave.split = d.d_split;
 			d.wave.root_map = d.d_root_map;
 			RT_CUDA(ctx, rt::wave_launch(d.view, p, d.wave, grid, d.sm_count, stream));
@@ -1750,6 +1760,9 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 128));
 		RT_CREATE(cudaHostAlloc(&d.h_flags, sizeof(unsigned int) * 64, cudaHostAllocMapped | cudaHostAllocPortable));
+		RT_CREATE(cudaHostAlloc(&d.h_wave_jobs, sizeof(unsigned int) * 2, cudaHostAllocMapped | cudaHostAllocPortable));
+		d.h_wave_jobs[0] = d.h_wave_jobs[1] = 0u;
+		RT_CREATE(cudaHostGetDevicePointer((void**)&d.d_wave_jobs, d.h_wave_jobs, 0));
 		memset(d.h_flags, 0, sizeof(unsigned int) * 64);
 		RT_CREATE(cudaHostGetDevicePointer((void**)&d.d_flags, d.h_flags, 0));
 		RT_CREATE(cudaMalloc(&d.d_band_table, 8192));
@@ -1804,7 +1817,7 @@ int rt_destroy(rt_context* ctx)
 		cudaSetDevice(d.device);
 		if (d.stream) cudaStreamSynchronize(d.stream);
 		cudaFree(d.d_static); cudaFree(d.d_mesh); cudaFree(d.d_frame); cudaFree(d.d_counters); cudaFree(d.d_band_done); cudaFree(d.d_queues);
-		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map); cudaFree(d.d_band_table); cudaFreeHost(d.h_band_table); cudaFreeHost(d.h_flags);
+		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map); cudaFree(d.d_band_table); cudaFreeHost(d.h_band_table); cudaFreeHost(d.h_flags); cudaFreeHost(d.h_wave_jobs);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
 		if (d.ev_foreign) cudaEventDestroy(d.ev_foreign);
 		cudaFree(d.cells.d_cost); cudaFree(d.cells.d_order); cudaFreeHost(d.cells.h_cost); cudaFreeHost(d.cells.h_order);

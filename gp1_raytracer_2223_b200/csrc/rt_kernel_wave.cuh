@@ -154,6 +154,12 @@ namespace wave
 		asm volatile("cp.async.commit_group;" ::: "memory");
 		return node_words;
 	}
+	// nobody needs the copy after all: it still has to land before the next one is started into the same memory
+	__device__ __forceinline__ void stage_abandon()
+	{
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
+		__syncwarp();
+	}
 	// waits for the copy and rewrites the links as offsets into it: the root is record 0, its descendants follow; a
 	// leaf's first triangle counts from the part's first triangle
 	__device__ __forceinline__ void stage_finish(float4* region, int node_words, const int32_t* entry, unsigned int lane)
@@ -296,16 +302,18 @@ namespace wave
 	}
 
 	// ---- K2 ----------------------------------------------------------------------------------------------------------
+	template <bool PARTS>
 	__global__ void __launch_bounds__(kWalkWarps * 32, 8)
 	view_walk_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
 		extern __shared__ __align__(16) unsigned char dynamic_smem[];
-		float4* region = reinterpret_cast<float4*>(dynamic_smem + (threadIdx.x >> 5) * kRegionBytes);
+		float4* region = reinterpret_cast<float4*>(dynamic_smem + (PARTS ? (threadIdx.x >> 5) * kRegionBytes : 0u));       // (no shared memory without PARTS)
 		// jobs are handed out by a counter: their costs differ by orders of magnitude
 		const unsigned int lane = threadIdx.x & 31;
 		const unsigned int n_jobs = min(w.counters[0], w.view_capacity);
-		// whole subtrees or their parts (rt_wave_params.h): parts while the kernel would otherwise wait for its longest job
-		const unsigned int shift = n_jobs < w.parts_below ? kFineShift : 0, n_units = n_jobs << shift;
+		// whole subtrees or their parts (rt_wave_params.h; the host chooses, wave_launch)
+		constexpr unsigned int shift = PARTS ? kFineShift : 0;
+		const unsigned int n_units = n_jobs << shift;
 		// units are handed out by a counter, one at a time: their costs differ by orders of magnitude, and a warp that
 		// reserved units ahead would sit on them while it works through a long one
 		for (;;)
@@ -330,13 +338,16 @@ namespace wave
 				const float4* tri = dev.triangles + 3 * (size_t)first_tri;
 				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
 				const int cull = __float_as_int(info.x);
+				// the copy starts before anything is known about the rays: it is in flight while their masks arrive
+				const unsigned long long subtrees_reached = w.view_alive[(size_t)pixel * dev.n_meshes + m];
+				const bool staged = PARTS && (flags & kPartStageable) != 0;      // whole subtrees are walked where they are: few of a tile's rays see much of one
+				int node_words = 0;
+				if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
 				// rays that never reach the subtree, or do not get from its root to this part, sit the unit out
-				bool reaches = me.valid && ((w.view_alive[(size_t)pixel * dev.n_meshes + m] >> s) & 1ull);
-				if (__ballot_sync(0xffffffffu, reaches) != 0u)
+				bool reaches = me.valid && ((subtrees_reached >> s) & 1ull);
+				if (__ballot_sync(0xffffffffu, reaches) == 0u) { if (staged) stage_abandon(); }
+				else
 				{
-					const bool staged = (flags & kPartStageable) != 0;
-					int node_words = 0;
-					if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
 					Ray ray{};
 					if (reaches) ray = view_ray(p, me.px, me.py);
 					if (staged)
@@ -410,8 +421,8 @@ namespace wave
 	}
 
 	// ---- K3 ----------------------------------------------------------------------------------------------------------
-	// gridDim.z = lights: a pixel's shadow rays are set up by one thread each (the top of the tree is a chain of dependent
-	// steps, and a small frame has too few pixels to hide three of them back to back)
+	// gridDim.z = 1 or the number of lights: in a small frame a pixel's shadow rays are set up by one thread each (the top
+	// of the tree is a chain of dependent steps, and the frame has too few pixels to hide three of them back to back)
 	__global__ void __launch_bounds__(kThreads)
 	shadow_setup_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
@@ -425,56 +436,62 @@ namespace wave
 		const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
 		const unsigned int pixel = cta * kThreads + threadIdx.x;
 		const unsigned int tile = cta * kSignalsPerTile + (threadIdx.x >> 5);
-		const int li = (int)blockIdx.z;
 		Counters<false> cnt;
 		const Pk K = make_pk(dev);
 
-		bool open = false;
+		bool did = false;
 		V3 origin_offset = v3(0.f, 0.f, 0.f);
 		if (me.valid)
 		{
 			const Ray view = view_ray(p, me.px, me.py);
 			const Hit hit = hit_of_key(sc, dev, view, w.hit_key[pixel]);
-			open = hit.did;
+			did = hit.did;
 			origin_offset = hit.origin + hit.normal * 0.0001f;          // Renderer.cpp:126
 		}
-		if (li == 0) w.shadow_origin[pixel] = make_float4(origin_offset.x, origin_offset.y, origin_offset.z, open ? 1.f : 0.f);
+		if (blockIdx.z == 0) w.shadow_origin[pixel] = make_float4(origin_offset.x, origin_offset.y, origin_offset.z, did ? 1.f : 0.f);
 
-		Ray ray{};
-		if (open)
-		{
-			ray = shadow_ray_to(sc.light_a(li), __float_as_int(sc.light_b(li).w), origin_offset);
-			float t;
 #pragma unroll 1
-			for (int i = 0; i < dev.n_spheres && open; ++i)
-				if (hit_sphere<true>(sc.sphere(i), ray, t, cnt)) open = false;
-			if (open && planes_any(K, sc, dev.n_planes, ray, cnt)) open = false;
-			if (!open) atomicOr(w.occluded + pixel, 1u << li);
-		}
-#pragma unroll 1
-		for (int m = 0; m < dev.n_meshes; ++m)
+		for (int li = (int)blockIdx.z; li < dev.n_lights; li += (int)gridDim.z)
 		{
-			const float4 info = sc.mesh(3 * m + 2);
-			if (__float_as_int(info.w) == 0) continue;
-			const int32_t* split = w.split + (size_t)m * kSplitStride;
-			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-			unsigned long long alive = 0ull;
-			if (open) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
-			w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] = alive;
-			emit_jobs(alive, tile, ((unsigned int)li << 16) | ((unsigned int)m << 8), w.shadow_jobs, w.counters + 1, w.shadow_capacity, w.counters + 4);
+			bool open = did;
+			Ray ray{};
+			if (open)
+			{
+				ray = shadow_ray_to(sc.light_a(li), __float_as_int(sc.light_b(li).w), origin_offset);
+				float t;
+#pragma unroll 1
+				for (int i = 0; i < dev.n_spheres && open; ++i)
+					if (hit_sphere<true>(sc.sphere(i), ray, t, cnt)) open = false;
+				if (open && planes_any(K, sc, dev.n_planes, ray, cnt)) open = false;
+				if (!open) atomicOr(w.occluded + pixel, 1u << li);
+			}
+#pragma unroll 1
+			for (int m = 0; m < dev.n_meshes; ++m)
+			{
+				const float4 info = sc.mesh(3 * m + 2);
+				if (__float_as_int(info.w) == 0) continue;
+				const int32_t* split = w.split + (size_t)m * kSplitStride;
+				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+				unsigned long long alive = 0ull;
+				if (open) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
+				w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] = alive;
+				emit_jobs(alive, tile, ((unsigned int)li << 16) | ((unsigned int)m << 8), w.shadow_jobs, w.counters + 1, w.shadow_capacity, w.counters + 4);
+			}
 		}
 	}
 
 	// ---- K4 ----------------------------------------------------------------------------------------------------------
+	template <bool PARTS>
 	__global__ void __launch_bounds__(kWalkWarps * 32, 8)
 	shadow_walk_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
 		extern __shared__ __align__(16) unsigned char dynamic_smem[];
-		float4* region = reinterpret_cast<float4*>(dynamic_smem + (threadIdx.x >> 5) * kRegionBytes);
+		float4* region = reinterpret_cast<float4*>(dynamic_smem + (PARTS ? (threadIdx.x >> 5) * kRegionBytes : 0u));       // (no shared memory without PARTS)
 		const unsigned int lane = threadIdx.x & 31;
 		const unsigned int n_jobs = min(w.counters[1], w.shadow_capacity);
-		// whole subtrees or their parts (rt_wave_params.h): parts while the kernel would otherwise wait for its longest job
-		const unsigned int shift = n_jobs < w.parts_below ? kFineShift : 0, n_units = n_jobs << shift;
+		// whole subtrees or their parts (rt_wave_params.h; the host chooses, wave_launch)
+		constexpr unsigned int shift = PARTS ? kFineShift : 0;
+		const unsigned int n_units = n_jobs << shift;
 		// units are handed out by a counter, one at a time: their costs differ by orders of magnitude, and a warp that
 		// reserved units ahead would sit on them while it works through a long one
 		for (;;)
@@ -501,13 +518,17 @@ namespace wave
 				const int shadow_cull = cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : (cull == RT_CULL_FRONT_FACE ? RT_CULL_BACK_FACE : RT_CULL_NONE);
 				// rays that never reach the subtree, do not get from its root to this part, or are already known to be in shadow
 				// (racy read: an optimisation only) sit the unit out
-				const float4 so = w.shadow_origin[pixel];                  // (with the two loads below: one round trip)
-				bool reaches = ((w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] >> s) & 1ull) && !(w.occluded[pixel] & bit);
-				if (__ballot_sync(0xffffffffu, reaches) != 0u)
+				// the copy starts before anything is known about the rays: it is in flight while their masks arrive
+				const float4 so = w.shadow_origin[pixel];
+				const unsigned long long subtrees_reached = w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m];
+				const unsigned int known_occluded = w.occluded[pixel];
+				const bool staged = PARTS && (flags & kPartStageable) != 0;      // whole subtrees are walked where they are: few of a tile's rays see much of one
+				int node_words = 0;
+				if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
+				bool reaches = ((subtrees_reached >> s) & 1ull) && !(known_occluded & bit);
+				if (__ballot_sync(0xffffffffu, reaches) == 0u) { if (staged) stage_abandon(); }
+				else
 				{
-					const bool staged = (flags & kPartStageable) != 0;
-					int node_words = 0;
-					if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
 					Ray ray{};
 					if (reaches)
 					{
@@ -589,6 +610,8 @@ namespace wave
 			row[me.px] = pixel;
 		}
 		if (p.band_done) signal_band_done(p);
+		// what the host sizes the next frame's walk kernels by (rt_api.cu, launch())
+		if (w.jobs_report && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { w.jobs_report[0] = w.counters[0]; w.jobs_report[1] = w.counters[1]; }
 	}
 }
 }

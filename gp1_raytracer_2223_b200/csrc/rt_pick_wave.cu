@@ -29,25 +29,33 @@ namespace rt
 		int n_ev = 0;
 		auto mark = [&]() { if (timing) { cudaEventCreate(&ev[n_ev]); cudaEventRecord(ev[n_ev], stream); ++n_ev; } };
 		mark();
-		// the walkers: one wave of CTAs of kWalkWarps warps, each warp with room for its job's subtree; jobs come from a counter
-		constexpr size_t walk_smem = (size_t)wave::kWalkWarps * wave::kRegionBytes;
+		// the walkers: one wave of CTAs of kWalkWarps warps, units come from a counter; with PARTS every warp has room for
+		// the part it is walking
+		constexpr size_t parts_smem = (size_t)wave::kWalkWarps * wave::kRegionBytes;
 		static const unsigned int walkers_per_sm = [&]
 		{
-			int a = 0, b = 0;
-			cudaFuncSetAttribute(wave::view_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem);
-			cudaFuncSetAttribute(wave::shadow_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem);
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, wave::view_walk_kernel, wave::kWalkWarps * 32, walk_smem);
-			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, wave::shadow_walk_kernel, wave::kWalkWarps * 32, walk_smem);
-			return (unsigned int)std::max(1, std::min(a, b));
+			int n[4] = {};
+			cudaFuncSetAttribute(wave::view_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)parts_smem);
+			cudaFuncSetAttribute(wave::shadow_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)parts_smem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n[0], wave::view_walk_kernel<true>, wave::kWalkWarps * 32, parts_smem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n[1], wave::shadow_walk_kernel<true>, wave::kWalkWarps * 32, parts_smem);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n[2], wave::view_walk_kernel<false>, wave::kWalkWarps * 32, 0);
+			cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n[3], wave::shadow_walk_kernel<false>, wave::kWalkWarps * 32, 0);
+			return (unsigned int)std::max(1, *std::min_element(n, n + 4));
 		}();
 		const unsigned int walkers = (unsigned int)sm_count * walkers_per_sm;
 		wave::primary_kernel<<<grid, kThreads, smem, stream>>>(dev, p, w);
 		mark();
-		wave::view_walk_kernel<<<walkers, wave::kWalkWarps * 32, walk_smem, stream>>>(dev, p, w);
+		if (w.view_parts) wave::view_walk_kernel<true><<<walkers, wave::kWalkWarps * 32, parts_smem, stream>>>(dev, p, w);
+		else wave::view_walk_kernel<false><<<walkers, wave::kWalkWarps * 32, 0, stream>>>(dev, p, w);
 		mark();
-		if (p.shadows && dev.n_lights > 0) wave::shadow_setup_kernel<<<dim3(grid.x, grid.y, (unsigned int)dev.n_lights), kThreads, smem, stream>>>(dev, p, w);
+		if (p.shadows && dev.n_lights > 0) wave::shadow_setup_kernel<<<dim3(grid.x, grid.y, w.setup_per_light ? (unsigned int)dev.n_lights : 1u), kThreads, smem, stream>>>(dev, p, w);
 		mark();
-		if (p.shadows && dev.n_lights > 0) wave::shadow_walk_kernel<<<walkers, wave::kWalkWarps * 32, walk_smem, stream>>>(dev, p, w);
+		if (p.shadows && dev.n_lights > 0)
+		{
+			if (w.shadow_parts) wave::shadow_walk_kernel<true><<<walkers, wave::kWalkWarps * 32, parts_smem, stream>>>(dev, p, w);
+			else wave::shadow_walk_kernel<false><<<walkers, wave::kWalkWarps * 32, 0, stream>>>(dev, p, w);
+		}
 		mark();
 		switch (p.lighting_mode)
 		{
@@ -82,8 +90,8 @@ namespace rt
 					fprintf(stderr, "wave: %s units: clocks mean %.0f, p50 %u, p90 %u, p99 %u, max %u; sum / (%d SMs x 64 warps) = %.0f clocks\n",
 					        name, sum / (double)n, c[n / 2], c[n * 9 / 10], c[n * 99 / 100], c[n - 1], sm_count, sum / (sm_count * 64.0));
 				};
-				report("view", 0, (size_t)wave::kFine * std::min(counters[0], w.view_capacity));
-				report("shadow", (size_t)wave::kFine * w.view_capacity, (size_t)wave::kFine * std::min(counters[1], w.shadow_capacity));
+				report("view", 0, (size_t)(w.view_parts ? wave::kFine : 1) * std::min(counters[0], w.view_capacity));
+				report("shadow", (size_t)wave::kFine * w.view_capacity, (size_t)(w.shadow_parts ? wave::kFine : 1) * std::min(counters[1], w.shadow_capacity));
 			}
 		}
 		if (w.job_cycles) cudaFree(w.job_cycles);

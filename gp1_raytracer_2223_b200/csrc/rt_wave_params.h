@@ -17,9 +17,11 @@ namespace wave
 	constexpr int kMaxSubtrees = 64;
 	constexpr int kFineShift = 2, kFine = 1 << kFineShift;
 	constexpr int kFineAncestors = 3;
-	// Cutting finer only pays while the machine would wait for the longest unit: every unit sets its rays up again.  A
-	// walk kernel with WaveParams::parts_below jobs or more takes whole subtrees as its units (it is bound by the sum of
-	// its work, not by the longest piece; choosing per job by the number of rays in it measured worse).
+	// Cutting finer only pays while the machine would wait for the longest unit: every unit sets its rays up again, and
+	// the shared memory the parts are copied into is taken from the L1 that whole-subtree walks live on.  So a walk
+	// kernel with many jobs takes whole subtrees as its units, from global memory (it is bound by the sum of its work, not
+	// by the longest piece).  The host chooses per launch (WaveParams::view_parts / shadow_parts) from the job counts of
+	// the frame before; choosing per job by the number of rays in it measured worse.
 	// per mesh: [0] = subtree count, [1] = offset of the mesh's node -> subtree map in `root_map`, then per subtree
 	// kFine + 1 records of kSplitWords ints, the subtree's parts and then (record kFine) the subtree as a whole:
 	//   [0] root, [1] end      byte offsets of node records (rt::BvhLink): the walk of the part starts at `root` and is over
@@ -56,7 +58,9 @@ namespace wave
 		const int32_t* split;              // kMaxMeshes * kSplitStride
 		const uint8_t* root_map;           // per node of every mesh: subtree number + 1 if the node is a subtree root, else 0
 		unsigned int view_capacity, shadow_capacity;
-		unsigned int parts_below;          // a walk kernel with fewer jobs than this takes the subtrees' parts as its units
+		unsigned int view_parts, shadow_parts;      // 1: that walk kernel takes the subtrees' parts as its units (the host's choice)
+		unsigned int* jobs_report;         // mapped host memory: the shade kernel leaves {view jobs, shadow jobs} there
+		unsigned int setup_per_light;      // 1: shadow setup runs one thread per (pixel, light)
 		unsigned int* job_cycles;          // measurement only (RT_B200_WAVE_JOB_CLOCKS): clocks per unit of the view walk, then of the shadow walk; normally null
 	};
 }
