@@ -37,6 +37,12 @@ namespace rt
 {
 namespace wave
 {
+	// Programmatic dependent launch (wave_launch): the next kernel of the chain may become resident once every CTA of this
+	// one has said so; it must not touch anything this kernel's predecessors wrote before wait_for_previous_launch().
+	// Without the launch attribute both are no-ops.
+	__device__ __forceinline__ void let_next_launch_begin() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+	__device__ __forceinline__ void wait_for_previous_launch() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 	__device__ __forceinline__ unsigned long long make_key(float t, unsigned int primitive) { return ((unsigned long long)__float_as_uint(t) << 32) | primitive; }
 
 	// pixel of thread `tid` of CTA (bx, k) of the launch: the tiled kernel's mapping (render_kernel)
@@ -252,6 +258,7 @@ namespace wave
 	__global__ void __launch_bounds__(kThreads)
 	primary_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
+		let_next_launch_begin();
 		extern __shared__ __align__(16) unsigned char dynamic_smem[];
 		SharedScene& storage = *reinterpret_cast<SharedScene*>(dynamic_smem);
 		stage_scene<kThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
@@ -310,6 +317,8 @@ namespace wave
 		float4* region = reinterpret_cast<float4*>(dynamic_smem + (PARTS ? (threadIdx.x >> 5) * kRegionBytes : 0u));       // (no shared memory without PARTS)
 		// jobs are handed out by a counter: their costs differ by orders of magnitude
 		const unsigned int lane = threadIdx.x & 31;
+		let_next_launch_begin();
+		wait_for_previous_launch();
 		const unsigned int n_jobs = min(w.counters[0], w.view_capacity);
 		// whole subtrees or their parts (rt_wave_params.h; the host chooses, wave_launch)
 		constexpr unsigned int shift = PARTS ? kFineShift : 0;
@@ -426,10 +435,12 @@ namespace wave
 	__global__ void __launch_bounds__(kThreads)
 	shadow_setup_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
 	{
+		let_next_launch_begin();
 		extern __shared__ __align__(16) unsigned char dynamic_smem[];
 		SharedScene& storage = *reinterpret_cast<SharedScene*>(dynamic_smem);
-		stage_scene<kThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
+		stage_scene<kThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));         // (the scene tables are not a kernel's output)
 		__syncthreads();
+		wait_for_previous_launch();
 		const Staged sc = staged_handle(storage);
 
 		const Where me = where_am_i(p, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
@@ -488,6 +499,8 @@ namespace wave
 		extern __shared__ __align__(16) unsigned char dynamic_smem[];
 		float4* region = reinterpret_cast<float4*>(dynamic_smem + (PARTS ? (threadIdx.x >> 5) * kRegionBytes : 0u));       // (no shared memory without PARTS)
 		const unsigned int lane = threadIdx.x & 31;
+		let_next_launch_begin();
+		wait_for_previous_launch();
 		const unsigned int n_jobs = min(w.counters[1], w.shadow_capacity);
 		// whole subtrees or their parts (rt_wave_params.h; the host chooses, wave_launch)
 		constexpr unsigned int shift = PARTS ? kFineShift : 0;
@@ -565,6 +578,7 @@ namespace wave
 		SharedScene& storage = *reinterpret_cast<SharedScene*>(dynamic_smem);
 		stage_scene<kThreads>(storage, dev, v3(p.cam_ox, p.cam_oy, p.cam_oz));
 		__syncthreads();
+		wait_for_previous_launch();
 		const Staged sc = staged_handle(storage);
 
 		const Where me = where_am_i(p, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);

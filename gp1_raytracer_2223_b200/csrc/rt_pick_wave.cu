@@ -9,6 +9,25 @@
 
 namespace rt
 {
+	namespace
+	{
+		// A launch that may begin before the launch ahead of it in the stream has finished (programmatic dependent launch):
+		// its CTAs become resident as that kernel's drain away, run their prologue - staging the scene - and then wait in
+		// wait_for_previous_launch() until everything the previous kernel wrote is visible.  A small frame is five short
+		// kernels; this takes the launch latency and the prologues out of the gaps between them.
+		template <class... Params, class... Args>
+		cudaError_t launch_chained(bool chained, void (*kernel)(Params...), dim3 grid, unsigned int threads, size_t smem, cudaStream_t stream, const Args&... args)
+		{
+			cudaLaunchConfig_t config = {};
+			config.gridDim = grid; config.blockDim = dim3(threads); config.dynamicSmemBytes = smem; config.stream = stream;
+			cudaLaunchAttribute attribute[1];
+			attribute[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+			attribute[0].val.programmaticStreamSerializationAllowed = 1;
+			config.attrs = attribute; config.numAttrs = chained ? 1u : 0u;
+			return cudaLaunchKernelEx(&config, kernel, args...);
+		}
+	}
+
 	cudaError_t wave_launch(const SceneDevice& dev, const FrameParams& p, const wave::WaveParams& w_in, dim3 grid, int sm_count, cudaStream_t stream)
 	{
 		wave::WaveParams w = w_in;
@@ -44,26 +63,36 @@ namespace rt
 			return (unsigned int)std::max(1, *std::min_element(n, n + 4));
 		}();
 		const unsigned int walkers = (unsigned int)sm_count * walkers_per_sm;
+		static const bool chained = getenv("RT_B200_WAVE_NO_CHAIN") == nullptr;
+		const dim3 walk_grid(walkers);
+		const unsigned int walk_threads = wave::kWalkWarps * 32;
 		wave::primary_kernel<<<grid, kThreads, smem, stream>>>(dev, p, w);
 		mark();
-		if (w.view_parts) wave::view_walk_kernel<true><<<walkers, wave::kWalkWarps * 32, parts_smem, stream>>>(dev, p, w);
-		else wave::view_walk_kernel<false><<<walkers, wave::kWalkWarps * 32, 0, stream>>>(dev, p, w);
-		mark();
-		if (p.shadows && dev.n_lights > 0) wave::shadow_setup_kernel<<<dim3(grid.x, grid.y, w.setup_per_light ? (unsigned int)dev.n_lights : 1u), kThreads, smem, stream>>>(dev, p, w);
+		if (w.view_parts) e = launch_chained(chained, wave::view_walk_kernel<true>, walk_grid, walk_threads, parts_smem, stream, dev, p, w);
+		else e = launch_chained(chained, wave::view_walk_kernel<false>, walk_grid, walk_threads, 0, stream, dev, p, w);
+		if (e != cudaSuccess) return e;
 		mark();
 		if (p.shadows && dev.n_lights > 0)
 		{
-			if (w.shadow_parts) wave::shadow_walk_kernel<true><<<walkers, wave::kWalkWarps * 32, parts_smem, stream>>>(dev, p, w);
-			else wave::shadow_walk_kernel<false><<<walkers, wave::kWalkWarps * 32, 0, stream>>>(dev, p, w);
+			e = launch_chained(chained, wave::shadow_setup_kernel, dim3(grid.x, grid.y, w.setup_per_light ? (unsigned int)dev.n_lights : 1u), kThreads, smem, stream, dev, p, w);
+			if (e != cudaSuccess) return e;
+		}
+		mark();
+		if (p.shadows && dev.n_lights > 0)
+		{
+			if (w.shadow_parts) e = launch_chained(chained, wave::shadow_walk_kernel<true>, walk_grid, walk_threads, parts_smem, stream, dev, p, w);
+			else e = launch_chained(chained, wave::shadow_walk_kernel<false>, walk_grid, walk_threads, 0, stream, dev, p, w);
+			if (e != cudaSuccess) return e;
 		}
 		mark();
 		switch (p.lighting_mode)
 		{
-		case RT_LIGHTING_OBSERVED_AREA: wave::shade_kernel<RT_LIGHTING_OBSERVED_AREA><<<grid, kThreads, smem, stream>>>(dev, p, w); break;
-		case RT_LIGHTING_RADIANCE: wave::shade_kernel<RT_LIGHTING_RADIANCE><<<grid, kThreads, smem, stream>>>(dev, p, w); break;
-		case RT_LIGHTING_BRDF: wave::shade_kernel<RT_LIGHTING_BRDF><<<grid, kThreads, smem, stream>>>(dev, p, w); break;
-		default: wave::shade_kernel<RT_LIGHTING_COMBINED><<<grid, kThreads, smem, stream>>>(dev, p, w); break;
+		case RT_LIGHTING_OBSERVED_AREA: e = launch_chained(chained, wave::shade_kernel<RT_LIGHTING_OBSERVED_AREA>, grid, kThreads, smem, stream, dev, p, w); break;
+		case RT_LIGHTING_RADIANCE: e = launch_chained(chained, wave::shade_kernel<RT_LIGHTING_RADIANCE>, grid, kThreads, smem, stream, dev, p, w); break;
+		case RT_LIGHTING_BRDF: e = launch_chained(chained, wave::shade_kernel<RT_LIGHTING_BRDF>, grid, kThreads, smem, stream, dev, p, w); break;
+		default: e = launch_chained(chained, wave::shade_kernel<RT_LIGHTING_COMBINED>, grid, kThreads, smem, stream, dev, p, w); break;
 		}
+		if (e != cudaSuccess) return e;
 		mark();
 		if (timing)
 		{
