@@ -512,3 +512,36 @@ def test_wavefront_kernel_in_every_mode_and_on_strips(gpu):
     identical, max_err, n_diff = compare_frames(surface, want)
     assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (n_diff, max_err)
     r.close()
+
+
+@pytest.mark.parametrize("knobs", [{"RT_B200_WAVE_PARTS_BELOW": "0"}, {"RT_B200_WAVE_PARTS_BELOW": "1000000"},
+                                   {"RT_B200_WAVE_PARTS_BELOW": "1000000", "RT_B200_WAVE_PARTS": "2", "RT_B200_WAVE_SUBTREES": "7"},
+                                   {"RT_B200_WAVE_NO_CHAIN": "1"}])
+def test_wavefront_units_whole_subtrees_and_parts(gpu, knobs):
+    """The walk kernels of RT_KERNEL_WAVEFRONT take whole subtrees (from global memory) or parts of subtrees (copied into
+    shared memory, after the boxes between the subtree's root and the part) as their units; the host picks per launch.
+    Forced either way, with an odd cut of the tree, and without programmatic dependent launch: the reference's frames
+    all the same.  The knobs are read once per process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = '''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from conftest import MAX_LSB, MIN_IDENTICAL, compare_frames, load_golden_frame
+from test_gpu_parity import EXACT, make_renderer
+for name in ("optional_320", "optional_320_steps2", "w4ref_101x203", "bunny_333x77", "bunny_640_noshadow", "w4ref_320_cam"):
+    r = make_renderer(name)
+    r.ctx.set_mesh_path(2)
+    r.ctx.set_kernel_variant(4)
+    for frame in range(3):          # the second frame on, the host knows the job counts of the one before
+        identical, max_err, n_diff = compare_frames(r.Render(), load_golden_frame(name))
+        assert (n_diff == 0) if name in EXACT else (identical >= MIN_IDENTICAL and max_err <= MAX_LSB), (name, frame, n_diff, max_err)
+    assert r.ctx.timing()["kernel_launches"] in (3, 5), r.ctx.timing()
+    r.close()
+print("ok")
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **knobs), timeout=300)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stdout + res.stderr

@@ -17,7 +17,8 @@ for name in ("bunny_333x77", "w4ref_101x203", "w3_320_brdf", "optional_320"):
     want = load_golden_frame(name)
     for path in (1, 2):
         if path == 2 and not sc.meshes: continue
-        for variant in (1, 2, 3):
+        for variant in (1, 2, 3, 4):                          # 4 = wavefront: BVH body only (falls back to AUTO otherwise)
+            if variant == 4 and path != 2: continue
             r.ctx.set_mesh_path(path); r.ctx.set_kernel_variant(variant)
             got = r.Render()
             d = int((got != want).sum()); bad += d > want.size // 1000
