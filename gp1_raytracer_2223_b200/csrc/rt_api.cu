@@ -912,6 +912,7 @@ namespace
 				RT_CUDA(ctx, cudaDeviceSynchronize());
 				if (d.d_wave) RT_CUDA(ctx, cudaFree(d.d_wave));
 				d.d_wave = nullptr;
+				d.wave_pixels = d.wave_view_tasks = d.wave_shadow_tasks = 0;
 				const size_t n_m = std::max<size_t>(ctx->meshes.size(), 1), n_l = (size_t)std::max(ctx->n_lights, 1);
 				const size_t bytes = pixels * (8 + 16 + 4 + 8 * n_m + 8 * n_m * n_l) + (view_jobs + shadow_jobs) * 8 + 256;
 				RT_CUDA(ctx, cudaMalloc(&d.d_wave, bytes));
@@ -1760,8 +1761,8 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		for (cudaEvent_t& e : d.ev_band) RT_CREATE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_band_done, sizeof(unsigned int) * 128));
 		RT_CREATE(cudaHostAlloc(&d.h_flags, sizeof(unsigned int) * 64, cudaHostAllocMapped | cudaHostAllocPortable));
-		RT_CREATE(cudaHostAlloc(&d.h_wave_jobs, sizeof(unsigned int) * 2, cudaHostAllocMapped | cudaHostAllocPortable));
-		d.h_wave_jobs[0] = d.h_wave_jobs[1] = 0u;
+		RT_CREATE(cudaHostAlloc(&d.h_wave_jobs, sizeof(unsigned int) * 4, cudaHostAllocMapped | cudaHostAllocPortable));
+		d.h_wave_jobs[0] = d.h_wave_jobs[1] = d.h_wave_jobs[2] = d.h_wave_jobs[3] = 0u;
 		RT_CREATE(cudaHostGetDevicePointer((void**)&d.d_wave_jobs, d.h_wave_jobs, 0));
 		memset(d.h_flags, 0, sizeof(unsigned int) * 64);
 		RT_CREATE(cudaHostGetDevicePointer((void**)&d.d_flags, d.h_flags, 0));

@@ -254,6 +254,25 @@ namespace wave
 		return in;
 	}
 
+	// What a view ray hits before any mesh is looked at: spheres, then planes (Scene.cpp:29-52), as a key
+	__device__ __forceinline__ unsigned long long primary_key(const Staged sc, const SceneDevice& dev, const Pk& K, const Ray& ray)
+	{
+		Counters<false> cnt;
+		float best_t = FLT_MAX;
+		int best_sphere = -1, best_plane = -1;
+#pragma unroll 1
+		for (int i = 0; i < dev.n_spheres; ++i)
+		{
+			float t;
+			const float4 sv = sc.sphere_view(i);
+			if (hit_sphere_from<false>(v3(sv), sv.w, sc.sphere(i).w, ray, t, cnt) && t < best_t) { best_t = t; best_sphere = i; }
+		}
+		planes_closest(K, sc, dev.n_planes, ray, best_t, best_plane, cnt);
+		if (best_plane >= 0) return make_key(best_t, kPlaneBase + (unsigned int)best_plane);
+		if (best_sphere >= 0) return make_key(best_t, (unsigned int)best_sphere);
+		return kNoHit;
+	}
+
 	// ---- K1 ----------------------------------------------------------------------------------------------------------
 	__global__ void __launch_bounds__(kThreads)
 	primary_kernel(const __grid_constant__ SceneDevice dev, const __grid_constant__ FrameParams p, const __grid_constant__ WaveParams w)
@@ -268,7 +287,6 @@ namespace wave
 		const Where me = where_am_i(p, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
 		const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
 		const unsigned int pixel = cta * kThreads + threadIdx.x;
-		Counters<false> cnt;
 		const Pk K = make_pk(dev);
 
 		Ray ray{};
@@ -276,18 +294,7 @@ namespace wave
 		if (me.valid)
 		{
 			ray = view_ray(p, me.px, me.py);
-			float best_t = FLT_MAX;
-			int best_sphere = -1, best_plane = -1;
-#pragma unroll 1
-			for (int i = 0; i < dev.n_spheres; ++i)
-			{
-				float t;
-				const float4 sv = sc.sphere_view(i);
-				if (hit_sphere_from<false>(v3(sv), sv.w, sc.sphere(i).w, ray, t, cnt) && t < best_t) { best_t = t; best_sphere = i; }
-			}
-			planes_closest(K, sc, dev.n_planes, ray, best_t, best_plane, cnt);
-			if (best_plane >= 0) key = make_key(best_t, kPlaneBase + (unsigned int)best_plane);
-			else if (best_sphere >= 0) key = make_key(best_t, (unsigned int)best_sphere);
+			key = primary_key(sc, dev, K, ray);
 		}
 		w.hit_key[pixel] = key;
 		w.occluded[pixel] = 0u;            // K3 and K4 only ever set bits
@@ -305,6 +312,65 @@ namespace wave
 			if (me.valid) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
 			w.view_alive[(size_t)pixel * dev.n_meshes + m] = alive;
 			emit_jobs(alive, tile, (unsigned int)m << 8, w.view_jobs, w.counters, w.view_capacity, w.counters + 4);
+		}
+	}
+
+	// One unit of the view walk: the rays of warp tile `tile` in subtree `s` of mesh `m` - the whole subtree (part ==
+	// kFine) or one of its parts.  `region`: the warp's piece of shared memory (PARTS only).
+	template <bool PARTS>
+	__device__ __forceinline__ void view_unit(const SceneDevice& dev, const FrameParams& p, const WaveParams& w, float4* region, unsigned int lane,
+	                                          unsigned int tile, unsigned int m, unsigned int s, unsigned int part)
+	{
+		const int32_t* entry = w.split + (size_t)m * kSplitStride + kSplitHeader + (s * (kFine + 1) + part) * kSplitWords;
+		const int flags = __ldg(entry + 6);
+		if (flags & kPartPresent)
+		{
+			const unsigned int cta = tile / kSignalsPerTile;
+			const int tid = (int)((tile % kSignalsPerTile) * 32u + lane);
+			const Where me = where_am_i(p, (int)(cta % (unsigned int)p.grid_x), (int)(cta / (unsigned int)p.grid_x), tid);
+			const unsigned int pixel = cta * kThreads + (unsigned int)tid;
+			const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
+			const int first_tri = __float_as_int(b1.z);
+			const float4* tri = dev.triangles + 3 * (size_t)first_tri;
+			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+			const int cull = __float_as_int(info.x);
+			// the copy starts before anything is known about the rays: it is in flight while their masks arrive
+			const unsigned long long subtrees_reached = w.view_alive[(size_t)pixel * dev.n_meshes + m];
+			const bool staged = PARTS && (flags & kPartStageable) != 0;      // whole subtrees are walked where they are: few of a tile's rays see much of one
+			int node_words = 0;
+			if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
+			// rays that never reach the subtree, or do not get from its root to this part, sit the unit out
+			bool reaches = me.valid && ((subtrees_reached >> s) & 1ull);
+			if (__ballot_sync(0xffffffffu, reaches) == 0u) { if (staged) stage_abandon(); }
+			else
+			{
+				Ray ray{};
+				if (reaches) ray = view_ray(p, me.px, me.py);
+				if (staged)
+				{
+					stage_finish(region, node_words, entry, lane);
+					if (reaches) reaches = ray.nan_safe ? enters_staged<true>(region, __ldg(entry + 7), ray) : enters_staged<false>(region, __ldg(entry + 7), ray);
+				}
+				else if (reaches) reaches = ray.nan_safe ? enters_part<true>(nodes, entry, ray) : enters_part<false>(nodes, entry, ray);
+				if (reaches)
+				{
+					const float best_t = __uint_as_float((unsigned int)(w.hit_key[pixel] >> 32));       // a stale read only makes the bound looser
+					// (the bound only decides which candidates are worth an atomic: the triangle tests never see it)
+					float t = FLT_MAX;
+					int best_tri = -1;
+					if (staged)
+					{
+						if (ray.nan_safe) walk_staged<false, true>(cull, region, node_words, ray, t, best_tri);
+						else walk_staged<false, false>(cull, region, node_words, ray, t, best_tri);
+						best_tri += __ldg(entry + 4);
+					}
+					else if (ray.nan_safe) walk_subtree<false, true>(cull, nodes, tri, entry, ray, t, best_tri);
+					else walk_subtree<false, false>(cull, nodes, tri, entry, ray, t, best_tri);
+					if (t < FLT_MAX && t <= best_t)
+						atomicMin(w.hit_key + pixel, make_key(t, kTriangleBase + (unsigned int)(first_tri + best_tri)));
+				}
+				__syncwarp();                // the next unit overwrites the copy
+			}
 		}
 	}
 
@@ -334,57 +400,7 @@ namespace wave
 			const long long unit_began = w.job_cycles ? clock64() : 0ll;
 			const uint2 word = w.view_jobs[unit >> shift];
 			const unsigned int tile = word.x, m = (word.y >> 8) & 0xffu, s = word.y & 0xffu;
-			const int32_t* entry = w.split + (size_t)m * kSplitStride + kSplitHeader + (s * (kFine + 1) + (shift ? unit % kFine : kFine)) * kSplitWords;
-			const int flags = __ldg(entry + 6);
-			if (flags & kPartPresent)
-			{
-				const unsigned int cta = tile / kSignalsPerTile;
-				const int tid = (int)((tile % kSignalsPerTile) * 32u + lane);
-				const Where me = where_am_i(p, (int)(cta % (unsigned int)p.grid_x), (int)(cta / (unsigned int)p.grid_x), tid);
-				const unsigned int pixel = cta * kThreads + (unsigned int)tid;
-				const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
-				const int first_tri = __float_as_int(b1.z);
-				const float4* tri = dev.triangles + 3 * (size_t)first_tri;
-				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				const int cull = __float_as_int(info.x);
-				// the copy starts before anything is known about the rays: it is in flight while their masks arrive
-				const unsigned long long subtrees_reached = w.view_alive[(size_t)pixel * dev.n_meshes + m];
-				const bool staged = PARTS && (flags & kPartStageable) != 0;      // whole subtrees are walked where they are: few of a tile's rays see much of one
-				int node_words = 0;
-				if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
-				// rays that never reach the subtree, or do not get from its root to this part, sit the unit out
-				bool reaches = me.valid && ((subtrees_reached >> s) & 1ull);
-				if (__ballot_sync(0xffffffffu, reaches) == 0u) { if (staged) stage_abandon(); }
-				else
-				{
-					Ray ray{};
-					if (reaches) ray = view_ray(p, me.px, me.py);
-					if (staged)
-					{
-						stage_finish(region, node_words, entry, lane);
-						if (reaches) reaches = ray.nan_safe ? enters_staged<true>(region, __ldg(entry + 7), ray) : enters_staged<false>(region, __ldg(entry + 7), ray);
-					}
-					else if (reaches) reaches = ray.nan_safe ? enters_part<true>(nodes, entry, ray) : enters_part<false>(nodes, entry, ray);
-					if (reaches)
-					{
-						const float best_t = __uint_as_float((unsigned int)(w.hit_key[pixel] >> 32));       // a stale read only makes the bound looser
-						// (the bound only decides which candidates are worth an atomic: the triangle tests never see it)
-						float t = FLT_MAX;
-						int best_tri = -1;
-						if (staged)
-						{
-							if (ray.nan_safe) walk_staged<false, true>(cull, region, node_words, ray, t, best_tri);
-							else walk_staged<false, false>(cull, region, node_words, ray, t, best_tri);
-							best_tri += __ldg(entry + 4);
-						}
-						else if (ray.nan_safe) walk_subtree<false, true>(cull, nodes, tri, entry, ray, t, best_tri);
-						else walk_subtree<false, false>(cull, nodes, tri, entry, ray, t, best_tri);
-						if (t < FLT_MAX && t <= best_t)
-							atomicMin(w.hit_key + pixel, make_key(t, kTriangleBase + (unsigned int)(first_tri + best_tri)));
-					}
-					__syncwarp();                // the next unit overwrites the copy
-				}
-			}
+			view_unit<PARTS>(dev, p, w, region, lane, tile, m, s, shift ? unit % kFine : (unsigned int)kFine);
 			if (w.job_cycles) { __syncwarp(); if (lane == 0) w.job_cycles[unit] = (unsigned int)(clock64() - unit_began); }
 		}
 	}
@@ -429,6 +445,17 @@ namespace wave
 		return h;
 	}
 
+	// Scene::DoesHit's spheres and planes (Scene.cpp:71-89) for one shadow ray
+	__device__ __forceinline__ bool blocked_before_meshes(const Staged sc, const SceneDevice& dev, const Pk& K, const Ray& ray)
+	{
+		Counters<false> cnt;
+		float t;
+#pragma unroll 1
+		for (int i = 0; i < dev.n_spheres; ++i)
+			if (hit_sphere<true>(sc.sphere(i), ray, t, cnt)) return true;
+		return planes_any(K, sc, dev.n_planes, ray, cnt);
+	}
+
 	// ---- K3 ----------------------------------------------------------------------------------------------------------
 	// gridDim.z = 1 or the number of lights: in a small frame a pixel's shadow rays are set up by one thread each (the top
 	// of the tree is a chain of dependent steps, and the frame has too few pixels to hide three of them back to back)
@@ -447,7 +474,6 @@ namespace wave
 		const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
 		const unsigned int pixel = cta * kThreads + threadIdx.x;
 		const unsigned int tile = cta * kSignalsPerTile + (threadIdx.x >> 5);
-		Counters<false> cnt;
 		const Pk K = make_pk(dev);
 
 		bool did = false;
@@ -469,12 +495,7 @@ namespace wave
 			if (open)
 			{
 				ray = shadow_ray_to(sc.light_a(li), __float_as_int(sc.light_b(li).w), origin_offset);
-				float t;
-#pragma unroll 1
-				for (int i = 0; i < dev.n_spheres && open; ++i)
-					if (hit_sphere<true>(sc.sphere(i), ray, t, cnt)) open = false;
-				if (open && planes_any(K, sc, dev.n_planes, ray, cnt)) open = false;
-				if (!open) atomicOr(w.occluded + pixel, 1u << li);
+				if (blocked_before_meshes(sc, dev, K, ray)) { open = false; atomicOr(w.occluded + pixel, 1u << li); }
 			}
 #pragma unroll 1
 			for (int m = 0; m < dev.n_meshes; ++m)
@@ -487,6 +508,62 @@ namespace wave
 				if (open) alive = ray.nan_safe ? walk_top<true>(nodes, w.root_map + __ldg(split + 1), ray) : walk_top<false>(nodes, w.root_map + __ldg(split + 1), ray);
 				w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m] = alive;
 				emit_jobs(alive, tile, ((unsigned int)li << 16) | ((unsigned int)m << 8), w.shadow_jobs, w.counters + 1, w.shadow_capacity, w.counters + 4);
+			}
+		}
+	}
+
+	// One unit of the shadow walk: the shadow rays towards light `li` of warp tile `tile` in subtree `s` of mesh `m`
+	template <bool PARTS>
+	__device__ __forceinline__ void shadow_unit(const SceneDevice& dev, const FrameParams& p, const WaveParams& w, float4* region, unsigned int lane,
+	                                            unsigned int tile, unsigned int li, unsigned int m, unsigned int s, unsigned int part)
+	{
+		const int32_t* entry = w.split + (size_t)m * kSplitStride + kSplitHeader + (s * (kFine + 1) + part) * kSplitWords;
+		const int flags = __ldg(entry + 6);
+		if (flags & kPartPresent)
+		{
+			const unsigned int cta = tile / kSignalsPerTile;
+			const unsigned int pixel = cta * kThreads + (tile % kSignalsPerTile) * 32u + lane;
+			const unsigned int bit = 1u << li;
+			const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
+			const float4* tri = dev.triangles + 3 * (size_t)__float_as_int(b1.z);
+			const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
+			const int cull = __float_as_int(info.x);
+			// Utils.h:114-127: shadow rays see the opposite cull mode
+			const int shadow_cull = cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : (cull == RT_CULL_FRONT_FACE ? RT_CULL_BACK_FACE : RT_CULL_NONE);
+			// rays that never reach the subtree, do not get from its root to this part, or are already known to be in shadow
+			// (racy read: an optimisation only) sit the unit out
+			// the copy starts before anything is known about the rays: it is in flight while their masks arrive
+			const float4 so = w.shadow_origin[pixel];
+			const unsigned long long subtrees_reached = w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m];
+			const unsigned int known_occluded = w.occluded[pixel];
+			const bool staged = PARTS && (flags & kPartStageable) != 0;      // whole subtrees are walked where they are: few of a tile's rays see much of one
+			int node_words = 0;
+			if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
+			bool reaches = ((subtrees_reached >> s) & 1ull) && !(known_occluded & bit);
+			if (__ballot_sync(0xffffffffu, reaches) == 0u) { if (staged) stage_abandon(); }
+			else
+			{
+				Ray ray{};
+				if (reaches)
+				{
+					const float4 la = make_float4(__ldg(dev.light_ox + li), __ldg(dev.light_oy + li), __ldg(dev.light_oz + li), 0.f);
+					ray = shadow_ray_to(la, __ldg(dev.light_type + li), v3(so));
+				}
+				if (staged)
+				{
+					stage_finish(region, node_words, entry, lane);
+					if (reaches) reaches = ray.nan_safe ? enters_staged<true>(region, __ldg(entry + 7), ray) : enters_staged<false>(region, __ldg(entry + 7), ray);
+				}
+				else if (reaches) reaches = ray.nan_safe ? enters_part<true>(nodes, entry, ray) : enters_part<false>(nodes, entry, ray);
+				if (reaches)
+				{
+					float t = FLT_MAX; int tri_id = -1;
+					bool blocked;
+					if (staged) blocked = ray.nan_safe ? walk_staged<true, true>(shadow_cull, region, node_words, ray, t, tri_id) : walk_staged<true, false>(shadow_cull, region, node_words, ray, t, tri_id);
+					else blocked = ray.nan_safe ? walk_subtree<true, true>(shadow_cull, nodes, tri, entry, ray, t, tri_id) : walk_subtree<true, false>(shadow_cull, nodes, tri, entry, ray, t, tri_id);
+					if (blocked) atomicOr(w.occluded + pixel, bit);
+				}
+				__syncwarp();                // the next unit overwrites the copy
 			}
 		}
 	}
@@ -516,56 +593,49 @@ namespace wave
 			const long long unit_began = w.job_cycles ? clock64() : 0ll;
 			const uint2 word = w.shadow_jobs[unit >> shift];
 			const unsigned int tile = word.x, li = (word.y >> 16) & 0xffu, m = (word.y >> 8) & 0xffu, s = word.y & 0xffu;
-			const int32_t* entry = w.split + (size_t)m * kSplitStride + kSplitHeader + (s * (kFine + 1) + (shift ? unit % kFine : kFine)) * kSplitWords;
-			const int flags = __ldg(entry + 6);
-			if (flags & kPartPresent)
-			{
-				const unsigned int cta = tile / kSignalsPerTile;
-				const unsigned int pixel = cta * kThreads + (tile % kSignalsPerTile) * 32u + lane;
-				const unsigned int bit = 1u << li;
-				const float4 b1 = __ldg(dev.mesh_table + 3 * m + 1), info = __ldg(dev.mesh_table + 3 * m + 2);
-				const float4* tri = dev.triangles + 3 * (size_t)__float_as_int(b1.z);
-				const float4* nodes = dev.bvh_nodes + 2 * (size_t)__float_as_int(info.z);
-				const int cull = __float_as_int(info.x);
-				// Utils.h:114-127: shadow rays see the opposite cull mode
-				const int shadow_cull = cull == RT_CULL_BACK_FACE ? RT_CULL_FRONT_FACE : (cull == RT_CULL_FRONT_FACE ? RT_CULL_BACK_FACE : RT_CULL_NONE);
-				// rays that never reach the subtree, do not get from its root to this part, or are already known to be in shadow
-				// (racy read: an optimisation only) sit the unit out
-				// the copy starts before anything is known about the rays: it is in flight while their masks arrive
-				const float4 so = w.shadow_origin[pixel];
-				const unsigned long long subtrees_reached = w.shadow_alive[((size_t)pixel * dev.n_lights + li) * dev.n_meshes + m];
-				const unsigned int known_occluded = w.occluded[pixel];
-				const bool staged = PARTS && (flags & kPartStageable) != 0;      // whole subtrees are walked where they are: few of a tile's rays see much of one
-				int node_words = 0;
-				if (staged) node_words = stage_begin(region, nodes, tri, entry, lane);
-				bool reaches = ((subtrees_reached >> s) & 1ull) && !(known_occluded & bit);
-				if (__ballot_sync(0xffffffffu, reaches) == 0u) { if (staged) stage_abandon(); }
-				else
-				{
-					Ray ray{};
-					if (reaches)
-					{
-						const float4 la = make_float4(__ldg(dev.light_ox + li), __ldg(dev.light_oy + li), __ldg(dev.light_oz + li), 0.f);
-						ray = shadow_ray_to(la, __ldg(dev.light_type + li), v3(so));
-					}
-					if (staged)
-					{
-						stage_finish(region, node_words, entry, lane);
-						if (reaches) reaches = ray.nan_safe ? enters_staged<true>(region, __ldg(entry + 7), ray) : enters_staged<false>(region, __ldg(entry + 7), ray);
-					}
-					else if (reaches) reaches = ray.nan_safe ? enters_part<true>(nodes, entry, ray) : enters_part<false>(nodes, entry, ray);
-					if (reaches)
-					{
-						float t = FLT_MAX; int tri_id = -1;
-						bool blocked;
-						if (staged) blocked = ray.nan_safe ? walk_staged<true, true>(shadow_cull, region, node_words, ray, t, tri_id) : walk_staged<true, false>(shadow_cull, region, node_words, ray, t, tri_id);
-						else blocked = ray.nan_safe ? walk_subtree<true, true>(shadow_cull, nodes, tri, entry, ray, t, tri_id) : walk_subtree<true, false>(shadow_cull, nodes, tri, entry, ray, t, tri_id);
-						if (blocked) atomicOr(w.occluded + pixel, bit);
-					}
-					__syncwarp();                // the next unit overwrites the copy
-				}
-			}
+			shadow_unit<PARTS>(dev, p, w, region, lane, tile, li, m, s, shift ? unit % kFine : (unsigned int)kFine);
 			if (w.job_cycles) { __syncwarp(); if (lane == 0) w.job_cycles[(size_t)w.view_capacity * kFine + unit] = (unsigned int)(clock64() - unit_began); }
+		}
+	}
+
+	// Renderer.cpp:120-181 for one pixel, given what it hit and which lights are blocked
+	__device__ __forceinline__ uint32_t shade_pixel(int mode, const Staged sc, const SceneDevice& dev, const FrameParams& p, const Ray& view, unsigned long long key, unsigned int occluded)
+	{
+		Counters<false> cnt;
+		const Hit hit = hit_of_key(sc, dev, view, key);
+		float shadow_factor = 1.f;
+		V3 color = v3(0.f, 0.f, 0.f);
+		if (hit.did)
+		{
+			const V3 origin_offset = hit.origin + hit.normal * 0.0001f;     // Renderer.cpp:126
+			const ViewInRegisters view_neg{ neg(view.d) };                  // Renderer.cpp:150
+#pragma unroll 1
+			for (int li = 0; li < dev.n_lights; ++li)
+			{
+				if ((occluded >> li) & 1u) { shadow_factor = mul(shadow_factor, 0.95f); continue; }     // Renderer.cpp:137-141
+				const float4 la = sc.light_a(li), lb = sc.light_b(li);
+				const Ray to_light = shadow_ray_to(la, __float_as_int(lb.w), origin_offset);
+				color = add_light(mode, color, sc, la, lb, to_light.d, hit.origin, hit.normal, hit.material, view_neg, cnt);
+			}
+			color = color * shadow_factor;                                  // Renderer.cpp:173
+		}
+		return pack_pixel(p, color);
+	}
+	// the pixel of every lane of a warp tile into the frame; `k` = the tile's strip of the launch (all lanes call)
+	__device__ __forceinline__ void store_pixel(const FrameParams& p, const Where& me, int k, uint32_t pixel)
+	{
+		const int dst_row = p.dst_full_frame ? me.py : (k * kBlockH + me.local_y);
+		uint32_t* row = p.dst + (size_t)dst_row * (size_t)p.width;
+		if (p.vector_store)
+		{
+			const uint32_t p1 = __shfl_down_sync(0xffffffffu, pixel, 1);
+			const uint32_t p2 = __shfl_down_sync(0xffffffffu, pixel, 2);
+			const uint32_t p3 = __shfl_down_sync(0xffffffffu, pixel, 3);
+			if (me.valid && (threadIdx.x & 3) == 0) *reinterpret_cast<uint4*>(row + me.px) = make_uint4(pixel, p1, p2, p3);
+		}
+		else if (me.valid)
+		{
+			row[me.px] = pixel;
 		}
 	}
 
@@ -584,45 +654,9 @@ namespace wave
 		const Where me = where_am_i(p, (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
 		const unsigned int cta = blockIdx.y * gridDim.x + blockIdx.x;
 		const unsigned int pixel_index = cta * kThreads + threadIdx.x;
-		Counters<false> cnt;
 		uint32_t pixel = 0;
-		if (me.valid)
-		{
-			const Ray view = view_ray(p, me.px, me.py);
-			const Hit hit = hit_of_key(sc, dev, view, w.hit_key[pixel_index]);
-			float shadow_factor = 1.f;
-			V3 color = v3(0.f, 0.f, 0.f);
-			if (hit.did)
-			{
-				const V3 origin_offset = hit.origin + hit.normal * 0.0001f;     // Renderer.cpp:126
-				const unsigned int occluded = w.occluded[pixel_index];
-				const ViewInRegisters view_neg{ neg(view.d) };                  // Renderer.cpp:150
-#pragma unroll 1
-				for (int li = 0; li < dev.n_lights; ++li)
-				{
-					if ((occluded >> li) & 1u) { shadow_factor = mul(shadow_factor, 0.95f); continue; }     // Renderer.cpp:137-141
-					const float4 la = sc.light_a(li), lb = sc.light_b(li);
-					const Ray to_light = shadow_ray_to(la, __float_as_int(lb.w), origin_offset);
-					color = add_light(MODE, color, sc, la, lb, to_light.d, hit.origin, hit.normal, hit.material, view_neg, cnt);
-				}
-				color = color * shadow_factor;                                  // Renderer.cpp:173
-			}
-			pixel = pack_pixel(p, color);
-		}
-
-		const int dst_row = p.dst_full_frame ? me.py : ((int)blockIdx.y * kBlockH + me.local_y);
-		uint32_t* row = p.dst + (size_t)dst_row * (size_t)p.width;
-		if (p.vector_store)
-		{
-			const uint32_t p1 = __shfl_down_sync(0xffffffffu, pixel, 1);
-			const uint32_t p2 = __shfl_down_sync(0xffffffffu, pixel, 2);
-			const uint32_t p3 = __shfl_down_sync(0xffffffffu, pixel, 3);
-			if (me.valid && (threadIdx.x & 3) == 0) *reinterpret_cast<uint4*>(row + me.px) = make_uint4(pixel, p1, p2, p3);
-		}
-		else if (me.valid)
-		{
-			row[me.px] = pixel;
-		}
+		if (me.valid) pixel = shade_pixel(MODE, sc, dev, p, view_ray(p, me.px, me.py), w.hit_key[pixel_index], w.occluded[pixel_index]);
+		store_pixel(p, me, (int)blockIdx.y, pixel);
 		if (p.band_done) signal_band_done(p);
 		// what the host sizes the next frame's walk kernels by (rt_api.cu, launch())
 		if (w.jobs_report && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { w.jobs_report[0] = w.counters[0]; w.jobs_report[1] = w.counters[1]; }
