@@ -1581,7 +1581,10 @@ namespace
 		static const int requested = [] { const char* e = getenv("RT_B200_PIPELINE_BANDS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 64) ? v : 0; }();
 		// a band should hold enough of THIS device's CTAs to be worth a copy of its own
 		const int max_bands = std::max(1, (int)(((long long)my_strips * grid_x) / 512));
-		const int bands = std::max(1, std::min(std::min(requested ? requested : 16, max_bands), total_strips));
+		// 32 bands when the host issues the copies as the watcher reports them (a finer pipeline: the frame's last copy is a
+		// thirty-second of it; 24-32 measured best, 48 and up pay per copy), 16 when the copy stream waits on the counters itself
+		static const bool host_issues = getenv("RT_B200_NO_BAND_WATCHER") == nullptr;
+		const int bands = std::max(1, std::min(std::min(requested ? requested : (host_issues ? 32 : 16), max_bands), total_strips));
 		const int strips_per_band = (total_strips + bands - 1) / bands;
 		const BandSchedule schedule = make_band_schedule(total_strips, bands);
 
