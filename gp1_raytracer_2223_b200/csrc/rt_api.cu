@@ -1655,6 +1655,12 @@ namespace
 	int render_direct(rt_context* ctx, const rt_camera* camera, const rt_frame_desc* frame, uint32_t* host_dst, int32_t pitch_bytes,
 	                  int n_present, int strip_first, int strip_step)
 	{
+		// RT_B200_HOST_TIMING=1 (measurement only): where this thread's time goes, per frame, on stderr
+		static const bool host_timing = getenv("RT_B200_HOST_TIMING") != nullptr;
+		using Clock = std::chrono::steady_clock;
+		Clock::time_point mark[6];
+		auto stamp = [&](int i) { if (host_timing) mark[i] = Clock::now(); };
+		stamp(0);
 		int rc = validate_frame(ctx, camera, frame);
 		if (rc != RT_OK) return rc;
 		const int W = frame->width, H = frame->height;
@@ -1662,11 +1668,13 @@ namespace
 		const size_t span = (size_t)pitch_bytes * (size_t)(H - 1) + (size_t)W * 4u;
 		void* target = nullptr;
 		if ((rc = prepare_host(ctx, host_dst, span, &target)) != RT_OK) return rc;
+		stamp(1);
 		ctx->timing = rt_timing{};
 		ctx->last_width = W; ctx->last_height = H;
 		const rt::FrameParams base = make_params(camera, frame);
 		for (int k = 0; k < n_present; ++k)
 			if ((rc = enqueue_direct_present(ctx, ctx->devs[k], base, strip_first + k, strip_step, target, pitch_bytes)) != RT_OK) return rc;
+		stamp(2);
 		// watched launches: this thread issues every device's band copies as the bands arrive
 		for (bool all_done = false; !all_done;)
 		{
@@ -1678,6 +1686,7 @@ namespace
 				all_done = all_done && done;
 			}
 		}
+		stamp(3);
 		float kernel_ms = 0.f, total_ms = 0.f;
 		for (int k = 0; k < n_present; ++k)
 		{
@@ -1685,6 +1694,7 @@ namespace
 			RT_CUDA(ctx, cudaSetDevice(d.device));
 			RT_CUDA(ctx, cudaStreamSynchronize(d.copy_stream));
 			RT_CUDA(ctx, cudaStreamSynchronize(d.stream));
+			stamp(4);
 			float k_ms = 0.f, t_ms = 0.f;
 			RT_CUDA(ctx, cudaEventElapsedTime(&k_ms, d.ev_begin, d.ev_kernel));
 			RT_CUDA(ctx, cudaEventElapsedTime(&t_ms, d.ev_begin, d.ev_done));
@@ -1694,6 +1704,13 @@ namespace
 		if (target != host_dst)
 			for (int k = 0; k < n_present; ++k) unbounce_strips(host_dst, target, W, H, pitch_bytes, strip_first + k, strip_step);
 		ctx->timing.kernel_ms = kernel_ms; ctx->timing.gather_ms = 0.f; ctx->timing.d2h_ms = std::max(0.f, total_ms - kernel_ms); ctx->timing.total_ms = total_ms;
+		stamp(5);
+		if (host_timing)
+		{
+			auto us = [&](int a, int b) { return std::chrono::duration<double, std::micro>(mark[b] - mark[a]).count(); };
+			fprintf(stderr, "rt_render host: prepare %.1f us, enqueue %.1f us, issue copies as bands arrive %.1f us, wait for the streams %.1f us, timing + return %.1f us; device: kernel %.1f us, kernel + copies %.1f us\n",
+			        us(0, 1), us(1, 2), us(2, 3), us(3, 4), us(4, 5), kernel_ms * 1e3, total_ms * 1e3);
+		}
 		return RT_OK;
 	}
 }
