@@ -35,6 +35,7 @@ namespace
 		std::vector<float4> nodes;       // 2 per BVH node, threaded (rt::BvhLink); empty when the mesh came without nodes
 		std::vector<int32_t> split;      // rt::wave::kSplitStride words: the tree cut into subtrees (RT_KERNEL_WAVEFRONT); empty: none
 		std::vector<uint8_t> root_map;   // per node: subtree number + 1 for the subtrees' roots, else 0
+		bool split_built = false;        // split / root_map belong to `nodes` (built when a launch first wants them: build_split)
 		float aabb_min[3] = { 0, 0, 0 };
 		float aabb_max[3] = { 0, 0, 0 };
 		int32_t cull_mode = RT_CULL_BACK_FACE;
@@ -141,6 +142,8 @@ namespace
 		// RT_KERNEL_WAVEFRONT: the split tables of all meshes and the per-pixel scratch of the five launches
 		int32_t* d_split = nullptr;
 		uint8_t* d_root_map = nullptr;
+		unsigned long long split_version = 0;               // of the split tables in d_split / d_root_map (rt_context::split_version)
+		cudaEvent_t ev_split = nullptr;                     // after the last copy out of the pinned mirrors
 		size_t root_map_capacity = 0;
 		void* d_wave = nullptr;
 		size_t wave_pixels = 0, wave_view_tasks = 0, wave_shadow_tasks = 0, wave_meshes = 0, wave_lights = 0;
@@ -160,6 +163,7 @@ struct rt_context
 
 	// pinned host mirror of the static block (SoA, as uploaded) and of the mesh block
 	int32_t* h_split = nullptr;         // pinned mirror of the split tables (kMaxMeshes * kSplitStride words)
+	unsigned long long split_version = 1, h_split_version = 0;     // of the meshes' split tables / of what the pinned mirrors hold
 	uint8_t* h_root_map = nullptr;      // pinned mirror of the node -> subtree maps of all meshes, back to back
 	size_t h_root_map_capacity = 0;
 	uint8_t* h_static = nullptr;
@@ -208,6 +212,7 @@ namespace
 	} while (0)
 
 	inline float bits_as_float(int32_t v) { float f; memcpy(&f, &v, 4); return f; }
+	inline int32_t float_bits(float f) { int32_t v; memcpy(&v, &f, 4); return v; }
 
 	// Bitwise comparison of an uploaded array with its slice of the pinned mirror: an upload that changes nothing (the
 	// drop-in re-sends the whole scene every frame) must not dirty the block, wait for copies or bump the scene version.
@@ -383,43 +388,9 @@ namespace
 			first += count; first_node += node_count;
 		}
 		for (int k = 0; k < 6; ++k) tris[n_tris + k] = make_float4(0.f, 0.f, 0.f, 0.f);
-		constexpr size_t split_words = (size_t)rt::kMaxMeshes * rt::wave::kSplitStride;
-		memset(ctx->h_split, 0, split_words * sizeof(int32_t));
-		size_t map_bytes = 16;
-		for (const HostMesh& hm : ctx->meshes) map_bytes += hm.root_map.size();
-		if (map_bytes > ctx->h_root_map_capacity)
-		{
-			if (ctx->h_root_map) cudaFreeHost(ctx->h_root_map);
-			ctx->h_root_map = nullptr; ctx->h_root_map_capacity = 0;
-			RT_CUDA(ctx, cudaHostAlloc(&ctx->h_root_map, map_bytes * 2, cudaHostAllocPortable));
-			ctx->h_root_map_capacity = map_bytes * 2;
-		}
-		{
-			size_t at = 0;
-			for (size_t m = 0; m < ctx->meshes.size(); ++m)
-			{
-				const HostMesh& hm = ctx->meshes[m];
-				if (hm.split.empty()) continue;
-				int32_t* block = ctx->h_split + m * rt::wave::kSplitStride;
-				memcpy(block, hm.split.data(), sizeof(int32_t) * rt::wave::kSplitStride);
-				block[1] = (int32_t)at;
-				memcpy(ctx->h_root_map + at, hm.root_map.data(), hm.root_map.size());
-				at += hm.root_map.size();
-			}
-		}
 		for (DeviceState& d : ctx->devs)
 		{
 			RT_CUDA(ctx, cudaSetDevice(d.device));
-			if (map_bytes > d.root_map_capacity)
-			{
-				RT_CUDA(ctx, cudaDeviceSynchronize());
-				if (d.d_root_map) RT_CUDA(ctx, cudaFree(d.d_root_map));
-				d.d_root_map = nullptr;
-				RT_CUDA(ctx, cudaMalloc(&d.d_root_map, map_bytes * 2));
-				d.root_map_capacity = map_bytes * 2;
-			}
-			RT_CUDA(ctx, cudaMemcpyAsync(d.d_root_map, ctx->h_root_map, map_bytes, cudaMemcpyHostToDevice, d.stream));
-			RT_CUDA(ctx, cudaMemcpyAsync(d.d_split, ctx->h_split, split_words * sizeof(int32_t), cudaMemcpyHostToDevice, d.stream));
 			if (total > d.mesh_capacity)
 			{
 				RT_CUDA(ctx, cudaDeviceSynchronize());
@@ -837,6 +808,60 @@ namespace
 		return RT_OK;
 	}
 
+	void build_split(HostMesh& hm);
+
+	// The split tables of RT_KERNEL_WAVEFRONT on device `d`, current with the meshes: built per mesh when first wanted
+	// (build_split), staged once per change in the pinned mirrors, copied on the launch's stream.
+	int ensure_splits(rt_context* ctx, DeviceState& d, cudaStream_t stream)
+	{
+		bool rebuilt = false;
+		for (HostMesh& hm : ctx->meshes)
+			if (!hm.split_built) { build_split(hm); hm.split_built = true; rebuilt = true; }
+		if (rebuilt) ++ctx->split_version;
+		if (d.split_version == ctx->split_version) return RT_OK;
+		size_t map_bytes = 16;
+		for (const HostMesh& hm : ctx->meshes) map_bytes += hm.root_map.size();
+		const size_t split_words = ctx->meshes.size() * (size_t)rt::wave::kSplitStride;
+		if (ctx->h_split_version != ctx->split_version)
+		{
+			// nobody may still be reading the mirrors' old contents
+			for (DeviceState& o : ctx->devs) if (o.split_version) RT_CUDA(ctx, cudaEventSynchronize(o.ev_split));
+			if (map_bytes > ctx->h_root_map_capacity)
+			{
+				if (ctx->h_root_map) cudaFreeHost(ctx->h_root_map);
+				ctx->h_root_map = nullptr; ctx->h_root_map_capacity = 0;
+				RT_CUDA(ctx, cudaHostAlloc(&ctx->h_root_map, map_bytes * 2, cudaHostAllocPortable));
+				ctx->h_root_map_capacity = map_bytes * 2;
+			}
+			memset(ctx->h_split, 0, split_words * sizeof(int32_t));
+			size_t at = 0;
+			for (size_t m = 0; m < ctx->meshes.size(); ++m)
+			{
+				const HostMesh& hm = ctx->meshes[m];
+				if (hm.split.empty()) continue;
+				int32_t* block = ctx->h_split + m * rt::wave::kSplitStride;
+				memcpy(block, hm.split.data(), sizeof(int32_t) * rt::wave::kSplitStride);
+				block[1] = (int32_t)at;
+				memcpy(ctx->h_root_map + at, hm.root_map.data(), hm.root_map.size());
+				at += hm.root_map.size();
+			}
+			ctx->h_split_version = ctx->split_version;
+		}
+		if (map_bytes > d.root_map_capacity)
+		{
+			RT_CUDA(ctx, cudaDeviceSynchronize());
+			if (d.d_root_map) RT_CUDA(ctx, cudaFree(d.d_root_map));
+			d.d_root_map = nullptr; d.root_map_capacity = 0;
+			RT_CUDA(ctx, cudaMalloc(&d.d_root_map, map_bytes * 2));
+			d.root_map_capacity = map_bytes * 2;
+		}
+		RT_CUDA(ctx, cudaMemcpyAsync(d.d_root_map, ctx->h_root_map, map_bytes, cudaMemcpyHostToDevice, stream));
+		if (split_words) RT_CUDA(ctx, cudaMemcpyAsync(d.d_split, ctx->h_split, split_words * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+		RT_CUDA(ctx, cudaEventRecord(d.ev_split, stream));
+		d.split_version = ctx->split_version;
+		return RT_OK;
+	}
+
 	// `watched` (optional): p.host_flags asks for the band watcher (rt_kernel.cuh, watch_bands); set to true when the launch
 	// has one - only the persistent kernel can - else the caller orders its copies with stream waits.
 	int launch(rt_context* ctx, DeviceState& d, rt::FrameParams p, cudaStream_t stream, int n_strips, bool* watched = nullptr)
@@ -855,26 +880,32 @@ namespace
 		const bool decodable = grid.x > 1u && (unsigned long long)grid.x * grid.y * grid.x < (1ull << 32);
 		int variant = ctx->kernel_variant;
 		const long long tiles = (long long)grid.x * (long long)grid.y;
-		// RT_KERNEL_WAVEFRONT needs the BVH body, host-uploaded trees (their split tables) and few enough lights for one mask word
-		bool wave_possible = path == RT_MESH_PATH_BVH && ctx->n_lights <= 16 && tiles * rt::kSignalsPerTile < (1ll << 23);
-		long long mesh_nodes = 0, wave_subtrees = 0;
-		for (const HostMesh& hm : ctx->meshes)
-		{
-			if (hm.triangles.empty()) continue;
-			if (hm.split.empty()) wave_possible = false; else wave_subtrees += hm.split[0];
-			mesh_nodes += (long long)(hm.nodes.size() / 2);
-		}
-		// the job lists are sized for the worst case (every tile reaches every subtree for every light): keep them below 64 MB
-		if (tiles * rt::kSignalsPerTile * std::max(wave_subtrees, 1ll) * std::max(ctx->n_lights, 1) > (8ll << 20)) wave_possible = false;
-		if (tiles * rt::kThreads * (long long)std::max<size_t>(ctx->meshes.size(), 1) * std::max(ctx->n_lights, 1) > (16ll << 20)) wave_possible = false;     // the per-ray subtree masks: <= 128 MB
-		if (variant == RT_KERNEL_WAVEFRONT && !wave_possible) variant = RT_KERNEL_AUTO;
+		// RT_KERNEL_WAVEFRONT needs the BVH body, host-uploaded trees (their split tables) and few enough lights for one mask word.
 		// AUTO: rays as the unit of work pay when the frame alone cannot fill the machine (fewer than ~4 warp tiles per
 		// resident warp) while its pixels are expensive (deep trees walked without pruning): measured on
 		// Scene_W4_OptionalScene, see DESIGN.md
 		static const long long wave_min_nodes = [] { const char* e = getenv("RT_B200_WAVE_MIN_NODES"); return e ? atoll(e) : 1024ll; }();
 		static const long long wave_max_tiles_per_sm = [] { const char* e = getenv("RT_B200_WAVE_MAX_TILES_PER_SM"); return e ? atoll(e) : 320ll; }();
-		if (variant == RT_KERNEL_AUTO && wave_possible && mesh_nodes >= wave_min_nodes && tiles * rt::kSignalsPerTile <= wave_max_tiles_per_sm * d.sm_count)
-			variant = RT_KERNEL_WAVEFRONT;
+		long long mesh_nodes = 0, wave_subtrees = 0;
+		for (const HostMesh& hm : ctx->meshes) if (!hm.triangles.empty()) mesh_nodes += (long long)(hm.nodes.size() / 2);
+		bool wave_possible = path == RT_MESH_PATH_BVH && ctx->n_lights <= 16 && tiles * rt::kSignalsPerTile < (1ll << 23);
+		const bool wave_by_choice = variant == RT_KERNEL_AUTO && mesh_nodes >= wave_min_nodes && tiles * rt::kSignalsPerTile <= wave_max_tiles_per_sm * d.sm_count;
+		if (wave_possible && (variant == RT_KERNEL_WAVEFRONT || wave_by_choice))
+		{
+			const int src = ensure_splits(ctx, d, stream);       // (only now: the tables cost host time per mesh upload)
+			if (src != RT_OK) return src;
+			for (const HostMesh& hm : ctx->meshes)
+			{
+				if (hm.triangles.empty()) continue;
+				if (hm.split.empty()) wave_possible = false; else wave_subtrees += hm.split[0];
+			}
+		}
+		else wave_possible = false;
+		// the job lists are sized for the worst case (every tile reaches every subtree for every light): keep them below 64 MB
+		if (tiles * rt::kSignalsPerTile * std::max(wave_subtrees, 1ll) * std::max(ctx->n_lights, 1) > (8ll << 20)) wave_possible = false;
+		if (tiles * rt::kThreads * (long long)std::max<size_t>(ctx->meshes.size(), 1) * std::max(ctx->n_lights, 1) > (16ll << 20)) wave_possible = false;     // the per-ray subtree masks: <= 128 MB
+		if (variant == RT_KERNEL_WAVEFRONT && !wave_possible) variant = RT_KERNEL_AUTO;
+		if (wave_by_choice && wave_possible) variant = RT_KERNEL_WAVEFRONT;
 		KernelFn persistent = nullptr;
 		int wave = 0;
 		if (variant == RT_KERNEL_AUTO || variant == RT_KERNEL_PERSISTENT)
@@ -1134,11 +1165,9 @@ namespace
 {
 	// Turns the reference's BVHNode array into the threaded layout of rt::BvhLink.  Every index is
 	// validated: a malformed tree is an error, never a hang or an out-of-bounds read on the GPU.
-	int thread_bvh(rt_context* ctx, const rt_mesh_desc* mesh, std::vector<float4>& out, std::vector<int32_t>& split, std::vector<uint8_t>& root_map)
+	int thread_bvh(rt_context* ctx, const rt_mesh_desc* mesh, std::vector<float4>& out)
 	{
 		out.clear();
-		split.clear();
-		root_map.clear();
 		const int32_t n = mesh->bvh_node_count;
 		if (!mesh->bvh_nodes || n <= 0 || mesh->triangle_count == 0) return RT_OK;
 		if (n > rt::BvhLink::kMaxNodes) return fail(ctx, RT_ERR_CAPACITY, "%d BVH nodes exceed the capacity of %d", n, rt::BvhLink::kMaxNodes);
@@ -1181,109 +1210,131 @@ namespace
 		}
 		if (covered != mesh->triangle_count) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "BVH leaves cover %lld of %d triangles", (long long)covered, mesh->triangle_count);
 
-		// RT_KERNEL_WAVEFRONT: cut the tree into at most kMaxSubtrees subtrees of comparable size and every subtree into at
-		// most kFine parts (rt_wave_params.h); a part is walked from its root until the walk leaves through the root's
-		// escape link.
-		{
-			using namespace rt::wave;
-			std::vector<int32_t> size((size_t)n, 1), escape((size_t)n, -1);
-			std::vector<int32_t> order;           // pre-order, to accumulate sizes bottom-up
-			{
-				std::vector<Item> st;
-				st.push_back({ 0, -1 });
-				while (!st.empty())
-				{
-					const Item it = st.back(); st.pop_back();
-					order.push_back(it.node); escape[(size_t)it.node] = it.escape;
-					const rt_bvh_node& nd = mesh->bvh_nodes[it.node];
-					if (nd.idx_count == 0) { st.push_back({ (int32_t)nd.left_node + 1, it.escape }); st.push_back({ (int32_t)nd.left_node, (int32_t)nd.left_node + 1 }); }
-				}
-				for (size_t i = order.size(); i-- > 0;)
-				{
-					const rt_bvh_node& nd = mesh->bvh_nodes[order[i]];
-					if (nd.idx_count == 0) size[(size_t)order[i]] = 1 + size[nd.left_node] + size[nd.left_node + 1];
-				}
-			}
-			// what a subtree spans: node records and triangles (lowest / highest index below the root, triangles of its leaves)
-			std::vector<int32_t> node_lo((size_t)n, INT32_MAX), node_hi((size_t)n, -1), tri_lo((size_t)n, INT32_MAX), tri_hi((size_t)n, -1), tri_sum((size_t)n, 0);
-			for (size_t i = order.size(); i-- > 0;)
-			{
-				const int32_t node = order[i];
-				const rt_bvh_node& nd = mesh->bvh_nodes[node];
-				if (nd.idx_count > 0)
-				{
-					tri_lo[(size_t)node] = (int32_t)(nd.first_idx / 3);
-					tri_hi[(size_t)node] = (int32_t)((nd.first_idx + nd.idx_count) / 3) - 1;
-					tri_sum[(size_t)node] = (int32_t)(nd.idx_count / 3);
-					continue;
-				}
-				for (int32_t child = (int32_t)nd.left_node; child <= (int32_t)nd.left_node + 1; ++child)
-				{
-					node_lo[(size_t)node] = std::min(node_lo[(size_t)node], std::min(child, node_lo[(size_t)child]));
-					node_hi[(size_t)node] = std::max(node_hi[(size_t)node], std::max(child, node_hi[(size_t)child]));
-					tri_lo[(size_t)node] = std::min(tri_lo[(size_t)node], tri_lo[(size_t)child]);
-					tri_hi[(size_t)node] = std::max(tri_hi[(size_t)node], tri_hi[(size_t)child]);
-					tri_sum[(size_t)node] += tri_sum[(size_t)child];
-				}
-			}
-			// cut(root, pieces, depth): start from `root` and keep replacing the largest inner piece by its two children
-			// (each remembers the nodes between `root` and itself) until there are `pieces` or nothing is left to cut
-			struct Piece { int32_t node; std::vector<int32_t> above; };
-			auto cut = [&](int32_t root, int pieces, int depth)
-			{
-				std::vector<Piece> out_pieces;
-				out_pieces.push_back({ root, {} });
-				while ((int)out_pieces.size() < pieces)
-				{
-					int pick = -1;
-					for (size_t e = 0; e < out_pieces.size(); ++e)
-					{
-						if (mesh->bvh_nodes[out_pieces[e].node].idx_count != 0 || (int)out_pieces[e].above.size() >= depth) continue;
-						if (pick < 0 || size[(size_t)out_pieces[e].node] > size[(size_t)out_pieces[(size_t)pick].node]) pick = (int)e;
-					}
-					if (pick < 0) break;
-					const Piece parent = out_pieces[(size_t)pick];
-					const int32_t left = (int32_t)mesh->bvh_nodes[parent.node].left_node;
-					std::vector<int32_t> above = parent.above;
-					above.push_back(parent.node);
-					out_pieces[(size_t)pick] = { left, above };
-					out_pieces.insert(out_pieces.begin() + pick + 1, Piece{ left + 1, above });
-				}
-				return out_pieces;
-			};
-			static const int cap = [] { const char* e = getenv("RT_B200_WAVE_SUBTREES"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxSubtrees) ? v : kMaxSubtrees; }();
-			static const int fine_cap = [] { const char* e = getenv("RT_B200_WAVE_PARTS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kFine) ? v : kFine; }();
-			const std::vector<Piece> subtrees = cut(0, n >= 64 ? cap : 1, n);        // a shallow tree is one job
-			split.assign((size_t)kSplitStride, 0);
-			split[0] = (int32_t)subtrees.size();
-			root_map.assign((size_t)n, 0);
-			for (size_t e = 0; e < subtrees.size(); ++e) root_map[(size_t)subtrees[e].node] = (uint8_t)(e + 1);
-			for (size_t e = 0; e < subtrees.size(); ++e)
-			{
-				std::vector<Piece> parts = cut(subtrees[e].node, fine_cap, kFineAncestors);
-				for (size_t f = 0; f <= (size_t)kFine; ++f)
-				{
-					if (f < (size_t)kFine && f >= parts.size()) continue;
-					const Piece piece = f < (size_t)kFine ? parts[f] : Piece{ subtrees[e].node, {} };
-					const int32_t node = piece.node;
-					int32_t* rec = split.data() + kSplitHeader + (e * (kFine + 1) + f) * kSplitWords;
-					rec[0] = node * rt::BvhLink::kNodeBytes;
-					rec[1] = rt::BvhLink::miss(escape[(size_t)node]);
-					const int32_t below = size[(size_t)node] - 1, tris = tri_sum[(size_t)node];
-					const bool nodes_contiguous = below == 0 || (node_lo[(size_t)node] == (int32_t)mesh->bvh_nodes[node].left_node && node_hi[(size_t)node] - node_lo[(size_t)node] + 1 == below);
-					const bool tris_contiguous = tri_hi[(size_t)node] - tri_lo[(size_t)node] + 1 == tris;
-					rec[2] = below ? node_lo[(size_t)node] * rt::BvhLink::kNodeBytes : 0;
-					rec[3] = below;
-					rec[4] = tri_lo[(size_t)node];
-					rec[5] = tris;
-					rec[6] = kPartPresent | ((nodes_contiguous && tris_contiguous && (size_t)(1 + below) * 32 + (size_t)tris * 48 <= (size_t)kStageBytes) ? kPartStageable : 0);
-					rec[7] = (int32_t)piece.above.size();
-					for (size_t k = 0; k < piece.above.size(); ++k) rec[8 + k] = piece.above[k] * rt::BvhLink::kNodeBytes;
-				}
-			}
-		}
 		return RT_OK;
 	}
+}
+
+namespace
+{
+	// RT_KERNEL_WAVEFRONT: cut a host-uploaded tree into at most kMaxSubtrees subtrees of comparable size and every subtree
+	// into at most kFine parts (rt_wave_params.h); a part is walked from its root until the walk leaves through the root's
+	// escape link.  Reads the threaded records (thread_bvh validated them); built when a launch first wants the tables
+	// (ensure_splits): a mesh that is uploaded anew every frame and never rendered this way does not pay for them.
+	void build_split(HostMesh& hm)
+	{
+		hm.split.clear();
+		hm.root_map.clear();
+		const int32_t n = (int32_t)(hm.nodes.size() / 2);
+		if (n <= 0 || hm.device_bvh) return;
+		struct NodeView { bool leaf; int32_t left, first, count; };
+		auto view = [&](int32_t node)
+		{
+			const int hit = float_bits(hm.nodes[2 * (size_t)node + 1].z);
+			NodeView v{};
+			v.leaf = rt::BvhLink::is_leaf(hit);
+			if (v.leaf) { v.first = rt::BvhLink::leaf_first(hit); v.count = rt::BvhLink::leaf_count(hit); }
+			else v.left = hit / rt::BvhLink::kNodeBytes;
+			return v;
+		};
+		struct Item { int32_t node, escape; };
+		using namespace rt::wave;
+		std::vector<int32_t> size((size_t)n, 1), escape((size_t)n, -1);
+		std::vector<int32_t> order;           // pre-order, to accumulate sizes bottom-up
+		{
+			std::vector<Item> st;
+			st.push_back({ 0, -1 });
+			while (!st.empty())
+			{
+				const Item it = st.back(); st.pop_back();
+				order.push_back(it.node); escape[(size_t)it.node] = it.escape;
+				const NodeView nd = view(it.node);
+				if (!nd.leaf) { st.push_back({ nd.left + 1, it.escape }); st.push_back({ nd.left, nd.left + 1 }); }
+			}
+			for (size_t i = order.size(); i-- > 0;)
+			{
+				const NodeView nd = view(order[i]);
+				if (!nd.leaf) size[(size_t)order[i]] = 1 + size[(size_t)nd.left] + size[(size_t)nd.left + 1];
+			}
+		}
+		// what a subtree spans: node records and triangles (lowest / highest index below the root, triangles of its leaves)
+		std::vector<int32_t> node_lo((size_t)n, INT32_MAX), node_hi((size_t)n, -1), tri_lo((size_t)n, INT32_MAX), tri_hi((size_t)n, -1), tri_sum((size_t)n, 0);
+		for (size_t i = order.size(); i-- > 0;)
+		{
+			const int32_t node = order[i];
+			const NodeView nd = view(node);
+			if (nd.leaf)
+			{
+				tri_lo[(size_t)node] = nd.first;
+				tri_hi[(size_t)node] = nd.first + nd.count - 1;
+				tri_sum[(size_t)node] = nd.count;
+				continue;
+			}
+			for (int32_t child = nd.left; child <= nd.left + 1; ++child)
+			{
+				node_lo[(size_t)node] = std::min(node_lo[(size_t)node], std::min(child, node_lo[(size_t)child]));
+				node_hi[(size_t)node] = std::max(node_hi[(size_t)node], std::max(child, node_hi[(size_t)child]));
+				tri_lo[(size_t)node] = std::min(tri_lo[(size_t)node], tri_lo[(size_t)child]);
+				tri_hi[(size_t)node] = std::max(tri_hi[(size_t)node], tri_hi[(size_t)child]);
+				tri_sum[(size_t)node] += tri_sum[(size_t)child];
+			}
+		}
+		// cut(root, pieces, depth): start from `root` and keep replacing the largest inner piece by its two children
+		// (each remembers the nodes between `root` and itself) until there are `pieces` or nothing is left to cut
+		struct Piece { int32_t node; std::vector<int32_t> above; };
+		auto cut = [&](int32_t root, int pieces, int depth)
+		{
+			std::vector<Piece> out_pieces;
+			out_pieces.push_back({ root, {} });
+			while ((int)out_pieces.size() < pieces)
+			{
+				int pick = -1;
+				for (size_t e = 0; e < out_pieces.size(); ++e)
+				{
+					if (view(out_pieces[e].node).leaf || (int)out_pieces[e].above.size() >= depth) continue;
+					if (pick < 0 || size[(size_t)out_pieces[e].node] > size[(size_t)out_pieces[(size_t)pick].node]) pick = (int)e;
+				}
+				if (pick < 0) break;
+				const Piece parent = out_pieces[(size_t)pick];
+				const int32_t left = view(parent.node).left;
+				std::vector<int32_t> above = parent.above;
+				above.push_back(parent.node);
+				out_pieces[(size_t)pick] = { left, above };
+				out_pieces.insert(out_pieces.begin() + pick + 1, Piece{ left + 1, above });
+			}
+			return out_pieces;
+		};
+		static const int cap = [] { const char* e = getenv("RT_B200_WAVE_SUBTREES"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxSubtrees) ? v : kMaxSubtrees; }();
+		static const int fine_cap = [] { const char* e = getenv("RT_B200_WAVE_PARTS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kFine) ? v : kFine; }();
+		const std::vector<Piece> subtrees = cut(0, n >= 64 ? cap : 1, n);        // a shallow tree is one job
+		hm.split.assign((size_t)kSplitStride, 0);
+		hm.split[0] = (int32_t)subtrees.size();
+		hm.root_map.assign((size_t)n, 0);
+		for (size_t e = 0; e < subtrees.size(); ++e) hm.root_map[(size_t)subtrees[e].node] = (uint8_t)(e + 1);
+		for (size_t e = 0; e < subtrees.size(); ++e)
+		{
+			std::vector<Piece> parts = cut(subtrees[e].node, fine_cap, kFineAncestors);
+			for (size_t f = 0; f <= (size_t)kFine; ++f)
+			{
+				if (f < (size_t)kFine && f >= parts.size()) continue;
+				const Piece piece = f < (size_t)kFine ? parts[f] : Piece{ subtrees[e].node, {} };
+				const int32_t node = piece.node;
+				int32_t* rec = hm.split.data() + kSplitHeader + (e * (kFine + 1) + f) * kSplitWords;
+				rec[0] = node * rt::BvhLink::kNodeBytes;
+				rec[1] = rt::BvhLink::miss(escape[(size_t)node]);
+				const int32_t below = size[(size_t)node] - 1, tris = tri_sum[(size_t)node];
+				const bool nodes_contiguous = below == 0 || (node_lo[(size_t)node] == view(node).left && node_hi[(size_t)node] - node_lo[(size_t)node] + 1 == below);
+				const bool tris_contiguous = tri_hi[(size_t)node] - tri_lo[(size_t)node] + 1 == tris;
+				rec[2] = below ? node_lo[(size_t)node] * rt::BvhLink::kNodeBytes : 0;
+				rec[3] = below;
+				rec[4] = tri_lo[(size_t)node];
+				rec[5] = tris;
+				rec[6] = kPartPresent | ((nodes_contiguous && tris_contiguous && (size_t)(1 + below) * 32 + (size_t)tris * 48 <= (size_t)kStageBytes) ? kPartStageable : 0);
+				rec[7] = (int32_t)piece.above.size();
+				for (size_t k = 0; k < piece.above.size(); ++k) rec[8 + k] = piece.above[k] * rt::BvhLink::kNodeBytes;
+			}
+		}
+	}
+
 }
 
 namespace
@@ -1773,6 +1824,7 @@ int rt_create(const int32_t* device_ids, int32_t n_devices, rt_context** out_ctx
 		RT_CREATE(cudaEventCreateWithFlags(&d.ev_upload, cudaEventDisableTiming));
 		RT_CREATE(cudaEventRecord(d.ev_upload, d.stream));
 		RT_CREATE(cudaEventCreateWithFlags(&d.ev_foreign, cudaEventDisableTiming));
+		RT_CREATE(cudaEventCreateWithFlags(&d.ev_split, cudaEventDisableTiming));
 		RT_CREATE(cudaMalloc(&d.d_counters, sizeof(unsigned long long) * RT_COUNTER_SLOTS));
 		RT_CREATE(cudaEventCreate(&d.ev_begin));
 		RT_CREATE(cudaEventCreate(&d.ev_kernel));
@@ -1841,6 +1893,7 @@ int rt_destroy(rt_context* ctx)
 		cudaFree(d.d_split); cudaFree(d.d_wave); cudaFree(d.d_root_map); cudaFree(d.d_band_table); cudaFreeHost(d.h_band_table); cudaFreeHost(d.h_flags); cudaFreeHost(d.h_wave_jobs);
 		if (d.ev_upload) cudaEventDestroy(d.ev_upload);
 		if (d.ev_foreign) cudaEventDestroy(d.ev_foreign);
+		if (d.ev_split) cudaEventDestroy(d.ev_split);
 		cudaFree(d.cells.d_cost); cudaFree(d.cells.d_order); cudaFreeHost(d.cells.h_cost); cudaFreeHost(d.cells.h_order);
 		for (cudaEvent_t e : d.cells.ev_cost) if (e) cudaEventDestroy(e);
 		for (cudaEvent_t e : d.cells.ev_order) if (e) cudaEventDestroy(e);
@@ -2109,7 +2162,8 @@ int rt_upload_mesh(rt_context* ctx, int32_t mesh_id, const rt_mesh_desc* mesh)
 	hm.cull_mode = mesh->cull_mode;
 	hm.material = mesh->material_index;
 	if (mesh->bvh_node_count < 0) return fail(ctx, RT_ERR_INVALID_ARGUMENT, "negative BVH node count");
-	const int brc = thread_bvh(ctx, mesh, hm.nodes, hm.split, hm.root_map);
+	hm.split.clear(); hm.root_map.clear(); hm.split_built = false;
+	const int brc = thread_bvh(ctx, mesh, hm.nodes);
 	if (brc != RT_OK) { hm.uploaded = false; return brc; }
 	hm.uploaded = true;
 	ctx->mesh_dirty = true;
