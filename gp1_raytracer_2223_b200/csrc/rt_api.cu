@@ -1542,6 +1542,13 @@ namespace
 		const int tail_rows = H - (total_strips - 1) * rt::kBlockH;          // rows of the frame's last strip
 		if (last == total_strips - 1 && tail_rows != rt::kBlockH) --full;
 		const size_t row_bytes = (size_t)W * 4u;
+		if (pitch_bytes == 4 * W && step == 1)
+		{
+			// one device's consecutive strips in a tightly packed surface: one contiguous range (incl. a short last strip)
+			const size_t rows = (size_t)full * rt::kBlockH + (full < count ? (size_t)tail_rows : 0u);
+			RT_CUDA(ctx, cudaMemcpyAsync((char*)target + (size_t)first * rt::kBlockH * row_bytes, d.d_frame + (size_t)first * rt::kBlockH * W, rows * row_bytes, cudaMemcpyDeviceToHost, d.copy_stream));
+			return RT_OK;
+		}
 		if (pitch_bytes == 4 * W)
 		{
 			if (full > 0)
