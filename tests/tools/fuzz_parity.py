@@ -32,6 +32,11 @@ for seed in range(first, first + count):
             if variant == 4 and gpu_path != 2: continue
             r.ctx.set_mesh_path(gpu_path); r.ctx.set_kernel_variant(variant)
             got = r.Render()
+            if variant == 4:
+                again = r.Render()         # the second wavefront frame chooses its units by the first one's job counts
+                if not np.array_equal(got, again):
+                    bad += 1
+                    print(f"seed {seed}: two wavefront frames of the same scene differ in {int((got != again).sum())} px")
             total += 1
             nd = int((got != want).sum())
             if nd:
