@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Differential fuzzing: seeded random scenes (tests/random_scenes.py) rendered by the CUDA path (both mesh bodies,
-every kernel variant) and by the CPU oracle; reports every differing pixel.  Usage: python tests/tools/fuzz_parity.py [first_seed] [count]"""
+every kernel variant) and by the CPU oracle; reports every differing pixel.  Usage: python tests/tools/fuzz_parity.py [first_seed] [count] [max triangles per mesh]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -10,12 +10,13 @@ from gp1_raytracer_2223_b200 import Renderer
 from oracle import rt_oracle
 
 first, count = (int(sys.argv[1]) if len(sys.argv) > 1 else 1000), (int(sys.argv[2]) if len(sys.argv) > 2 else 100)
+max_triangles = int(sys.argv[3]) if len(sys.argv) > 3 else 120          # per mesh; thousands make trees deep enough for subtrees with several parts
 bad = total = 0
 for seed in range(first, first + count):
     rng = np.random.default_rng(seed)
     pow_materials = bool(rng.integers(0, 2))
     scene = random_scene(seed, n_spheres=int(rng.integers(0, 7)), n_planes=int(rng.integers(0, 8)), n_meshes=int(rng.integers(0, 4)),
-                         n_triangles=int(rng.integers(1, 120)), n_lights=int(rng.integers(0, 6)), pow_materials=pow_materials)
+                         n_triangles=int(rng.integers(1, max_triangles)), n_lights=int(rng.integers(0, 6)), pow_materials=pow_materials)
     # random camera jitter, occasionally axis aligned (zero direction components)
     if rng.integers(0, 4) == 0:
         scene.camera.right[:] = (1, 0, 0); scene.camera.up[:] = (0, 1, 0); scene.camera.forward[:] = (0, 0, 1)
