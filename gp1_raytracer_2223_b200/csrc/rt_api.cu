@@ -1219,122 +1219,116 @@ namespace
 	// RT_KERNEL_WAVEFRONT: cut a host-uploaded tree into at most kMaxSubtrees subtrees of comparable size and every subtree
 	// into at most kFine parts (rt_wave_params.h); a part is walked from its root until the walk leaves through the root's
 	// escape link.  Reads the threaded records (thread_bvh validated them); built when a launch first wants the tables
-	// (ensure_splits): a mesh that is uploaded anew every frame and never rendered this way does not pay for them.
+	// (ensure_splits): a mesh that is uploaded anew every frame and never rendered this way does not pay for them, and
+	// one that is (an animated Scene_W4_OptionalScene) pays two linear passes over its nodes - this runs between the
+	// caller's Render() and the first kernel of the frame.
 	void build_split(HostMesh& hm)
 	{
+		using namespace rt::wave;
 		hm.split.clear();
 		hm.root_map.clear();
 		const int32_t n = (int32_t)(hm.nodes.size() / 2);
 		if (n <= 0 || hm.device_bvh) return;
-		struct NodeView { bool leaf; int32_t left, first, count; };
-		auto view = [&](int32_t node)
+		auto hit_of = [&](int32_t node) { return float_bits(hm.nodes[2 * (size_t)node + 1].z); };
+		auto miss_of = [&](int32_t node) { return float_bits(hm.nodes[2 * (size_t)node + 1].w); };
+		auto left_of = [&](int32_t node) { return hit_of(node) / rt::BvhLink::kNodeBytes; };
+		auto is_leaf = [&](int32_t node) { return rt::BvhLink::is_leaf(hit_of(node)); };
+		// Children sit behind their parent in the reference's array (nodesUsed only grows, DataTypes.h:372-373): one pass
+		// down marks what the root reaches, one pass up adds up what every subtree spans - nodes below it (count, lowest
+		// and highest index) and triangles (count, first, last).  A tree in another order gets no tables (the wavefront
+		// form is then not offered for the scene).
+		thread_local std::vector<int32_t> scratch;
+		scratch.assign(6 * (size_t)n, 0);
+		int32_t* size = scratch.data(), * node_lo = size + n, * node_hi = node_lo + n, * tri_lo = node_hi + n, * tri_hi = tri_lo + n, * tri_sum = tri_hi + n;
+		size[0] = 1;
+		for (int32_t i = 0; i < n; ++i)
 		{
-			const int hit = float_bits(hm.nodes[2 * (size_t)node + 1].z);
-			NodeView v{};
-			v.leaf = rt::BvhLink::is_leaf(hit);
-			if (v.leaf) { v.first = rt::BvhLink::leaf_first(hit); v.count = rt::BvhLink::leaf_count(hit); }
-			else v.left = hit / rt::BvhLink::kNodeBytes;
-			return v;
-		};
-		struct Item { int32_t node, escape; };
-		using namespace rt::wave;
-		std::vector<int32_t> size((size_t)n, 1), escape((size_t)n, -1);
-		std::vector<int32_t> order;           // pre-order, to accumulate sizes bottom-up
-		{
-			std::vector<Item> st;
-			st.push_back({ 0, -1 });
-			while (!st.empty())
-			{
-				const Item it = st.back(); st.pop_back();
-				order.push_back(it.node); escape[(size_t)it.node] = it.escape;
-				const NodeView nd = view(it.node);
-				if (!nd.leaf) { st.push_back({ nd.left + 1, it.escape }); st.push_back({ nd.left, nd.left + 1 }); }
-			}
-			for (size_t i = order.size(); i-- > 0;)
-			{
-				const NodeView nd = view(order[i]);
-				if (!nd.leaf) size[(size_t)order[i]] = 1 + size[(size_t)nd.left] + size[(size_t)nd.left + 1];
-			}
+			if (!size[i] || is_leaf(i)) continue;
+			const int32_t left = left_of(i);
+			if (left <= i || left + 1 >= n) return;
+			size[left] = size[left + 1] = 1;
 		}
-		// what a subtree spans: node records and triangles (lowest / highest index below the root, triangles of its leaves)
-		std::vector<int32_t> node_lo((size_t)n, INT32_MAX), node_hi((size_t)n, -1), tri_lo((size_t)n, INT32_MAX), tri_hi((size_t)n, -1), tri_sum((size_t)n, 0);
-		for (size_t i = order.size(); i-- > 0;)
+		for (int32_t i = n; i-- > 0;)
 		{
-			const int32_t node = order[i];
-			const NodeView nd = view(node);
-			if (nd.leaf)
+			if (!size[i]) continue;
+			const int hit = hit_of(i);
+			if (rt::BvhLink::is_leaf(hit))
 			{
-				tri_lo[(size_t)node] = nd.first;
-				tri_hi[(size_t)node] = nd.first + nd.count - 1;
-				tri_sum[(size_t)node] = nd.count;
+				tri_lo[i] = rt::BvhLink::leaf_first(hit);
+				tri_sum[i] = rt::BvhLink::leaf_count(hit);
+				tri_hi[i] = tri_lo[i] + tri_sum[i] - 1;
+				node_lo[i] = INT32_MAX; node_hi[i] = -1;
 				continue;
 			}
-			for (int32_t child = nd.left; child <= nd.left + 1; ++child)
-			{
-				node_lo[(size_t)node] = std::min(node_lo[(size_t)node], std::min(child, node_lo[(size_t)child]));
-				node_hi[(size_t)node] = std::max(node_hi[(size_t)node], std::max(child, node_hi[(size_t)child]));
-				tri_lo[(size_t)node] = std::min(tri_lo[(size_t)node], tri_lo[(size_t)child]);
-				tri_hi[(size_t)node] = std::max(tri_hi[(size_t)node], tri_hi[(size_t)child]);
-				tri_sum[(size_t)node] += tri_sum[(size_t)child];
-			}
+			const int32_t l = hit / rt::BvhLink::kNodeBytes, r = l + 1;
+			size[i] = 1 + size[l] + size[r];
+			node_lo[i] = std::min(l, std::min(node_lo[l], node_lo[r]));
+			node_hi[i] = std::max(r, std::max(node_hi[l], node_hi[r]));
+			tri_lo[i] = std::min(tri_lo[l], tri_lo[r]);
+			tri_hi[i] = std::max(tri_hi[l], tri_hi[r]);
+			tri_sum[i] = tri_sum[l] + tri_sum[r];
 		}
-		// cut(root, pieces, depth): start from `root` and keep replacing the largest inner piece by its two children
-		// (each remembers the nodes between `root` and itself) until there are `pieces` or nothing is left to cut
-		struct Piece { int32_t node; std::vector<int32_t> above; };
-		auto cut = [&](int32_t root, int pieces, int depth)
+		// cut(root, pieces, depth): start from `root` and keep replacing the largest inner piece by its two children (each
+		// remembers the nodes between `root` and itself, as far as a part's record has room) until there are `pieces` or
+		// nothing is left to cut
+		struct Piece { int32_t node, depth, above[kFineAncestors]; };
+		auto cut = [&](int32_t root, int pieces, int depth, Piece* out)
 		{
-			std::vector<Piece> out_pieces;
-			out_pieces.push_back({ root, {} });
-			while ((int)out_pieces.size() < pieces)
+			int count = 1;
+			out[0] = Piece{ root, 0, {} };
+			while (count < pieces)
 			{
 				int pick = -1;
-				for (size_t e = 0; e < out_pieces.size(); ++e)
+				for (int e = 0; e < count; ++e)
 				{
-					if (view(out_pieces[e].node).leaf || (int)out_pieces[e].above.size() >= depth) continue;
-					if (pick < 0 || size[(size_t)out_pieces[e].node] > size[(size_t)out_pieces[(size_t)pick].node]) pick = (int)e;
+					if (is_leaf(out[e].node) || out[e].depth >= depth) continue;
+					if (pick < 0 || size[out[e].node] > size[out[pick].node]) pick = e;
 				}
 				if (pick < 0) break;
-				const Piece parent = out_pieces[(size_t)pick];
-				const int32_t left = view(parent.node).left;
-				std::vector<int32_t> above = parent.above;
-				above.push_back(parent.node);
-				out_pieces[(size_t)pick] = { left, above };
-				out_pieces.insert(out_pieces.begin() + pick + 1, Piece{ left + 1, above });
+				Piece child = out[pick];
+				if (child.depth < kFineAncestors) child.above[child.depth] = child.node;
+				++child.depth;
+				child.node = left_of(out[pick].node);
+				for (int e = count; e > pick + 1; --e) out[e] = out[e - 1];
+				out[pick] = child;
+				++child.node;
+				out[pick + 1] = child;
+				++count;
 			}
-			return out_pieces;
+			return count;
 		};
 		static const int cap = [] { const char* e = getenv("RT_B200_WAVE_SUBTREES"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kMaxSubtrees) ? v : kMaxSubtrees; }();
 		static const int fine_cap = [] { const char* e = getenv("RT_B200_WAVE_PARTS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= kFine) ? v : kFine; }();
-		const std::vector<Piece> subtrees = cut(0, n >= 64 ? cap : 1, n);        // a shallow tree is one job
+		Piece subtrees[kMaxSubtrees], parts[kFine];
+		const int n_subtrees = cut(0, n >= 64 ? cap : 1, INT32_MAX, subtrees);        // a shallow tree is one job
 		hm.split.assign((size_t)kSplitStride, 0);
-		hm.split[0] = (int32_t)subtrees.size();
+		hm.split[0] = n_subtrees;
 		hm.root_map.assign((size_t)n, 0);
-		for (size_t e = 0; e < subtrees.size(); ++e) hm.root_map[(size_t)subtrees[e].node] = (uint8_t)(e + 1);
-		for (size_t e = 0; e < subtrees.size(); ++e)
+		for (int e = 0; e < n_subtrees; ++e) hm.root_map[(size_t)subtrees[e].node] = (uint8_t)(e + 1);
+		for (int e = 0; e < n_subtrees; ++e)
 		{
-			std::vector<Piece> parts = cut(subtrees[e].node, fine_cap, kFineAncestors);
-			for (size_t f = 0; f <= (size_t)kFine; ++f)
+			const int n_parts = cut(subtrees[e].node, fine_cap, kFineAncestors, parts);
+			for (int f = 0; f <= kFine; ++f)
 			{
-				if (f < (size_t)kFine && f >= parts.size()) continue;
-				const Piece piece = f < (size_t)kFine ? parts[f] : Piece{ subtrees[e].node, {} };
+				if (f < kFine && f >= n_parts) continue;
+				const Piece piece = f < kFine ? parts[f] : Piece{ subtrees[e].node, 0, {} };
 				const int32_t node = piece.node;
-				int32_t* rec = hm.split.data() + kSplitHeader + (e * (kFine + 1) + f) * kSplitWords;
+				int32_t* rec = hm.split.data() + kSplitHeader + ((size_t)e * (kFine + 1) + (size_t)f) * kSplitWords;
 				rec[0] = node * rt::BvhLink::kNodeBytes;
-				rec[1] = rt::BvhLink::miss(escape[(size_t)node]);
-				const int32_t below = size[(size_t)node] - 1, tris = tri_sum[(size_t)node];
-				const bool nodes_contiguous = below == 0 || (node_lo[(size_t)node] == view(node).left && node_hi[(size_t)node] - node_lo[(size_t)node] + 1 == below);
-				const bool tris_contiguous = tri_hi[(size_t)node] - tri_lo[(size_t)node] + 1 == tris;
-				rec[2] = below ? node_lo[(size_t)node] * rt::BvhLink::kNodeBytes : 0;
+				rec[1] = miss_of(node);
+				const int32_t below = size[node] - 1, tris = tri_sum[node];
+				const bool nodes_contiguous = below == 0 || (node_lo[node] == left_of(node) && node_hi[node] - node_lo[node] + 1 == below);
+				const bool tris_contiguous = tri_hi[node] - tri_lo[node] + 1 == tris;
+				rec[2] = below ? node_lo[node] * rt::BvhLink::kNodeBytes : 0;
 				rec[3] = below;
-				rec[4] = tri_lo[(size_t)node];
+				rec[4] = tri_lo[node];
 				rec[5] = tris;
 				rec[6] = kPartPresent | ((nodes_contiguous && tris_contiguous && (size_t)(1 + below) * 32 + (size_t)tris * 48 <= (size_t)kStageBytes) ? kPartStageable : 0);
-				rec[7] = (int32_t)piece.above.size();
-				for (size_t k = 0; k < piece.above.size(); ++k) rec[8 + k] = piece.above[k] * rt::BvhLink::kNodeBytes;
+				rec[7] = piece.depth;
+				for (int k = 0; k < piece.depth; ++k) rec[8 + k] = piece.above[k] * rt::BvhLink::kNodeBytes;
 			}
 		}
 	}
-
 }
 
 namespace
