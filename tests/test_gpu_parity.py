@@ -373,6 +373,31 @@ def test_in_process_multi_device_presents(gpu):
         r.close()
 
 
+def test_in_process_multi_device_wavefront(gpu):
+    """Several devices in one context with RT_KERNEL_WAVEFRONT: every device renders its strips with the five launches
+    and its own copy of the split tables (built once per mesh, copied per device when its first launch wants them);
+    a re-uploaded mesh rebuilds them.  Frames against the reference's."""
+    torch = gpu
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    for name in ("optional_320", "w4ref_101x203", "bunny_333x77"):
+        want = load_golden_frame(name)
+        r = make_renderer(name, device_ids=list(range(n)))
+        r.ctx.set_mesh_path(2)
+        r.ctx.set_kernel_variant(4)
+        scene = load_golden_scene(name)
+        for frame in range(3):
+            if frame == 2:
+                r.ctx.upload_mesh_descriptor(0, r.ctx.mesh_descriptor(scene.meshes[0]))      # the same mesh again: new tables
+            identical, max_err, n_diff = compare_frames(r.Render(), want)
+            assert (n_diff == 0) if name in EXACT else (identical >= MIN_IDENTICAL and max_err <= MAX_LSB), (name, frame, n_diff, max_err)
+            r.render_device()
+            identical, max_err, n_diff = compare_frames(r.download(), want)
+            assert identical >= MIN_IDENTICAL and max_err <= MAX_LSB, (name, frame, n_diff, max_err)
+        r.close()
+
+
 def test_axis_parallel_rays_take_the_literal_slab_test(gpu):
     """Rays with a zero direction component have an infinite 1/dir; on a box face through the ray origin the
     slab products are 0 * inf = NaN and std::min/max semantics decide (reference source/Utils.h:197-215).
