@@ -373,6 +373,22 @@ def test_in_process_multi_device_presents(gpu):
         r.close()
 
 
+def test_wavefront_tables_follow_the_scene(gpu):
+    """One context, RT_KERNEL_WAVEFRONT, scenes swapped under it: three meshes, then one small mesh, then one deep mesh, and
+    back - the split tables are rebuilt for whatever meshes the launch finds (ensure_splits), block by block."""
+    r = make_renderer("w4ref_640")
+    r.ctx.set_mesh_path(2)
+    r.ctx.set_kernel_variant(4)
+    for name in ("w4ref_640", "bunny_640", "optional_640", "w4ref_640", "optional_640", "bunny_640"):
+        info = MANIFEST[name]
+        assert (info["width"], info["height"]) == (640, 480)
+        r.SetScene(load_golden_scene(name))
+        for frame in range(2):
+            identical, max_err, n_diff = compare_frames(r.Render(), load_golden_frame(name))
+            assert (n_diff == 0) if name in EXACT else (identical >= MIN_IDENTICAL and max_err <= MAX_LSB), (name, frame, n_diff, max_err)
+    r.close()
+
+
 def test_in_process_multi_device_wavefront(gpu):
     """Several devices in one context with RT_KERNEL_WAVEFRONT: every device renders its strips with the five launches
     and its own copy of the split tables (built once per mesh, copied per device when its first launch wants them);
